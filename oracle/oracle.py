@@ -1,0 +1,424 @@
+"""CPU oracle for Pandora's dense cost-volume hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``bench.py`` (``cpu_baseline`` leg and ``--impl reference``) and
+``__graft_entry__.smoke()`` may import this module.  ``pandora_b200`` never does.
+
+Two layers:
+
+* ``libpandora_oracle.so`` (``oracle/pandora_oracle.c``, plain C): census, cross support, CBCA,
+  reverse cost volume, SGM and WTA restated from the reference's C++ / the published algorithm.
+* numpy restatements of the reference's *Python* glue that cannot be imported in this image
+  (xarray, json_checker, rasterio and transitions are absent): SAD/SSD, ZNCC, the 3x3 NaN-median,
+  the CBCA driver, cost-volume allocation, validity mask and ``cv_masked`` (no-mask branch).
+
+All citations are relative to ``/root/reference/src/pandora``.
+
+Pinning: every function below is checked in ``tests/test_oracle_goldens.py`` against the literal
+golden arrays of the reference's own unit tests (``tests/golden/reference_goldens.npz``, extracted
+by ``tests/golden/extract_reference_goldens.py``) and, for census / cross support / CBCA / reverse,
+against the unmodified reference C++ compiled into ``oracle/_ref`` (``tests/test_oracle_vs_ref.py``).
+**SGM: parity unpinned** -- libSGM is an un-vendored dependency (pyproject.toml:59-61) and the
+reference holds no numeric SGM test; see the header of ``pbo_sgm`` in ``pandora_oracle.c``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import warnings
+from math import ceil, floor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# validity-mask bits, constants.py:28-55
+MSK_INVALID = 0b01111000011
+MSK_LEFT_NODATA_OR_BORDER = 1 << 0
+MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING = 1 << 1
+MSK_RIGHT_INCOMPLETE_DISPARITY_RANGE = 1 << 2
+
+
+def build(force: bool = False) -> str:
+    """Compile ``pandora_oracle.c`` (gcc) if the shared object is missing or stale."""
+    so = os.path.join(_HERE, "_build", "libpandora_oracle.so")
+    src = os.path.join(_HERE, "pandora_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O3", "-std=c11", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off", src, "-o", so, "-lm"]
+        )
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        f32p, i16p, u8p = (ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_uint8))
+        ci, cf, cl = ctypes.c_int, ctypes.c_float, ctypes.c_long
+        _LIB.pbo_census_cost.argtypes = [f32p, f32p, ci, ci, ci, ci, ci, f32p]
+        _LIB.pbo_census_cost.restype = ci
+        _LIB.pbo_cross_support.argtypes = [f32p, ci, ci, ci, cf, i16p]
+        _LIB.pbo_cross_support.restype = None
+        _LIB.pbo_cbca_slice.argtypes = [f32p, cl, cl, ci, ci, ci, i16p, i16p, f32p, f32p]
+        _LIB.pbo_cbca_slice.restype = ci
+        _LIB.pbo_cbca_volume.argtypes = [f32p, ci, ci, ci, ci, i16p, i16p, f32p]
+        _LIB.pbo_cbca_volume.restype = ci
+        _LIB.pbo_reverse_cost_volume.argtypes = [f32p, ci, ci, ci, ci, f32p]
+        _LIB.pbo_reverse_cost_volume.restype = None
+        _LIB.pbo_sgm.argtypes = [f32p, ci, ci, ci, cf, cf, cf, ci, ci, f32p]
+        _LIB.pbo_sgm.restype = ci
+        _LIB.pbo_wta.argtypes = [f32p, ci, ci, ci, f32p, ci, cf, f32p, u8p]
+        _LIB.pbo_wta.restype = None
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+# --------------------------------------------------------------------------------------------
+# cost volume container pieces: matching_cost/matching_cost.py:330-427
+# --------------------------------------------------------------------------------------------
+def disparity_range(dmin: int, dmax: int) -> np.ndarray:
+    """``get_disparity_range`` for subpix == 1, matching_cost.py:409-427."""
+    return np.arange(dmin, dmax + 1)
+
+
+def allocate_cost_volume(H: int, W: int, dmin: int, dmax: int) -> np.ndarray:
+    """NaN-filled float32 (row, col, disp) volume, matching_cost.py:377-407."""
+    return np.full((H, W, dmax - dmin + 1), np.nan, dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# Census: matching_cost/census.py:109-153 + cpp/src/census.cpp:45-180
+# --------------------------------------------------------------------------------------------
+def census_cost_volume(left, right, window: int, dmin: int, dmax: int):
+    """Returns (cv float32 (H, W, D), attrs) -- ``type_measure='min'``, ``cmax=w*w`` (census.py:116-122)."""
+    left, right = _f32(left), _f32(right)
+    H, W = left.shape
+    D = dmax - dmin + 1
+    cv = np.empty((H, W, D), dtype=np.float32)
+    rc = lib().pbo_census_cost(_p(left, ctypes.c_float), _p(right, ctypes.c_float), H, W, window, dmin, D, _p(cv, ctypes.c_float))
+    if rc:
+        raise ValueError(f"pbo_census_cost failed: {rc}")
+    return cv, {"type_measure": "min", "cmax": int(window**2)}
+
+
+# --------------------------------------------------------------------------------------------
+# SAD / SSD: matching_cost/sad_ssd.py:110-207, 209-224, 340-368 ; point_interval matching_cost.py:429-482
+# --------------------------------------------------------------------------------------------
+def point_interval(nx_left: int, nx_right: int, disp: float):
+    """matching_cost.py:429-482."""
+    if abs(disp) > nx_left:
+        point_p = (nx_left, nx_left)
+    else:
+        point_p = (max(0 - disp, 0), min(nx_left - disp, nx_left))
+    if abs(disp) > nx_right:
+        point_q = (nx_right, nx_right)
+    else:
+        point_q = (max(0 + disp, 0), min(nx_right + disp, nx_right))
+    rnd = ceil if disp < 0 else floor
+    return (int(rnd(point_p[0])), int(rnd(point_p[1]))), (int(rnd(point_q[0])), int(rnd(point_q[1])))
+
+
+def pixel_wise_aggregation(cost_volume: np.ndarray, window: int) -> np.ndarray:
+    """Window sum through a strided view exactly as sad_ssd.py:340-368 (same numpy reduction)."""
+    nb_disp, nx_, ny_ = cost_volume.shape
+    str_disp, str_col, str_row = cost_volume.strides
+    shape_windows = (window, window, nb_disp, nx_ - (window - 1), ny_ - (window - 1))
+    strides_windows = (str_row, str_col, str_disp, str_col, str_row)
+    view = np.lib.stride_tricks.as_strided(cost_volume, shape_windows, strides_windows, writeable=False)
+    return np.sum(view, (0, 1))
+
+
+def sad_ssd_cost_volume(left, right, window: int, dmin: int, dmax: int, method: str = "sad"):
+    """sad_ssd.py:75-207 for subpix == 1, single band.  Images are used in their own dtype like the
+    reference (tests feed float64, the pipeline float32)."""
+    left = np.asarray(left)
+    right = np.asarray(right)
+    H, W = left.shape
+    off = (window - 1) // 2
+    disps = disparity_range(dmin, dmax)
+    mx = max(abs(np.amax(left) - np.amin(right)), abs(np.amax(right) - np.amin(left)))
+    cmax = int(mx * window**2) if method == "sad" else int(mx**2 * window**2)
+    cv_enlarge = np.full((len(disps), W + 2 * off, H + 2 * off), np.nan, dtype=np.float32)
+    cv = cv_enlarge[:, off : W + off, off : H + off] if off else cv_enlarge
+    for k, d in enumerate(disps):
+        p, q = point_interval(W, W, d)
+        diff = left[:, p[0] : p[1]] - right[:, q[0] : q[1]]
+        cost = abs(diff) if method == "sad" else diff**2
+        cv[k, p[0] : p[1], :] = np.swapaxes(cost, 0, 1)
+    out = pixel_wise_aggregation(cv_enlarge, window)
+    out = np.swapaxes(out, 0, 2)
+    if off:
+        out[:off, :, :] = np.nan
+        out[-off:, :, :] = np.nan
+        out[:, :off, :] = np.nan
+        out[:, -off:, :] = np.nan
+    return np.ascontiguousarray(out), {"type_measure": "min", "cmax": cmax}
+
+
+# --------------------------------------------------------------------------------------------
+# ZNCC: matching_cost/zncc.py:73-241, 244-277 ; img_tools.py:834-879 (mean), 915-952 (std)
+# --------------------------------------------------------------------------------------------
+def compute_mean_raster(img: np.ndarray, win: int) -> np.ndarray:
+    """img_tools.py:834-879 -- float64 integral images (np.r_ with np.zeros promotes)."""
+    ny_, nx_ = img.shape
+    r_mean = np.r_[np.zeros((1, nx_)), img]
+    r_mean = np.nancumsum(r_mean, axis=0)
+    r_mean = r_mean[win:, :] - r_mean[:-win, :]
+    r_mean = np.c_[np.zeros(ny_ - (win - 1)), r_mean]
+    r_mean = np.cumsum(r_mean, axis=1)
+    r_mean = r_mean[:, win:] - r_mean[:, :-win]
+    return r_mean / float(win * win)
+
+
+def compute_std_raster(img: np.ndarray, win: int) -> np.ndarray:
+    """img_tools.py:915-952."""
+    mean_ = compute_mean_raster(img, win)
+    mean_power_two = compute_mean_raster(img**2, win)
+    var = mean_power_two - mean_**2
+    var[np.where(var < (10 ** (-15) * abs(mean_power_two)))] = 0
+    return np.sqrt(var)
+
+
+def zncc_cost_volume(left, right, window: int, dmin: int, dmax: int):
+    """zncc.py:114-241 for subpix == 1, single band."""
+    left = np.asarray(left)
+    right = np.asarray(right)
+    H, W = left.shape
+    off = (window - 1) // 2
+    disps = disparity_range(dmin, dmax)
+    l_std, r_std = compute_std_raster(left, window), compute_std_raster(right, window)
+    l_mean, r_mean = compute_mean_raster(left, window), compute_mean_raster(right, window)
+    cv = np.full((len(disps), W, H), np.nan, dtype=np.float32)
+    cv_crop = cv[:, off : W - off, off : H - off] if off else cv
+    for k, d in enumerate(disps):
+        p, q = point_interval(W, W, d)
+        if abs(d) > W - (int(window / 2) * 2):                       # zncc.py:108-110
+            p, q = (W, W), (W, W)
+        p_std = (p[0], p[1] - (int(window / 2) * 2))
+        q_std = (q[0], q[1] - (int(window / 2) * 2))
+        prod = left[:, p[0] : p[1]] * right[:, q[0] : q[1]]
+        if prod.shape[1] < window:
+            continue
+        zncc_ = compute_mean_raster(prod, window)
+        zncc_ -= l_mean[:, p_std[0] : p_std[1]] * r_mean[:, q_std[0] : q_std[1]]
+        divide_standard = np.multiply(l_std[:, p_std[0] : p_std[1]], r_std[:, q_std[0] : q_std[1]])
+        valid = np.where(divide_standard > 0)
+        zncc_[valid] /= divide_standard[valid]
+        zncc_[np.where(divide_standard <= 0)] = 0
+        cv_crop[k, p[0] : p_std[1], :] = np.swapaxes(zncc_, 0, 1)
+    return np.ascontiguousarray(np.swapaxes(cv, 0, 2)), {"type_measure": "max", "cmax": 1}
+
+
+# --------------------------------------------------------------------------------------------
+# validity mask (no-mask branch) and cv_masked: criteria.py:66-158, 291-353 ; matching_cost.py:770-872
+# --------------------------------------------------------------------------------------------
+def validity_mask(H: int, W: int, dmin: int, dmax: int, offset: int) -> np.ndarray:
+    """criteria.py:106-147 without left/right ``msk``; columns are 0..W-1."""
+    vm = np.zeros((H, W), dtype=np.uint16)
+    col = np.arange(W)
+    if dmax < 0:
+        bit_1 = np.where((col + dmax) < (col[0] + offset))[0]
+        vm[:, np.where(((col + dmax) >= (col[0] + offset)) & ((col + dmin) < (col[0] + offset)))[0]] += (
+            MSK_RIGHT_INCOMPLETE_DISPARITY_RANGE
+        )
+    elif dmin > 0:
+        bit_1 = np.where((col + dmin) > (col[-1] - offset))[0]
+        vm[:, np.where(((col + dmin) <= (col[-1] - offset)) & ((col + dmax) > (col[-1] - offset)))[0]] += (
+            MSK_RIGHT_INCOMPLETE_DISPARITY_RANGE
+        )
+    else:
+        bit_1 = np.array([], dtype=int)
+        vm[:, np.where(((col + dmin) < (col[0] + offset)) | (col + dmax > (col[-1]) - offset))[0]] += (
+            MSK_RIGHT_INCOMPLETE_DISPARITY_RANGE
+        )
+    vm[:, bit_1] += MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING
+    return vm
+
+
+def cv_masked(cv: np.ndarray, vm: np.ndarray, offset: int) -> None:
+    """matching_cost.py:815-872 with no ``msk`` and a fixed disparity range: the mask additions and
+    the per-pixel range masking are value no-ops; what remains is
+    ``mask_invalid_variable_disparity_range`` (criteria.py:291-322) and ``mask_border`` (:325-353)."""
+    missing = np.min(np.isnan(cv), axis=2)
+    upd = missing & ((vm & MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING) == 0)
+    vm[upd] += MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING
+    if offset > 0:
+        vm[:offset, :] = MSK_LEFT_NODATA_OR_BORDER
+        vm[-offset:, :] = MSK_LEFT_NODATA_OR_BORDER
+        vm[offset:-offset, :offset] = MSK_LEFT_NODATA_OR_BORDER
+        vm[offset:-offset, -offset:] = MSK_LEFT_NODATA_OR_BORDER
+
+
+# --------------------------------------------------------------------------------------------
+# 3x3 NaN-aware median (CBCA pre-filter): filter/median.py:134-179 + common.py:184-199
+# --------------------------------------------------------------------------------------------
+def median_filter3(data: np.ndarray, size: int = 3) -> np.ndarray:
+    data = np.asarray(data)
+    out = np.copy(data)
+    invalid = np.isnan(out)
+    ny_, nx_ = data.shape
+    r = size // 2
+    if ny_ >= size and nx_ >= size:
+        shp = (ny_ - size + 1, nx_ - size + 1, size, size)
+        win = np.lib.stride_tricks.as_strided(data, shape=shp, strides=data.strides + data.strides)
+        with warnings.catch_warnings():
+            warnings.filterwarnings("ignore", r"All-NaN (slice|axis) encountered")
+            # the reference chunks by 100x100 only to bound memory; chunking does not change values
+            for y0 in range(0, shp[0], 100):
+                for x0 in range(0, shp[1], 100):
+                    blk = win[y0 : y0 + 100, x0 : x0 + 100]
+                    out[r + y0 : r + y0 + blk.shape[0], r + x0 : r + x0 + blk.shape[1]] = np.nanmedian(blk, axis=(2, 3))
+    out[invalid] = np.nan
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# CBCA: aggregation/cbca.py:90-295 + cpp/src/aggregation.cpp:28-355
+# --------------------------------------------------------------------------------------------
+def cross_support(img, len_arms: int, intensity: float) -> np.ndarray:
+    img = _f32(img)
+    H, W = img.shape
+    out = np.empty((H, W, 4), dtype=np.int16)
+    lib().pbo_cross_support(_p(img, ctypes.c_float), H, W, int(len_arms), float(intensity), _p(out, ctypes.c_int16))
+    return out
+
+
+def computes_cross_supports(left, right, offset: int, distance: int, intensity: float):
+    """cbca.py:184-295 for subpix == 1 without masks: median, NaN->inf, crop by offset, arms."""
+    res = []
+    for img in (left, right):
+        m = median_filter3(np.copy(np.asarray(img)))
+        m = np.nan_to_num(m, copy=False, nan=np.inf)
+        if offset:
+            m = m[offset:-offset, offset:-offset]
+        res.append(cross_support(m, distance, intensity))
+    return res[0], res[1]
+
+
+def cbca_slice(cost2d: np.ndarray, cross_l: np.ndarray, cross_r: np.ndarray, d: int):
+    """One call of the reference's ``aggregation_cpp.cbca`` (valid columns derived from d)."""
+    H, W = cost2d.shape
+    assert cost2d.dtype == np.float32
+    step4 = np.empty((H, W), dtype=np.float32)
+    sum4 = np.empty((H, W), dtype=np.float32)
+    rs, cs = (s // 4 for s in cost2d.strides)
+    rc = lib().pbo_cbca_slice(
+        _p(cost2d, ctypes.c_float), rs, cs, H, W, int(d), _p(cross_l, ctypes.c_int16), _p(cross_r, ctypes.c_int16),
+        _p(step4, ctypes.c_float), _p(sum4, ctypes.c_float),
+    )
+    if rc:
+        raise MemoryError("pbo_cbca_slice")
+    return step4, sum4
+
+
+def cbca_cost_volume(left, right, cv: np.ndarray, offset: int, dmin: int, distance: int = 5, intensity: float = 30.0,
+                     cmax=None):
+    """cbca.py:127-182: returns (aggregated copy of cv, new cmax)."""
+    cross_l, cross_r = computes_cross_supports(left, right, offset, distance, intensity)
+    out = np.array(cv, dtype=np.float32, copy=True)
+    view = out[offset:-offset, offset:-offset] if offset else out
+    src = np.ascontiguousarray(view)
+    H, W, D = src.shape
+    agg = np.empty_like(src)
+    rc = lib().pbo_cbca_volume(
+        _p(src, ctypes.c_float), H, W, D, int(dmin), _p(cross_l, ctypes.c_int16), _p(cross_r, ctypes.c_int16), _p(agg, ctypes.c_float)
+    )
+    if rc:
+        raise MemoryError("pbo_cbca_volume")
+    view[...] = agg
+    return out, (None if cmax is None else cmax * ((distance * 2) - 1) ** 2)
+
+
+# --------------------------------------------------------------------------------------------
+# SGM (unpinned, see module docstring) and WTA
+# --------------------------------------------------------------------------------------------
+def sgm_invalid_value(cmax: float, p2: float) -> float:
+    return float(cmax + p2 + 1)
+
+
+def sgm_cost_volume(cv: np.ndarray, p1: float = 8, p2: float = 32, cmax: float = 25, type_measure: str = "min",
+                    overcounting: bool = False, n_dirs: int = 8) -> np.ndarray:
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    src = -cv if type_measure == "max" else cv
+    out = np.empty_like(src)
+    rc = lib().pbo_sgm(_p(src, ctypes.c_float), H, W, D, float(p1), float(p2), sgm_invalid_value(cmax, p2),
+                       int(bool(overcounting)), int(n_dirs), _p(out, ctypes.c_float))
+    if rc:
+        raise ValueError(f"pbo_sgm failed: {rc}")
+    return -out if type_measure == "max" else out
+
+
+def wta(cv: np.ndarray, disps, type_measure: str = "min", invalid_disparity: float = -9999.0):
+    """disparity.py:434-455, 483-553 restated with numpy itself (argmin/argmax over axis 2)."""
+    cv = np.asarray(cv)
+    disps = np.asarray(disps)
+    nan = np.isnan(cv)
+    work = cv.copy()
+    if type_measure == "max":
+        work[nan] = -np.inf
+        idx = np.argmax(work, axis=2)
+    else:
+        work[nan] = np.inf
+        idx = np.argmin(work, axis=2)
+    disp = disps[idx].astype(np.float32)
+    invalid_mc = np.min(nan, axis=2)
+    disp[invalid_mc] = invalid_disparity
+    return disp, invalid_mc
+
+
+def wta_c(cv: np.ndarray, disps, type_measure: str = "min", invalid_disparity: float = -9999.0):
+    """Same through the C restatement (used for the timed CPU baseline on large volumes)."""
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    dc = _f32(disps)
+    disp = np.empty((H, W), dtype=np.float32)
+    inv = np.empty((H, W), dtype=np.uint8)
+    lib().pbo_wta(_p(cv, ctypes.c_float), H, W, D, _p(dc, ctypes.c_float), int(type_measure == "max"),
+                  float(invalid_disparity), _p(disp, ctypes.c_float), _p(inv, ctypes.c_uint8))
+    return disp, inv.astype(bool)
+
+
+def wta_validity_mask(vm: np.ndarray, invalid_mc: np.ndarray) -> np.ndarray:
+    """disparity.py:468-474."""
+    out = vm.copy()
+    new_inv = invalid_mc & ((out & MSK_INVALID) == 0)
+    out[new_inv] = MSK_INVALID
+    return out
+
+
+def reverse_cost_volume(left_cv: np.ndarray, min_disp: int) -> np.ndarray:
+    """matching_cost/cpp/src/matching_cost.cpp:26-57."""
+    left_cv = _f32(left_cv)
+    H, W, D = left_cv.shape
+    out = np.empty_like(left_cv)
+    lib().pbo_reverse_cost_volume(_p(left_cv, ctypes.c_float), H, W, D, int(min_disp), _p(out, ctypes.c_float))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# deterministic synthetic stereo pair used by tests and bench
+# --------------------------------------------------------------------------------------------
+def synthetic_pair(H: int, W: int, D: int, seed: int = 20240607, block: int = 64):
+    """Integer-valued float32 pair in [0, 255]; right = left warped by a piecewise-constant
+    disparity field g in [-(D-1), 0] (left(r,c) ~ right(r, c+g))."""
+    rng = np.random.default_rng(seed)
+    tex = rng.integers(0, 256, (H + 2, W + D + 2)).astype(np.int64)
+    sm = sum(tex[dy : dy + H, dx : dx + W + D] for dy in range(3) for dx in range(3)) // 9
+    g = -rng.integers(0, D, ((H + block - 1) // block, (W + block - 1) // block))
+    gfull = np.kron(g, np.ones((block, block), dtype=np.int64))[:H, :W]
+    cols = np.arange(W)[None, :]
+    left = sm[:, D : D + W]
+    # right(r, c) = T[r, D + c - g(r,c)]  so that left(r,c) == right(r, c + g) inside a block
+    right = np.take_along_axis(sm, np.clip(D + cols - gfull, 0, W + D - 1), axis=1)
+    return left.astype(np.float32), right.astype(np.float32), gfull.astype(np.float32)

@@ -1,0 +1,306 @@
+/*
+ * oracle/pandora_oracle.c  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain single-threaded C restatement of the CPU algorithms on Pandora's dense cost-volume hot
+ * path.  It is the checker the CUDA kernels are compared with; only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it.  The product
+ * (pandora_b200/) never imports, links or calls anything in this directory.
+ *
+ * Each function cites the reference file:line it restates (paths relative to /root/reference).
+ * Pinning status (see tests/test_oracle_goldens.py, tests/test_oracle_vs_ref.py):
+ *   census / cross_support / cbca : pinned to the reference's golden vectors AND to the compiled
+ *                                   reference C++ (oracle/_ref) on randomised inputs, bit-exact.
+ *   reverse_cost_volume           : pinned to the reference's C++ doctest vectors and oracle/_ref.
+ *   sgm                           : PARITY UNPINNED.  The arithmetic lives in the un-vendored
+ *                                   dependency pandora_plugin_libsgm==1.5.7 (pyproject.toml:59-61);
+ *                                   this file restates Hirschmueller's published 8-path recurrence
+ *                                   with the semantic choices listed above pbo_sgm().
+ *
+ * Build: make -C oracle   ->  oracle/_build/libpandora_oracle.so
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PBO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------ */
+/* Census transform: src/pandora/matching_cost/cpp/src/census.cpp:45-95                         */
+/* bit b (row-major over the w x w window, centre included) = neighbour > centre (strict).     */
+/* Only Hamming distances are observable so the packing (64-bit words here) is free.           */
+/* Border pixels (closer than half window to an edge) keep an all-zero descriptor.             */
+/* ------------------------------------------------------------------------------------------ */
+static int census_words(int w) { return (w * w + 63) / 64; }
+
+static void census_transform(const float *img, int H, int W, int w, uint64_t *out) {
+    const int half = w / 2, nw = census_words(w);
+    memset(out, 0, (size_t)H * W * nw * sizeof(uint64_t));
+    for (int y = half; y < H - half; ++y) {
+        for (int x = half; x < W - half; ++x) {
+            const float c = img[(size_t)y * W + x];
+            uint64_t *dst = out + ((size_t)y * W + x) * nw;
+            int b = 0;
+            for (int wy = y - half; wy <= y + half; ++wy)
+                for (int wx = x - half; wx <= x + half; ++wx, ++b)
+                    if (img[(size_t)wy * W + wx] > c) dst[b >> 6] |= (uint64_t)1 << (b & 63);
+        }
+    }
+}
+
+/* Census matching cost: census.cpp:97-180 (subpix == 1 branch) + the NaN pre-fill of
+ * matching_cost/census.py:138.  cv is (H, W, D) float32, disparity fastest.
+ * cv[y,x,k] = popcount(cL[y,x] ^ cR[y,x+dmin+k]) iff the left centre and the right centre are both
+ * at least `half` away from every image edge; everything else is NaN.                          */
+PBO_API int pbo_census_cost(const float *left, const float *right, int H, int W, int w, int dmin, int D,
+                            float *cv) {
+    if (w < 1 || (w & 1) == 0 || w > 13) return -1;
+    const int half = w / 2, nw = census_words(w);
+    const size_t n = (size_t)H * W * D;
+    for (size_t i = 0; i < n; ++i) cv[i] = NAN;
+    uint64_t *cl = (uint64_t *)malloc((size_t)H * W * nw * sizeof(uint64_t));
+    uint64_t *cr = (uint64_t *)malloc((size_t)H * W * nw * sizeof(uint64_t));
+    if (!cl || !cr) { free(cl); free(cr); return -2; }
+    census_transform(left, H, W, w, cl);
+    census_transform(right, H, W, w, cr);
+    for (int y = half; y < H - half; ++y)
+        for (int x = half; x < W - half; ++x) {
+            const uint64_t *a = cl + ((size_t)y * W + x) * nw;
+            float *dst = cv + ((size_t)y * W + x) * D;
+            for (int k = 0; k < D; ++k) {
+                const int xr = x + dmin + k;
+                if (xr < half || xr >= W - half) continue;
+                const uint64_t *b = cr + ((size_t)y * W + xr) * nw;
+                int cost = 0;
+                for (int i = 0; i < nw; ++i) cost += __builtin_popcountll(a[i] ^ b[i]);
+                dst[k] = (float)cost;
+            }
+        }
+    free(cl); free(cr);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Cross support arms: src/pandora/aggregation/cpp/src/aggregation.cpp:224-321                  */
+/* out is (H, W, 4) int16 in the order (left, right, up, bottom).                               */
+/* ------------------------------------------------------------------------------------------ */
+PBO_API void pbo_cross_support(const float *img, int H, int W, int len_arms, float intensity, int16_t *out) {
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int16_t *o = out + ((size_t)y * W + x) * 4;
+            const float c = img[(size_t)y * W + x];
+            if (!isfinite(c)) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+            int l = 0, r = 0, u = 0, b = 0;
+            for (int q = x - 1; q > x - len_arms && q >= 0; --q) {
+                if (fabsf(c - img[(size_t)y * W + q]) >= intensity) break;
+                ++l;
+            }
+            for (int q = x + 1; q < x + len_arms && q < W; ++q) {
+                if (fabsf(c - img[(size_t)y * W + q]) >= intensity) break;
+                ++r;
+            }
+            for (int q = y - 1; q > y - len_arms && q >= 0; --q) {
+                if (fabsf(c - img[(size_t)q * W + x]) >= intensity) break;
+                ++u;
+            }
+            for (int q = y + 1; q < y + len_arms && q < H; ++q) {
+                if (fabsf(c - img[(size_t)q * W + x]) >= intensity) break;
+                ++b;
+            }
+            /* minimum support of one pixel per arm when the direct neighbour is a finite pixel */
+            if (l < 1 && x >= 1 && isfinite(img[(size_t)y * W + x - 1])) l = 1;
+            if (r < 1 && x < W - 1 && isfinite(img[(size_t)y * W + x + 1])) r = 1;
+            if (u < 1 && y >= 1 && isfinite(img[(size_t)(y - 1) * W + x])) u = 1;
+            if (b < 1 && y < H - 1 && isfinite(img[(size_t)(y + 1) * W + x])) b = 1;
+            o[0] = (int16_t)l; o[1] = (int16_t)r; o[2] = (int16_t)u; o[3] = (int16_t)b;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CBCA for ONE disparity slice: aggregation.cpp:28-221 (cbca_step_1..4) driven by             */
+/* aggregation/cbca.py:152-171.  `cost` is a strided (H, W) view: element (y,x) at               */
+/* cost[y*row_stride + x*col_stride].  Valid columns are those with 0 <= x + d < W.             */
+/* Returns step4 (sum of costs over the cross) and sum4 (support size WITHOUT the +1 anchor,    */
+/* exactly like the reference's C++; the driver adds the 1).  float32 prefix sums like the      */
+/* reference, the "col - left - 1 == -1" read is the zero pad column (aggregation.cpp:113-114). */
+/* ------------------------------------------------------------------------------------------ */
+PBO_API int pbo_cbca_slice(const float *cost, long row_stride, long col_stride, int H, int W, int d,
+                           const int16_t *cross_l, const int16_t *cross_r, float *step4, float *sum4) {
+    float *s1 = (float *)calloc((size_t)H * (W + 1), sizeof(float));      /* horizontal prefix, col 0 = pad */
+    float *s2 = (float *)calloc((size_t)H * W, sizeof(float));
+    float *n2 = (float *)calloc((size_t)H * W, sizeof(float));
+    float *s3 = (float *)calloc((size_t)(H + 1) * W, sizeof(float));      /* vertical prefix, row 0 = pad */
+    if (!s1 || !s2 || !n2 || !s3) { free(s1); free(s2); free(n2); free(s3); return -2; }
+    for (int y = 0; y < H; ++y) {
+        float acc = 0.f;
+        for (int x = 0; x < W; ++x) {
+            const float v = cost[y * row_stride + x * col_stride];
+            if (!isnan(v)) acc = acc + v;
+            s1[(size_t)y * (W + 1) + x + 1] = acc;
+        }
+    }
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int xr = x + d;
+            if (xr < 0 || xr >= W) continue;
+            const int16_t *a = cross_l + ((size_t)y * W + x) * 4;
+            const int16_t *b = cross_r + ((size_t)y * W + xr) * 4;
+            const int l = a[0] < b[0] ? a[0] : b[0];
+            const int r = a[1] < b[1] ? a[1] : b[1];
+            s2[(size_t)y * W + x] = s1[(size_t)y * (W + 1) + x + r + 1] - s1[(size_t)y * (W + 1) + x - l];
+            n2[(size_t)y * W + x] = (float)(l + r);
+        }
+    for (int x = 0; x < W; ++x) s3[(size_t)W + x] = s2[x];
+    for (int y = 1; y < H; ++y)
+        for (int x = 0; x < W; ++x) s3[(size_t)(y + 1) * W + x] = s3[(size_t)y * W + x] + s2[(size_t)y * W + x];
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            step4[(size_t)y * W + x] = 0.f;
+            sum4[(size_t)y * W + x] = n2[(size_t)y * W + x];
+        }
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int xr = x + d;
+            if (xr < 0 || xr >= W) continue;
+            const int16_t *a = cross_l + ((size_t)y * W + x) * 4;
+            const int16_t *b = cross_r + ((size_t)y * W + xr) * 4;
+            const int t = a[2] < b[2] ? a[2] : b[2];
+            const int bo = a[3] < b[3] ? a[3] : b[3];
+            step4[(size_t)y * W + x] = s3[(size_t)(y + bo + 1) * W + x] - s3[(size_t)(y - t) * W + x];
+            float n = sum4[(size_t)y * W + x] + (float)(t + bo);
+            if (t > 0) { float s = 0.f; for (int i = 1; i <= t; ++i) s += n2[(size_t)(y - i) * W + x]; n += s; }
+            if (bo > 0) { float s = 0.f; for (int i = 1; i <= bo; ++i) s += n2[(size_t)(y + i) * W + x]; n += s; }
+            sum4[(size_t)y * W + x] = n;
+        }
+    free(s1); free(s2); free(n2); free(s3);
+    return 0;
+}
+
+/* Whole-volume CBCA driver: aggregation/cbca.py:127-177 for subpix == 1, on the already cropped
+ * (H, W, D) view (contiguous).  out[y,x,k] = (0*c + step4) / (sum4 + 1): NaN where the input is NaN. */
+PBO_API int pbo_cbca_volume(const float *cv, int H, int W, int D, int dmin, const int16_t *cross_l,
+                            const int16_t *cross_r, float *out) {
+    float *step4 = (float *)malloc((size_t)H * W * sizeof(float));
+    float *sum4 = (float *)malloc((size_t)H * W * sizeof(float));
+    if (!step4 || !sum4) { free(step4); free(sum4); return -2; }
+    for (int k = 0; k < D; ++k) {
+        int rc = pbo_cbca_slice(cv + k, (long)W * D, D, H, W, dmin + k, cross_l, cross_r, step4, sum4);
+        if (rc) { free(step4); free(sum4); return rc; }
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const size_t p = (size_t)y * W + x;
+                float agg = cv[p * D + k] * 0.f;           /* NaN-preserving zero, cbca.py:146-147 */
+                agg = agg + step4[p];
+                out[p * D + k] = agg / (sum4[p] + 1.f);
+            }
+    }
+    free(step4); free(sum4);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Right cost volume from the left one: matching_cost/cpp/src/matching_cost.cpp:26-57           */
+/* ------------------------------------------------------------------------------------------ */
+PBO_API void pbo_reverse_cost_volume(const float *left_cv, int H, int W, int D, int min_disp, float *right_cv) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            for (int k = 0; k < D; ++k) {
+                const int c = j + k + min_disp;
+                right_cv[((size_t)i * W + j) * D + k] =
+                    (c >= 0 && c < W) ? left_cv[((size_t)i * W + c) * D + (D - 1 - k)] : NAN;
+            }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* SGM 8-path regularisation.  PARITY UNPINNED against pandora_plugin_libsgm==1.5.7 / libSGM     */
+/* (not vendored, pyproject.toml:59-61; behaviour documented in                                  */
+/* docs/source/userguide/plugins/plugin_libsgm.rst:9-146, boundary optimization/optimization.py  */
+/* :104-123, call site state_machine.py:415-419).  Semantics fixed here:          */
+/*  (i)   NaN costs are replaced by `invalid_value` (the plugin wrapper passes cmax + P2 + 1)    */
+/*        and take part in the recurrence as ordinary finite costs; NaN is restored at the end.  */
+/*  (ii)  first pixel of a path: L_r = C.                                                        */
+/*  (iii) 8 directions, accumulated into S in the order E, W, S, N, SE, NW, SW, NE.              */
+/*  (iv)  step (Hirschmueller 2008, eq. 13), all float32, evaluated in exactly this order:       */
+/*          m  = min_k Lp[k]                                                                     */
+/*          t  = min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1)     (missing neighbour skipped)          */
+/*          t  = min(t, m + P2)                                                                  */
+/*          L[d] = C[d] + (t - m)                                                                */
+/*  (v)   overcounting != 0: S -= (n_dirs - 1) * C  (rst:101-107).                               */
+/*  type_measure == "max" volumes are negated by the caller before and after.                    */
+/* ------------------------------------------------------------------------------------------ */
+static void sgm_step(const float *C, const float *Lp, float *L, int D, float P1, float P2) {
+    float m = Lp[0];
+    for (int k = 1; k < D; ++k) m = fminf(m, Lp[k]);
+    const float mp2 = m + P2;
+    for (int d = 0; d < D; ++d) {
+        float t = Lp[d];
+        if (D > 1) {
+            float nb;
+            if (d == 0) nb = Lp[1];
+            else if (d == D - 1) nb = Lp[D - 2];
+            else nb = fminf(Lp[d - 1], Lp[d + 1]);
+            t = fminf(t, nb + P1);
+        }
+        t = fminf(t, mp2);
+        L[d] = C[d] + (t - m);
+    }
+}
+
+static const int SGM_DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, -1}, {1, -1}, {-1, 1}};
+
+PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
+                    int overcounting, int n_dirs, float *cv_out) {
+    if (n_dirs < 1 || n_dirs > 8) return -1;
+    const size_t n = (size_t)H * W * D;
+    float *C = (float *)malloc(n * sizeof(float));
+    float *bufa = (float *)malloc((size_t)D * sizeof(float));
+    float *bufb = (float *)malloc((size_t)D * sizeof(float));
+    if (!C || !bufa || !bufb) { free(C); free(bufa); free(bufb); return -2; }
+    for (size_t i = 0; i < n; ++i) { C[i] = isnan(cv_in[i]) ? invalid_value : cv_in[i]; cv_out[i] = 0.f; }
+    for (int r = 0; r < n_dirs; ++r) {
+        const int dy = SGM_DIRS[r][0], dx = SGM_DIRS[r][1];
+        for (int y0 = 0; y0 < H; ++y0)
+            for (int x0 = 0; x0 < W; ++x0) {
+                const int py = y0 - dy, px = x0 - dx;
+                if (py >= 0 && py < H && px >= 0 && px < W) continue;     /* not a path start */
+                float *Lp = bufa, *L = bufb;
+                int y = y0, x = x0, first = 1;
+                while (y >= 0 && y < H && x >= 0 && x < W) {
+                    const float *c = C + ((size_t)y * W + x) * D;
+                    float *s = cv_out + ((size_t)y * W + x) * D;
+                    if (first) { memcpy(L, c, (size_t)D * sizeof(float)); first = 0; }
+                    else sgm_step(c, Lp, L, D, P1, P2);
+                    for (int d = 0; d < D; ++d) s[d] = s[d] + L[d];
+                    float *tmp = Lp; Lp = L; L = tmp;
+                    y += dy; x += dx;
+                }
+            }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (overcounting) cv_out[i] = cv_out[i] - (float)(n_dirs - 1) * C[i];
+        if (isnan(cv_in[i])) cv_out[i] = NAN;
+    }
+    free(C); free(bufa); free(bufb);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Winner-takes-all: disparity/disparity.py:434-455, 483-553.  First index wins ties, NaN is     */
+/* +inf (min) / -inf (max); an all-NaN pixel gets invalid_disparity.  all_nan (optional) gets 1   */
+/* for those pixels.                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+PBO_API void pbo_wta(const float *cv, int H, int W, int D, const float *disp_coord, int is_max,
+                     float invalid_disparity, float *disp_map, uint8_t *all_nan) {
+    for (size_t p = 0; p < (size_t)H * W; ++p) {
+        const float *c = cv + p * D;
+        int best = 0, any = 0;
+        float bv = is_max ? -INFINITY : INFINITY;
+        for (int k = 0; k < D; ++k) {
+            if (isnan(c[k])) continue;
+            any = 1;
+            if (is_max ? (c[k] > bv) : (c[k] < bv)) { bv = c[k]; best = k; }
+        }
+        disp_map[p] = any ? disp_coord[best] : invalid_disparity;
+        if (all_nan) all_nan[p] = (uint8_t)!any;
+    }
+}
