@@ -1,0 +1,162 @@
+/*
+ * pandora_b200.h -- C-ABI of the B200-native (sm_100a) implementation of Pandora's dense
+ * cost-volume hot path (Census / SAD / SSD / ZNCC -> CBCA -> SGM -> WTA).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/pybind types.  The
+ * reference's own native boundary for this path is four pybind11 modules functions
+ * (all paths relative to /root/reference/src/pandora):
+ *
+ *   compute_matching_costs   matching_cost/cpp/includes/census.hpp:44-51       -> pb200_census_cost_volume[_host]
+ *   reverse_cost_volume      matching_cost/cpp/includes/matching_cost.hpp:39-46 -> pb200_reverse_cost_volume[_host]
+ *   cross_support            aggregation/cpp/includes/aggregation.hpp:47-53     -> pb200_cross_support[_host]
+ *   cbca                     aggregation/cpp/includes/aggregation.hpp:55-65     -> pb200_cbca_aggregate / pb200_cbca_host
+ *
+ * and, for the steps the reference runs in numpy or in the un-vendored libSGM plugin:
+ *
+ *   SadSsd.compute_cost_volume   matching_cost/sad_ssd.py:75-207        -> pb200_sad_ssd_cost_volume
+ *   Zncc.compute_cost_volume     matching_cost/zncc.py:114-241          -> pb200_zncc_cost_volume
+ *   MedianFilter.median_filter   filter/median.py:134-179 (size 3)      -> pb200_median3
+ *   optimize_cv (libSGM plugin)  optimization/optimization.py:104-123   -> pb200_sgm
+ *   WinnerTakesAll.to_disp       disparity/disparity.py:400-480         -> pb200_wta
+ *   mask_invalid_variable_disparity_range / mask_border  criteria.py:291-353 -> pb200_validity_mask
+ *
+ * Conventions
+ *   - every cost volume is float32, C-contiguous (row, col, disp): disparity is the fastest axis,
+ *     NaN = not computable (matching_cost/matching_cost.py:394-397).
+ *   - "d_" pointers are DEVICE pointers owned by the caller; "_host" entry points take HOST
+ *     pointers, do the H2D/D2H copies themselves and synchronise before returning.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream and re-entrant across streams.
+ *   - return value: PB200_OK or a negative error code; pb200_last_error() gives a thread-local
+ *     message.  No exception crosses this boundary.  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point returns PB200_ERR_CUDA.
+ *   - disparities are integers (subpix == 1): disparity index k <-> dmin + k.
+ */
+#ifndef PANDORA_B200_H
+#define PANDORA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PB200_API __attribute__((visibility("default")))
+#else
+#define PB200_API
+#endif
+
+#define PB200_OK 0
+#define PB200_ERR_BAD_ARG (-1)     /* NULL pointer, non-positive size, D out of range ...            */
+#define PB200_ERR_UNSUPPORTED (-2) /* window not in {3,5,7,9,11,13}, D above the kernel's maximum ... */
+#define PB200_ERR_CUDA (-3)        /* CUDA runtime error (message in pb200_last_error)               */
+#define PB200_ERR_WORKSPACE (-4)   /* workspace too small                                             */
+
+#define PB200_SGM_MAX_DISP 512     /* one warp holds a whole disparity vector: D <= 32 lanes * 16     */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+PB200_API int pb200_version(void);                 /* 100 * major + minor                                        */
+PB200_API const char *pb200_last_error(void);      /* thread-local, never NULL                                   */
+PB200_API int pb200_device_count(void);            /* number of visible CUDA devices (0 when none / no driver)   */
+PB200_API uint64_t pb200_kernel_launches(void);    /* kernels launched by this library since load (this process) */
+
+/* ---- matching cost ---------------------------------------------------------------------------- */
+/* bytes of device scratch pb200_census_cost_volume needs (two planar census-descriptor images). */
+PB200_API size_t pb200_census_workspace_bytes(int H, int W, int window);
+
+/* Census cost volume (replaces compute_matching_costs, census.cpp:97-180 + the NaN pre-fill of census.py:138).
+ * d_cv[y,x,k] = popcount(cL[y,x] ^ cR[y,x+dmin+k]) or NaN.  window in {3,5,7,9,11,13}.
+ * Optional fused winner-takes-all: when d_disp != NULL the kernel also writes
+ * d_disp[y,x] = dmin + argmin_k (first minimum) or invalid_disparity when every k is NaN
+ * (same rule as pb200_wta), and, when d_all_nan != NULL, 1/0 into d_all_nan[y,x]. */
+PB200_API int pb200_census_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
+                             float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
+                             float invalid_disparity, uint8_t *d_all_nan, void *stream);
+
+/* SAD (squared == 0) / SSD (squared != 0) cost volume, window odd >= 1 (sad_ssd.py:180-206). */
+PB200_API int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
+                              int squared, float *d_cv, void *stream);
+
+/* ZNCC cost volume, window odd >= 1, float64 window statistics like img_tools.py:834-952. */
+PB200_API size_t pb200_zncc_workspace_bytes(int H, int W);
+PB200_API int pb200_zncc_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
+                           float *d_cv, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* right(i,j,k) = left(i, j+k+min_disp, D-1-k) or NaN (matching_cost.cpp:26-57). */
+PB200_API int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, int D, int min_disp, float *d_right_cv, void *stream);
+
+/* ---- aggregation (CBCA) ----------------------------------------------------------------------- */
+/* 3x3 NaN-aware median; border ring and NaN pixels unchanged (filter/median.py:134-179). */
+PB200_API int pb200_median3(const float *d_in, int H, int W, float *d_out, void *stream);
+
+/* Cross-support arms (aggregation.cpp:224-321) of the (H, W) view starting at d_img with row pitch
+ * `pitch` (elements).  nan_as_inf != 0 treats NaN pixels as +inf (cbca.py:233).  d_cross is
+ * (H, W, 4) int16 in the order (left, right, up, bottom). */
+PB200_API int pb200_cross_support(const float *d_img, int H, int W, int pitch, int len_arms, float intensity, int nan_as_inf,
+                        int16_t *d_cross, void *stream);
+
+/* Cross-based aggregation of a whole volume (cbca.py:127-177 + aggregation.cpp:28-221), all
+ * disparities in one launch.  The volume is the full (H, W, D) one; `offset` = half window: only
+ * the interior [offset, H-offset) x [offset, W-offset) is aggregated (supports are (H-2o, W-2o, 4)),
+ * the border ring is copied unchanged.  d_cv_out may not alias d_cv_in. */
+PB200_API int pb200_cbca_aggregate(const float *d_cv_in, float *d_cv_out, int H, int W, int D, int dmin, int offset,
+                         const int16_t *d_cross_left, const int16_t *d_cross_right, int len_arms, void *stream);
+
+/* ---- optimisation (SGM) ----------------------------------------------------------------------- */
+PB200_API size_t pb200_sgm_workspace_bytes(int H, int W, int D);
+
+/* 8-path semi-global matching on a min-type cost volume (negate max-type volumes around the call).
+ * NaN -> invalid_value inside, NaN restored in the output.  overcounting != 0 subtracts 7*C.
+ * d_cv_out may not alias d_cv_in.  Optional fused WTA like pb200_census_cost_volume.
+ * Path-state hand-over for row-tiled multi-GPU runs: when d_halo_in_top / d_halo_in_bottom are not
+ * NULL they hold the three downward (S, SE, SW) / upward (N, NE, NW) path states (3, W, D) of the
+ * row just above / below this tile; d_halo_out_* receive this tile's last / first row states.
+ * `passes` selects what to run: bit 0 horizontal (E, W), bit 1 downward (S, SE, SW), bit 2 upward
+ * (N, NE, NW).  The passes must run in that order on a tile; E initialises d_cv_out and NW (the last
+ * direction) finalises it (NaN restore, overcounting, fused WTA).  Use 7 for a single-GPU call. */
+PB200_API int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
+              int overcounting, int passes, const float *d_halo_in_top, const float *d_halo_in_bottom,
+              float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,
+              uint8_t *d_all_nan, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- disparity (WTA) -------------------------------------------------------------------------- */
+/* d_disp[y,x] = dmin + argmin_k cv (is_max: argmax), NaN never wins, first index on ties, all-NaN ->
+ * invalid_disparity (disparity.py:434-455, 483-553).  d_all_nan (optional) gets 1 for all-NaN pixels. */
+PB200_API int pb200_wta(const float *d_cv, int H, int W, int D, int dmin, int is_max, float invalid_disparity, float *d_disp,
+              uint8_t *d_all_nan, void *stream);
+
+/* criteria.validity_mask without input masks (criteria.py:106-147): bit 2 (incomplete range) / bit 1
+ * (range missing) per column from [dmin, dmax] and the half-window `offset`.  d_mask (H, W) uint16. */
+PB200_API int pb200_validity_mask_init(uint16_t *d_mask, int H, int W, int dmin, int dmax, int offset, void *stream);
+
+/* Validity-mask side effects after the fill (criteria.py:291-353): pixels flagged in d_all_nan get
+ * bit 1 when not already set, then the `offset`-wide border ring is overwritten with 1.
+ * d_mask is (H, W) uint16, updated in place; wta_invalidate != 0 additionally applies
+ * disparity.py:470-474 (all-NaN pixels without an invalid bit := PANDORA_MSK_PIXEL_INVALID). */
+PB200_API int pb200_validity_mask(uint16_t *d_mask, const uint8_t *d_all_nan, int H, int W, int offset, int wta_invalidate,
+                        void *stream);
+
+/* ---- host-buffer entry points (what a reference-side binding calls; synchronous) --------------- */
+/* compute_matching_costs(img_left, [img_right], cv, disps, w, w): dmin = lround(disps[0]) (census.cpp:109). */
+PB200_API int pb200_census_cost_volume_host(const float *left, const float *right, int H, int W, int window,
+                                  const float *disps, int D, float *cv);
+PB200_API int pb200_reverse_cost_volume_host(const float *left_cv, int H, int W, int D, int min_disp, float *right_cv);
+PB200_API int pb200_cross_support_host(const float *image, int H, int W, int len_arms, float intensity, int16_t *cross);
+/* one aggregation_cpp.cbca call: (H, W) float32 slice, supports (H, W, 4), n valid columns
+ * range_col[i] -> range_col_right[i]; outputs step4 and sum4 (H, W) like aggregation.cpp:323-355. */
+PB200_API int pb200_cbca_host(const float *input, int H, int W, const int16_t *cross_left, const int16_t *cross_right,
+                    const int64_t *range_col, const int64_t *range_col_right, int n, float *step4, float *sum4);
+/* whole pipeline on host images: matching cost (method 0 census, 1 sad, 2 ssd, 3 zncc) ->
+ * optional CBCA (cbca_distance > 0) -> optional SGM (sgm_p2 > 0) -> WTA.  disp_map (H, W) float32 and
+ * validity_mask (H, W) uint16 (may be NULL) are written; cv_out (may be NULL) receives the final volume. */
+PB200_API int pb200_disparity_host(const float *left, const float *right, int H, int W, int method, int window, int dmin,
+                         int dmax, int cbca_distance, float cbca_intensity, float sgm_p1, float sgm_p2,
+                         int sgm_overcounting, float invalid_disparity, float *disp_map, uint16_t *validity_mask,
+                         float *cv_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANDORA_B200_H */

@@ -219,7 +219,7 @@ PBO_API void pbo_reverse_cost_volume(const float *left_cv, int H, int W, int D, 
 /*  (i)   NaN costs are replaced by `invalid_value` (the plugin wrapper passes cmax + P2 + 1)    */
 /*        and take part in the recurrence as ordinary finite costs; NaN is restored at the end.  */
 /*  (ii)  first pixel of a path: L_r = C.                                                        */
-/*  (iii) 8 directions, accumulated into S in the order E, W, S, N, SE, NW, SW, NE.              */
+/*  (iii) 8 directions, accumulated into S in the order E, W, S, SE, SW, N, NE, NW.              */
 /*  (iv)  step (Hirschmueller 2008, eq. 13), all float32, evaluated in exactly this order:       */
 /*          m  = min_k Lp[k]                                                                     */
 /*          t  = min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1)     (missing neighbour skipped)          */
@@ -246,7 +246,7 @@ static void sgm_step(const float *C, const float *Lp, float *L, int D, float P1,
     }
 }
 
-static const int SGM_DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, -1}, {1, -1}, {-1, 1}};
+static const int SGM_DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {1, 1}, {1, -1}, {-1, 0}, {-1, 1}, {-1, -1}};
 
 PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
                     int overcounting, int n_dirs, float *cv_out) {

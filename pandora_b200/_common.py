@@ -1,0 +1,66 @@
+"""Shared pieces of the step classes: config errors, engine cache, device-residency helpers."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from .dataset import DataArray, LazyVolume
+
+
+class ConfigError(ValueError):
+    """Bad step configuration (the reference raises json_checker's DictCheckerError here; the message
+    names the offending key the same way, e.g. tests/test_matching_cost/test_matching_cost_census.py:48-52)."""
+
+
+_ENGINES: Dict[str, object] = {}
+
+
+def get_engine(device: Optional[str] = None):
+    """One Engine per device, created on first use.  Raises when CUDA / the native library is missing."""
+    import torch  # noqa: PLC0415
+
+    from .engine import Engine  # noqa: PLC0415
+
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("pandora_b200 needs a CUDA device: there is no CPU fallback")
+        device = f"cuda:{torch.cuda.current_device()}"
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = Engine(device)
+        _ENGINES[device] = eng
+    return eng
+
+
+def image_array(ds, band: Optional[str] = None) -> np.ndarray:
+    """``ds["im"].data`` (optionally one band) as float32, like census.py:124-147."""
+    data = ds["im"].data
+    if band is not None:
+        idx = list(ds.coords["band_im"].data).index(band)
+        data = data[idx, :, :]
+    return np.ascontiguousarray(data, dtype=np.float32)
+
+
+def device_volume(engine, cv):
+    """The cost volume of dataset ``cv`` as a device tensor: the resident copy when a previous
+    pandora_b200 step left one, else an upload of the host array."""
+    var = cv["cost_volume"]
+    if isinstance(var, DataArray):
+        t = var.device_tensor()
+        if t is not None:
+            return t
+    return engine.to_device(np.ascontiguousarray(var.data, dtype=np.float32))
+
+
+def store_volume(cv, tensor, keep_on_device: bool = True) -> None:
+    """Put a device tensor back into ``cv["cost_volume"]``: lazily for the shim dataset, with an
+    immediate D2H copy for a real xarray dataset (xarray coerces to numpy anyway)."""
+    var = cv["cost_volume"] if "cost_volume" in cv else None
+    if keep_on_device and (var is None or isinstance(var, DataArray)):
+        if var is None:
+            cv["cost_volume"] = (("row", "col", "disp"), LazyVolume(tensor))
+        else:
+            var.data = LazyVolume(tensor)
+    else:
+        cv["cost_volume"].data = tensor.detach().cpu().numpy()

@@ -1,0 +1,363 @@
+// census.cu -- Census transform + Hamming cost-volume fill (+ optional fused winner-takes-all).
+//
+// Replaces census_transform / compute_matching_costs of the reference
+// (src/pandora/matching_cost/cpp/src/census.cpp:45-95, 97-180) and the NaN pre-fill of
+// matching_cost/census.py:138.  Semantics:
+//   bit b (row-major over the w x w window) = neighbour > centre (strict float compare)
+//   cv[y,x,k] = popcount(cL[y,x] ^ cR[y,x+dmin+k])  iff  half <= y < H-half, half <= x < W-half and
+//               half <= x+dmin+k < W-half ; NaN otherwise.
+//
+// Data layout in HBM
+//   descriptors: planar uint32  [NW][H][pitch]   (NW = ceil(w*w/32) words, pitch = roundup4(W) + 4 so
+//                that every row is 16-byte aligned and can be bulk-copied by TMA).  Bit 31 of the LAST
+//                word is never a census bit (w*w mod 32 <= 25 for every legal window); the transform
+//                sets it for pixels whose window leaves the image, which makes the fill branch-free:
+//                n = popc(a^b) | (int(a^b) >> 31)  ->  all ones -> NaN after the int->float trick.
+//   cost volume: float32 (H, W, D), disparity fastest (the reference layout): the cells of TX
+//                consecutive pixels of one row are ONE contiguous span of TX*D*4 bytes.
+//
+// Fill kernel (HBM-store bound: 4*D bytes written per pixel, 8 bytes read):
+//   persistent CTAs loop over (row, TX-pixel) tiles; TMA (cp.async.bulk, mbarrier completion) stages
+//   the left descriptors of the tile and the TX+D-1 right descriptors it can meet into shared
+//   memory; every thread owns 4 consecutive disparities and slides over consecutive pixels keeping
+//   its 4 right descriptors in registers (one LDS per new pixel); results go to a dense
+//   [TX][D] float tile in shared memory (conflict-free 16-byte STS) which one elected thread
+//   hands to the TMA store engine (cp.async.bulk.global.shared::cta) as a single contiguous span,
+//   double-buffered so the next tile is computed while the previous one drains to HBM.
+#include "common.cuh"
+
+namespace pb200 {
+
+static inline int census_nwords(int w) { return (w * w + 31) / 32; }
+static inline int census_pitch(int W) { return ((W + 3) & ~3) + 4; }
+
+// ------------------------------------------------------------------------------------------------
+// transform
+// ------------------------------------------------------------------------------------------------
+template <int WIN>
+__global__ void __launch_bounds__(256) census_transform_kernel(const float *__restrict__ img, int H, int W, int pitch,
+                                                               uint32_t *__restrict__ desc) {
+    constexpr int HALF = WIN / 2;
+    constexpr int NW = (WIN * WIN + 31) / 32;
+    constexpr int TW = 32, TH = 8;
+    __shared__ float tile[TH + 2 * HALF][TW + 2 * HALF + 1];
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.y * TW + threadIdx.x; i < (TH + 2 * HALF) * (TW + 2 * HALF); i += TW * TH) {
+        const int ty = i / (TW + 2 * HALF), tx = i % (TW + 2 * HALF);
+        const int gy = y0 + ty - HALF, gx = x0 + tx - HALF;
+        tile[ty][tx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(size_t)gy * W + gx] : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= pitch || y >= H) return;
+    uint32_t words[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) words[i] = 0u;
+    const bool inside = (x >= HALF && x < W - HALF && y >= HALF && y < H - HALF);
+    if (inside) {
+        const float c = tile[threadIdx.y + HALF][threadIdx.x + HALF];
+#pragma unroll
+        for (int wy = 0; wy < WIN; ++wy)
+#pragma unroll
+            for (int wx = 0; wx < WIN; ++wx) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int b = wy * WIN + wx;
+                if (tile[threadIdx.y + wy][threadIdx.x + wx] > c) words[b >> 5] |= 1u << (b & 31);
+            }
+    } else {
+        words[NW - 1] = 0x80000000u;  // "window leaves the image" flag (also for the pitch padding)
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) desc[((size_t)i * H + y) * pitch + x] = words[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill
+// ------------------------------------------------------------------------------------------------
+struct FillParams {
+    const uint32_t *descL;
+    const uint32_t *descR;
+    float *cv;
+    float *disp;        // optional fused WTA output
+    uint8_t *all_nan;   // optional
+    int H, W, D, dmin, half, pitch;
+    int TX;             // pixels per tile (multiple of 4)
+    int CH;             // consecutive pixels per work item
+    int tiles_x;
+    long n_tiles;
+    int r_len;          // staged right descriptors per word plane (multiple of 4)
+    float invalid_disparity;
+};
+
+template <int NW>
+__device__ __forceinline__ uint32_t hamming_flagged(const uint32_t (&a)[NW], const uint32_t (&b)[NW]) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < NW - 1; ++i) n += __popc(a[i] ^ b[i]);
+    const uint32_t v = a[NW - 1] ^ b[NW - 1];
+    return (n + __popc(v)) | (uint32_t)((int32_t)v >> 31);
+}
+
+template <int NW, bool VEC4>
+__global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [2][TX*D] float out tiles | [NW][r_len] right words | [NW][TX] left words | mbarrier
+    float *sOut = reinterpret_cast<float *>(smem_raw);
+    const int tile_elems = p.TX * p.D;
+    uint32_t *sR = reinterpret_cast<uint32_t *>(sOut + 2 * (size_t)((tile_elems + 3) & ~3));
+    uint32_t *sL = sR + NW * p.r_len;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sL + NW * p.TX);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int G = (p.D + 3) >> 2;             // groups of 4 disparities
+    const int n_chunks = p.TX / p.CH;
+    uint32_t parity = 0;
+    int it = 0;
+    for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int y = (int)(tile / p.tiles_x);
+        const int x0 = (int)(tile % p.tiles_x) * p.TX;
+        const int npx = min(p.TX, p.W - x0);
+        float *out = sOut + (size_t)(it & 1) * ((tile_elems + 3) & ~3);
+        // the bulk store issued two tiles ago read from this buffer: make sure it has been drained
+        if (tid == 0) tma_store_wait_read<1>();
+        __syncthreads();
+
+        const bool row_ok = (y >= p.half && y < p.H - p.half);
+        if (row_ok) {
+            // ---- stage descriptors through TMA --------------------------------------------------
+            const int lo = x0 + p.dmin;                 // right position of (pixel 0, k = 0)
+            const int base = lo & ~3;                   // smem index j <-> right column base + j (floor to 4, also for lo < 0)
+            const int clo = max(base, 0);
+            const int chi = min(base + p.r_len, p.pitch);
+            if (tid == 0) {
+                uint32_t bytes = 0;
+                if (chi > clo) bytes += (uint32_t)NW * (uint32_t)(chi - clo) * 4u;
+                bytes += (uint32_t)NW * (uint32_t)p.TX * 4u;
+                mbar_expect_tx(bar, bytes);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    if (chi > clo)
+                        tma_load_1d(sR + w * p.r_len + (clo - base), p.descR + ((size_t)w * p.H + y) * p.pitch + clo,
+                                    (uint32_t)(chi - clo) * 4u, bar);
+                    // pitch >= roundup4(W) + 4 and x0 + TX <= roundup(W, TX): clamp the tail to the pitch
+                    tma_load_1d(sL + w * p.TX, p.descL + ((size_t)w * p.H + y) * p.pitch + x0, (uint32_t)p.TX * 4u, bar);
+                }
+            }
+            // right columns outside the stored row: flag as invalid by hand (disjoint from the TMA range)
+            for (int j = tid; j < p.r_len; j += blockDim.x) {
+                const int c = base + j;
+                if (c < clo || c >= chi) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) sR[w * p.r_len + j] = (w == NW - 1) ? 0x80000000u : 0u;
+                }
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            __syncthreads();
+
+            // ---- compute: work item = (chunk of CH consecutive pixels, group of 4 disparities) -----
+            const int shift = lo - base;                // 0..3
+            for (int item = tid; item < n_chunks * G; item += blockDim.x) {
+                const int g = item % G, ch = item / G;
+                const int k0 = g * 4;
+                const int p0 = ch * p.CH;
+                uint32_t win[4][NW];                    // right descriptors for k0..k0+3 at the current pixel
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) win[q + 1][w] = sR[w * p.r_len + shift + p0 + k0 + q];
+                for (int pp = p0; pp < p0 + p.CH; ++pp) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        win[0][w] = win[1][w];
+                        win[1][w] = win[2][w];
+                        win[2][w] = win[3][w];
+                        win[3][w] = sR[w * p.r_len + shift + pp + k0 + 3];
+                    }
+                    uint32_t a[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) a[w] = sL[w * p.TX + pp];
+                    float4 r;
+                    if ((int32_t)a[NW - 1] < 0) {       // left window leaves the image: whole pixel NaN
+                        r = make_float4(nan_f(), nan_f(), nan_f(), nan_f());
+                    } else {
+                        r.x = small_int_to_float(hamming_flagged<NW>(a, win[0]));
+                        r.y = small_int_to_float(hamming_flagged<NW>(a, win[1]));
+                        r.z = small_int_to_float(hamming_flagged<NW>(a, win[2]));
+                        r.w = small_int_to_float(hamming_flagged<NW>(a, win[3]));
+                    }
+                    float *dst = out + (size_t)pp * p.D + k0;
+                    if (VEC4) {
+                        *reinterpret_cast<float4 *>(dst) = r;
+                    } else {
+                        dst[0] = r.x;
+                        if (k0 + 1 < p.D) dst[1] = r.y;
+                        if (k0 + 2 < p.D) dst[2] = r.z;
+                        if (k0 + 3 < p.D) dst[3] = r.w;
+                    }
+                }
+            }
+        } else {
+            for (int i = tid; i < npx * p.D; i += blockDim.x) out[i] = nan_f();
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- hand the tile to the TMA store engine (or store by hand when the span is unaligned) ----
+        const size_t goff = ((size_t)y * p.W + x0) * p.D;
+        const uint32_t bytes = (uint32_t)npx * (uint32_t)p.D * 4u;
+        const bool bulk_ok = ((goff & 3) == 0) && ((bytes & 15u) == 0);
+        if (bulk_ok) {
+            if (tid == 0) {
+                tma_store_1d(p.cv + goff, out, bytes);
+                tma_store_commit();
+            }
+        } else {
+            for (int i = tid; i < npx * p.D; i += blockDim.x) p.cv[goff + i] = out[i];
+        }
+
+        // ---- optional fused WTA straight from the shared-memory tile -----------------------------
+        if (p.disp != nullptr) {
+            const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+            for (int pp = warp; pp < npx; pp += nwarps) {
+                // costs are integers < 2^16: key = cost << 16 | k keeps the first minimum
+                uint32_t best = 0xFFFFFFFFu;
+                const float *src = out + (size_t)pp * p.D;
+                for (int k = lane; k < p.D; k += 32) {
+                    const float v = src[k];
+                    if (v == v) best = min(best, ((uint32_t)v << 16) | (uint32_t)k);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (lane == 0) {
+                    const size_t pix = (size_t)y * p.W + x0 + pp;
+                    const bool none = (best == 0xFFFFFFFFu);
+                    p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
+                    if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                }
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait<0>();
+}
+
+template <int WIN>
+static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, cudaStream_t s) {
+    dim3 block(32, 8), grid(ceil_div(pitch, 32), ceil_div(H, 8));
+    census_transform_kernel<WIN><<<grid, block, 0, s>>>(img, H, W, pitch, desc);
+    PB200_LAUNCH_CHECK("census_transform_kernel");
+    return PB200_OK;
+}
+
+template <int NW>
+static int launch_fill(const FillParams &p, size_t smem, int grid, cudaStream_t s) {
+    if ((p.D & 3) == 0) {
+        PB200_CUDA(cudaFuncSetAttribute(census_fill_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        census_fill_kernel<NW, true><<<grid, 256, smem, s>>>(p);
+    } else {
+        PB200_CUDA(cudaFuncSetAttribute(census_fill_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        census_fill_kernel<NW, false><<<grid, 256, smem, s>>>(p);
+    }
+    PB200_LAUNCH_CHECK("census_fill_kernel");
+    return PB200_OK;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" size_t pb200_census_workspace_bytes(int H, int W, int window) {
+    if (H <= 0 || W <= 0 || window < 3) return 0;
+    return 2 * (size_t)census_nwords(window) * H * census_pitch(W) * sizeof(uint32_t);
+}
+
+extern "C" int pb200_census_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin,
+                                        int D, float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
+                                        float invalid_disparity, uint8_t *d_all_nan, void *stream) {
+    if (!d_left || !d_right || !d_cv || !d_workspace || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_census_cost_volume: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (window != 3 && window != 5 && window != 7 && window != 9 && window != 11 && window != 13) {
+        set_error("pb200_census_cost_volume: window_size %d not in {3,5,7,9,11,13}", window);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (D > 2048 || (d_disp && D > 65535)) {
+        set_error("pb200_census_cost_volume: D=%d above the supported maximum (2048)", D);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < pb200_census_workspace_bytes(H, W, window)) {
+        set_error("pb200_census_cost_volume: workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nw = census_nwords(window), pitch = census_pitch(W);
+    uint32_t *descL = (uint32_t *)d_workspace;
+    uint32_t *descR = descL + (size_t)nw * H * pitch;
+    int rc;
+#define PB200_T(WIN)                                                       \
+    case WIN:                                                              \
+        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, s);         \
+        if (rc == PB200_OK) rc = launch_transform<WIN>(d_right, H, W, pitch, descR, s); \
+        break;
+    switch (window) {
+        PB200_T(3) PB200_T(5) PB200_T(7) PB200_T(9) PB200_T(11) PB200_T(13)
+        default: rc = PB200_ERR_UNSUPPORTED;
+    }
+#undef PB200_T
+    if (rc != PB200_OK) return rc;
+
+    FillParams p;
+    p.descL = descL; p.descR = descR; p.cv = d_cv; p.disp = d_disp; p.all_nan = d_all_nan;
+    p.H = H; p.W = W; p.D = D; p.dmin = dmin; p.half = window / 2; p.pitch = pitch;
+    int TX = (8192 / D) & ~3;                       // <= 32 KB of float per tile
+    if (TX < 4) TX = 4;
+    if (TX > 128) TX = 128;
+    while (TX > 4 && TX >= 2 * (((W + 3) & ~3))) TX >>= 1;   // do not make tiles much wider than the image
+    TX &= ~3;
+    p.TX = TX;
+    const int G = (D + 3) / 4;
+    int CH = TX;                                    // largest chunk that still gives >= 256 work items
+    while (CH > 1 && (TX / CH) * G < 256) CH >>= 1;
+    while (TX % CH) CH >>= 1;
+    p.CH = CH;
+    p.tiles_x = ceil_div(W, TX);
+    p.n_tiles = (long)p.tiles_x * H;
+    p.r_len = (TX + D + 3 + 3 + 3) & ~3;            // shift (<=3) + TX + D - 1 + window slack, rounded to 4
+    p.invalid_disparity = invalid_disparity;
+    // the left-descriptor bulk copy reads TX words from x0: keep it inside the pitch
+    if ((long)(p.tiles_x) * TX > pitch) {
+        // shrink TX until the last tile fits (pitch >= roundup4(W)+4, so TX=4 always fits)
+        while (p.TX > 4 && (long)ceil_div(W, p.TX) * p.TX > pitch) p.TX -= 4;
+        TX = p.TX;
+        CH = TX;
+        while (CH > 1 && (TX / CH) * G < 256) CH >>= 1;
+        while (TX % CH) CH >>= 1;
+        p.CH = CH;
+        p.tiles_x = ceil_div(W, TX);
+        p.n_tiles = (long)p.tiles_x * H;
+        p.r_len = (TX + D + 9) & ~3;
+    }
+    const size_t tile_elems = ((size_t)TX * D + 3) & ~(size_t)3;
+    const size_t smem = 2 * tile_elems * 4 + (size_t)nw * p.r_len * 4 + (size_t)nw * TX * 4 + 16;
+    int per_sm = (int)(200 * 1024 / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    long grid = (long)sm_count() * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    switch (nw) {
+        case 1: return launch_fill<1>(p, smem, (int)grid, s);
+        case 2: return launch_fill<2>(p, smem, (int)grid, s);
+        case 3: return launch_fill<3>(p, smem, (int)grid, s);
+        case 4: return launch_fill<4>(p, smem, (int)grid, s);
+        case 6: return launch_fill<6>(p, smem, (int)grid, s);
+        default: set_error("census: unexpected descriptor size"); return PB200_ERR_UNSUPPORTED;
+    }
+}

@@ -1,0 +1,91 @@
+// common.cuh -- shared helpers for the sm_100a kernels of pandora_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "pandora_b200.h"
+
+namespace pb200 {
+
+// ---- error plumbing (api.cu owns the storage) ---------------------------------------------------
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t err, const char *what);
+void count_launch(int n = 1);
+
+#define PB200_CUDA(call)                                                \
+    do {                                                                \
+        int _rc = ::pb200::check_cuda((call), #call);                   \
+        if (_rc != PB200_OK) return _rc;                                \
+    } while (0)
+
+#define PB200_LAUNCH_CHECK(name)                                        \
+    do {                                                                \
+        ::pb200::count_launch();                                        \
+        int _rc = ::pb200::check_cuda(cudaGetLastError(), name);        \
+        if (_rc != PB200_OK) return _rc;                                \
+    } while (0)
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+int sm_count();
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float nan_f() { return __int_as_float(0x7fc00000); }
+
+// exact float of a small non-negative integer (< 2^23) without I2F: one LOP + one FADD.
+__device__ __forceinline__ float small_int_to_float(uint32_t n) {
+    return __int_as_float(0x4B000000u | n) - 8388608.0f;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + TMA (cp.async.bulk) wrappers: 1-D bulk copies, SASS UBLKCP -----------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (bytes multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk_group completion)
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// streaming (evict-first) vector store / load for data touched once
+__device__ __forceinline__ void st_cs_f4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+__device__ __forceinline__ float4 ld_cs_f4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+
+}  // namespace pb200

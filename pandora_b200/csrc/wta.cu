@@ -1,0 +1,165 @@
+// wta.cu -- winner-takes-all disparity selection, validity-mask side effects, right cost volume.
+//
+// Replaces WinnerTakesAll.to_disp / argmin_split / argmax_split (src/pandora/disparity/disparity.py:
+// 400-553), mask_invalid_variable_disparity_range + mask_border (criteria.py:291-353) and
+// reverse_cost_volume (matching_cost/cpp/src/matching_cost.cpp:26-57).
+//
+// WTA is HBM-read bound (4*D bytes per pixel in, 4 out): one warp per pixel, lanes read 16-byte
+// vectors so a warp instruction covers 512 contiguous bytes of the pixel's disparity vector; the
+// (value, index) pair is reduced with warp shuffles, lowest index winning ties like np.argmin.
+#include "common.cuh"
+
+namespace pb200 {
+
+template <bool IS_MAX>
+__device__ __forceinline__ void wta_take(float v, int k, float &bv, int &bk, bool &any) {
+    if (v != v) return;                       // NaN never wins (disparity.py:434-444)
+    any = true;
+    if (IS_MAX ? (v > bv) : (v < bv)) { bv = v; bk = k; }
+    else if (v == bv && k < bk) bk = k;
+}
+
+template <bool IS_MAX, bool VEC4>
+__global__ void __launch_bounds__(256) wta_kernel(const float *__restrict__ cv, long n_pix, int D, int dmin,
+                                                  float invalid_disparity, float *__restrict__ disp,
+                                                  uint8_t *__restrict__ all_nan) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long pix = warp0; pix < n_pix; pix += nwarps) {
+        const float *src = cv + pix * D;
+        float bv = IS_MAX ? -CUDART_INF_F : CUDART_INF_F;
+        int bk = 0x7fffffff;
+        bool any = false;
+        if (VEC4) {
+            for (int k = lane * 4; k < D; k += 128) {
+                const float4 v = ld_cs_f4(src + k);
+                wta_take<IS_MAX>(v.x, k, bv, bk, any);
+                wta_take<IS_MAX>(v.y, k + 1, bv, bk, any);
+                wta_take<IS_MAX>(v.z, k + 2, bv, bk, any);
+                wta_take<IS_MAX>(v.w, k + 3, bv, bk, any);
+            }
+        } else {
+            for (int k = lane; k < D; k += 32) wta_take<IS_MAX>(__ldcs(src + k), k, bv, bk, any);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const bool oany = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
+            if (IS_MAX ? (ov > bv) : (ov < bv)) { bv = ov; bk = ok; }
+            else if (ov == bv && ok < bk) bk = ok;
+            any = any || oany;
+        }
+        if (lane == 0) {
+            // best value still the initial +-inf: every entry is +-inf or NaN, and since NaNs were replaced by
+            // the same inf np.argmin / np.argmax return index 0
+            if (bv == (IS_MAX ? -CUDART_INF_F : CUDART_INF_F)) bk = 0;
+            disp[pix] = any ? (float)(dmin + bk) : invalid_disparity;
+            if (all_nan) all_nan[pix] = any ? 0 : 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) validity_mask_kernel(uint16_t *__restrict__ mask, const uint8_t *__restrict__ all_nan,
+                                                            int H, int W, int offset, int wta_invalidate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)H * W) return;
+    const int y = (int)(i / W), x = (int)(i % W);
+    uint16_t m = mask[i];
+    const bool missing = all_nan != nullptr && all_nan[i] != 0;
+    if (missing && (m & 2) == 0) m += 2;                                   // criteria.py:291-322
+    if (offset > 0 && (y < offset || y >= H - offset || x < offset || x >= W - offset)) m = 1;  // :325-353
+    if (wta_invalidate && missing && (m & 0x3C3) == 0) m = 0x3C3;          // disparity.py:470-474
+    mask[i] = m;
+}
+
+// criteria.validity_mask, no-mask branch (criteria.py:106-147): per-column flags from the disparity range
+__global__ void __launch_bounds__(256) validity_init_kernel(uint16_t *__restrict__ mask, int H, int W, int dmin, int dmax, int off) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)H * W) return;
+    const int x = (int)(i % W);
+    uint16_t m = 0;
+    if (dmax < 0) {
+        if (x + dmax < off) m = 2;                                         // range missing
+        else if (x + dmin < off) m = 4;                                    // range incomplete
+    } else if (dmin > 0) {
+        if (x + dmin > W - 1 - off) m = 2;
+        else if (x + dmax > W - 1 - off) m = 4;
+    } else {
+        if (x + dmin < off || x + dmax > W - 1 - off) m = 4;
+    }
+    mask[i] = m;
+}
+
+__global__ void __launch_bounds__(256) reverse_cv_kernel(const float *__restrict__ left, int H, int W, int D, int min_disp,
+                                                         float *__restrict__ right) {
+    const long n = (long)H * W * D;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % D);
+        const long pix = i / D;
+        const int j = (int)(pix % W);
+        const long row = pix / W;
+        const int c = j + k + min_disp;
+        right[i] = (c >= 0 && c < W) ? left[(row * W + c) * D + (D - 1 - k)] : nan_f();
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_wta(const float *d_cv, int H, int W, int D, int dmin, int is_max, float invalid_disparity,
+                         float *d_disp, uint8_t *d_all_nan, void *stream) {
+    if (!d_cv || !d_disp || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_wta: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long n_pix = (long)H * W;
+    long blocks = (n_pix + 7) / 8;                    // 8 warps per block, one pixel per warp per trip
+    const long cap = (long)sm_count() * 8 * 8;
+    if (blocks > cap) blocks = cap;
+    const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_cv) & 15) == 0);
+#define PB200_W(MX, V) wta_kernel<MX, V><<<(int)blocks, 256, 0, s>>>(d_cv, n_pix, D, dmin, invalid_disparity, d_disp, d_all_nan)
+    if (is_max) { if (vec) PB200_W(true, true); else PB200_W(true, false); }
+    else        { if (vec) PB200_W(false, true); else PB200_W(false, false); }
+#undef PB200_W
+    PB200_LAUNCH_CHECK("wta_kernel");
+    return PB200_OK;
+}
+
+extern "C" int pb200_validity_mask(uint16_t *d_mask, const uint8_t *d_all_nan, int H, int W, int offset, int wta_invalidate,
+                                   void *stream) {
+    if (!d_mask || H <= 0 || W <= 0 || offset < 0) {
+        set_error("pb200_validity_mask: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    validity_mask_kernel<<<ceil_div((long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(d_mask, d_all_nan, H, W, offset, wta_invalidate);
+    PB200_LAUNCH_CHECK("validity_mask_kernel");
+    return PB200_OK;
+}
+
+extern "C" int pb200_validity_mask_init(uint16_t *d_mask, int H, int W, int dmin, int dmax, int offset, void *stream) {
+    if (!d_mask || H <= 0 || W <= 0 || offset < 0 || dmax < dmin) {
+        set_error("pb200_validity_mask_init: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    validity_init_kernel<<<ceil_div((long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(d_mask, H, W, dmin, dmax, offset);
+    PB200_LAUNCH_CHECK("validity_init_kernel");
+    return PB200_OK;
+}
+
+extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, int D, int min_disp, float *d_right_cv,
+                                         void *stream) {
+    if (!d_left_cv || !d_right_cv || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_reverse_cost_volume: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    long blocks = ((long)H * W * D + 255) / 256;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    reverse_cv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_left_cv, H, W, D, min_disp, d_right_cv);
+    PB200_LAUNCH_CHECK("reverse_cv_kernel");
+    return PB200_OK;
+}

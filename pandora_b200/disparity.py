@@ -1,0 +1,78 @@
+"""disparity step: mirror of AbstractDisparity / WinnerTakesAll (src/pandora/disparity/disparity.py:42-553)."""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from ._common import ConfigError, device_volume, get_engine
+from .dataset import Dataset
+
+
+class AbstractDisparity:
+    disparity_methods_avail: Dict[str, type] = {}
+
+    def __new__(cls, **cfg):
+        if cls is AbstractDisparity:
+            method = cfg.get("disparity_method")
+            try:
+                return super().__new__(cls.disparity_methods_avail[method])
+            except (KeyError, TypeError):
+                raise KeyError(f"No disparity method named {method} supported") from None
+        return super().__new__(cls)
+
+    @classmethod
+    def register_subclass(cls, short_name: str):
+        def decorator(subclass):
+            cls.disparity_methods_avail[short_name] = subclass
+            return subclass
+
+        return decorator
+
+    def to_disp(self, cv, img_left=None, img_right=None):
+        raise NotImplementedError
+
+
+@AbstractDisparity.register_subclass("wta")
+class WinnerTakesAll(AbstractDisparity):
+    _INVALID_DISPARITY = -9999
+
+    def __init__(self, **cfg):
+        self.cfg = self.check_conf(**cfg)
+        self._invalid_disparity = self.cfg["invalid_disparity"]
+
+    def check_conf(self, **cfg) -> dict:
+        if "invalid_disparity" not in cfg:
+            cfg["invalid_disparity"] = self._INVALID_DISPARITY
+        elif cfg["invalid_disparity"] == "NaN":
+            cfg["invalid_disparity"] = np.nan
+        for key in cfg:
+            if key not in ("disparity_method", "invalid_disparity"):
+                raise ConfigError(f"Unknown key {key!r} in the disparity configuration")
+        if not isinstance(cfg["invalid_disparity"], (int, float)):
+            raise ConfigError("invalid_disparity must be an int, a float or 'NaN'")
+        return cfg
+
+    def desc(self) -> None:
+        print("Winner takes all method")
+
+    def to_disp(self, cv, img_left=None, img_right=None):
+        """disparity.py:400-480: ``disparity_map`` float32, ``validity_mask`` and ``cv["disp_indices"]``."""
+        eng = get_engine()
+        cv_t = device_volume(eng, cv)
+        H, W, D = (int(s) for s in cv_t.shape)
+        disps = np.asarray(cv.coords["disp"].data)
+        dmin, dmax = int(round(float(disps[0]))), int(round(float(disps[-1])))
+        is_max = cv.attrs.get("type_measure") == "max"
+        disp_t, flags = eng.wta(cv_t, dmin, is_max, float(self._invalid_disparity))
+        disp = disp_t.cpu().numpy()
+        out = Dataset({"disparity_map": (("row", "col"), disp)},
+                      coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=cv.attrs)
+        cv["disp_indices"] = (("row", "col"), disp.copy())
+        if "validity_mask" in cv:
+            mask_t = eng.to_device(np.ascontiguousarray(cv["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+            mask_t = eng.validity_mask(H, W, dmin, dmax, 0, flags, wta_invalidate=True, mask=mask_t)
+            out["validity_mask"] = (("row", "col"), mask_t.cpu().numpy().view(np.uint16))
+        if "confidence_measure" in cv:
+            out["confidence_measure"] = cv["confidence_measure"]
+        return out

@@ -1,0 +1,182 @@
+"""Device-side engine: owns nothing but torch tensors used as HBM buffers and calls the C-ABI kernels.
+
+PyTorch is plumbing here (allocation, streams, ``torch.distributed``); every operation below is one or
+a few launches of the hand-written sm_100a kernels in ``pandora_b200/csrc`` through
+``libpandora_b200.so``.  All volumes are float32 ``(row, col, disp)`` tensors, disparity fastest --
+the layout of Pandora's cost volume (``matching_cost/matching_cost.py:394-397`` in the reference).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+
+METHODS = {"census": 0, "sad": 1, "ssd": 2, "zncc": 3}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One engine per CUDA device.  Methods are asynchronous on the current torch stream."""
+
+    def __init__(self, device: Optional[torch.device | str | int] = None):
+        self.lib = _native.load()
+        if not torch.cuda.is_available() or self.lib.pb200_device_count() <= 0:
+            raise RuntimeError("pandora_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._ws = {}
+
+    # ---- helpers ------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def to_device(self, arr, dtype=torch.float32) -> torch.Tensor:
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.device, dtype=dtype).contiguous()
+        host = np.ascontiguousarray(arr, dtype=np.float32 if dtype == torch.float32 else None)
+        return torch.from_numpy(host).to(self.device, non_blocking=False)
+
+    def empty(self, shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    @staticmethod
+    def _hw(img: torch.Tensor) -> Tuple[int, int]:
+        assert img.dim() == 2 and img.dtype == torch.float32 and img.is_contiguous()
+        return int(img.shape[0]), int(img.shape[1])
+
+    # ---- matching cost ------------------------------------------------------------------------------
+    def census(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int,
+               out: Optional[torch.Tensor] = None, fuse_wta: bool = False, invalid_disparity: float = -9999.0):
+        """Census cost volume; with ``fuse_wta`` also returns (disparity map, all-NaN flags)."""
+        H, W = self._hw(left)
+        D = dmax - dmin + 1
+        cv = self.empty((H, W, D)) if out is None else out
+        nbytes = self.lib.pb200_census_workspace_bytes(H, W, window)
+        ws = self._workspace("census", nbytes)
+        disp = self.empty((H, W)) if fuse_wta else None
+        flags = self.empty((H, W), torch.uint8) if fuse_wta else None
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_cost_volume(
+                _ptr(left), _ptr(right), H, W, window, dmin, D, _ptr(cv), _ptr(ws), ws.numel(),
+                _ptr(disp), float(invalid_disparity), _ptr(flags), self._stream()))
+        return (cv, disp, flags) if fuse_wta else cv
+
+    def sad_ssd(self, left, right, window: int, dmin: int, dmax: int, squared: bool = False, out=None) -> torch.Tensor:
+        H, W = self._hw(left)
+        D = dmax - dmin + 1
+        cv = self.empty((H, W, D)) if out is None else out
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_sad_ssd_cost_volume(_ptr(left), _ptr(right), H, W, window, dmin, D, int(squared),
+                                                             _ptr(cv), self._stream()))
+        return cv
+
+    def zncc(self, left, right, window: int, dmin: int, dmax: int, out=None) -> torch.Tensor:
+        H, W = self._hw(left)
+        D = dmax - dmin + 1
+        cv = self.empty((H, W, D)) if out is None else out
+        ws = self._workspace("zncc", self.lib.pb200_zncc_workspace_bytes(H, W))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_zncc_cost_volume(_ptr(left), _ptr(right), H, W, window, dmin, D, _ptr(cv), _ptr(ws),
+                                                          ws.numel(), self._stream()))
+        return cv
+
+    def matching_cost(self, method: str, left, right, window: int, dmin: int, dmax: int, out=None) -> torch.Tensor:
+        if method == "census":
+            return self.census(left, right, window, dmin, dmax, out=out)
+        if method in ("sad", "ssd"):
+            return self.sad_ssd(left, right, window, dmin, dmax, squared=(method == "ssd"), out=out)
+        if method == "zncc":
+            return self.zncc(left, right, window, dmin, dmax, out=out)
+        raise KeyError(f"No matching cost method named {method} supported")
+
+    def reverse_cost_volume(self, left_cv: torch.Tensor, min_disp: int) -> torch.Tensor:
+        H, W, D = (int(s) for s in left_cv.shape)
+        out = torch.empty_like(left_cv)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_reverse_cost_volume(_ptr(left_cv), H, W, D, int(min_disp), _ptr(out), self._stream()))
+        return out
+
+    # ---- aggregation --------------------------------------------------------------------------------
+    def median3(self, img: torch.Tensor) -> torch.Tensor:
+        H, W = self._hw(img)
+        out = torch.empty_like(img)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_median3(_ptr(img), H, W, _ptr(out), self._stream()))
+        return out
+
+    def cross_support(self, img: torch.Tensor, len_arms: int, intensity: float, offset: int = 0, nan_as_inf: bool = False):
+        """Arms of ``img[offset:-offset, offset:-offset]`` (a strided view: no copy), (H', W', 4) int16."""
+        H, W = self._hw(img)
+        Hi, Wi = H - 2 * offset, W - 2 * offset
+        out = self.empty((Hi, Wi, 4), torch.int16)
+        base = img.data_ptr() + (offset * W + offset) * 4
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_cross_support(base, Hi, Wi, W, int(len_arms), float(intensity), int(nan_as_inf),
+                                                       _ptr(out), self._stream()))
+        return out
+
+    def cbca_supports(self, left, right, offset: int, distance: int, intensity: float):
+        """computes_cross_supports (cbca.py:184-295) for subpix 1 without masks."""
+        cl = self.cross_support(self.median3(left), distance, intensity, offset, nan_as_inf=True)
+        cr = self.cross_support(self.median3(right), distance, intensity, offset, nan_as_inf=True)
+        return cl, cr
+
+    def cbca(self, left, right, cv: torch.Tensor, offset: int, dmin: int, distance: int = 5, intensity: float = 30.0,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        H, W, D = (int(s) for s in cv.shape)
+        cl, cr = self.cbca_supports(left, right, offset, distance, intensity)
+        res = torch.empty_like(cv) if out is None else out
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_cbca_aggregate(_ptr(cv), _ptr(res), H, W, D, int(dmin), int(offset), _ptr(cl), _ptr(cr),
+                                                        int(distance), self._stream()))
+        return res
+
+    # ---- optimisation -------------------------------------------------------------------------------
+    def sgm(self, cv: torch.Tensor, p1: float, p2: float, invalid_value: float, overcounting: bool = False,
+            out: Optional[torch.Tensor] = None, fuse_wta: bool = False, dmin: int = 0, invalid_disparity: float = -9999.0,
+            passes: int = 7, halo_in_top=None, halo_in_bottom=None, halo_out_bottom=None, halo_out_top=None,
+            disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
+        H, W, D = (int(s) for s in cv.shape)
+        res = torch.empty_like(cv) if out is None else out
+        if fuse_wta and disp is None:
+            disp = self.empty((H, W))
+            flags = self.empty((H, W), torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_sgm(
+                _ptr(cv), _ptr(res), H, W, D, float(p1), float(p2), float(invalid_value), int(bool(overcounting)), int(passes),
+                _ptr(halo_in_top), _ptr(halo_in_bottom), _ptr(halo_out_bottom), _ptr(halo_out_top),
+                _ptr(disp) if fuse_wta else None, int(dmin), float(invalid_disparity), _ptr(flags) if fuse_wta else None,
+                None, 0, self._stream()))
+        return (res, disp, flags) if fuse_wta else res
+
+    # ---- disparity ----------------------------------------------------------------------------------
+    def wta(self, cv: torch.Tensor, dmin: int, is_max: bool = False, invalid_disparity: float = -9999.0):
+        H, W, D = (int(s) for s in cv.shape)
+        disp = self.empty((H, W))
+        flags = self.empty((H, W), torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_wta(_ptr(cv), H, W, D, int(dmin), int(is_max), float(invalid_disparity), _ptr(disp),
+                                             _ptr(flags), self._stream()))
+        return disp, flags
+
+    def validity_mask(self, H: int, W: int, dmin: int, dmax: int, offset: int, flags: Optional[torch.Tensor] = None,
+                      wta_invalidate: bool = False, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            if mask is None:
+                mask = self.empty((H, W), torch.int16)       # uint16 bit flags stored in an int16 tensor
+                _native.check(self.lib.pb200_validity_mask_init(_ptr(mask), H, W, int(dmin), int(dmax), int(offset), self._stream()))
+            _native.check(self.lib.pb200_validity_mask(_ptr(mask), _ptr(flags), H, W, int(offset), int(wta_invalidate),
+                                                       self._stream()))
+        return mask

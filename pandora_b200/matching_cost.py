@@ -1,0 +1,199 @@
+"""matching_cost step: mirror of the reference's AbstractMatchingCost plugin API
+(src/pandora/matching_cost/matching_cost.py:45-950) with B200 kernels behind compute_cost_volume.
+
+Same factory / registry / method names / config keys / error behaviour as the reference:
+``AbstractMatchingCost(**cfg)`` dispatches on ``cfg["matching_cost_method"]`` (KeyError when unknown,
+matching_cost.py:80-107); subclasses register with ``@AbstractMatchingCost.register_subclass``.
+The compute happens in ``Engine`` (CUDA); nothing here falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import constants as cst
+from ._common import ConfigError, device_volume, get_engine, image_array, store_volume
+from .dataset import Dataset
+
+
+class AbstractMatchingCost:
+    """Abstract matching-cost step (reference: matching_cost.py:45-131)."""
+
+    matching_cost_methods_avail: Dict[str, type] = {}
+    _WINDOW_SIZE, _SUBPIX, _BAND, _STEP_COL, _SPLINE_ORDER = 5, 1, None, 1, 1
+    _VALID_WINDOWS: Optional[Tuple[int, ...]] = None
+
+    def __new__(cls, **cfg):
+        if cls is AbstractMatchingCost:
+            method = cfg.get("matching_cost_method")
+            try:
+                return super().__new__(cls.matching_cost_methods_avail[method])
+            except (KeyError, TypeError):
+                raise KeyError(f"No matching cost method named {method} supported") from None
+        return super().__new__(cls)
+
+    @classmethod
+    def register_subclass(cls, short_name: str, *args):
+        def decorator(subclass):
+            cls.matching_cost_methods_avail[short_name] = subclass
+            for arg in args:
+                cls.matching_cost_methods_avail[arg] = subclass
+            return subclass
+
+        return decorator
+
+    def __init__(self, **cfg):
+        self.instantiate_class(**cfg)
+
+    # -- configuration: matching_cost.py:140-184 ----------------------------------------------------
+    def instantiate_class(self, **cfg) -> None:
+        self.cfg = self.check_conf(**cfg)
+        self._window_size = int(self.cfg["window_size"])
+        self._subpix = int(self.cfg["subpix"])
+        self._band = self.cfg["band"]
+        self._step_col = int(self.cfg["step"])
+        self._method = str(self.cfg["matching_cost_method"])
+        self._spline_order = int(self.cfg["spline_order"])
+        del self.cfg["spline_order"]
+
+    def check_conf(self, **cfg) -> dict:
+        cfg.setdefault("window_size", self._WINDOW_SIZE)
+        cfg.setdefault("subpix", self._SUBPIX)
+        cfg.setdefault("band", self._BAND)
+        if "step" in cfg and cfg["step"] != 1:
+            raise ValueError("Step parameter cannot be different from 1")
+        cfg.setdefault("step", self._STEP_COL)
+        cfg.setdefault("spline_order", self._SPLINE_ORDER)
+        allowed = {"matching_cost_method", "window_size", "subpix", "band", "step", "spline_order"}
+        for key in cfg:
+            if key not in allowed:
+                raise ConfigError(f"Unknown key {key!r} in the matching_cost configuration")
+        w = cfg["window_size"]
+        if not isinstance(w, int) or isinstance(w, bool):
+            raise ConfigError(f"window_size must be an int, got {w!r}")
+        if self._VALID_WINDOWS is not None and w not in self._VALID_WINDOWS:
+            raise ConfigError(f"window_size {w} not in {self._VALID_WINDOWS}")
+        if self._VALID_WINDOWS is None and (w < 1 or w % 2 == 0):
+            raise ConfigError(f"window_size {w} must be odd and > 0")
+        if cfg["subpix"] not in (1, 2, 4):
+            raise ConfigError(f"subpix {cfg['subpix']} not in [1, 2, 4]")
+        if cfg["subpix"] != 1:
+            raise ConfigError("subpix: only 1 is implemented by the B200 kernels (SURVEY.md 8d: subpix=1 on the hot path)")
+        if not (cfg["band"] is None or isinstance(cfg["band"], str)):
+            raise ConfigError("band must be a str or None")
+        if not (isinstance(cfg["spline_order"], int) and 1 <= cfg["spline_order"] <= 5):
+            raise ConfigError("spline_order must be an int in [1, 5]")
+        return cfg
+
+    def desc(self) -> None:
+        print(f"{self._method} similarity measure")
+
+    # -- cost-volume container: matching_cost.py:330-427 ---------------------------------------------
+    @staticmethod
+    def get_min_max_from_grid(disp_min, disp_max) -> Tuple[int, int]:
+        return int(np.nanmin(disp_min)), int(np.nanmax(disp_max))
+
+    @staticmethod
+    def get_disparity_range(disparity_min: int, disparity_max: int, subpix: int = 1) -> np.ndarray:
+        if subpix != 1:
+            raise ConfigError("subpix: only 1 is implemented")
+        return np.arange(disparity_min, disparity_max + 1)
+
+    def allocate_cost_volume(self, image, disparity_grids, cfg=None) -> Dataset:
+        """Empty cost-volume dataset with the reference's coordinates and attributes (matching_cost.py:
+        377-407).  The NaN-filled host array of the reference is NOT allocated: the volume is created on
+        the device by compute_cost_volume (17 GB at 4096x4096x256 would be written twice otherwise)."""
+        c_row = np.asarray(image.coords["row"].data)
+        c_col = np.asarray(image.coords["col"].data)
+        dmin, dmax = self.get_min_max_from_grid(*disparity_grids)
+        disps = self.get_disparity_range(dmin, dmax, self._subpix)
+        index_col = np.arange(c_col[0], c_col[-1] + 1, self._step_col)
+        cv = Dataset(coords={"row": c_row, "col": index_col, "disp": disps}, attrs=dict(image.attrs))
+        cv.attrs.update({
+            "sampling_interval": self._step_col,
+            "col_to_compute": index_col,
+            "window_size": self._window_size,
+            "subpixel": self._subpix,
+            "band_correl": self._band,
+            "offset_row_col": int((self._window_size - 1) / 2),
+            "measure": self._method,
+        })
+        return cv
+
+    # -- compute -------------------------------------------------------------------------------------
+    def compute_cost_volume(self, img_left, img_right, cost_volume):
+        raise NotImplementedError
+
+    def _disp_bounds(self, cost_volume) -> Tuple[int, int]:
+        disps = np.asarray(cost_volume.coords["disp"].data)
+        return int(round(float(disps[0]))), int(round(float(disps[-1])))
+
+    def cv_masked(self, img_left, img_right, cost_volume, disp_min, disp_max) -> None:
+        """matching_cost.py:770-872, no-mask / fixed-range branch: the cost values are unchanged, the
+        validity mask gets ``mask_invalid_variable_disparity_range`` and ``mask_border`` on the device."""
+        if "msk" in getattr(img_left, "data_vars", {}) or "msk" in getattr(img_right, "data_vars", {}):
+            raise NotImplementedError("input masks are not on the B200 hot path yet (SURVEY.md 8f rank 1)")
+        dmin_g, dmax_g = self.get_min_max_from_grid(disp_min, disp_max)
+        dmin, dmax = self._disp_bounds(cost_volume)
+        if np.nanmax(disp_min) != dmin_g or np.nanmin(disp_max) != dmax_g or dmin_g != dmin or dmax_g != dmax:
+            raise NotImplementedError("variable disparity grids are not on the B200 hot path yet (SURVEY.md 8f rank 1)")
+        eng = get_engine()
+        cv_t = device_volume(eng, cost_volume)
+        H, W, _ = (int(s) for s in cv_t.shape)
+        off = int(cost_volume.attrs["offset_row_col"])
+        is_max = cost_volume.attrs.get("type_measure") == "max"
+        _, flags = eng.wta(cv_t, dmin, is_max)                        # all-NaN detection pass
+        mask = eng.validity_mask(H, W, dmin, dmax, off, flags)
+        cost_volume["validity_mask"] = (("row", "col"), mask.cpu().numpy().view(np.uint16))
+
+
+@AbstractMatchingCost.register_subclass("census")
+class Census(AbstractMatchingCost):
+    """Census matching cost (reference: matching_cost/census.py:39-153, cpp/src/census.cpp)."""
+
+    _VALID_WINDOWS = (3, 5, 7, 9, 11, 13)
+
+    def compute_cost_volume(self, img_left, img_right, cost_volume):
+        eng = get_engine()
+        dmin, dmax = self._disp_bounds(cost_volume)
+        cost_volume.attrs.update({"type_measure": "min", "cmax": int(self._window_size**2)})     # census.py:116-122
+        left = eng.to_device(image_array(img_left, self._band))
+        right = eng.to_device(image_array(img_right, self._band))
+        store_volume(cost_volume, eng.census(left, right, self._window_size, dmin, dmax))
+        return cost_volume
+
+
+@AbstractMatchingCost.register_subclass("sad", "ssd")
+class SadSsd(AbstractMatchingCost):
+    """SAD / SSD matching cost (reference: matching_cost/sad_ssd.py:39-368)."""
+
+    def compute_cost_volume(self, img_left, img_right, cost_volume):
+        eng = get_engine()
+        dmin, dmax = self._disp_bounds(cost_volume)
+        l_np, r_np = image_array(img_left, self._band), image_array(img_right, self._band)
+        mx = max(abs(np.amax(l_np) - np.amin(r_np)), abs(np.amax(r_np) - np.amin(l_np)))          # sad_ssd.py:125-137
+        cmax = int(mx * self._window_size**2) if self._method == "sad" else int(mx**2 * self._window_size**2)
+        cost_volume.attrs.update({"type_measure": "min", "cmax": cmax})
+        cv = eng.sad_ssd(eng.to_device(l_np), eng.to_device(r_np), self._window_size, dmin, dmax, squared=self._method == "ssd")
+        store_volume(cost_volume, cv)
+        return cost_volume
+
+
+@AbstractMatchingCost.register_subclass("zncc")
+class Zncc(AbstractMatchingCost):
+    """ZNCC matching cost (reference: matching_cost/zncc.py:38-277)."""
+
+    def compute_cost_volume(self, img_left, img_right, cost_volume):
+        eng = get_engine()
+        dmin, dmax = self._disp_bounds(cost_volume)
+        cost_volume.attrs.update({"type_measure": "max", "cmax": 1})                             # zncc.py:171-176
+        left = eng.to_device(image_array(img_left, self._band))
+        right = eng.to_device(image_array(img_right, self._band))
+        store_volume(cost_volume, eng.zncc(left, right, self._window_size, dmin, dmax))
+        return cost_volume
+
+
+def validity_mask_flags():
+    """Re-export of the bit flags for callers that only import this module."""
+    return cst

@@ -1,0 +1,97 @@
+"""optimization step: mirror of AbstractOptimization (src/pandora/optimization/optimization.py:34-123)
+plus the SGM implementation the reference gets from the external libSGM plugin
+(docs/source/userguide/plugins/plugin_libsgm.rst; un-vendored, so numeric parity is pinned against
+oracle/pandora_oracle.c only -- "parity unpinned" against libSGM itself)."""
+from __future__ import annotations
+
+from typing import Dict
+
+from ._common import ConfigError, device_volume, get_engine, store_volume
+
+
+class UniformMargins:
+    """margins.UniformMargins(40) of the reference (optimization.py:43, marge.py:85-101) as a plain tuple holder."""
+
+    def __init__(self, value: int):
+        self.left = self.up = self.right = self.down = value
+
+    def astuple(self):
+        return (self.left, self.up, self.right, self.down)
+
+
+class AbstractOptimization:
+    optimization_methods_avail: Dict[str, type] = {}
+    margins = UniformMargins(40)
+
+    def __new__(cls, _img=None, **cfg):
+        if cls is AbstractOptimization:
+            method = cfg.get("optimization_method")
+            try:
+                return super().__new__(cls.optimization_methods_avail[method])
+            except (KeyError, TypeError):
+                raise KeyError(f"No optimization method named {method} supported") from None
+        return super().__new__(cls)
+
+    @classmethod
+    def register_subclass(cls, short_name: str):
+        def decorator(subclass):
+            cls.optimization_methods_avail[short_name] = subclass
+            return subclass
+
+        return decorator
+
+    def desc(self):
+        print("Optimization method description")
+
+    def optimize_cv(self, cv, img_left, img_right):
+        raise NotImplementedError
+
+
+@AbstractOptimization.register_subclass("sgm")
+class Sgm(AbstractOptimization):
+    """8-path SGM with constant penalties (plugin_libsgm.rst:88-211: P1 = 8, P2 = 32 defaults for Census)."""
+
+    _P1, _P2 = 8, 32
+
+    def __init__(self, _img=None, **cfg):
+        self.cfg = self.check_conf(**cfg)
+        pen = self.cfg["penalty"]
+        self._p1, self._p2 = float(pen["P1"]), float(pen["P2"])
+        self._overcounting = bool(self.cfg["overcounting"])
+
+    def check_conf(self, **cfg) -> dict:
+        cfg.setdefault("overcounting", False)
+        cfg.setdefault("min_cost_paths", False)
+        cfg.setdefault("use_confidence", None)
+        pen = dict(cfg.get("penalty") or {})
+        pen.setdefault("penalty_method", "sgm_penalty")
+        pen.setdefault("p2_method", "constant")
+        pen.setdefault("P1", self._P1)
+        pen.setdefault("P2", self._P2)
+        cfg["penalty"] = pen
+        for key in cfg:
+            if key not in ("optimization_method", "overcounting", "min_cost_paths", "use_confidence", "penalty", "geometric_prior"):
+                raise ConfigError(f"Unknown key {key!r} in the optimization configuration")
+        if pen["penalty_method"] != "sgm_penalty" or pen["p2_method"] != "constant":
+            raise ConfigError("penalty: only penalty_method='sgm_penalty' with p2_method='constant' is implemented")
+        if not pen["P1"] > 0 or not pen["P2"] > pen["P1"]:
+            raise ConfigError("penalty: P1 > 0 and P2 > P1 are required")
+        if cfg["min_cost_paths"] or cfg["use_confidence"]:
+            raise ConfigError("min_cost_paths / use_confidence are not implemented by the B200 SGM kernels")
+        return cfg
+
+    def desc(self):
+        print("Semi-global matching optimization (B200)")
+
+    def optimize_cv(self, cv, img_left, img_right):
+        eng = get_engine()
+        cv_t = device_volume(eng, cv)
+        cmax = float(cv.attrs["cmax"])
+        is_max = cv.attrs.get("type_measure") == "max"
+        src = -cv_t if is_max else cv_t
+        out = eng.sgm(src, self._p1, self._p2, cmax + self._p2 + 1.0, self._overcounting)
+        if is_max:
+            out = -out
+        store_volume(cv, out)
+        cv.attrs["optimization"] = "sgm"
+        return cv

@@ -1,0 +1,381 @@
+"""GPU parity tests: every CUDA kernel, called through the C-ABI (ctypes -> libpandora_b200.so), against
+the CPU oracle on the same seeded inputs, and against the reference's golden vectors.
+
+Bar: bit-exact (np.testing.assert_array_equal, NaN == NaN) for integer / index work and for every
+float path whose operation order is reproduced (SAD/SSD, SGM); stated tolerances otherwise (ZNCC,
+CBCA on float costs).  Run on the B200 box with ``pytest -m gpu``.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CENSUS = "test_matching_cost/test_matching_cost_census.py"
+SAD = "test_matching_cost/test_matching_cost_sad.py"
+AGG = "test_aggregation.py"
+DISP = "test_disparity.py"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pandora_b200
+
+    return pandora_b200.get_engine("cuda:0")
+
+
+def dev(eng, a):
+    return eng.to_device(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rand_pair(seed, H, W, levels=256, as_float=False):
+    g = np.random.default_rng(seed)
+    if as_float:
+        return (g.random((H, W)) * 255).astype(np.float32), (g.random((H, W)) * 255).astype(np.float32)
+    return g.integers(0, levels, (H, W)).astype(np.float32), g.integers(0, levels, (H, W)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# Census
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w", [3, 5, 7, 9, 11, 13])
+@pytest.mark.parametrize("shape,rng", [((37, 53), (-9, 6)), ((29, 64), (-40, -3)), ((40, 45), (2, 33)), ((16, 20), (-30, 30))])
+def test_census_vs_oracle(eng, oracle, w, shape, rng):
+    left, right = rand_pair(w * 1000 + shape[1], *shape, levels=7)       # few levels: ties exercise the strict '>'
+    dmin, dmax = rng
+    ref, _ = oracle.census_cost_volume(left, right, w, dmin, dmax)
+    got = host(eng.census(dev(eng, left), dev(eng, right), w, dmin, dmax))
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("D", [1, 3, 61, 64, 100, 128, 256, 300])
+def test_census_disparity_counts(eng, oracle, D):
+    left, right = rand_pair(D, 21, 333)
+    dmin = -(D - 1) + 2
+    ref, _ = oracle.census_cost_volume(left, right, 5, dmin, dmin + D - 1)
+    got = host(eng.census(dev(eng, left), dev(eng, right), 5, dmin, dmin + D - 1))
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_census_float_images_and_tiny(eng, oracle):
+    left, right = rand_pair(5, 33, 47, as_float=True)
+    ref, _ = oracle.census_cost_volume(left, right, 5, -11, 4)
+    np.testing.assert_array_equal(host(eng.census(dev(eng, left), dev(eng, right), 5, -11, 4)), ref)
+    # image smaller than the window: everything NaN
+    left, right = rand_pair(6, 4, 4)
+    got = host(eng.census(dev(eng, left), dev(eng, right), 5, -1, 1))
+    assert np.isnan(got).all()
+
+
+def test_census_fused_wta(eng, oracle):
+    for (H, W, dmin, dmax, w) in [(45, 130, -63, 0, 5), (33, 77, -5, 9, 3), (20, 50, 3, 40, 7)]:
+        left, right = rand_pair(H * W, H, W, levels=5)
+        ref, _ = oracle.census_cost_volume(left, right, w, dmin, dmax)
+        exp_disp, exp_inv = oracle.wta(ref, oracle.disparity_range(dmin, dmax), "min", -9999)
+        cv, disp, flags = eng.census(dev(eng, left), dev(eng, right), w, dmin, dmax, fuse_wta=True)
+        np.testing.assert_array_equal(host(cv), ref)
+        np.testing.assert_array_equal(host(disp), exp_disp)
+        np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_census_reference_goldens(eng, goldens, case):
+    """tests/test_matching_cost/test_matching_cost_census.py:379-729 through the CUDA path."""
+    k = f"{CENSUS}::test_census[{case}]::"
+    w = int(goldens[k + "window_size"])
+    dmin, dmax = (int(v) for v in goldens[k + "disp_interval"])
+    got = host(eng.census(dev(eng, goldens[k + "left_data"]), dev(eng, goldens[k + "right_data"]), w, dmin, dmax))
+    np.testing.assert_array_equal(got[:, :, int(goldens[k + "tested_layer"])], goldens[k + "ref_out"])
+
+
+def test_census_cost_golden_w3(eng, goldens):
+    k = f"{CENSUS}::test_census_cost::"
+    got = host(eng.census(dev(eng, goldens[k + "data"]), dev(eng, goldens[k + "data#1"]), 3, -1, 1))
+    for i, name in enumerate(["census_ground_truth_d1", "census_ground_truth_d2", "census_ground_truth_d3"]):
+        np.testing.assert_array_equal(got[:, :, i], goldens[k + name])
+
+
+# ------------------------------------------------------------------------------------------------
+# SAD / SSD / ZNCC
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["sad", "ssd"])
+@pytest.mark.parametrize("w", [1, 3, 5, 7])
+@pytest.mark.parametrize("as_float", [False, True])
+def test_sad_ssd_vs_oracle(eng, oracle, method, w, as_float):
+    left, right = rand_pair(w + 10 * as_float, 23, 41, as_float=as_float)
+    ref, _ = oracle.sad_ssd_cost_volume(left, right, w, -7, 5, method)
+    got = host(eng.sad_ssd(dev(eng, left), dev(eng, right), w, -7, 5, squared=(method == "ssd")))
+    np.testing.assert_array_equal(got, ref)      # bit-exact even for float images: same summation order as numpy
+
+
+def test_sad_reference_goldens(eng, goldens):
+    left = goldens["common.py::matching_cost_tests_setup::data"]
+    right = goldens["common.py::matching_cost_tests_setup::data#1"]
+    k = f"{SAD}::TestMatchingCostSAD.test_sad_cost::"
+    np.testing.assert_array_equal(host(eng.sad_ssd(dev(eng, left), dev(eng, right), 1, -1, 1))[:, :, 1], goldens[k + "ad_ground_truth"])
+    np.testing.assert_array_equal(host(eng.sad_ssd(dev(eng, left), dev(eng, right), 5, -1, 1))[:, :, 1], goldens[k + "sad_ground_truth"])
+    k = f"{SAD}::TestMatchingCostSAD.test_cost_volume::"
+    got = host(eng.sad_ssd(dev(eng, goldens[k + "data"]), dev(eng, goldens[k + "data#1"]), 3, -2, 1))
+    np.testing.assert_array_equal(got, goldens[k + "ground_truth"])
+
+
+@pytest.mark.parametrize("w", [1, 3, 5, 9])
+@pytest.mark.parametrize("as_float", [False, True])
+def test_zncc_vs_oracle(eng, oracle, w, as_float):
+    left, right = rand_pair(w + 50 * as_float, 25, 38, as_float=as_float)
+    ref, _ = oracle.zncc_cost_volume(left, right, w, -6, 4)
+    got = host(eng.zncc(dev(eng, left), dev(eng, right), w, -6, 4))
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)     # tolerance stated by north_star: 1e-5 relative
+
+
+# ------------------------------------------------------------------------------------------------
+# WTA, validity mask, reverse
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [1, 5, 61, 64, 256, 300])
+@pytest.mark.parametrize("mode", ["min", "max"])
+def test_wta_vs_oracle(eng, oracle, D, mode):
+    g = np.random.default_rng(D)
+    cv = g.integers(0, 6, (19, 23, D)).astype(np.float32)           # many ties
+    cv[g.random(cv.shape) < 0.3] = np.nan
+    cv[0, 0, :] = np.nan                                            # all-NaN pixel
+    cv[0, 1, :] = np.inf if mode == "min" else -np.inf              # all-inf pixel -> index 0
+    cv[0, 2, : max(1, D // 2)] = np.nan
+    disps = np.arange(-3, -3 + D)
+    exp, exp_inv = oracle.wta(cv, disps, mode, -9999)
+    disp, flags = eng.wta(dev(eng, cv), -3, mode == "max", -9999)
+    np.testing.assert_array_equal(host(disp), exp)
+    np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+
+
+def test_validity_mask_vs_oracle(eng, oracle):
+    for (dmin, dmax, off) in [(-4, 3, 2), (-9, -2, 1), (2, 8, 2), (-3, 3, 0)]:
+        left, right = rand_pair(off + dmax, 17, 31)
+        w = 2 * off + 1
+        cv = oracle.census_cost_volume(left, right, w, dmin, dmax)[0] if w >= 3 else oracle.sad_ssd_cost_volume(left, right, 1, dmin, dmax)[0]
+        vm = oracle.validity_mask(17, 31, dmin, dmax, off)
+        oracle.cv_masked(cv, vm, off)
+        _, inv = oracle.wta(cv, np.arange(dmin, dmax + 1))
+        exp = oracle.wta_validity_mask(vm, inv)
+        _, flags = eng.wta(dev(eng, cv), dmin)
+        m1 = eng.validity_mask(17, 31, dmin, dmax, off, flags)
+        np.testing.assert_array_equal(host(m1).view(np.uint16), vm)
+        m2 = eng.validity_mask(17, 31, dmin, dmax, 0, flags, wta_invalidate=True, mask=m1.clone())
+        np.testing.assert_array_equal(host(m2).view(np.uint16), exp)
+
+
+def test_reverse_cost_volume(eng, oracle):
+    g = np.random.default_rng(3)
+    cv = g.random((7, 29, 11)).astype(np.float32)
+    cv[g.random(cv.shape) < 0.2] = np.nan
+    for md in (-10, -4, 0, 5):
+        np.testing.assert_array_equal(host(eng.reverse_cost_volume(dev(eng, cv), md)), oracle.reverse_cost_volume(cv, md))
+
+
+# ------------------------------------------------------------------------------------------------
+# CBCA
+# ------------------------------------------------------------------------------------------------
+def test_median3_vs_oracle(eng, oracle):
+    g = np.random.default_rng(4)
+    img = (g.random((41, 37)) * 100).astype(np.float32)
+    img[g.random(img.shape) < 0.25] = np.nan
+    np.testing.assert_array_equal(host(eng.median3(dev(eng, img))), oracle.median_filter3(img))
+    img = g.integers(0, 255, (20, 33)).astype(np.float32)
+    np.testing.assert_array_equal(host(eng.median3(dev(eng, img))), oracle.median_filter3(img))
+
+
+@pytest.mark.parametrize("arms,tau,off", [(3, 5.0, 0), (5, 30.0, 2), (9, 2.5, 1), (1, 4.0, 0), (17, 50.0, 3)])
+def test_cross_support_vs_oracle(eng, oracle, arms, tau, off):
+    g = np.random.default_rng(arms)
+    img = g.integers(0, 60, (27, 35)).astype(np.float32)
+    img[g.random(img.shape) < 0.05] = np.nan
+    ref_in = np.nan_to_num(img.copy(), nan=np.inf)
+    if off:
+        ref_in = np.ascontiguousarray(ref_in[off:-off, off:-off])
+    got = host(eng.cross_support(dev(eng, img), arms, tau, off, nan_as_inf=True))
+    np.testing.assert_array_equal(got, oracle.cross_support(ref_in, arms, tau))
+
+
+def test_cross_support_golden(eng, goldens):
+    left = goldens[f"{AGG}::TestAggregation.setUp::data"]
+    k = f"{AGG}::TestAggregation.test_cross_support_region::csr_ground_truth_"
+    csr = host(eng.cross_support(dev(eng, left), 3, 5.0))
+    for i, name in enumerate(["left_arm", "right_arm", "top_arm", "bottom_arm"]):
+        np.testing.assert_array_equal(csr[:, :, i], goldens[k + name])
+
+
+@pytest.mark.parametrize("cfg", [(31, 45, -9, 4, 5, 5, 30.0), (40, 33, -20, -1, 3, 3, 12.0), (25, 60, 0, 37, 5, 9, 40.0),
+                                 (50, 41, -3, 3, 7, 17, 25.0), (12, 14, -2, 2, 3, 5, 1000.0)])
+def test_cbca_census_vs_oracle(eng, oracle, cfg):
+    H, W, dmin, dmax, w, dist, tau = cfg
+    left, right = rand_pair(H + W, H, W)
+    cv, attrs = oracle.census_cost_volume(left, right, w, dmin, dmax)
+    ref, _ = oracle.cbca_cost_volume(left, right, cv, w // 2, dmin, dist, tau)
+    got = host(eng.cbca(dev(eng, left), dev(eng, right), dev(eng, cv), w // 2, dmin, dist, tau))
+    np.testing.assert_array_equal(got, ref)          # integer costs: sums and counts exact, one division
+
+
+def test_cbca_float_costs_tolerance(eng, oracle):
+    left, right = rand_pair(9, 33, 47, as_float=True)
+    cv, _ = oracle.zncc_cost_volume(left, right, 3, -6, 6)
+    ref, _ = oracle.cbca_cost_volume(left, right, cv, 1, -6, 5, 30.0)
+    got = host(eng.cbca(dev(eng, left), dev(eng, right), dev(eng, cv), 1, -6, 5, 30.0))
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    # the reference's float32 row-prefix differences carry ~1e-7 * |prefix| absolute error: compare
+    # with an absolute tolerance scaled by the row prefix magnitude (|cost| <= 1, W = 47)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=47 * 1.2e-7)
+
+
+def test_cbca_reference_goldens(eng, goldens, oracle):
+    left = goldens[f"{AGG}::TestAggregation.setUp::data"].astype(np.float32)
+    right = goldens[f"{AGG}::TestAggregation.setUp::data#1"].astype(np.float32)
+    cv = np.full((3, 5, 3), np.nan, dtype=np.float32)
+    cv[:, 1:, 0] = abs(left[:, 1:] - right[:, :4])
+    cv[:, :, 1] = abs(left - right)
+    cv[:, :4, 2] = abs(left[:, :4] - right[:, 1:])
+    got = host(eng.cbca(dev(eng, left), dev(eng, right), dev(eng, cv), 0, -1, 3, 5.0))
+    np.testing.assert_allclose(got, goldens[f"{AGG}::TestAggregation.test_compute_cbca::aggregated_ground_truth"], rtol=1e-7)
+    k = f"{AGG}::TestAggregation.test_compute_cbca_with_offset::"
+    left, right = goldens[k + "data"], goldens[k + "data#1"]
+    cv = host(eng.sad_ssd(dev(eng, left), dev(eng, right), 3, -1, 1))
+    got = host(eng.cbca(dev(eng, left), dev(eng, right), dev(eng, cv), 1, -1, 3, 5.0))
+    np.testing.assert_allclose(got, goldens[k + "aggregated_ground_truth"], rtol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# SGM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(9, 11, 5), (23, 31, 61), (17, 40, 64), (12, 19, 200), (10, 13, 300), (1, 30, 16), (30, 1, 16)])
+@pytest.mark.parametrize("over", [False, True])
+def test_sgm_integer_costs_vs_oracle(eng, oracle, shape, over):
+    g = np.random.default_rng(sum(shape))
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.15] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25, overcounting=over)
+    got = host(eng.sgm(dev(eng, cv), 8, 32, oracle.sgm_invalid_value(25, 32), overcounting=over))
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_sgm_float_costs_bit_exact(eng, oracle):
+    g = np.random.default_rng(12)
+    cv = g.random((21, 27, 48)).astype(np.float32)
+    cv[g.random(cv.shape) < 0.1] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 0.3, 1.7, cmax=1.0)
+    got = host(eng.sgm(dev(eng, cv), 0.3, 1.7, oracle.sgm_invalid_value(1.0, 1.7)))
+    np.testing.assert_array_equal(got, ref)          # same operation order as the oracle -> identical rounding
+
+
+def test_sgm_fused_wta_and_census_pipeline(eng, oracle):
+    left, right, _ = oracle.synthetic_pair(48, 160, 64)
+    cv, attrs = oracle.census_cost_volume(left, right, 5, -63, 0)
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=attrs["cmax"])
+    exp_disp, exp_inv = oracle.wta(ref, np.arange(-63, 1))
+    S, disp, flags = eng.sgm(eng.census(dev(eng, left), dev(eng, right), 5, -63, 0), 8, 32, 58.0, fuse_wta=True, dmin=-63)
+    np.testing.assert_array_equal(host(S), ref)
+    np.testing.assert_array_equal(host(disp), exp_disp)
+    np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+
+
+def test_sgm_row_tiles_with_halo_equal_whole_image(eng, oracle):
+    """Row-tiled execution with path-state hand-over (the multi-GPU scheme, run here on one GPU) is bit-identical."""
+    import torch
+
+    left, right, _ = oracle.synthetic_pair(40, 96, 32)
+    cv = eng.census(dev(eng, left), dev(eng, right), 5, -31, 0)
+    whole = host(eng.sgm(cv, 8, 32, 58.0))
+    H, W, D = cv.shape
+    cuts = [0, 13, 27, 40]
+    tiles = [cv[a:b].contiguous() for a, b in zip(cuts[:-1], cuts[1:])]
+    outs = [torch.empty_like(t) for t in tiles]
+    n = len(tiles)
+    for t, o in zip(tiles, outs):
+        eng.sgm(t, 8, 32, 58.0, out=o, passes=1)
+    halo = None
+    for i in range(n):                                   # downward sweep, top tile first
+        nxt = torch.empty((3, W, D), device=cv.device)
+        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], passes=2, halo_in_top=halo, halo_out_bottom=nxt)
+        halo = nxt
+    halo = None
+    for i in reversed(range(n)):                         # upward sweep, bottom tile first
+        nxt = torch.empty((3, W, D), device=cv.device)
+        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], passes=4, halo_in_bottom=halo, halo_out_top=nxt)
+        halo = nxt
+    np.testing.assert_array_equal(np.concatenate([host(o) for o in outs]), whole)
+    np.testing.assert_array_equal(whole, oracle.sgm_cost_volume(host(cv), 8, 32, cmax=25))
+
+
+# ------------------------------------------------------------------------------------------------
+# host-buffer C-ABI entry points (what a reference-side binding calls)
+# ------------------------------------------------------------------------------------------------
+def _p(a):
+    return a.ctypes.data
+
+
+def test_host_entry_points(eng, oracle):
+    from pandora_b200 import _native
+
+    lib = _native.load()
+    left, right = rand_pair(77, 30, 44)
+    disps = np.arange(-8, 3).astype(np.float32)
+    cv = np.empty((30, 44, 11), dtype=np.float32)
+    _native.check(lib.pb200_census_cost_volume_host(_p(left), _p(right), 30, 44, 5, _p(disps), 11, _p(cv)))
+    ref, _ = oracle.census_cost_volume(left, right, 5, -8, 2)
+    np.testing.assert_array_equal(cv, ref)
+
+    rcv = np.empty_like(cv)
+    _native.check(lib.pb200_reverse_cost_volume_host(_p(cv), 30, 44, 11, -2, _p(rcv)))
+    np.testing.assert_array_equal(rcv, oracle.reverse_cost_volume(cv, -2))
+
+    img = np.nan_to_num(left.copy())
+    cross = np.empty((30, 44, 4), dtype=np.int16)
+    _native.check(lib.pb200_cross_support_host(_p(img), 30, 44, 5, 30.0, _p(cross)))
+    np.testing.assert_array_equal(cross, oracle.cross_support(img, 5, 30.0))
+
+    cross_r = oracle.cross_support(right, 5, 30.0)
+    for k, d in enumerate(range(-8, 3)):
+        sl = np.ascontiguousarray(cv[:, :, k])
+        cols = np.arange(44, dtype=np.int64)
+        ok = (cols + d >= 0) & (cols + d < 44)
+        rc, rcr = np.ascontiguousarray(cols[ok]), np.ascontiguousarray(cols[ok] + d)
+        s4 = np.empty((30, 44), dtype=np.float32)
+        n4 = np.empty((30, 44), dtype=np.float32)
+        _native.check(lib.pb200_cbca_host(_p(sl), 30, 44, _p(cross), _p(cross_r), _p(rc), _p(rcr), len(rc), _p(s4), _p(n4)))
+        e4, en = oracle.cbca_slice(sl, cross, cross_r, d)
+        np.testing.assert_array_equal(s4, e4)
+        np.testing.assert_array_equal(n4, en)
+
+
+def test_disparity_host_pipelines(eng, oracle):
+    from pandora_b200 import _native
+
+    lib = _native.load()
+    left, right, _ = oracle.synthetic_pair(40, 120, 48)
+    H, W = left.shape
+    dmin, dmax = -47, 0
+    for (cbca, sgm) in [(0, 0.0), (5, 0.0), (0, 32.0), (5, 32.0)]:
+        disp = np.empty((H, W), dtype=np.float32)
+        vm = np.empty((H, W), dtype=np.uint16)
+        out = np.empty((H, W, 48), dtype=np.float32)
+        _native.check(lib.pb200_disparity_host(_p(left), _p(right), H, W, 0, 5, dmin, dmax, cbca, 30.0, 8.0, sgm, 0, -9999.0,
+                                               _p(disp), _p(vm), _p(out)))
+        cv, attrs = oracle.census_cost_volume(left, right, 5, dmin, dmax)
+        mask = oracle.validity_mask(H, W, dmin, dmax, 2)
+        oracle.cv_masked(cv, mask, 2)
+        cmax = attrs["cmax"]
+        if cbca:
+            cv, cmax = oracle.cbca_cost_volume(left, right, cv, 2, dmin, cbca, 30.0, cmax)
+        if sgm:
+            cv = oracle.sgm_cost_volume(cv, 8, sgm, cmax=cmax)
+        exp, inv = oracle.wta(cv, np.arange(dmin, dmax + 1))
+        np.testing.assert_array_equal(out, cv)
+        np.testing.assert_array_equal(disp, exp)
+        np.testing.assert_array_equal(vm, oracle.wta_validity_mask(mask, inv))

@@ -1,0 +1,156 @@
+"""CPU tests: host-side mirror of the reference plugin API, the dataset shim, and the C-ABI library's
+symbol table (no compute call is made without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pandora_b200 as pb
+from pandora_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "pandora_b200.h")).read()
+    declared = set(re.findall(r"PB200_API[^;(]*?\b(pb200_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pandora_b200.h but not exported"
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+
+
+def test_library_loads_and_reports_no_device_without_gpu():
+    lib = _native.load()
+    assert lib.pb200_version() >= 100
+    assert lib.pb200_device_count() >= 0
+    assert isinstance(lib.pb200_last_error(), bytes)
+
+
+def test_no_cpu_fallback_when_cuda_is_missing():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pb.get_engine()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mc = pb.AbstractMatchingCost(matching_cost_method="census", window_size=5)
+        ds = pb.create_image_dataset(np.zeros((8, 8), np.float32), disparity=[-1, 1])
+        cv = mc.allocate_cost_volume(ds, (ds["disparity"].data[0], ds["disparity"].data[1]))
+        mc.compute_cost_volume(ds, ds, cv)
+
+
+def test_bad_arguments_are_rejected_before_any_cuda_call():
+    lib = _native.load()
+    assert lib.pb200_wta(None, 4, 4, 4, 0, 0, 0.0, None, None, None) == _native.ERR_BAD_ARG
+    assert b"pb200_wta" in lib.pb200_last_error()
+    assert lib.pb200_census_cost_volume(1, 1, 8, 8, 4, 0, 4, 1, 1, 1 << 20, None, 0.0, None, None) == _native.ERR_UNSUPPORTED
+    assert lib.pb200_sgm(1, 2, 4, 4, 1000, 8.0, 32.0, 58.0, 0, 7, None, None, None, None, None, 0, 0.0, None, None, 0, None) == _native.ERR_UNSUPPORTED
+    assert lib.pb200_census_workspace_bytes(10, 10, 5) == 2 * 10 * 16 * 4
+
+
+# ---- plugin registries / factories (reference: matching_cost.py:80-131 etc.) -----------------------
+def test_registries_and_factories():
+    assert set(pb.AbstractMatchingCost.matching_cost_methods_avail) >= {"census", "sad", "ssd", "zncc"}
+    assert isinstance(pb.AbstractMatchingCost(matching_cost_method="ssd", window_size=3), pb.SadSsd)
+    assert isinstance(pb.AbstractAggregation(aggregation_method="cbca"), pb.CrossBasedCostAggregation)
+    assert isinstance(pb.AbstractOptimization(None, optimization_method="sgm"), pb.Sgm)
+    assert isinstance(pb.AbstractDisparity(disparity_method="wta"), pb.WinnerTakesAll)
+    for factory, key in [(pb.AbstractMatchingCost, "matching_cost_method"), (pb.AbstractAggregation, "aggregation_method"),
+                         (pb.AbstractDisparity, "disparity_method")]:
+        with pytest.raises(KeyError, match="supported"):
+            factory(**{key: "nope"})
+    with pytest.raises(KeyError, match="No optimization method named sgmm supported"):     # tests/test_plugins.py:96-123
+        pb.AbstractOptimization(None, optimization_method="sgmm")
+
+    @pb.AbstractMatchingCost.register_subclass("my_cost", "alias_cost")
+    class MyCost(pb.AbstractMatchingCost):
+        pass
+
+    assert isinstance(pb.AbstractMatchingCost(matching_cost_method="alias_cost"), MyCost)
+    del pb.AbstractMatchingCost.matching_cost_methods_avail["my_cost"], pb.AbstractMatchingCost.matching_cost_methods_avail["alias_cost"]
+
+
+@pytest.mark.parametrize("window_size", [3, 5, 7, 9, 11, 13])
+def test_census_nominal_window_size(window_size):                 # test_matching_cost_census.py:42-46
+    assert pb.AbstractMatchingCost(matching_cost_method="census", window_size=window_size).cfg["window_size"] == window_size
+
+
+@pytest.mark.parametrize("window_size", [-5, -1, 0, 1, 2, 4, 6, 8, 14, 15])
+def test_census_invalid_window_size(window_size):                 # test_matching_cost_census.py:48-52
+    with pytest.raises(pb.ConfigError) as err:
+        pb.AbstractMatchingCost(matching_cost_method="census", window_size=window_size)
+    assert "window_size" in err.value.args[0]
+
+
+def test_matching_cost_defaults_and_step():
+    mc = pb.AbstractMatchingCost(matching_cost_method="zncc")
+    assert mc.cfg == {"matching_cost_method": "zncc", "window_size": 5, "subpix": 1, "band": None, "step": 1}
+    with pytest.raises(ValueError, match="Step parameter cannot be different from 1"):     # matching_cost.py:176-178
+        pb.AbstractMatchingCost(matching_cost_method="sad", step=2)
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractMatchingCost(matching_cost_method="sad", subpix=3)
+
+
+def test_cbca_sgm_wta_config():
+    agg = pb.AbstractAggregation(aggregation_method="cbca")
+    assert agg.cfg == {"aggregation_method": "cbca", "cbca_intensity": 30.0, "cbca_distance": 5}        # cbca.py:46-47
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractAggregation(aggregation_method="cbca", cbca_distance=0)
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractAggregation(aggregation_method="cbca", cbca_intensity=-1.0)
+    opt = pb.AbstractOptimization(None, optimization_method="sgm")
+    assert opt.cfg["penalty"]["P1"] == 8 and opt.cfg["penalty"]["P2"] == 32                              # plugin_libsgm.rst:198-211
+    assert pb.AbstractOptimization.margins.astuple() == (40, 40, 40, 40)                                  # tests/test_optimization.py:28-30
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractOptimization(None, optimization_method="sgm", penalty={"P1": 8, "P2": 4})
+    wta = pb.AbstractDisparity(disparity_method="wta")
+    assert wta.cfg["invalid_disparity"] == -9999                                                         # disparity.py:357
+    assert np.isnan(pb.AbstractDisparity(disparity_method="wta", invalid_disparity="NaN").cfg["invalid_disparity"])
+
+
+def test_allocate_cost_volume_container():
+    """matching_cost.py:377-407: coordinates and attributes of the (empty) cost-volume dataset."""
+    img = pb.create_image_dataset(np.zeros((6, 9), np.float32), disparity=[-3, 2], row0=10, col0=20)
+    mc = pb.AbstractMatchingCost(matching_cost_method="census", window_size=5)
+    cv = mc.allocate_cost_volume(img, (img["disparity"].data[0], img["disparity"].data[1]))
+    np.testing.assert_array_equal(cv.coords["disp"].data, np.arange(-3, 3))
+    np.testing.assert_array_equal(cv.coords["row"].data, np.arange(10, 16))
+    np.testing.assert_array_equal(cv.coords["col"].data, np.arange(20, 29))
+    for k, v in {"window_size": 5, "subpixel": 1, "band_correl": None, "offset_row_col": 2, "measure": "census",
+                 "sampling_interval": 1}.items():
+        assert cv.attrs[k] == v
+    assert cv.sizes == {"row": 6, "col": 9, "disp": 6}
+
+
+def test_dataset_shim_lazy_volume():
+    class FakeTensor:
+        shape = (2, 3, 4)
+        calls = 0
+
+        def detach(self):
+            return self
+
+        def cpu(self):
+            FakeTensor.calls += 1
+            return self
+
+        def numpy(self):
+            return np.ones((2, 3, 4), np.float32)
+
+    ds = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3), "disp": np.arange(4)})
+    ds["cost_volume"] = (("row", "col", "disp"), pb.LazyVolume(FakeTensor()))
+    assert ds["cost_volume"].device_tensor() is not None and FakeTensor.calls == 0
+    assert ds["cost_volume"].data.sum() == 24 and FakeTensor.calls == 1
+    assert ds["cost_volume"].device_tensor() is None            # host copy is authoritative once handed out
+    assert "cost_volume" in ds and "msk" not in ds.data_vars
+
+
+def test_run_rejects_steps_outside_the_hot_path():
+    img = pb.create_image_dataset(np.zeros((6, 9), np.float32), disparity=[-1, 1])
+    with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
+        pb.run(img, img, {"pipeline": {"refinement": {"refinement_method": "vfit"}}})
