@@ -113,11 +113,14 @@ PB200_API size_t pb200_sgm_workspace_bytes(int H, int W, int D);
  * Path-state hand-over for row-tiled multi-GPU runs: when d_halo_in_top / d_halo_in_bottom are not
  * NULL they hold the three downward (S, SE, SW) / upward (N, NE, NW) path states (3, W, D) of the
  * row just above / below this tile; d_halo_out_* receive this tile's last / first row states.
- * `passes` selects what to run: bit 0 horizontal (E, W), bit 1 downward (S, SE, SW), bit 2 upward
- * (N, NE, NW).  The passes must run in that order on a tile; E initialises d_cv_out and NW (the last
- * direction) finalises it (NaN restore, overcounting, fused WTA).  Use 7 for a single-GPU call. */
+ * `dir_mask` selects the directions to run, bit r = r-th direction of E, W, S, SE, SW, N, NE, NW (always
+ * executed in that order).  `init_final` bit 0: the first direction of this call initialises d_cv_out
+ * (otherwise it accumulates into it); bit 1: the last direction of this call finalises it (NaN restore,
+ * overcounting, fused WTA).  A single-GPU call uses dir_mask = 0xFF, init_final = 3; a tiled run splits
+ * the directions over several calls (pandora_b200/tiling.py).  Halo planes are indexed by the direction's
+ * rank inside its group: (S, SE, SW) for the top/bottom-out pair, (N, NE, NW) for the other. */
 PB200_API int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
-              int overcounting, int passes, const float *d_halo_in_top, const float *d_halo_in_bottom,
+              int overcounting, int dir_mask, int init_final, const float *d_halo_in_top, const float *d_halo_in_bottom,
               float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,
               uint8_t *d_all_nan, void *d_workspace, size_t workspace_bytes, void *stream);
 
@@ -131,10 +134,10 @@ PB200_API int pb200_wta(const float *d_cv, int H, int W, int D, int dmin, int is
  * (range missing) per column from [dmin, dmax] and the half-window `offset`.  d_mask (H, W) uint16. */
 PB200_API int pb200_validity_mask_init(uint16_t *d_mask, int H, int W, int dmin, int dmax, int offset, void *stream);
 
-/* Validity-mask side effects after the fill (criteria.py:291-353): pixels flagged in d_all_nan get
- * bit 1 when not already set, then the `offset`-wide border ring is overwritten with 1.
- * d_mask is (H, W) uint16, updated in place; wta_invalidate != 0 additionally applies
- * disparity.py:470-474 (all-NaN pixels without an invalid bit := PANDORA_MSK_PIXEL_INVALID). */
+/* Validity-mask updates, d_mask (H, W) uint16 in place.  wta_invalidate == 0: the cv_masked side effects
+ * (criteria.py:291-353): pixels flagged in d_all_nan get bit 1 when not already set, then the
+ * `offset`-wide border ring is overwritten with 1.  wta_invalidate != 0: the WTA rule only
+ * (disparity.py:470-474): all-NaN pixels without an invalid bit := PANDORA_MSK_PIXEL_INVALID. */
 PB200_API int pb200_validity_mask(uint16_t *d_mask, const uint8_t *d_all_nan, int H, int W, int offset, int wta_invalidate,
                         void *stream);
 

@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
         _LIB.pbo_reverse_cost_volume.restype = None
         _LIB.pbo_sgm.argtypes = [f32p, ci, ci, ci, cf, cf, cf, ci, ci, f32p]
         _LIB.pbo_sgm.restype = ci
+        _LIB.pbo_sgm_direction.argtypes = [f32p, f32p, ci, ci, ci, cf, cf, ci, ci, f32p, f32p]
+        _LIB.pbo_sgm_direction.restype = ci
         _LIB.pbo_wta.argtypes = [f32p, ci, ci, ci, f32p, ci, cf, f32p, u8p]
         _LIB.pbo_wta.restype = None
     return _LIB
@@ -357,6 +359,18 @@ def sgm_cost_volume(cv: np.ndarray, p1: float = 8, p2: float = 32, cmax: float =
     if rc:
         raise ValueError(f"pbo_sgm failed: {rc}")
     return -out if type_measure == "max" else out
+
+
+def sgm_direction(C: np.ndarray, S: np.ndarray, p1: float, p2: float, direction: int, init: bool, halo_in=None, halo_out=None):
+    """One direction (index into E, W, S, SE, SW, N, NE, NW) on a row tile, in place on S; C holds no NaN."""
+    H, W, D = C.shape
+    assert C.dtype == np.float32 and S.dtype == np.float32 and C.flags.c_contiguous and S.flags.c_contiguous
+    hi = None if halo_in is None else _p(halo_in, ctypes.c_float)
+    ho = None if halo_out is None else _p(halo_out, ctypes.c_float)
+    rc = lib().pbo_sgm_direction(_p(C, ctypes.c_float), _p(S, ctypes.c_float), H, W, D, float(p1), float(p2), int(direction),
+                                 int(bool(init)), hi, ho)
+    if rc:
+        raise ValueError(f"pbo_sgm_direction failed: {rc}")
 
 
 def wta(cv: np.ndarray, disps, type_measure: str = "min", invalid_disparity: float = -9999.0):

@@ -284,6 +284,42 @@ PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2,
     return 0;
 }
 
+/* One direction of pbo_sgm on a row tile, with the path-state hand-over used by row-tiled (multi-GPU)
+ * runs: S (H, W, D) is accumulated in place (S += L, or S = L when init != 0); C must already hold
+ * invalid_value instead of NaN.  halo_in (W, D) holds the L vectors of the row just outside the tile
+ * (above for dy > 0, below for dy < 0) or is NULL; halo_out (W, D) receives the tile's last row. */
+PBO_API int pbo_sgm_direction(const float *C, float *S, int H, int W, int D, float P1, float P2, int dir, int init,
+                              const float *halo_in, float *halo_out) {
+    if (dir < 0 || dir > 7) return -1;
+    const int dy = SGM_DIRS[dir][0], dx = SGM_DIRS[dir][1];
+    float *bufa = (float *)malloc((size_t)D * sizeof(float));
+    float *bufb = (float *)malloc((size_t)D * sizeof(float));
+    if (!bufa || !bufb) { free(bufa); free(bufb); return -2; }
+    for (int y0 = 0; y0 < H; ++y0)
+        for (int x0 = 0; x0 < W; ++x0) {
+            const int py = y0 - dy, px = x0 - dx;
+            if (py >= 0 && py < H && px >= 0 && px < W) continue;
+            float *Lp = bufa, *L = bufb;
+            int y = y0, x = x0, first = 1;
+            if (halo_in && dy != 0 && py == (dy > 0 ? -1 : H) && px >= 0 && px < W) {
+                memcpy(Lp, halo_in + (size_t)px * D, (size_t)D * sizeof(float));
+                first = 0;
+            }
+            while (y >= 0 && y < H && x >= 0 && x < W) {
+                const float *c = C + ((size_t)y * W + x) * D;
+                float *s = S + ((size_t)y * W + x) * D;
+                if (first) { memcpy(L, c, (size_t)D * sizeof(float)); first = 0; }
+                else sgm_step(c, Lp, L, D, P1, P2);
+                for (int d = 0; d < D; ++d) s[d] = init ? L[d] : s[d] + L[d];
+                if (halo_out && dy != 0 && y == (dy > 0 ? H - 1 : 0)) memcpy(halo_out + (size_t)x * D, L, (size_t)D * sizeof(float));
+                float *tmp = Lp; Lp = L; L = tmp;
+                y += dy; x += dx;
+            }
+        }
+    free(bufa); free(bufb);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Winner-takes-all: disparity/disparity.py:434-455, 483-553.  First index wins ties, NaN is     */
 /* +inf (min) / -inf (max); an all-NaN pixel gets invalid_disparity.  all_nan (optional) gets 1   */

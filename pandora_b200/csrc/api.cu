@@ -236,7 +236,7 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
             set_error("pb200_disparity_host: SGM on a max-type measure is not wired in the host pipeline");
             return PB200_ERR_UNSUPPORTED;
         }
-        PB200_RC(pb200_sgm(cur, other, H, W, D, sgm_p1, sgm_p2, cmax + sgm_p2 + 1.f, sgm_overcounting, 7, nullptr, nullptr, nullptr,
+        PB200_RC(pb200_sgm(cur, other, H, W, D, sgm_p1, sgm_p2, cmax + sgm_p2 + 1.f, sgm_overcounting, 0xFF, 3, nullptr, nullptr, nullptr,
                            nullptr, ddisp.as<float>(), dmin, invalid_disparity, dnan.as<uint8_t>(), nullptr, 0, nullptr));
         float *t = cur; cur = other; other = t;
         have_disp = true;
@@ -247,6 +247,7 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
     PB200_CUDA(cudaMemcpy(disp_map, ddisp.p, img, cudaMemcpyDeviceToHost));
     if (validity_mask) {
         PB200_RC(pb200_validity_mask_init(dmask.as<uint16_t>(), H, W, dmin, dmax, off, nullptr));
+        PB200_RC(pb200_validity_mask(dmask.as<uint16_t>(), dnan.as<uint8_t>(), H, W, off, 0, nullptr));
         PB200_RC(pb200_validity_mask(dmask.as<uint16_t>(), dnan.as<uint8_t>(), H, W, off, 1, nullptr));
         PB200_CUDA(cudaMemcpy(validity_mask, dmask.p, px * 2, cudaMemcpyDeviceToHost));
     }

@@ -29,8 +29,9 @@ struct SgmParams {
     int H, W, D;
     float p1, p2, invalid_value;
     int dy, dx;           // direction
-    int mode;             // 0: first direction (S = L), 1: accumulate, 2: last (finalise)
+    int mode;             // 0: first direction (S = L), 1: accumulate, 2: accumulate + finalise, 3: first and final at once
     int overcounting;
+    float over_scale;     // n_directions - 1 (7 for the 8-path sum)
     const float *halo_in;   // (W, D) path states of the row just outside the tile for this direction, or NULL
     float *halo_out;        // (W, D) receives the states of this tile's last row in travel direction, or NULL
     float *disp;            // fused WTA (mode 2), or NULL
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(128) sgm_path_kernel(const SgmParams p) {
         const bool more = (ny >= 0 && ny < H && nx >= 0 && nx < W);
         if (more) load_vec<NPL, VEC>(c_ptr + stride, lane, D, cnext);      // prefetch the next pixel's costs
         float sacc[NPL];
-        if (p.mode != 0) load_vec<NPL, VEC>(s_ptr, lane, D, sacc);
+        if (p.mode == 1 || p.mode == 2) load_vec<NPL, VEC>(s_ptr, lane, D, sacc);
 
         float L[NPL];
         if (!have_prev) {
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(128) sgm_path_kernel(const SgmParams p) {
 #pragma unroll
             for (int j = 0; j < NPL; ++j) {
                 const float c = craw[j];
-                float s = sacc[j] + L[j];
-                if (p.overcounting) s = s - 7.0f * ((c != c) ? p.invalid_value : c);
+                float s = (p.mode == 3) ? L[j] : sacc[j] + L[j];
+                if (p.overcounting) s = s - p.over_scale * ((c != c) ? p.invalid_value : c);
                 if (c != c) s = nan_f();
                 sacc[j] = s;
                 const int d = lane * NPL + j;
@@ -239,11 +240,11 @@ extern "C" size_t pb200_sgm_workspace_bytes(int H, int W, int D) {
 }
 
 extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
-                         int overcounting, int passes, const float *d_halo_in_top, const float *d_halo_in_bottom,
+                         int overcounting, int dir_mask, int init_final, const float *d_halo_in_top, const float *d_halo_in_bottom,
                          float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,
                          uint8_t *d_all_nan, void *d_workspace, size_t workspace_bytes, void *stream) {
     (void)d_workspace; (void)workspace_bytes;
-    if (!d_cv_in || !d_cv_out || d_cv_in == d_cv_out || H <= 0 || W <= 0 || D <= 0 || (passes & 7) == 0) {
+    if (!d_cv_in || !d_cv_out || d_cv_in == d_cv_out || H <= 0 || W <= 0 || D <= 0 || (dir_mask & 0xFF) == 0) {
         set_error("pb200_sgm: bad argument");
         return PB200_ERR_BAD_ARG;
     }
@@ -255,15 +256,23 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
     // direction table in accumulation order; group 0 horizontal, 1 downward, 2 upward
     static const int dirs[8][3] = {{0, 1, 0}, {0, -1, 0}, {1, 0, 1}, {1, 1, 1}, {1, -1, 1}, {-1, 0, 2}, {-1, 1, 2}, {-1, -1, 2}};
     const size_t plane = (size_t)W * D;
+    int first_dir = -1, last_dir = -1;
+    for (int r = 0; r < 8; ++r)
+        if (dir_mask & (1 << r)) {
+            if (first_dir < 0) first_dir = r;
+            last_dir = r;
+        }
     for (int r = 0; r < 8; ++r) {
         const int group = dirs[r][2];
-        if (!(passes & (1 << group))) continue;
+        if (!(dir_mask & (1 << r))) continue;
         SgmParams p;
         p.cv = d_cv_in; p.S = d_cv_out; p.H = H; p.W = W; p.D = D;
         p.p1 = p1; p.p2 = p2; p.invalid_value = invalid_value;
         p.dy = dirs[r][0]; p.dx = dirs[r][1];
-        p.mode = (r == 0) ? 0 : (r == 7 ? 2 : 1);
+        const bool is_init = (init_final & 1) && r == first_dir, is_final = (init_final & 2) && r == last_dir;
+        p.mode = is_init ? (is_final ? 3 : 0) : (is_final ? 2 : 1);
         p.overcounting = overcounting;
+        p.over_scale = 7.0f;
         p.halo_in = nullptr; p.halo_out = nullptr;
         if (group == 1) {
             if (d_halo_in_top) p.halo_in = d_halo_in_top + (size_t)(r - 2) * plane;
@@ -272,8 +281,8 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
             if (d_halo_in_bottom) p.halo_in = d_halo_in_bottom + (size_t)(r - 5) * plane;
             if (d_halo_out_top) p.halo_out = d_halo_out_top + (size_t)(r - 5) * plane;
         }
-        p.disp = (r == 7) ? d_disp : nullptr;
-        p.all_nan = (r == 7) ? d_all_nan : nullptr;
+        p.disp = is_final ? d_disp : nullptr;
+        p.all_nan = is_final ? d_all_nan : nullptr;
         p.dmin = dmin; p.invalid_disparity = invalid_disparity;
         int rc;
         if (D <= 32) rc = launch_dir<1>(p, s);

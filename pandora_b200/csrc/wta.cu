@@ -68,9 +68,12 @@ __global__ void __launch_bounds__(256) validity_mask_kernel(uint16_t *__restrict
     const int y = (int)(i / W), x = (int)(i % W);
     uint16_t m = mask[i];
     const bool missing = all_nan != nullptr && all_nan[i] != 0;
-    if (missing && (m & 2) == 0) m += 2;                                   // criteria.py:291-322
-    if (offset > 0 && (y < offset || y >= H - offset || x < offset || x >= W - offset)) m = 1;  // :325-353
-    if (wta_invalidate && missing && (m & 0x3C3) == 0) m = 0x3C3;          // disparity.py:470-474
+    if (wta_invalidate) {
+        if (missing && (m & 0x3C3) == 0) m = 0x3C3;                        // disparity.py:470-474
+    } else {
+        if (missing && (m & 2) == 0) m += 2;                               // criteria.py:291-322
+        if (offset > 0 && (y < offset || y >= H - offset || x < offset || x >= W - offset)) m = 1;  // :325-353
+    }
     mask[i] = m;
 }
 

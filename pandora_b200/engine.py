@@ -146,7 +146,7 @@ class Engine:
     # ---- optimisation -------------------------------------------------------------------------------
     def sgm(self, cv: torch.Tensor, p1: float, p2: float, invalid_value: float, overcounting: bool = False,
             out: Optional[torch.Tensor] = None, fuse_wta: bool = False, dmin: int = 0, invalid_disparity: float = -9999.0,
-            passes: int = 7, halo_in_top=None, halo_in_bottom=None, halo_out_bottom=None, halo_out_top=None,
+            dir_mask: int = 0xFF, init_final: int = 3, halo_in_top=None, halo_in_bottom=None, halo_out_bottom=None, halo_out_top=None,
             disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
         H, W, D = (int(s) for s in cv.shape)
         res = torch.empty_like(cv) if out is None else out
@@ -155,7 +155,7 @@ class Engine:
             flags = self.empty((H, W), torch.uint8)
         with torch.cuda.device(self.device):
             _native.check(self.lib.pb200_sgm(
-                _ptr(cv), _ptr(res), H, W, D, float(p1), float(p2), float(invalid_value), int(bool(overcounting)), int(passes),
+                _ptr(cv), _ptr(res), H, W, D, float(p1), float(p2), float(invalid_value), int(bool(overcounting)), int(dir_mask), int(init_final),
                 _ptr(halo_in_top), _ptr(halo_in_bottom), _ptr(halo_out_bottom), _ptr(halo_out_top),
                 _ptr(disp) if fuse_wta else None, int(dmin), float(invalid_disparity), _ptr(flags) if fuse_wta else None,
                 None, 0, self._stream()))

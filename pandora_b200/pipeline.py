@@ -152,7 +152,8 @@ class StereoPipeline:
 
     def validity_mask(self):
         """uint16 validity mask of the last run (criteria + WTA rules), as a device tensor (int16 storage)."""
-        return self.eng.validity_mask(self.H, self.W, self.dmin, self.dmax, self.offset, self.flags, wta_invalidate=True)
+        mask = self.eng.validity_mask(self.H, self.W, self.dmin, self.dmax, self.offset, self.flags)
+        return self.eng.validity_mask(self.H, self.W, self.dmin, self.dmax, self.offset, self.flags, wta_invalidate=True, mask=mask)
 
     def bytes_h2d(self) -> int:
         return 2 * self.H * self.W * 4

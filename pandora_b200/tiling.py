@@ -1,0 +1,190 @@
+"""Row-tiled multi-GPU execution of the hot path (one process per GPU, ``torch.distributed``).
+
+The image is cut into horizontal tiles, one per rank (rank 0 = top).  Census / SAD / ZNCC / CBCA / WTA
+shard by rows with a small halo of INPUT image rows fetched once from the neighbours
+(``exchange_image_halo``) -- no collective on the data path.  SGM has one real exchange step: the
+downward paths (S, SE, SW) need the last row's path states ``L_r`` of the tile above, the upward paths
+(N, NE, NW) the first row's states of the tile below.  They travel as point-to-point messages of
+``W x D`` floats per direction between neighbours only (NCCL send/recv over NVLink; gloo in the CPU
+tests), which keeps the result bit-identical to the single-GPU run for integer-valued costs --
+unlike Pandora's own tiling convention, a fixed 40-pixel margin (marge.py:85-101 in the reference),
+which is an approximation.
+
+Schedule: the horizontal directions are tile-local and run first.  The two vertical waves start at
+opposite ends (rank 0 downward, rank N-1 upward); every rank orders its six vertical directions by the
+time their halo can arrive (``direction_order``), which makes the dependency graph acyclic -- a rank
+never waits for a neighbour that is waiting for it.  Each wave uses its own process group so that the
+two flows between a pair of neighbours are not serialised on one communicator.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+DIR_NAMES = ("E", "W", "S", "SE", "SW", "N", "NE", "NW")
+HORIZONTAL, DOWN, UP = (0, 1), (2, 3, 4), (5, 6, 7)
+
+
+def split_rows(total_rows: int, world: int) -> List[range]:
+    """Contiguous row ranges, as even as possible, top tile first."""
+    base, rem = divmod(total_rows, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append(range(start, start + n))
+        start += n
+    return out
+
+
+def direction_order(rank: int, world: int) -> List[int]:
+    """Order in which ``rank`` runs its six vertical directions: by earliest possible halo arrival
+    (downward wave reaches rank r at step r, upward wave at step world-1-r), downward first on ties."""
+    tasks = [(rank + i, 0, d) for i, d in enumerate(DOWN)] + [((world - 1 - rank) + i, 1, d) for i, d in enumerate(UP)]
+    return [d for _, _, d in sorted(tasks)]
+
+
+class SgmBackend:
+    """What the tile executor needs from a device: run one direction on the local tile."""
+
+    def new_halo(self):  # (W, D) float32 buffer
+        raise NotImplementedError
+
+    def run_direction(self, direction: int, init: bool, final: bool, halo_in, halo_out) -> None:
+        raise NotImplementedError
+
+
+class EngineSgmBackend(SgmBackend):
+    """CUDA backend: ``Engine.sgm`` restricted to one direction per call."""
+
+    def __init__(self, engine, cv, out, p1, p2, invalid_value, overcounting=False, disp=None, flags=None, dmin=0,
+                 invalid_disparity=-9999.0):
+        self.eng, self.cv, self.out = engine, cv, out
+        self.args = (p1, p2, invalid_value, overcounting)
+        self.disp, self.flags, self.dmin, self.invalid_disparity = disp, flags, dmin, invalid_disparity
+
+    def new_halo(self):
+        _, W, D = self.cv.shape
+        return self.eng.empty((W, D))
+
+    def run_direction(self, direction, init, final, halo_in, halo_out) -> None:
+        kw = {}
+        if direction in DOWN:
+            kw = {"halo_in_top": _group_view(halo_in, direction, DOWN), "halo_out_bottom": _group_view(halo_out, direction, DOWN)}
+        elif direction in UP:
+            kw = {"halo_in_bottom": _group_view(halo_in, direction, UP), "halo_out_top": _group_view(halo_out, direction, UP)}
+        fuse = final and self.disp is not None
+        self.eng.sgm(self.cv, *self.args, out=self.out, fuse_wta=fuse, dmin=self.dmin, invalid_disparity=self.invalid_disparity,
+                     dir_mask=1 << direction, init_final=(1 if init else 0) | (2 if final else 0), disp=self.disp, flags=self.flags,
+                     **kw)
+
+
+class _PlaneAlias:
+    """The C-ABI indexes halo planes by the direction's rank inside its group ((3, W, D) arrays); a single
+    (W, D) buffer is presented as plane ``idx`` of such an array by shifting the base pointer back."""
+
+    def __init__(self, tensor, idx: int):
+        self.tensor, self.idx = tensor, idx
+
+    def data_ptr(self) -> int:
+        return self.tensor.data_ptr() - self.idx * self.tensor.numel() * 4
+
+
+def _group_view(halo, direction: int, group: Sequence[int]):
+    return None if halo is None else _PlaneAlias(halo, group.index(direction))
+
+
+def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down=None, pg_up=None, order: Optional[List[int]] = None):
+    """Execute the 8 directions on this rank's tile with halo hand-over to the neighbours.
+
+    ``dist`` is ``torch.distributed`` (or None when world == 1); ``pg_down`` / ``pg_up`` are two process
+    groups spanning all ranks.  Returns the order in which the vertical directions were run.
+    """
+    order = direction_order(rank, world) if order is None else order
+    has_up_nb, has_down_nb = rank > 0, rank < world - 1
+    recv_bufs, recv_work, send_work, keep = {}, {}, [], []
+    if world > 1:
+        for d in order:                                   # pre-post every receive: they depend on nothing local
+            src = rank - 1 if d in DOWN else rank + 1
+            if (d in DOWN and has_up_nb) or (d in UP and has_down_nb):
+                recv_bufs[d] = backend.new_halo()
+                recv_work[d] = dist.irecv(recv_bufs[d], src=src, group=pg_down if d in DOWN else pg_up)
+    backend.run_direction(0, True, False, None, None)
+    backend.run_direction(1, False, False, None, None)
+    for i, d in enumerate(order):
+        halo_in = None
+        if d in recv_work:
+            recv_work[d].wait()
+            halo_in = recv_bufs[d]
+        send_to = None
+        if world > 1 and ((d in DOWN and has_down_nb) or (d in UP and has_up_nb)):
+            send_to = rank + 1 if d in DOWN else rank - 1
+        halo_out = backend.new_halo() if send_to is not None else None
+        backend.run_direction(d, False, i == len(order) - 1, halo_in, halo_out)
+        if send_to is not None:
+            keep.append(halo_out)
+            send_work.append(dist.isend(halo_out, dst=send_to, group=pg_down if d in DOWN else pg_up))
+    for w in send_work:
+        w.wait()
+    return order
+
+
+def exchange_image_halo(tile, half: int, rank: int, world: int, dist, group=None):
+    """Fetch ``half`` rows of INPUT image from each neighbour; returns (extended tile, rows added on top).
+
+    ``tile`` is a (rows, W) tensor (CPU for gloo, CUDA for nccl).  Matching-cost windows that straddle a
+    tile border then see exactly the pixels the untiled run sees."""
+    import torch  # noqa: PLC0415
+
+    if world == 1 or half == 0:
+        return tile, 0
+    W = tile.shape[1]
+    top = torch.empty((half, W), dtype=tile.dtype, device=tile.device) if rank > 0 else None
+    bot = torch.empty((half, W), dtype=tile.dtype, device=tile.device) if rank < world - 1 else None
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, tile[:half].contiguous(), rank - 1, group), dist.P2POp(dist.irecv, top, rank - 1, group)]
+    if rank < world - 1:
+        ops += [dist.P2POp(dist.isend, tile[-half:].contiguous(), rank + 1, group), dist.P2POp(dist.irecv, bot, rank + 1, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    parts = [p for p in (top, tile, bot) if p is not None]
+    return torch.cat(parts, dim=0), (half if rank > 0 else 0)
+
+
+class TiledStereoPipeline:
+    """Census -> SGM -> WTA on this rank's row tile of a tall image (the C3/C4 configuration, row-tiled)."""
+
+    def __init__(self, tile_rows: int, W: int, dmin: int, dmax: int, rank: int, world: int, dist=None, window: int = 5,
+                 p1: float = 8.0, p2: float = 32.0, invalid_disparity: float = -9999.0, device: Optional[str] = None):
+        import torch  # noqa: PLC0415
+
+        from ._common import get_engine  # noqa: PLC0415
+
+        self.torch, self.dist = torch, dist
+        self.eng = get_engine(device)
+        self.rank, self.world = rank, world
+        self.rows, self.W, self.dmin, self.dmax, self.window = tile_rows, W, dmin, dmax, window
+        self.D = dmax - dmin + 1
+        self.p1, self.p2, self.invalid_disparity = p1, p2, invalid_disparity
+        self.half = window // 2
+        self.top = self.half if rank > 0 else 0
+        self.bot = self.half if rank < world - 1 else 0
+        ext = tile_rows + self.top + self.bot
+        self.cv_ext = self.eng.empty((ext, W, self.D))
+        self.S = self.eng.empty((tile_rows, W, self.D))
+        self.disp = self.eng.empty((tile_rows, W))
+        self.flags = self.eng.empty((tile_rows, W), torch.uint8)
+        self.pg_down = dist.new_group(list(range(world))) if world > 1 else None
+        self.pg_up = dist.new_group(list(range(world))) if world > 1 else None
+
+    def run(self, left_tile, right_tile):
+        """``left_tile`` / ``right_tile``: this rank's (rows, W) float32 device tensors.  Returns the disparity tile."""
+        e = self.eng
+        l_ext, _ = exchange_image_halo(left_tile, self.half, self.rank, self.world, self.dist)
+        r_ext, _ = exchange_image_halo(right_tile, self.half, self.rank, self.world, self.dist)
+        e.census(l_ext.contiguous(), r_ext.contiguous(), self.window, self.dmin, self.dmax, out=self.cv_ext)
+        cv = self.cv_ext[self.top: self.top + self.rows]
+        # rows that are image border for the whole image only: tile-internal borders were computed from the halo
+        backend = EngineSgmBackend(e, cv, self.S, self.p1, self.p2, float(self.window**2) + self.p2 + 1.0, False, self.disp,
+                                   self.flags, self.dmin, self.invalid_disparity)
+        run_tiled_sgm(backend, self.rank, self.world, self.dist, self.pg_down, self.pg_up)
+        return self.disp

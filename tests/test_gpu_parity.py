@@ -298,16 +298,16 @@ def test_sgm_row_tiles_with_halo_equal_whole_image(eng, oracle):
     outs = [torch.empty_like(t) for t in tiles]
     n = len(tiles)
     for t, o in zip(tiles, outs):
-        eng.sgm(t, 8, 32, 58.0, out=o, passes=1)
+        eng.sgm(t, 8, 32, 58.0, out=o, dir_mask=0x03, init_final=1)
     halo = None
     for i in range(n):                                   # downward sweep, top tile first
         nxt = torch.empty((3, W, D), device=cv.device)
-        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], passes=2, halo_in_top=halo, halo_out_bottom=nxt)
+        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], dir_mask=0x1C, init_final=0, halo_in_top=halo, halo_out_bottom=nxt)
         halo = nxt
     halo = None
     for i in reversed(range(n)):                         # upward sweep, bottom tile first
         nxt = torch.empty((3, W, D), device=cv.device)
-        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], passes=4, halo_in_bottom=halo, halo_out_top=nxt)
+        eng.sgm(tiles[i], 8, 32, 58.0, out=outs[i], dir_mask=0xE0, init_final=2, halo_in_bottom=halo, halo_out_top=nxt)
         halo = nxt
     np.testing.assert_array_equal(np.concatenate([host(o) for o in outs]), whole)
     np.testing.assert_array_equal(whole, oracle.sgm_cost_volume(host(cv), 8, 32, cmax=25))

@@ -49,7 +49,7 @@ def test_bad_arguments_are_rejected_before_any_cuda_call():
     assert lib.pb200_wta(None, 4, 4, 4, 0, 0, 0.0, None, None, None) == _native.ERR_BAD_ARG
     assert b"pb200_wta" in lib.pb200_last_error()
     assert lib.pb200_census_cost_volume(1, 1, 8, 8, 4, 0, 4, 1, 1, 1 << 20, None, 0.0, None, None) == _native.ERR_UNSUPPORTED
-    assert lib.pb200_sgm(1, 2, 4, 4, 1000, 8.0, 32.0, 58.0, 0, 7, None, None, None, None, None, 0, 0.0, None, None, 0, None) == _native.ERR_UNSUPPORTED
+    assert lib.pb200_sgm(1, 2, 4, 4, 1000, 8.0, 32.0, 58.0, 0, 0xFF, 3, None, None, None, None, None, 0, 0.0, None, None, 0, None) == _native.ERR_UNSUPPORTED
     assert lib.pb200_census_workspace_bytes(10, 10, 5) == 2 * 10 * 16 * 4
 
 
