@@ -14,8 +14,8 @@ def synthetic_pair(H: int, W: int, D: int, seed: int = 20240607, block: int = 64
     rng = np.random.default_rng(seed)
     tex = rng.integers(0, 256, (H + 2, W + D + 2)).astype(np.int64)
     sm = sum(tex[dy: dy + H, dx: dx + W + D] for dy in range(3) for dx in range(3)) // 9
-    g = -rng.integers(0, D, ((H + block - 1) // block, (W + block - 1) // block))
-    gfull = np.kron(g, np.ones((block, block), dtype=np.int64))[:H, :W]
+    g = -rng.integers(0, D, ((H + block - 1) // block, 1))      # one disparity per band of `block` rows
+    gfull = np.kron(g, np.ones((block, W), dtype=np.int64))[:H, :W]
     cols = np.arange(W)[None, :]
     left = sm[:, D: D + W]
     right = np.take_along_axis(sm, np.clip(D + cols - gfull, 0, W + D - 1), axis=1)

@@ -159,7 +159,7 @@ def test_wta_vs_oracle(eng, oracle, D, mode):
 
 def test_validity_mask_vs_oracle(eng, oracle):
     for (dmin, dmax, off) in [(-4, 3, 2), (-9, -2, 1), (2, 8, 2), (-3, 3, 0)]:
-        left, right = rand_pair(off + dmax, 17, 31)
+        left, right = rand_pair(100 + off + dmax, 17, 31)
         w = 2 * off + 1
         cv = oracle.census_cost_volume(left, right, w, dmin, dmax)[0] if w >= 3 else oracle.sad_ssd_cost_volume(left, right, 1, dmin, dmax)[0]
         vm = oracle.validity_mask(17, 31, dmin, dmax, off)
