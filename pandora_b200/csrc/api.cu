@@ -236,8 +236,12 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
             set_error("pb200_disparity_host: SGM on a max-type measure is not wired in the host pipeline");
             return PB200_ERR_UNSUPPORTED;
         }
+        DevBuf sws;
+        const size_t swsb = pb200_sgm_workspace_bytes(H, W, D);
+        PB200_RC(sws.alloc(swsb));
         PB200_RC(pb200_sgm(cur, other, H, W, D, sgm_p1, sgm_p2, cmax + sgm_p2 + 1.f, sgm_overcounting, 0xFF, 3, nullptr, nullptr, nullptr,
-                           nullptr, ddisp.as<float>(), dmin, invalid_disparity, dnan.as<uint8_t>(), nullptr, 0, nullptr));
+                           nullptr, ddisp.as<float>(), dmin, invalid_disparity, dnan.as<uint8_t>(), sws.p, swsb, nullptr));
+        PB200_CUDA(cudaDeviceSynchronize());          // the workspace must outlive the sweeps
         float *t = cur; cur = other; other = t;
         have_disp = true;
     }

@@ -230,20 +230,376 @@ static int launch_dir(const SgmParams &p, cudaStream_t s) {
     return PB200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Vertical sweep: the three directions that advance one row per step (S, SE, SW or N, NE, NW) in ONE
+// launch.  Traffic per pixel drops from 3 x (read C + read S + write S) to read C + read S + write S.
+//
+// Mapping: the image is cut into column strips, one CTA per strip, all CTAs co-resident (cooperative
+// launch) and walking the rows together.  A warp owns CPW adjacent columns and processes, per row, the
+// three recurrences of each of its pixels: the vertical state stays in registers, the two diagonal
+// states of the previous row come from the neighbouring column through shared memory (double
+// buffered, one __syncthreads per row), and across a strip border through a 2-slot ring in global
+// memory (L2 resident) guarded by a release/acquire progress counter.  The outgoing border state of a
+// row is published early in the row step and consumed by the neighbour one step later, so the
+// exchange latency is off the critical path as long as neighbouring strips stay within one row.
+// ------------------------------------------------------------------------------------------------
+struct SweepParams {
+    const float *cv;
+    float *S;
+    int H, W, D;
+    float p1, p2, invalid_value;
+    int dy;                 // +1: S, SE, SW ; -1: N, NE, NW
+    int mode;               // as SgmParams::mode, for the group as a whole
+    int overcounting;
+    float over_scale;
+    const float *halo_in;   // (3, W, D) states of the row just outside the tile (order dx = 0, +1, -1) or NULL
+    float *halo_out;        // (3, W, D) states of this tile's last row in travel direction or NULL
+    float *disp;
+    uint8_t *all_nan;
+    int dmin;
+    float invalid_disparity;
+    unsigned long long *ring;   // [nstrips][2 sides][2 slots][32 * NPL] {tag, value} words, zero at launch
+};
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+    return d;
+}
+__device__ __forceinline__ float warp_min_redux(float a) {
+    float d;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(d) : "f"(a));   // CREDUX.MIN.F32
+    return d;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lane-major vector layout ([quad][lane][4]) for shared memory and the ring: every access instruction
+// of a warp covers one contiguous span (no bank conflicts, fully coalesced).
+template <int NPL>
+__device__ __forceinline__ void lm_store(float *base, int lane, const float (&v)[NPL]) {
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NPL / 4; ++q)
+            reinterpret_cast<float4 *>(base)[q * 32 + lane] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    } else if constexpr (NPL == 2) {
+        reinterpret_cast<float2 *>(base)[lane] = make_float2(v[0], v[1]);
+    } else {
+        base[lane] = v[0];
+    }
+}
+template <int NPL>
+__device__ __forceinline__ void lm_load(const float *base, int lane, float (&v)[NPL]) {
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NPL / 4; ++q) {
+            const float4 t = reinterpret_cast<const float4 *>(base)[q * 32 + lane];
+            v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+        }
+    } else if constexpr (NPL == 2) {
+        const float2 t = reinterpret_cast<const float2 *>(base)[lane];
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = base[lane];
+    }
+}
+template <int NPL>
+__device__ __forceinline__ void lm_load_cg(const float *base, int lane, float (&v)[NPL]) {   // L2 only: never a stale L1 line
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NPL / 4; ++q) {
+            const float4 t = __ldcg(reinterpret_cast<const float4 *>(base) + q * 32 + lane);
+            v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+        }
+    } else if constexpr (NPL == 2) {
+        const float2 t = __ldcg(reinterpret_cast<const float2 *>(base) + lane);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = __ldcg(base + lane);
+    }
+}
+
+// one recurrence step: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m), m = min_k Lp[k]
+template <int NPL>
+__device__ __forceinline__ void sgm_step_vec(const float (&cc)[NPL], const float (&Lp)[NPL], float (&L)[NPL], int lane, float p1,
+                                             float p2) {
+    float lm = Lp[0];
+#pragma unroll
+    for (int j = 1; j < NPL; ++j) lm = fminf(lm, Lp[j]);
+    const float m = warp_min_redux(lm);
+    const float up = __shfl_up_sync(0xffffffffu, Lp[NPL - 1], 1);
+    const float dn = __shfl_down_sync(0xffffffffu, Lp[0], 1);
+    const float left_edge = (lane == 0) ? CUDART_INF_F : up;
+    const float right_edge = (lane == 31) ? CUDART_INF_F : dn;
+    const float mp2 = m + p2;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const float lo = (j == 0) ? left_edge : Lp[j - 1];
+        const float hi = (j == NPL - 1) ? right_edge : Lp[j + 1];
+        const float t = fmin3(Lp[j], fminf(lo, hi) + p1, mp2);
+        L[j] = cc[j] + (t - m);
+    }
+}
+
+// Flag-in-data hand-over between strips (the "LL" scheme of collective libraries): every float travels as
+// one naturally aligned 64-bit word {row tag, value}.  A 64-bit scalar access is single-copy atomic, so a
+// word whose tag matches is valid by itself: no fence on the sender, one L2 round trip on the receiver.
+__device__ __forceinline__ void ll_store(unsigned long long *p, uint32_t tag, float v) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long *p) {
+    unsigned long long w;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+template <int NPL>
+__device__ __forceinline__ void ll_send(unsigned long long *slot, int lane, uint32_t tag, const float (&v)[NPL]) {
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) ll_store(slot + j * 32 + lane, tag, v[j]);
+}
+template <int NPL>
+__device__ __forceinline__ void ll_recv(const unsigned long long *slot, int lane, uint32_t tag, float (&v)[NPL]) {
+    unsigned long long w[NPL];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) w[j] = ll_load(slot + j * 32 + lane);
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
+    } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) v[j] = __uint_as_float((uint32_t)w[j]);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Warp roles: warps 0..nwarp-1 compute, warp nwarp is the exchange warp.  Compute warp w owns the strip
+// columns w and K-1-w (mirror pair), so warp 0 owns BOTH border columns and computes their outgoing
+// diagonal states first; the exchange warp then copies them to the ring (its release fence has no
+// long-latency traffic of its own to wait for), polls the neighbours' counters and drops their border
+// states into the halo columns of the shared-memory state buffer before the end-of-row barrier.
+template <int NPL, bool VEC>
+__global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) float sweep_smem[];
+    constexpr int VS = NPL * 32;                       // floats per state vector (padded to the warp)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x >> 5) - 1;
+    const int K = nwarp * 2;                           // columns per strip
+    const int strip = blockIdx.x, nstrips = gridDim.x;
+    const int H = p.H, W = p.W, D = p.D, dy = p.dy;
+    // shared: st[buf][diag][K + 2][VS]; diag 0: dx = +1, diag 1: dx = -1; column index = strip column + 1,
+    // index 0 / K+1 = border states of the left / right neighbour strip
+    auto st = [&](int buf, int diag, int col) -> float * { return sweep_smem + ((size_t)(buf * 2 + diag) * (K + 2) + col) * VS; };
+    const bool has_left = strip > 0, has_right = strip + 1 < nstrips;
+    const bool accumulate = (p.mode == 1 || p.mode == 2), final = (p.mode >= 2);
+    const size_t plane = (size_t)W * D;
+
+    if (warp == nwarp) {
+        // ---------------- exchange warp: receive the neighbours' border states of row i -------------------
+        for (int i = 0; i + 1 < H; ++i) {
+            const int cur = i & 1;
+            const uint32_t tag = (uint32_t)(i + 1);
+            if (has_left) {
+                float v[NPL];
+                ll_recv<NPL>(p.ring + ((size_t)((strip - 1) * 2 + 1) * 2 + cur) * VS, lane, tag, v);
+                lm_store<NPL>(st(cur, 0, 0), lane, v);
+            }
+            if (has_right) {
+                float v[NPL];
+                ll_recv<NPL>(p.ring + ((size_t)((strip + 1) * 2 + 0) * 2 + cur) * VS, lane, tag, v);
+                lm_store<NPL>(st(cur, 1, K + 1), lane, v);
+            }
+            __syncthreads();
+        }
+        __syncthreads();                               // last row: nothing to exchange
+        return;
+    }
+
+    // ---------------- compute warps -------------------------------------------------------------------
+    const int col[2] = {warp, K - 1 - warp};           // strip columns of this warp (mirror pair)
+    const int xs[2] = {strip * K + col[0], strip * K + col[1]};
+    float Lv[2][NPL];                                  // vertical states of the previous row
+    float cnext[2][NPL];
+    int y = dy > 0 ? 0 : H - 1;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (xs[c] < W) load_vec<NPL, VEC>(p.cv + ((size_t)y * W + xs[c]) * D, lane, D, cnext[c]);
+
+    for (int i = 0; i < H; ++i, y += dy) {
+        const int cur = i & 1, prv = cur ^ 1;
+        const bool first = (i == 0), last = (i == H - 1);
+        float cc[2][NPL], sacc[2][NPL];
+        uint32_t nanmask[2] = {0u, 0u};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const float v = cnext[c][j];
+                const bool isn = (v != v);
+                cc[c][j] = isn ? p.invalid_value : v;
+                nanmask[c] |= isn ? (1u << j) : 0u;
+            }
+            const int x = xs[c];
+            if (x < W) {
+                if (!last) load_vec<NPL, VEC>(p.cv + ((size_t)(y + dy) * W + x) * D, lane, D, cnext[c]);
+                if (accumulate) load_vec<NPL, VEC>(p.S + ((size_t)y * W + x) * D, lane, D, sacc[c]);
+            }
+        }
+        // one recurrence of column slot c, group rank g (dx = 0, +1, -1): result in Lout, state stored for the next row
+        auto run_dir = [&](const int c, const int g, float (&Lout)[NPL]) {
+            const int x = xs[c];
+            const int dx = (g == 0) ? 0 : (g == 1 ? 1 : -1);
+            const int px = x - dx;
+            float Lp[NPL];
+            bool have = false;
+            if (first) {
+                if (p.halo_in != nullptr && px >= 0 && px < W) {
+                    load_vec<NPL, VEC>(p.halo_in + (size_t)g * plane + (size_t)px * D, lane, D, Lp);
+                    have = true;
+                }
+            } else if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) Lp[j] = Lv[c][j];
+                have = true;
+            } else if (px >= 0 && px < W) {
+                have = true;
+                lm_load<NPL>(st(prv, g - 1, col[c] - dx + 1), lane, Lp);
+            }
+            if (have) {
+                sgm_step_vec<NPL>(cc[c], Lp, Lout, lane, p.p1, p.p2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) Lout[j] = cc[c][j];
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) Lv[c][j] = Lout[j];
+            } else {
+                lm_store<NPL>(st(cur, g - 1, col[c] + 1), lane, Lout);
+            }
+            if (last && p.halo_out != nullptr) store_vec<NPL, VEC>(p.halo_out + (size_t)g * plane + (size_t)x * D, lane, D, Lout);
+        };
+        // the outgoing border diagonals first (column slot 0: dx = -1, slot 1: dx = +1), so that warp 0 can hand the
+        // strip's border states to the exchange warp as early as possible
+        float Lb[2][NPL];
+        if (xs[0] < W) run_dir(0, 2, Lb[0]);
+        if (warp == 0 && has_left && !last) ll_send<NPL>(p.ring + ((size_t)(strip * 2 + 0) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[0]);
+        if (xs[1] < W) run_dir(1, 1, Lb[1]);
+        if (warp == 0 && has_right && !last) ll_send<NPL>(p.ring + ((size_t)(strip * 2 + 1) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[1]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int x = xs[c];
+            if (x >= W) continue;
+            float L0[NPL], Lo[NPL];
+            run_dir(c, 0, L0);
+            run_dir(c, c == 0 ? 1 : 2, Lo);
+            // ---- accumulate in the oracle's order (S/N, then dx = +1, then dx = -1) and finalise -----------
+            float out[NPL];
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                float s = accumulate ? sacc[c][j] + L0[j] : L0[j];
+                s = s + (c == 0 ? Lo[j] : Lb[1][j]);
+                s = s + (c == 0 ? Lb[0][j] : Lo[j]);
+                out[j] = s;
+            }
+            if (final) {
+                float bv = CUDART_INF_F;
+                int bk = 0x7fffffff;
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    float s = out[j];
+                    if (p.overcounting) s = s - p.over_scale * cc[c][j];
+                    if (nanmask[c] & (1u << j)) s = nan_f();
+                    out[j] = s;
+                    const int d = lane * NPL + j;
+                    if (d < D && s == s) {
+                        any = true;
+                        if (s < bv) { bv = s; bk = d; }
+                    }
+                }
+                if (p.disp != nullptr) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                        const bool oany = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
+                        if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+                        any = any || oany;
+                    }
+                    if (lane == 0) {
+                        const size_t pix = (size_t)y * W + x;
+                        if (bv == CUDART_INF_F) bk = 0;
+                        p.disp[pix] = any ? (float)(p.dmin + bk) : p.invalid_disparity;
+                        if (p.all_nan) p.all_nan[pix] = any ? 0 : 1;
+                    }
+                }
+            }
+            store_vec<NPL, VEC>(p.S + ((size_t)y * W + x) * D, lane, D, out);
+        }
+        __syncthreads();           // every diagonal state of this row (own and halo) is in st[cur] before the next row
+    }
+}
+
+template <int NPL>
+static int launch_sweep(SweepParams p, void *workspace, size_t workspace_bytes, cudaStream_t s, bool *done) {
+    *done = false;
+    const int nsm = sm_count();
+    int K = ceil_div(p.W, nsm);
+    if (K < 4) K = 4;
+    K = (K + 1) / 2 * 2;
+    const int nwarp = K / 2;
+    if (nwarp > 15) return PB200_OK;                               // image too wide for one co-resident wave: per-path kernels
+    const int nstrips = ceil_div(p.W, K);
+    const size_t VS = (size_t)NPL * 32;
+    const size_t smem = (size_t)2 * 2 * (K + 2) * VS * sizeof(float);
+    const size_t ring_bytes = (size_t)nstrips * 2 * 2 * VS * sizeof(unsigned long long);
+    if (workspace == nullptr || workspace_bytes < ring_bytes || smem > 200 * 1024) return PB200_OK;
+    const bool vec = (NPL % 4 == 0) && (p.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.cv) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.S) & 15) == 0) &&
+                     (!p.halo_in || (reinterpret_cast<uintptr_t>(p.halo_in) & 15) == 0) &&
+                     (!p.halo_out || (reinterpret_cast<uintptr_t>(p.halo_out) & 15) == 0);
+    void (*kern)(const SweepParams) = vec ? sgm_vsweep_kernel<NPL, (NPL % 4 == 0)> : sgm_vsweep_kernel<NPL, false>;
+    const int threads = (nwarp + 1) * 32;
+    PB200_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, threads, smem));
+    if ((long)per_sm * nsm < nstrips) return PB200_OK;             // cannot be co-resident
+    p.ring = reinterpret_cast<unsigned long long *>(workspace);
+    PB200_CUDA(cudaMemsetAsync(p.ring, 0, ring_bytes, s));                 // tag 0 = nothing published (row tags start at 1)
+    void *args[] = {(void *)&p};
+    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(nstrips), dim3(threads), args, smem, s));
+    PB200_LAUNCH_CHECK("sgm_vsweep_kernel");
+    *done = true;
+    return PB200_OK;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
 
 extern "C" size_t pb200_sgm_workspace_bytes(int H, int W, int D) {
-    (void)H; (void)W; (void)D;
-    return 16;   // the path-per-warp kernels keep all state in registers
+    (void)H;
+    // strip-sweep exchange rings + progress counters (launch_sweep): at most one strip per 4 columns
+    if (W <= 0 || D <= 0) return 16;
+    const size_t nstrips = (size_t)(W + 3) / 4;
+    const size_t vs = (size_t)((D + 31) / 32) * 32;
+    return nstrips * (2 * 2 * vs * sizeof(unsigned long long)) + 256;
 }
 
 extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
                          int overcounting, int dir_mask, int init_final, const float *d_halo_in_top, const float *d_halo_in_bottom,
                          float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,
                          uint8_t *d_all_nan, void *d_workspace, size_t workspace_bytes, void *stream) {
-    (void)d_workspace; (void)workspace_bytes;
     if (!d_cv_in || !d_cv_out || d_cv_in == d_cv_out || H <= 0 || W <= 0 || D <= 0 || (dir_mask & 0xFF) == 0) {
         set_error("pb200_sgm: bad argument");
         return PB200_ERR_BAD_ARG;
@@ -265,6 +621,32 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
     for (int r = 0; r < 8; ++r) {
         const int group = dirs[r][2];
         if (!(dir_mask & (1 << r))) continue;
+        // a complete vertical group (S, SE, SW or N, NE, NW) runs as one strip sweep when the image fits one
+        // co-resident wave and the caller gave a workspace; otherwise direction by direction below
+        if ((r == 2 || r == 5) && ((dir_mask >> r) & 7) == 7 && D <= 256) {
+            SweepParams q;
+            q.cv = d_cv_in; q.S = d_cv_out; q.H = H; q.W = W; q.D = D;
+            q.p1 = p1; q.p2 = p2; q.invalid_value = invalid_value;
+            q.dy = dirs[r][0];
+            const bool g_init = (init_final & 1) && r == first_dir, g_final = (init_final & 2) && (r + 2) == last_dir;
+            q.mode = g_init ? (g_final ? 3 : 0) : (g_final ? 2 : 1);
+            q.overcounting = overcounting;
+            q.over_scale = 7.0f;
+            q.halo_in = (r == 2) ? d_halo_in_top : d_halo_in_bottom;
+            q.halo_out = (r == 2) ? d_halo_out_bottom : d_halo_out_top;
+            q.disp = g_final ? d_disp : nullptr;
+            q.all_nan = g_final ? d_all_nan : nullptr;
+            q.dmin = dmin; q.invalid_disparity = invalid_disparity;
+            q.ring = nullptr;
+            bool done = false;
+            int rc;
+            if (D <= 32) rc = launch_sweep<1>(q, d_workspace, workspace_bytes, s, &done);
+            else if (D <= 64) rc = launch_sweep<2>(q, d_workspace, workspace_bytes, s, &done);
+            else if (D <= 128) rc = launch_sweep<4>(q, d_workspace, workspace_bytes, s, &done);
+            else rc = launch_sweep<8>(q, d_workspace, workspace_bytes, s, &done);
+            if (rc != PB200_OK) return rc;
+            if (done) { r += 2; continue; }
+        }
         SgmParams p;
         p.cv = d_cv_in; p.S = d_cv_out; p.H = H; p.W = W; p.D = D;
         p.p1 = p1; p.p2 = p2; p.invalid_value = invalid_value;

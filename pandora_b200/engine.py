@@ -153,12 +153,13 @@ class Engine:
         if fuse_wta and disp is None:
             disp = self.empty((H, W))
             flags = self.empty((H, W), torch.uint8)
+        ws = self._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, W, D))
         with torch.cuda.device(self.device):
             _native.check(self.lib.pb200_sgm(
                 _ptr(cv), _ptr(res), H, W, D, float(p1), float(p2), float(invalid_value), int(bool(overcounting)), int(dir_mask), int(init_final),
                 _ptr(halo_in_top), _ptr(halo_in_bottom), _ptr(halo_out_bottom), _ptr(halo_out_top),
                 _ptr(disp) if fuse_wta else None, int(dmin), float(invalid_disparity), _ptr(flags) if fuse_wta else None,
-                None, 0, self._stream()))
+                _ptr(ws), ws.numel(), self._stream()))
         return (res, disp, flags) if fuse_wta else res
 
     # ---- disparity ----------------------------------------------------------------------------------

@@ -5,16 +5,17 @@ shard by rows with a small halo of INPUT image rows fetched once from the neighb
 (``exchange_image_halo``) -- no collective on the data path.  SGM has one real exchange step: the
 downward paths (S, SE, SW) need the last row's path states ``L_r`` of the tile above, the upward paths
 (N, NE, NW) the first row's states of the tile below.  They travel as point-to-point messages of
-``W x D`` floats per direction between neighbours only (NCCL send/recv over NVLink; gloo in the CPU
+``3 x W x D`` floats per wave between neighbours only (NCCL send/recv over NVLink; gloo in the CPU
 tests), which keeps the result bit-identical to the single-GPU run for integer-valued costs --
 unlike Pandora's own tiling convention, a fixed 40-pixel margin (marge.py:85-101 in the reference),
 which is an approximation.
 
 Schedule: the horizontal directions are tile-local and run first.  The two vertical waves start at
-opposite ends (rank 0 downward, rank N-1 upward); every rank orders its six vertical directions by the
-time their halo can arrive (``direction_order``), which makes the dependency graph acyclic -- a rank
-never waits for a neighbour that is waiting for it.  Each wave uses its own process group so that the
-two flows between a pair of neighbours are not serialised on one communicator.
+opposite ends (rank 0 downward, rank N-1 upward); every rank runs its two vertical groups (one strip-sweep
+kernel launch each: S+SE+SW and N+NE+NW) in the order their halo can arrive (``group_order``), which makes
+the dependency graph acyclic -- a rank never waits for a neighbour that is waiting for it.  Each wave uses
+its own process group so that the two flows between a pair of neighbours are not serialised on one
+communicator; one message per border and wave carries the three (W, D) state planes.
 """
 from __future__ import annotations
 
@@ -35,25 +36,34 @@ def split_rows(total_rows: int, world: int) -> List[range]:
     return out
 
 
+def group_order(rank: int, world: int) -> List[int]:
+    """Order in which ``rank`` runs its two vertical groups (0 = downward S/SE/SW, 1 = upward N/NE/NW): by
+    earliest possible halo arrival (the downward wave reaches rank r at step r, the upward wave at step
+    world-1-r), downward first on ties.  A rank that runs "up" first sits in the lower half and one that runs
+    "down" first in the upper half, so no two ranks can wait on each other (acyclic dependency graph)."""
+    return [0, 1] if rank <= world - 1 - rank else [1, 0]
+
+
 def direction_order(rank: int, world: int) -> List[int]:
-    """Order in which ``rank`` runs its six vertical directions: by earliest possible halo arrival
-    (downward wave reaches rank r at step r, upward wave at step world-1-r), downward first on ties."""
-    tasks = [(rank + i, 0, d) for i, d in enumerate(DOWN)] + [((world - 1 - rank) + i, 1, d) for i, d in enumerate(UP)]
-    return [d for _, _, d in sorted(tasks)]
+    """The six vertical directions in execution order (groups stay together, see ``group_order``)."""
+    return [d for g in group_order(rank, world) for d in (DOWN, UP)[g]]
 
 
 class SgmBackend:
-    """What the tile executor needs from a device: run one direction on the local tile."""
+    """What the tile executor needs from a device: run the horizontal pair or one vertical group on the local tile."""
 
-    def new_halo(self):  # (W, D) float32 buffer
+    def new_halo(self):  # (3, W, D) float32 buffer: the three path states of one boundary row
         raise NotImplementedError
 
-    def run_direction(self, direction: int, init: bool, final: bool, halo_in, halo_out) -> None:
+    def run_horizontal(self, init: bool) -> None:
+        raise NotImplementedError
+
+    def run_group(self, group: int, final: bool, halo_in, halo_out) -> None:
         raise NotImplementedError
 
 
 class EngineSgmBackend(SgmBackend):
-    """CUDA backend: ``Engine.sgm`` restricted to one direction per call."""
+    """CUDA backend: ``Engine.sgm`` restricted to one direction group per call (one strip-sweep launch each)."""
 
     def __init__(self, engine, cv, out, p1, p2, invalid_value, overcounting=False, disp=None, flags=None, dmin=0,
                  invalid_disparity=-9999.0):
@@ -63,65 +73,51 @@ class EngineSgmBackend(SgmBackend):
 
     def new_halo(self):
         _, W, D = self.cv.shape
-        return self.eng.empty((W, D))
+        return self.eng.empty((3, W, D))
 
-    def run_direction(self, direction, init, final, halo_in, halo_out) -> None:
-        kw = {}
-        if direction in DOWN:
-            kw = {"halo_in_top": _group_view(halo_in, direction, DOWN), "halo_out_bottom": _group_view(halo_out, direction, DOWN)}
-        elif direction in UP:
-            kw = {"halo_in_bottom": _group_view(halo_in, direction, UP), "halo_out_top": _group_view(halo_out, direction, UP)}
+    def run_horizontal(self, init: bool) -> None:
+        self.eng.sgm(self.cv, *self.args, out=self.out, dir_mask=0x03, init_final=1 if init else 0)
+
+    def run_group(self, group, final, halo_in, halo_out) -> None:
+        if group == 0:
+            kw = {"halo_in_top": halo_in, "halo_out_bottom": halo_out}
+        else:
+            kw = {"halo_in_bottom": halo_in, "halo_out_top": halo_out}
         fuse = final and self.disp is not None
         self.eng.sgm(self.cv, *self.args, out=self.out, fuse_wta=fuse, dmin=self.dmin, invalid_disparity=self.invalid_disparity,
-                     dir_mask=1 << direction, init_final=(1 if init else 0) | (2 if final else 0), disp=self.disp, flags=self.flags,
-                     **kw)
-
-
-class _PlaneAlias:
-    """The C-ABI indexes halo planes by the direction's rank inside its group ((3, W, D) arrays); a single
-    (W, D) buffer is presented as plane ``idx`` of such an array by shifting the base pointer back."""
-
-    def __init__(self, tensor, idx: int):
-        self.tensor, self.idx = tensor, idx
-
-    def data_ptr(self) -> int:
-        return self.tensor.data_ptr() - self.idx * self.tensor.numel() * 4
-
-
-def _group_view(halo, direction: int, group: Sequence[int]):
-    return None if halo is None else _PlaneAlias(halo, group.index(direction))
+                     dir_mask=0x1C if group == 0 else 0xE0, init_final=2 if final else 0, disp=self.disp, flags=self.flags, **kw)
 
 
 def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down=None, pg_up=None, order: Optional[List[int]] = None):
     """Execute the 8 directions on this rank's tile with halo hand-over to the neighbours.
 
     ``dist`` is ``torch.distributed`` (or None when world == 1); ``pg_down`` / ``pg_up`` are two process
-    groups spanning all ranks.  Returns the order in which the vertical directions were run.
+    groups spanning all ranks (one per wave, so the two flows between a pair of neighbours are not serialised
+    on one communicator).  One message of (3, W, D) floats per tile border and wave.  Returns the group order.
     """
-    order = direction_order(rank, world) if order is None else order
+    order = group_order(rank, world) if order is None else order
     has_up_nb, has_down_nb = rank > 0, rank < world - 1
     recv_bufs, recv_work, send_work, keep = {}, {}, [], []
     if world > 1:
-        for d in order:                                   # pre-post every receive: they depend on nothing local
-            src = rank - 1 if d in DOWN else rank + 1
-            if (d in DOWN and has_up_nb) or (d in UP and has_down_nb):
-                recv_bufs[d] = backend.new_halo()
-                recv_work[d] = dist.irecv(recv_bufs[d], src=src, group=pg_down if d in DOWN else pg_up)
-    backend.run_direction(0, True, False, None, None)
-    backend.run_direction(1, False, False, None, None)
-    for i, d in enumerate(order):
+        for g in order:                                   # pre-post both receives: they depend on nothing local
+            src = rank - 1 if g == 0 else rank + 1
+            if (g == 0 and has_up_nb) or (g == 1 and has_down_nb):
+                recv_bufs[g] = backend.new_halo()
+                recv_work[g] = dist.irecv(recv_bufs[g], src=src, group=pg_down if g == 0 else pg_up)
+    backend.run_horizontal(True)
+    for i, g in enumerate(order):
         halo_in = None
-        if d in recv_work:
-            recv_work[d].wait()
-            halo_in = recv_bufs[d]
+        if g in recv_work:
+            recv_work[g].wait()
+            halo_in = recv_bufs[g]
         send_to = None
-        if world > 1 and ((d in DOWN and has_down_nb) or (d in UP and has_up_nb)):
-            send_to = rank + 1 if d in DOWN else rank - 1
+        if world > 1 and ((g == 0 and has_down_nb) or (g == 1 and has_up_nb)):
+            send_to = rank + 1 if g == 0 else rank - 1
         halo_out = backend.new_halo() if send_to is not None else None
-        backend.run_direction(d, False, i == len(order) - 1, halo_in, halo_out)
+        backend.run_group(g, i == len(order) - 1, halo_in, halo_out)
         if send_to is not None:
             keep.append(halo_out)
-            send_work.append(dist.isend(halo_out, dst=send_to, group=pg_down if d in DOWN else pg_up))
+            send_work.append(dist.isend(halo_out, dst=send_to, group=pg_down if g == 0 else pg_up))
     for w in send_work:
         w.wait()
     return order

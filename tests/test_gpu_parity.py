@@ -274,6 +274,38 @@ def test_sgm_float_costs_bit_exact(eng, oracle):
     np.testing.assert_array_equal(got, ref)          # same operation order as the oracle -> identical rounding
 
 
+@pytest.mark.parametrize("shape", [(20, 700, 64), (33, 300, 256), (7, 1200, 40), (64, 613, 130), (5, 4100, 8)])
+def test_sgm_strip_sweep_many_strips(eng, oracle, shape):
+    """Wide images: the vertical groups run as multi-strip cooperative sweeps (ring hand-over between CTAs);
+    the result must equal both the oracle and the direction-by-direction path kernels."""
+    import torch
+
+    g = np.random.default_rng(shape[1])
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.1] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25)
+    d_cv = dev(eng, cv)
+    got, disp, flags = eng.sgm(d_cv, 8, 32, 58.0, fuse_wta=True, dmin=-(shape[2] - 1))
+    np.testing.assert_array_equal(host(got), ref)
+    exp_disp, exp_inv = oracle.wta(ref, np.arange(-(shape[2] - 1), 1))
+    np.testing.assert_array_equal(host(disp), exp_disp)
+    np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+    one = torch.empty_like(d_cv)
+    for r in range(8):                                   # single-direction calls never take the sweep path
+        eng.sgm(d_cv, 8, 32, 58.0, out=one, dir_mask=1 << r, init_final=(1 if r == 0 else 0) | (2 if r == 7 else 0))
+    np.testing.assert_array_equal(host(one), ref)
+
+
+def test_sgm_strip_sweep_float_costs_repeatable(eng, oracle):
+    g = np.random.default_rng(77)
+    cv = g.random((19, 500, 96)).astype(np.float32)
+    cv[g.random(cv.shape) < 0.1] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 0.3, 1.7, cmax=1.0)
+    for _ in range(3):
+        got = host(eng.sgm(dev(eng, cv), 0.3, 1.7, oracle.sgm_invalid_value(1.0, 1.7)))
+        np.testing.assert_array_equal(got, ref)
+
+
 def test_sgm_fused_wta_and_census_pipeline(eng, oracle):
     left, right, _ = oracle.synthetic_pair(48, 160, 64)
     cv, attrs = oracle.census_cost_volume(left, right, 5, -63, 0)

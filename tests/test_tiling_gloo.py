@@ -13,27 +13,29 @@ from pandora_b200 import tiling
 
 
 def test_direction_order_is_deadlock_free():
-    for world in (1, 2, 3, 4, 8):
-        orders = [tiling.direction_order(r, world) for r in range(world)]
-        for o in orders:
-            assert sorted(o) == [2, 3, 4, 5, 6, 7]
-            assert [d for d in o if d in tiling.DOWN] == list(tiling.DOWN) and [d for d in o if d in tiling.UP] == list(tiling.UP)
-        # simulate: a rank may run direction d once its upstream neighbour has run d
+    for world in (1, 2, 3, 4, 5, 8):
+        orders = [tiling.group_order(r, world) for r in range(world)]
+        for r, o in enumerate(orders):
+            assert sorted(o) == [0, 1]
+            dirs = tiling.direction_order(r, world)
+            assert sorted(dirs) == [2, 3, 4, 5, 6, 7]
+            assert [d for d in dirs if d in tiling.DOWN] == list(tiling.DOWN) and [d for d in dirs if d in tiling.UP] == list(tiling.UP)
+        # simulate: a rank may run group g once its upstream neighbour has run g
         done = [set() for _ in range(world)]
         pos = [0] * world
         progressed = True
         while progressed:
             progressed = False
             for r in range(world):
-                while pos[r] < 6:
-                    d = orders[r][pos[r]]
-                    up = r - 1 if d in tiling.DOWN else r + 1
-                    if 0 <= up < world and d not in done[up]:
+                while pos[r] < 2:
+                    g = orders[r][pos[r]]
+                    up = r - 1 if g == 0 else r + 1
+                    if 0 <= up < world and g not in done[up]:
                         break
-                    done[r].add(d)
+                    done[r].add(g)
                     pos[r] += 1
                     progressed = True
-        assert all(p == 6 for p in pos), (world, pos)
+        assert all(p == 2 for p in pos), (world, pos)
 
 
 def test_split_rows():
@@ -42,20 +44,26 @@ def test_split_rows():
 
 
 class OracleBackend(tiling.SgmBackend):
-    """Per-direction SGM through the CPU oracle (test stand-in for EngineSgmBackend)."""
+    """Group-wise SGM through the CPU oracle (test stand-in for EngineSgmBackend)."""
 
     def __init__(self, orc, C, S, p1, p2):
         self.orc, self.C, self.S, self.p1, self.p2 = orc, C, S, p1, p2
         self.calls = []
 
     def new_halo(self):
-        return torch.zeros(self.C.shape[1:], dtype=torch.float32)
+        return torch.zeros((3,) + tuple(self.C.shape[1:]), dtype=torch.float32)
 
-    def run_direction(self, direction, init, final, halo_in, halo_out):
-        self.calls.append((direction, init, final))
-        hi = None if halo_in is None else halo_in.numpy()
-        ho = None if halo_out is None else halo_out.numpy()
-        self.orc.sgm_direction(self.C, self.S, self.p1, self.p2, direction, init, hi, ho)
+    def run_horizontal(self, init):
+        self.calls.append(("h", init, False))
+        self.orc.sgm_direction(self.C, self.S, self.p1, self.p2, 0, init, None, None)
+        self.orc.sgm_direction(self.C, self.S, self.p1, self.p2, 1, False, None, None)
+
+    def run_group(self, group, final, halo_in, halo_out):
+        self.calls.append((group, False, final))
+        for k, direction in enumerate((tiling.DOWN, tiling.UP)[group]):
+            hi = None if halo_in is None else halo_in[k].numpy()
+            ho = None if halo_out is None else halo_out[k].numpy()
+            self.orc.sgm_direction(self.C, self.S, self.p1, self.p2, direction, False, hi, ho)
 
 
 def _free_port():
@@ -82,8 +90,8 @@ def _worker(rank, world, port, H, W, D, tmpdir):
     St = np.zeros_like(Ct)
     backend = OracleBackend(orc, Ct, St, 8.0, 32.0)
     order = tiling.run_tiled_sgm(backend, rank, world, dist, pg_down, pg_up)
-    assert backend.calls[0] == (0, True, False) and backend.calls[-1][2] is True
-    assert [c[0] for c in backend.calls[2:]] == order
+    assert backend.calls[0] == ("h", True, False) and backend.calls[-1][2] is True
+    assert [c[0] for c in backend.calls[1:]] == order
     # image-halo exchange helper
     img = torch.arange(H * W, dtype=torch.float32).reshape(H, W)[rows.start: rows.stop].contiguous()
     ext, top = tiling.exchange_image_halo(img, 2, rank, world, dist)
