@@ -40,14 +40,14 @@ struct SgmParams {
     float invalid_disparity;
 };
 
-template <int NPL, bool VEC>
+template <int NPL, bool VEC, bool FULL = false>
 __device__ __forceinline__ void load_vec(const float *__restrict__ base, int lane, int D, float (&v)[NPL]) {
     if (VEC) {
 #pragma unroll
         for (int q = 0; q < NPL / 4; ++q) {
             const int d = lane * NPL + q * 4;
             float4 t = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
-            if (d < D) t = *reinterpret_cast<const float4 *>(base + d);      // D % 4 == 0 in this mode
+            if (FULL || d < D) t = *reinterpret_cast<const float4 *>(base + d);      // D % 4 == 0 in this mode
             v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
         }
     } else {
@@ -59,13 +59,13 @@ __device__ __forceinline__ void load_vec(const float *__restrict__ base, int lan
     }
 }
 
-template <int NPL, bool VEC>
+template <int NPL, bool VEC, bool FULL = false>
 __device__ __forceinline__ void store_vec(float *__restrict__ base, int lane, int D, const float (&v)[NPL]) {
     if (VEC) {
 #pragma unroll
         for (int q = 0; q < NPL / 4; ++q) {
             const int d = lane * NPL + q * 4;
-            if (d < D) *reinterpret_cast<float4 *>(base + d) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            if (FULL || d < D) *reinterpret_cast<float4 *>(base + d) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
     } else {
 #pragma unroll
@@ -388,7 +388,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 // diagonal states first; the exchange warp then copies them to the ring (its release fence has no
 // long-latency traffic of its own to wait for), polls the neighbours' counters and drops their border
 // states into the halo columns of the shared-memory state buffer before the end-of-row barrier.
-template <int NPL, bool VEC>
+// FULL: D == 32 * NPL (no tail checks, implies VEC); MODE / WTA >= 0: compile-time copies of p.mode / (p.disp != NULL)
+template <int NPL, bool VEC, bool FULL, int MODE, int WTA>
 __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) float sweep_smem[];
     constexpr int VS = NPL * 32;                       // floats per state vector (padded to the warp)
@@ -400,7 +401,9 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
     // index 0 / K+1 = border states of the left / right neighbour strip
     auto st = [&](int buf, int diag, int col) -> float * { return sweep_smem + ((size_t)(buf * 2 + diag) * (K + 2) + col) * VS; };
     const bool has_left = strip > 0, has_right = strip + 1 < nstrips;
-    const bool accumulate = (p.mode == 1 || p.mode == 2), final = (p.mode >= 2);
+    const int mode = (MODE >= 0) ? MODE : p.mode;
+    const bool accumulate = (mode == 1 || mode == 2), final = (mode >= 2);
+    const bool do_wta = (WTA >= 0) ? (WTA != 0) : (p.disp != nullptr);
     const size_t plane = (size_t)W * D;
 
     if (warp == nwarp) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
     int y = dy > 0 ? 0 : H - 1;
 #pragma unroll
     for (int c = 0; c < 2; ++c)
-        if (xs[c] < W) load_vec<NPL, VEC>(p.cv + ((size_t)y * W + xs[c]) * D, lane, D, cnext[c]);
+        if (xs[c] < W) load_vec<NPL, VEC, FULL>(p.cv + ((size_t)y * W + xs[c]) * D, lane, D, cnext[c]);
 
     for (int i = 0; i < H; ++i, y += dy) {
         const int cur = i & 1, prv = cur ^ 1;
@@ -450,8 +453,8 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
             }
             const int x = xs[c];
             if (x < W) {
-                if (!last) load_vec<NPL, VEC>(p.cv + ((size_t)(y + dy) * W + x) * D, lane, D, cnext[c]);
-                if (accumulate) load_vec<NPL, VEC>(p.S + ((size_t)y * W + x) * D, lane, D, sacc[c]);
+                if (!last) load_vec<NPL, VEC, FULL>(p.cv + ((size_t)(y + dy) * W + x) * D, lane, D, cnext[c]);
+                if (accumulate) load_vec<NPL, VEC, FULL>(p.S + ((size_t)y * W + x) * D, lane, D, sacc[c]);
             }
         }
         // one recurrence of column slot c, group rank g (dx = 0, +1, -1): result in Lout, state stored for the next row
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
             bool have = false;
             if (first) {
                 if (p.halo_in != nullptr && px >= 0 && px < W) {
-                    load_vec<NPL, VEC>(p.halo_in + (size_t)g * plane + (size_t)px * D, lane, D, Lp);
+                    load_vec<NPL, VEC, FULL>(p.halo_in + (size_t)g * plane + (size_t)px * D, lane, D, Lp);
                     have = true;
                 }
             } else if (g == 0) {
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
             } else {
                 lm_store<NPL>(st(cur, g - 1, col[c] + 1), lane, Lout);
             }
-            if (last && p.halo_out != nullptr) store_vec<NPL, VEC>(p.halo_out + (size_t)g * plane + (size_t)x * D, lane, D, Lout);
+            if (last && p.halo_out != nullptr) store_vec<NPL, VEC, FULL>(p.halo_out + (size_t)g * plane + (size_t)x * D, lane, D, Lout);
         };
         // the outgoing border diagonals first (column slot 0: dx = -1, slot 1: dx = +1), so that warp 0 can hand the
         // strip's border states to the exchange warp as early as possible
@@ -522,12 +525,12 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
                     if (nanmask[c] & (1u << j)) s = nan_f();
                     out[j] = s;
                     const int d = lane * NPL + j;
-                    if (d < D && s == s) {
+                    if (do_wta && (FULL || d < D) && s == s) {
                         any = true;
                         if (s < bv) { bv = s; bk = d; }
                     }
                 }
-                if (p.disp != nullptr) {
+                if (do_wta) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -544,7 +547,7 @@ __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p)
                     }
                 }
             }
-            store_vec<NPL, VEC>(p.S + ((size_t)y * W + x) * D, lane, D, out);
+            store_vec<NPL, VEC, FULL>(p.S + ((size_t)y * W + x) * D, lane, D, out);
         }
         __syncthreads();           // every diagonal state of this row (own and halo) is in st[cur] before the next row
     }
@@ -568,7 +571,18 @@ static int launch_sweep(SweepParams p, void *workspace, size_t workspace_bytes, 
                      ((reinterpret_cast<uintptr_t>(p.S) & 15) == 0) &&
                      (!p.halo_in || (reinterpret_cast<uintptr_t>(p.halo_in) & 15) == 0) &&
                      (!p.halo_out || (reinterpret_cast<uintptr_t>(p.halo_out) & 15) == 0);
-    void (*kern)(const SweepParams) = vec ? sgm_vsweep_kernel<NPL, (NPL % 4 == 0)> : sgm_vsweep_kernel<NPL, false>;
+    void (*kern)(const SweepParams) = vec ? sgm_vsweep_kernel<NPL, (NPL % 4 == 0), false, -1, -1> : sgm_vsweep_kernel<NPL, false, false, -1, -1>;
+    if constexpr (NPL >= 4) {
+        if (vec && p.D == NPL * 32) {                              // full-width vectors: specialised, branch-free variants
+            const bool wta = p.disp != nullptr;
+            switch (p.mode) {
+                case 0: kern = sgm_vsweep_kernel<NPL, true, true, 0, 0>; break;
+                case 1: kern = sgm_vsweep_kernel<NPL, true, true, 1, 0>; break;
+                case 2: kern = wta ? sgm_vsweep_kernel<NPL, true, true, 2, 1> : sgm_vsweep_kernel<NPL, true, true, 2, 0>; break;
+                default: kern = wta ? sgm_vsweep_kernel<NPL, true, true, 3, 1> : sgm_vsweep_kernel<NPL, true, true, 3, 0>; break;
+            }
+        }
+    }
     const int threads = (nwarp + 1) * 32;
     PB200_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
