@@ -20,6 +20,7 @@
 // Every pixel belongs to exactly one path per direction, so S needs no atomics as long as the
 // directions run one after the other on the stream.
 #include "common.cuh"
+#include "sgm_common.cuh"
 
 namespace pb200 {
 
@@ -38,6 +39,8 @@ struct SgmParams {
     uint8_t *all_nan;
     int dmin;
     float invalid_disparity;
+    const int *gate;        // when not NULL the kernel runs only if (*gate != 0) == (gate_run_if != 0) (narrow/wide path switch)
+    int gate_run_if;
 };
 
 template <int NPL, bool VEC, bool FULL = false>
@@ -84,6 +87,7 @@ __device__ __forceinline__ float warp_min(float v) {
 
 template <int NPL, bool VEC>
 __global__ void __launch_bounds__(128) sgm_path_kernel(const SgmParams p) {
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_run_if != 0)) return;
     const int lane = threadIdx.x & 31;
     const long path = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int H = p.H, W = p.W, D = p.D, dy = p.dy, dx = p.dx;
@@ -260,71 +264,9 @@ struct SweepParams {
     int dmin;
     float invalid_disparity;
     unsigned long long *ring;   // [nstrips][2 sides][2 slots][32 * NPL] {tag, value} words, zero at launch
+    const int *gate;            // see SgmParams::gate
+    int gate_run_if;
 };
-
-__device__ __forceinline__ float fmin3(float a, float b, float c) {
-    float d;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3
-    return d;
-}
-__device__ __forceinline__ float warp_min_redux(float a) {
-    float d;
-    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(d) : "f"(a));   // CREDUX.MIN.F32
-    return d;
-}
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// lane-major vector layout ([quad][lane][4]) for shared memory and the ring: every access instruction
-// of a warp covers one contiguous span (no bank conflicts, fully coalesced).
-template <int NPL>
-__device__ __forceinline__ void lm_store(float *base, int lane, const float (&v)[NPL]) {
-    if constexpr (NPL % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < NPL / 4; ++q)
-            reinterpret_cast<float4 *>(base)[q * 32 + lane] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-    } else if constexpr (NPL == 2) {
-        reinterpret_cast<float2 *>(base)[lane] = make_float2(v[0], v[1]);
-    } else {
-        base[lane] = v[0];
-    }
-}
-template <int NPL>
-__device__ __forceinline__ void lm_load(const float *base, int lane, float (&v)[NPL]) {
-    if constexpr (NPL % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < NPL / 4; ++q) {
-            const float4 t = reinterpret_cast<const float4 *>(base)[q * 32 + lane];
-            v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-        }
-    } else if constexpr (NPL == 2) {
-        const float2 t = reinterpret_cast<const float2 *>(base)[lane];
-        v[0] = t.x; v[1] = t.y;
-    } else {
-        v[0] = base[lane];
-    }
-}
-template <int NPL>
-__device__ __forceinline__ void lm_load_cg(const float *base, int lane, float (&v)[NPL]) {   // L2 only: never a stale L1 line
-    if constexpr (NPL % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < NPL / 4; ++q) {
-            const float4 t = __ldcg(reinterpret_cast<const float4 *>(base) + q * 32 + lane);
-            v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-        }
-    } else if constexpr (NPL == 2) {
-        const float2 t = __ldcg(reinterpret_cast<const float2 *>(base) + lane);
-        v[0] = t.x; v[1] = t.y;
-    } else {
-        v[0] = __ldcg(base + lane);
-    }
-}
 
 // one recurrence step: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m), m = min_k Lp[k]
 template <int NPL>
@@ -348,41 +290,6 @@ __device__ __forceinline__ void sgm_step_vec(const float (&cc)[NPL], const float
     }
 }
 
-// Flag-in-data hand-over between strips (the "LL" scheme of collective libraries): every float travels as
-// one naturally aligned 64-bit word {row tag, value}.  A 64-bit scalar access is single-copy atomic, so a
-// word whose tag matches is valid by itself: no fence on the sender, one L2 round trip on the receiver.
-__device__ __forceinline__ void ll_store(unsigned long long *p, uint32_t tag, float v) {
-    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_load(const unsigned long long *p) {
-    unsigned long long w;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    return w;
-}
-template <int NPL>
-__device__ __forceinline__ void ll_send(unsigned long long *slot, int lane, uint32_t tag, const float (&v)[NPL]) {
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) ll_store(slot + j * 32 + lane, tag, v[j]);
-}
-template <int NPL>
-__device__ __forceinline__ void ll_recv(const unsigned long long *slot, int lane, uint32_t tag, float (&v)[NPL]) {
-    unsigned long long w[NPL];
-    bool ok;
-    do {
-        ok = true;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) w[j] = ll_load(slot + j * 32 + lane);
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
-    } while (!__all_sync(0xffffffffu, ok));
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) v[j] = __uint_as_float((uint32_t)w[j]);
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
 // Warp roles: warps 0..nwarp-1 compute, warp nwarp is the exchange warp.  Compute warp w owns the strip
 // columns w and K-1-w (mirror pair), so warp 0 owns BOTH border columns and computes their outgoing
 // diagonal states first; the exchange warp then copies them to the ring (its release fence has no
@@ -391,6 +298,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 // FULL: D == 32 * NPL (no tail checks, implies VEC); MODE / WTA >= 0: compile-time copies of p.mode / (p.disp != NULL)
 template <int NPL, bool VEC, bool FULL, int MODE, int WTA>
 __global__ void __launch_bounds__(512, 1) sgm_vsweep_kernel(const SweepParams p) {
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_run_if != 0)) return;
     extern __shared__ __align__(16) float sweep_smem[];
     constexpr int VS = NPL * 32;                       // floats per state vector (padded to the warp)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x >> 5) - 1;
@@ -597,17 +505,19 @@ static int launch_sweep(SweepParams p, void *workspace, size_t workspace_bytes, 
     return PB200_OK;
 }
 
+int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, float p2, float invalid_value, int overcounting,
+                   float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
+                   cudaStream_t s, const int **gate);   // sgm_narrow.cu
+
 }  // namespace pb200
 
 using namespace pb200;
 
 extern "C" size_t pb200_sgm_workspace_bytes(int H, int W, int D) {
     (void)H;
-    // strip-sweep exchange rings + progress counters (launch_sweep): at most one strip per 4 columns
+    // strip-sweep exchange ring (launch_sweep / sgm_narrow.cu) + the narrow-path flag
     if (W <= 0 || D <= 0) return 16;
-    const size_t nstrips = (size_t)(W + 3) / 4;
-    const size_t vs = (size_t)((D + 31) / 32) * 32;
-    return nstrips * (2 * 2 * vs * sizeof(unsigned long long)) + 256;
+    return sgm_ring_max_bytes(W, D) + 512;
 }
 
 extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
@@ -623,6 +533,15 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
         return PB200_ERR_UNSUPPORTED;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // Exact packed-integer fast path (sgm_narrow.cu) for a whole 8-direction call on integer-valued costs: it
+    // verifies the data while it runs and raises a device flag when a cost is not a small integer; the float
+    // kernels below are then enqueued gated on that flag (they return at once when the fast path succeeded).
+    const int *gate = nullptr;
+    if (dir_mask == 0xFF && init_final == 3 && !d_halo_in_top && !d_halo_in_bottom && !d_halo_out_bottom && !d_halo_out_top) {
+        int rc = sgm_narrow_try(d_cv_in, d_cv_out, H, W, D, p1, p2, invalid_value, overcounting, d_disp, dmin, invalid_disparity,
+                                d_all_nan, d_workspace, workspace_bytes, s, &gate);
+        if (rc != PB200_OK) return rc;
+    }
     // direction table in accumulation order; group 0 horizontal, 1 downward, 2 upward
     static const int dirs[8][3] = {{0, 1, 0}, {0, -1, 0}, {1, 0, 1}, {1, 1, 1}, {1, -1, 1}, {-1, 0, 2}, {-1, 1, 2}, {-1, -1, 2}};
     const size_t plane = (size_t)W * D;
@@ -652,6 +571,7 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
             q.all_nan = g_final ? d_all_nan : nullptr;
             q.dmin = dmin; q.invalid_disparity = invalid_disparity;
             q.ring = nullptr;
+            q.gate = gate; q.gate_run_if = 1;
             bool done = false;
             int rc;
             if (D <= 32) rc = launch_sweep<1>(q, d_workspace, workspace_bytes, s, &done);
@@ -680,6 +600,7 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
         p.disp = is_final ? d_disp : nullptr;
         p.all_nan = is_final ? d_all_nan : nullptr;
         p.dmin = dmin; p.invalid_disparity = invalid_disparity;
+        p.gate = gate; p.gate_run_if = 1;
         int rc;
         if (D <= 32) rc = launch_dir<1>(p, s);
         else if (D <= 64) rc = launch_dir<2>(p, s);

@@ -1,0 +1,429 @@
+// sgm_narrow.cu -- exact packed-integer fast path of the 8-path SGM stage.
+//
+// Same recurrence and accumulation as sgm.cu / oracle/pandora_oracle.c::pbo_sgm, for the common case where
+// every cost, P1, P2 and the invalid value are small non-negative integers (Census / SAD on integer images):
+// then every L_r and every partial sum is an integer below 2^16, float32 arithmetic on them is exact, and the
+// same numbers can be computed with 16-bit integer SIMD (two disparities per 32-bit register; VIMNMX.U16x2 /
+// VIADDMNMX.U16x2, the DPX dynamic-programming instructions) and kept in 16-bit storage between the passes.
+// The result is bit-identical to the float path; only the traffic and the instruction count change:
+//
+//   pass E   read C float32 (4D B/pixel), check + pack it to C16, write C16 and P16 = L_E        (2D + 2D)
+//   pass W   read C16, read P16, P16 += L_W, write P16                                           (2D + 2D + 2D)
+//   sweep S  read C16, read P16, P16 += L_S + L_SE + L_SW, write P16                              (6D)
+//   sweep N  read C16, read P16, total = P16 + L_N + L_NE + L_NW -> float32 S (+ NaN, WTA)        (4D + 4D)
+//
+// = 28D bytes per pixel instead of 44D (float sweeps) or 92D (one launch per direction).  C16 and P16 live INSIDE
+// the caller's float32 output buffer (2 + 2 bytes per cell), in a private word order: word lane*NR + j of a
+// pixel holds the disparities (NR*lane + j) in its low and (D/2 + NR*lane + j) in its high half, so a lane's
+// registers are one aligned vector and both halves of a register have their d-1 / d+1 neighbours in the
+// adjacent register.  The last sweep converts in place: every lane overwrites exactly the bytes it loaded.
+//
+// The data condition (integer costs in [0, 8191 - P2]) is verified by pass E on every cell; a violation raises a
+// device flag, the remaining narrow kernels return at once and the float kernels, enqueued behind them and gated
+// on the same flag, redo the whole stage.  No host synchronisation is involved.
+#include "sgm_common.cuh"
+
+namespace pb200 {
+
+namespace {
+
+constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger than any state, INF + P cannot wrap
+constexpr uint32_t NANBITS = 0x80008000u;    // bit 15 of a C16 half: the original cost was NaN
+constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
+
+struct NarrowParams {
+    const float *cv;          // float32 (H, W, D) input costs (pass E only)
+    uint32_t *buf;            // the output buffer as packed words: per pixel [D/2 words C16][D/2 words P16]
+    int H, W, D;
+    uint32_t p1p1, p2p2;      // penalties replicated in both halves
+    uint32_t inv;             // invalid_value
+    float cost_ok_max;        // largest admissible cost
+    int *flag;                // raised (1) when the volume does not qualify
+    int dy, overcounting;     // sweeps
+    float *disp;
+    uint8_t *all_nan;
+    int dmin;
+    float invalid_disparity;
+    unsigned long long *ring;
+};
+
+template <int NR> struct Words;
+template <> struct Words<4> { using T = uint4; };
+template <> struct Words<2> { using T = uint2; };
+template <> struct Words<1> { using T = uint32_t; };
+
+template <int NR>
+__device__ __forceinline__ void ld_words(const uint32_t *p, uint32_t (&v)[NR]) {
+    const typename Words<NR>::T t = *reinterpret_cast<const typename Words<NR>::T *>(p);
+    if constexpr (NR == 4) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (NR == 2) { v[0] = t.x; v[1] = t.y; }
+    else v[0] = t;
+}
+template <int NR>
+__device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[NR]) {
+    if constexpr (NR == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    else if constexpr (NR == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
+    else *p = v[0];
+}
+template <int NR>
+__device__ __forceinline__ void ld_floats(const float *p, float (&v)[NR]) {
+    if constexpr (NR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (NR == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else v[0] = *p;
+}
+template <int NR>
+__device__ __forceinline__ void st_floats(float *p, const float (&v)[NR]) {
+    if constexpr (NR == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (NR == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
+// One recurrence step on packed states: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m).
+// Register j of a lane holds disparity NR*lane + j (low half) and D/2 + NR*lane + j (high half).
+template <int NR>
+__device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (&Lp)[NR], uint32_t (&L)[NR], int lane, uint32_t p1p1,
+                                      uint32_t p2p2) {
+    uint32_t mn = Lp[0];
+#pragma unroll
+    for (int j = 1; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
+    uint32_t m16 = min(mn & 0xFFFFu, mn >> 16);
+    m16 = __reduce_min_sync(0xffffffffu, m16);
+    const uint32_t mm = m16 * 0x10001u;
+    const uint32_t mp2 = mm + p2p2;
+    const uint32_t up = __shfl_sync(0xffffffffu, Lp[NR - 1], (lane + 31) & 31);
+    const uint32_t dn = __shfl_sync(0xffffffffu, Lp[0], (lane + 1) & 31);
+    // lane 0: d-1 of its low half does not exist, d-1 of its high half (D/2 - 1) is lane 31's last LOW half
+    const uint32_t lo0 = (lane == 0) ? ((up << 16) | INF16) : up;
+    // lane 31: d+1 of its low half (D/2) is lane 0's first HIGH half, d+1 of its high half does not exist
+    const uint32_t hiN = (lane == 31) ? ((dn >> 16) | (INF16 << 16)) : dn;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const uint32_t lo = (j == 0) ? lo0 : Lp[j - 1];
+        const uint32_t hi = (j == NR - 1) ? hiN : Lp[j + 1];
+        const uint32_t t = __vminu2(__viaddmin_u16x2(__vminu2(lo, hi), p1p1, Lp[j]), mp2);
+        L[j] = cc[j] + (t - mm);          // t >= m in both halves: no borrow, and cc + P2 < 2^16: no carry
+    }
+}
+
+// float32 cost -> 16-bit code (value, or invalid_value | 0x8000 for NaN); `bad` is raised for anything else
+__device__ __forceinline__ uint32_t encode_cost(float v, uint32_t inv, float ok_max, bool &bad) {
+    const float t = v + 8388608.0f;                       // exact integer extraction for 0 <= v < 2^23
+    const bool isn = (v != v);
+    const bool ok = (t - 8388608.0f == v) && (v >= 0.f) && (v <= ok_max);
+    bad = bad || !(ok || isn);
+    return isn ? (inv | 0x8000u) : (__float_as_uint(t) & 0xFFFFu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// horizontal passes: one warp per row
+// ------------------------------------------------------------------------------------------------
+template <int NR, bool FIRST>
+__global__ void __launch_bounds__(128) sgm_narrow_h_kernel(const NarrowParams p) {
+    if (!FIRST && *p.flag != 0) return;
+    const int lane = threadIdx.x & 31;
+    const long path = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (path >= p.H) return;
+    const int W = p.W, D = p.D;
+    const int dx = FIRST ? 1 : -1;
+    int x = FIRST ? 0 : W - 1;
+    const size_t pix0 = (size_t)path * W + x;
+    const long step = (long)dx * D;
+    uint32_t *b_ptr = p.buf + pix0 * D + lane * NR;         // this lane's C16 words; its P16 words are NR*32 further
+    const float *c_ptr = p.cv + pix0 * D + lane * NR;       // FIRST: low-half costs; high-half costs D/2 further
+    uint32_t Lp[NR];
+    bool bad = false;
+    // prefetch registers for the next pixel
+    float fa[NR], fb[NR];
+    uint32_t c16n[NR], p16n[NR];
+    if (FIRST) { ld_floats<NR>(c_ptr, fa); ld_floats<NR>(c_ptr + D / 2, fb); }
+    else { ld_words<NR>(b_ptr, c16n); ld_words<NR>(b_ptr + NR * 32, p16n); }
+    for (int i = 0; i < W; ++i) {
+        uint32_t c16[NR], p16[NR], cc[NR];
+        if (FIRST) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                c16[j] = encode_cost(fa[j], p.inv, p.cost_ok_max, bad) | (encode_cost(fb[j], p.inv, p.cost_ok_max, bad) << 16);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) { c16[j] = c16n[j]; p16[j] = p16n[j]; }
+        }
+        if (i + 1 < W) {
+            if (FIRST) { ld_floats<NR>(c_ptr + step, fa); ld_floats<NR>(c_ptr + step + D / 2, fb); }
+            else { ld_words<NR>(b_ptr + step, c16n); ld_words<NR>(b_ptr + step + NR * 32, p16n); }
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) cc[j] = c16[j] & ~NANBITS;
+        uint32_t L[NR];
+        if (i == 0) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) L[j] = cc[j];
+        } else {
+            nstep<NR>(cc, Lp, L, lane, p.p1p1, p.p2p2);
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            Lp[j] = L[j];
+            p16[j] = FIRST ? L[j] : p16[j] + L[j];
+        }
+        if (FIRST) st_words<NR>(b_ptr, c16);
+        st_words<NR>(b_ptr + NR * 32, p16);
+        b_ptr += step;
+        c_ptr += step;
+    }
+    if (FIRST && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertical sweeps: same strip / exchange-warp scheme as sgm_vsweep_kernel (sgm.cu), packed states
+// ------------------------------------------------------------------------------------------------
+template <int NR>
+__device__ __forceinline__ void ll_send_u32(unsigned long long *slot, int lane, uint32_t tag, const uint32_t (&v)[NR]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)v[j];
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot + j * 32 + lane), "l"(w) : "memory");
+    }
+}
+template <int NR>
+__device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int lane, uint32_t tag, uint32_t (&v)[NR]) {
+    unsigned long long w[NR];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
+    } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
+}
+
+template <int NR, bool FINAL, bool WTA>
+__global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowParams p) {
+    if (*p.flag != 0) return;
+    extern __shared__ __align__(16) uint32_t nsweep_smem[];
+    constexpr int VS = NR * 32;                          // words per packed state vector
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x >> 5) - 1;
+    const int K = nwarp * 2;
+    const int strip = blockIdx.x, nstrips = gridDim.x;
+    const int H = p.H, W = p.W, D = p.D, dy = p.dy;
+    auto st = [&](int buf, int diag, int col) -> uint32_t * { return nsweep_smem + ((size_t)(buf * 2 + diag) * (K + 2) + col) * VS; };
+    const bool has_left = strip > 0, has_right = strip + 1 < nstrips;
+
+    if (warp == nwarp) {                                  // exchange warp: neighbours' border states of row i -> halo columns
+        for (int i = 0; i + 1 < H; ++i) {
+            const int cur = i & 1;
+            const uint32_t tag = (uint32_t)(i + 1);
+            if (has_left) {
+                uint32_t v[NR];
+                ll_recv_u32<NR>(p.ring + ((size_t)((strip - 1) * 2 + 1) * 2 + cur) * VS, lane, tag, v);
+                st_words<NR>(st(cur, 0, 0) + lane * NR, v);
+            }
+            if (has_right) {
+                uint32_t v[NR];
+                ll_recv_u32<NR>(p.ring + ((size_t)((strip + 1) * 2 + 0) * 2 + cur) * VS, lane, tag, v);
+                st_words<NR>(st(cur, 1, K + 1) + lane * NR, v);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        return;
+    }
+
+    const int col[2] = {warp, K - 1 - warp};
+    const int xs[2] = {strip * K + col[0], strip * K + col[1]};
+    uint32_t Lv[2][NR], c16n[2][NR], p16n[2][NR];
+    int y = dy > 0 ? 0 : H - 1;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (xs[c] < W) {
+            const uint32_t *b = p.buf + ((size_t)y * W + xs[c]) * D + lane * NR;
+            ld_words<NR>(b, c16n[c]);
+            ld_words<NR>(b + VS, p16n[c]);
+        }
+
+    for (int i = 0; i < H; ++i, y += dy) {
+        const int cur = i & 1, prv = cur ^ 1;
+        const bool first = (i == 0), last = (i == H - 1);
+        uint32_t c16[2][NR], p16[2][NR], cc[2][NR];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                c16[c][j] = c16n[c][j];
+                p16[c][j] = p16n[c][j];
+                cc[c][j] = c16[c][j] & ~NANBITS;
+            }
+            if (xs[c] < W && !last) {
+                const uint32_t *b = p.buf + ((size_t)(y + dy) * W + xs[c]) * D + lane * NR;
+                ld_words<NR>(b, c16n[c]);
+                ld_words<NR>(b + VS, p16n[c]);
+            }
+        }
+        auto run_dir = [&](const int c, const int g, uint32_t (&Lout)[NR]) {
+            const int x = xs[c];
+            const int dx = (g == 0) ? 0 : (g == 1 ? 1 : -1);
+            const int px = x - dx;
+            uint32_t Lp[NR];
+            bool have = false;
+            if (!first) {
+                if (g == 0) {
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) Lp[j] = Lv[c][j];
+                    have = true;
+                } else if (px >= 0 && px < W) {
+                    have = true;
+                    ld_words<NR>(st(prv, g - 1, col[c] - dx + 1) + lane * NR, Lp);
+                }
+            }
+            if (have) {
+                nstep<NR>(cc[c], Lp, Lout, lane, p.p1p1, p.p2p2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Lout[j] = cc[c][j];
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Lv[c][j] = Lout[j];
+            } else {
+                st_words<NR>(st(cur, g - 1, col[c] + 1) + lane * NR, Lout);
+            }
+        };
+        uint32_t Lb[2][NR];
+        if (xs[0] < W) run_dir(0, 2, Lb[0]);
+        if (warp == 0 && has_left && !last) ll_send_u32<NR>(p.ring + ((size_t)(strip * 2 + 0) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[0]);
+        if (xs[1] < W) run_dir(1, 1, Lb[1]);
+        if (warp == 0 && has_right && !last) ll_send_u32<NR>(p.ring + ((size_t)(strip * 2 + 1) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[1]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int x = xs[c];
+            if (x >= W) continue;
+            uint32_t L0[NR], Lo[NR], tot[NR];
+            run_dir(c, 0, L0);
+            run_dir(c, c == 0 ? 1 : 2, Lo);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tot[j] = p16[c][j] + L0[j] + Lo[j] + Lb[c][j];
+            uint32_t *b = p.buf + ((size_t)y * W + x) * D + lane * NR;
+            if (!FINAL) {
+                st_words<NR>(b + VS, tot);
+            } else {
+                // total -> float32 (exact), overcounting, NaN restore, in place: this lane overwrites the bytes it loaded
+                float fa[NR], fb[NR];
+                uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    uint32_t t = tot[j];
+                    if (p.overcounting) t = t - 7u * cc[c][j];       // S >= 8 C in every half: no borrow
+                    const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                    const bool nlo = (c16[c][j] & 0x8000u) != 0, nhi = (c16[c][j] & 0x80000000u) != 0;
+                    fa[j] = nlo ? nan_f() : small_int_to_float(lo);
+                    fb[j] = nhi ? nan_f() : small_int_to_float(hi);
+                    if (WTA) {
+                        const uint32_t ka = (lo << 16) | (uint32_t)(lane * NR + j);
+                        const uint32_t kb = (hi << 16) | (uint32_t)(D / 2 + lane * NR + j);
+                        best = min(best, nlo ? 0xFFFFFFFFu : ka);
+                        best = min(best, nhi ? 0xFFFFFFFFu : kb);
+                    }
+                }
+                float *o = reinterpret_cast<float *>(b);
+                st_floats<NR>(o, fa);
+                st_floats<NR>(o + D / 2, fb);
+                if (WTA) {
+                    best = __reduce_min_sync(0xffffffffu, best);
+                    if (lane == 0) {
+                        const size_t pix = (size_t)y * W + x;
+                        const bool none = (best == 0xFFFFFFFFu);
+                        p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
+                        if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NR>
+int launch_narrow(NarrowParams p, int nstrips, int nwarp, void *workspace, size_t ring_bytes, cudaStream_t s, bool *done) {
+    *done = false;
+    const int nsm = sm_count();
+    const int K = nwarp * 2;
+    const size_t smem = (size_t)2 * 2 * (K + 2) * NR * 32 * sizeof(uint32_t);
+    const int threads = (nwarp + 1) * 32;
+    const bool wta = p.disp != nullptr;
+    void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, false, false>;
+    void (*fin)(const NarrowParams) = wta ? sgm_narrow_vsweep_kernel<NR, true, true> : sgm_narrow_vsweep_kernel<NR, true, false>;
+    int per_sm = 0;
+    PB200_CUDA(cudaFuncSetAttribute((const void *)mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB200_CUDA(cudaFuncSetAttribute((const void *)fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)mid, threads, smem));
+    if ((long)per_sm * nsm < nstrips) return PB200_OK;
+    PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fin, threads, smem));
+    if ((long)per_sm * nsm < nstrips) return PB200_OK;
+
+    PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
+    const int hgrid = ceil_div(p.H, 4);
+    sgm_narrow_h_kernel<NR, true><<<hgrid, 128, 0, s>>>(p);
+    PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<E>");
+    sgm_narrow_h_kernel<NR, false><<<hgrid, 128, 0, s>>>(p);
+    PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<W>");
+    p.ring = reinterpret_cast<unsigned long long *>(workspace);
+    for (int pass = 0; pass < 2; ++pass) {
+        p.dy = pass == 0 ? 1 : -1;
+        PB200_CUDA(cudaMemsetAsync(p.ring, 0, ring_bytes, s));
+        void *args[] = {(void *)&p};
+        PB200_CUDA(cudaLaunchCooperativeKernel((const void *)(pass == 0 ? mid : fin), dim3(nstrips), dim3(threads), args, smem, s));
+        PB200_LAUNCH_CHECK("sgm_narrow_vsweep_kernel");
+    }
+    *done = true;
+    return PB200_OK;
+}
+
+bool is_small_int(float v, int lo, int hi) { return v >= (float)lo && v <= (float)hi && v == (float)(int)v; }
+
+}  // namespace
+
+// Try the packed-integer path.  On return *gate is NULL when nothing was launched (the caller runs the float
+// kernels unconditionally) or points to the device flag the float kernels must be gated on.
+int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, float p2, float invalid_value, int overcounting,
+                   float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
+                   cudaStream_t s, const int **gate) {
+    *gate = nullptr;
+    if (D != 64 && D != 128 && D != 256) return PB200_OK;
+    if (!is_small_int(p1, 1, NARROW_MAX) || !is_small_int(p2, 1, NARROW_MAX) || p1 > p2 || !is_small_int(invalid_value, 0, NARROW_MAX) ||
+        (int)invalid_value + (int)p2 > NARROW_MAX)
+        return PB200_OK;
+    if ((reinterpret_cast<uintptr_t>(cv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return PB200_OK;
+    const int nsm = sm_count();
+    int K = ceil_div(W, nsm);
+    if (K < 4) K = 4;
+    K = (K + 1) / 2 * 2;
+    const int nwarp = K / 2;
+    if (nwarp > 15) return PB200_OK;
+    const int nstrips = ceil_div(W, K);
+    const int NR = D / 64;
+    const size_t ring_bytes = (size_t)nstrips * 2 * 2 * NR * 32 * sizeof(unsigned long long);
+    const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
+    if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
+
+    NarrowParams p;
+    p.cv = cv; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
+    p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
+    p.inv = (uint32_t)invalid_value;
+    p.cost_ok_max = (float)(NARROW_MAX - (int)p2);
+    p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
+    p.dy = 1; p.overcounting = overcounting;
+    p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
+    p.ring = nullptr;
+    bool done = false;
+    int rc;
+    if (NR == 4) rc = launch_narrow<4>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else if (NR == 2) rc = launch_narrow<2>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else rc = launch_narrow<1>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    if (rc != PB200_OK) return rc;
+    if (done) *gate = p.flag;
+    return PB200_OK;
+}
+
+}  // namespace pb200

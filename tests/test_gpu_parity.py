@@ -306,6 +306,49 @@ def test_sgm_strip_sweep_float_costs_repeatable(eng, oracle):
         np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape", [(9, 21, 64), (31, 333, 128), (16, 600, 256), (3, 4, 64), (1, 50, 128), (40, 1, 64)])
+@pytest.mark.parametrize("over", [False, True])
+def test_sgm_packed_integer_path(eng, oracle, shape, over):
+    """D in {64, 128, 256} with integer costs takes the packed 16-bit path (sgm_narrow.cu): bit-identical to the
+    oracle, including NaN cells, all-NaN pixels, overcounting and the fused WTA."""
+    g = np.random.default_rng(shape[0] * 1000 + shape[2])
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.15] = np.nan
+    cv[g.random(shape[:2]) < 0.1] = np.nan                   # whole pixels without any valid cost
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25, overcounting=over)
+    dmin = -(shape[2] - 1)
+    got, disp, flags = eng.sgm(dev(eng, cv), 8, 32, 58.0, overcounting=over, fuse_wta=True, dmin=dmin)
+    np.testing.assert_array_equal(host(got), ref)
+    exp_disp, exp_inv = oracle.wta(ref, np.arange(dmin, 1))
+    np.testing.assert_array_equal(host(disp), exp_disp)
+    np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+
+
+@pytest.mark.parametrize("kind", ["float", "one_fraction", "negative", "too_large", "big_penalty"])
+def test_sgm_packed_path_falls_back_exactly(eng, oracle, kind):
+    """Volumes that do not qualify for the packed path (checked on the device while it runs) are redone by the
+    float kernels behind the gate: the result is still bit-identical to the oracle."""
+    g = np.random.default_rng(3)
+    shape = (13, 37, 64)
+    p1, p2, cmax = 8.0, 32.0, 25.0
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    if kind == "float":
+        cv = (g.random(shape) * 25).astype(np.float32)
+    elif kind == "one_fraction":
+        cv[-1, -1, -1] = 3.5
+    elif kind == "negative":
+        cv[5, 7, 9] = -2.0
+    elif kind == "too_large":
+        cv[2, 3, 4] = 9000.0
+        cmax = 9000.0
+    elif kind == "big_penalty":
+        p2 = 9000.0
+    cv[g.random(shape) < 0.1] = np.nan
+    ref = oracle.sgm_cost_volume(cv, p1, p2, cmax=cmax)
+    got = host(eng.sgm(dev(eng, cv), p1, p2, oracle.sgm_invalid_value(cmax, p2)))
+    np.testing.assert_array_equal(got, ref)
+
+
 def test_sgm_fused_wta_and_census_pipeline(eng, oracle):
     left, right, _ = oracle.synthetic_pair(48, 160, 64)
     cv, attrs = oracle.census_cost_volume(left, right, 5, -63, 0)
