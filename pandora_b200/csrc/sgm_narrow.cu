@@ -100,7 +100,7 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
     for (int j = 0; j < NR; ++j) {
         const uint32_t lo = (j == 0) ? lo0 : Lp[j - 1];
         const uint32_t hi = (j == NR - 1) ? hiN : Lp[j + 1];
-        const uint32_t t = __vminu2(__viaddmin_u16x2(__vminu2(lo, hi), p1p1, Lp[j]), mp2);
+        const uint32_t t = __vimin3_u16x2(Lp[j], __vminu2(lo, hi) + p1p1, mp2);    // INF16 + P1 stays inside its half
         L[j] = cc[j] + (t - mm);          // t >= m in both halves: no borrow, and cc + P2 < 2^16: no carry
     }
 }
@@ -199,6 +199,24 @@ __device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int 
     for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
 }
 
+// shared-memory access by 32-bit shared address (no generic-pointer conversion in the row loop)
+template <int NR>
+__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&v)[NR]) {
+    if constexpr (NR == 4) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+    else if constexpr (NR == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr));
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr));
+}
+template <int NR>
+__device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&v)[NR]) {
+    if constexpr (NR == 4) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    else if constexpr (NR == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+    else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
+}
+
+// A path start (L = C) is the same as a step from a FLAT previous state (all disparities equal: m = Lp[d], so
+// t - m = 0).  The state buffers therefore start as zeros and image-border halo columns simply stay zero: the row
+// loop has no "first row" / "no predecessor" cases.  Columns right of the image (last strip) run on zero costs,
+// which keeps their leftward diagonal state flat, and have their loads / stores predicated off.
 template <int NR, bool FINAL, bool WTA>
 __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowParams p) {
     if (*p.flag != 0) return;
@@ -208,22 +226,30 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     const int K = nwarp * 2;
     const int strip = blockIdx.x, nstrips = gridDim.x;
     const int H = p.H, W = p.W, D = p.D, dy = p.dy;
-    auto st = [&](int buf, int diag, int col) -> uint32_t * { return nsweep_smem + ((size_t)(buf * 2 + diag) * (K + 2) + col) * VS; };
+    // shared: st[buf][diag][K + 2][VS] words; diag 0: dx = +1, diag 1: dx = -1; column index = strip column + 1
+    const uint32_t BUFB = (uint32_t)(2 * (K + 2) * VS) * 4u;            // bytes per buffer
+    const uint32_t DIAGB = (uint32_t)((K + 2) * VS) * 4u;               // bytes per diagonal plane
+    const uint32_t sbase = smem_u32(nsweep_smem) + (uint32_t)(lane * NR) * 4u;
+    for (int i = threadIdx.x; i < 2 * 2 * (K + 2) * VS; i += blockDim.x) nsweep_smem[i] = 0u;
+    __syncthreads();
     const bool has_left = strip > 0, has_right = strip + 1 < nstrips;
 
     if (warp == nwarp) {                                  // exchange warp: neighbours' border states of row i -> halo columns
+        const unsigned long long *ring_l = p.ring + (size_t)((strip - 1) * 2 + 1) * 2 * VS;
+        const unsigned long long *ring_r = p.ring + (size_t)((strip + 1) * 2 + 0) * 2 * VS;
+        const uint32_t halo_l = sbase, halo_r = sbase + DIAGB + (uint32_t)((K + 1) * VS) * 4u;
         for (int i = 0; i + 1 < H; ++i) {
             const int cur = i & 1;
             const uint32_t tag = (uint32_t)(i + 1);
             if (has_left) {
                 uint32_t v[NR];
-                ll_recv_u32<NR>(p.ring + ((size_t)((strip - 1) * 2 + 1) * 2 + cur) * VS, lane, tag, v);
-                st_words<NR>(st(cur, 0, 0) + lane * NR, v);
+                ll_recv_u32<NR>(ring_l + cur * VS, lane, tag, v);
+                sts_words<NR>(halo_l + cur * BUFB, v);
             }
             if (has_right) {
                 uint32_t v[NR];
-                ll_recv_u32<NR>(p.ring + ((size_t)((strip + 1) * 2 + 0) * 2 + cur) * VS, lane, tag, v);
-                st_words<NR>(st(cur, 1, K + 1) + lane * NR, v);
+                ll_recv_u32<NR>(ring_r + cur * VS, lane, tag, v);
+                sts_words<NR>(halo_r + cur * BUFB, v);
             }
             __syncthreads();
         }
@@ -231,116 +257,116 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
         return;
     }
 
+    // ---- compute warps: strip columns `warp` and K-1-warp ------------------------------------------------
     const int col[2] = {warp, K - 1 - warp};
     const int xs[2] = {strip * K + col[0], strip * K + col[1]};
-    uint32_t Lv[2][NR], c16n[2][NR], p16n[2][NR];
-    int y = dy > 0 ? 0 : H - 1;
+    const bool valid[2] = {xs[0] < W, xs[1] < W};
+    const bool send_l = (warp == 0) && has_left, send_r = (warp == 0) && has_right;
+    unsigned long long *ring_sl = p.ring + (size_t)(strip * 2 + 0) * 2 * VS, *ring_sr = p.ring + (size_t)(strip * 2 + 1) * 2 * VS;
+    // byte offsets inside a state buffer: own[c][diag] where this column stores, pred[c][diag] where its predecessor did
+    uint32_t own[2][2], pred[2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        own[c][0] = sbase + (uint32_t)((col[c] + 1) * VS) * 4u;
+        own[c][1] = own[c][0] + DIAGB;
+        pred[c][0] = own[c][0] - (uint32_t)VS * 4u;        // dx = +1: column to the left
+        pred[c][1] = own[c][1] + (uint32_t)VS * 4u;        // dx = -1: column to the right
+    }
+    const long row_stride = (long)dy * W * D;              // words
+    const int y0 = dy > 0 ? 0 : H - 1;
+    uint32_t *gp[2];                                       // this lane's C16 words of the current row; P16 words are VS further
+#pragma unroll
+    for (int c = 0; c < 2; ++c) gp[c] = p.buf + ((size_t)y0 * W + (valid[c] ? xs[c] : 0)) * D + lane * NR;
+
+    uint32_t Lv[2][NR], cA[2][NR], pA[2][NR], cB[2][NR], pB[2][NR];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
-        if (xs[c] < W) {
-            const uint32_t *b = p.buf + ((size_t)y * W + xs[c]) * D + lane * NR;
-            ld_words<NR>(b, c16n[c]);
-            ld_words<NR>(b + VS, p16n[c]);
-        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { Lv[c][j] = 0u; cA[c][j] = 0u; pA[c][j] = 0u; cB[c][j] = 0u; pB[c][j] = 0u; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (valid[c]) { ld_words<NR>(gp[c], cA[c]); ld_words<NR>(gp[c] + VS, pA[c]); }
 
-    for (int i = 0; i < H; ++i, y += dy) {
-        const int cur = i & 1, prv = cur ^ 1;
-        const bool first = (i == 0), last = (i == H - 1);
-        uint32_t c16[2][NR], p16[2][NR], cc[2][NR];
+    // one row: uses (c16, p16), prefetches the next row into (c16n, p16n)
+    auto row = [&](const int i, const uint32_t (&c16)[2][NR], const uint32_t (&p16)[2][NR], uint32_t (&c16n)[2][NR], uint32_t (&p16n)[2][NR]) {
+        const bool last = (i == H - 1);
+        const uint32_t curb = (uint32_t)(i & 1) * BUFB, prvb = BUFB - curb;
+        if (!last) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                c16[c][j] = c16n[c][j];
-                p16[c][j] = p16n[c][j];
-                cc[c][j] = c16[c][j] & ~NANBITS;
-            }
-            if (xs[c] < W && !last) {
-                const uint32_t *b = p.buf + ((size_t)(y + dy) * W + xs[c]) * D + lane * NR;
-                ld_words<NR>(b, c16n[c]);
-                ld_words<NR>(b + VS, p16n[c]);
-            }
+            for (int c = 0; c < 2; ++c)
+                if (valid[c]) { ld_words<NR>(gp[c] + row_stride, c16n[c]); ld_words<NR>(gp[c] + row_stride + VS, p16n[c]); }
         }
-        auto run_dir = [&](const int c, const int g, uint32_t (&Lout)[NR]) {
-            const int x = xs[c];
-            const int dx = (g == 0) ? 0 : (g == 1 ? 1 : -1);
-            const int px = x - dx;
-            uint32_t Lp[NR];
-            bool have = false;
-            if (!first) {
-                if (g == 0) {
+        uint32_t cc[2][NR];
 #pragma unroll
-                    for (int j = 0; j < NR; ++j) Lp[j] = Lv[c][j];
-                    have = true;
-                } else if (px >= 0 && px < W) {
-                    have = true;
-                    ld_words<NR>(st(prv, g - 1, col[c] - dx + 1) + lane * NR, Lp);
-                }
-            }
-            if (have) {
-                nstep<NR>(cc[c], Lp, Lout, lane, p.p1p1, p.p2p2);
-            } else {
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int j = 0; j < NR; ++j) Lout[j] = cc[c][j];
-            }
-            if (g == 0) {
-#pragma unroll
-                for (int j = 0; j < NR; ++j) Lv[c][j] = Lout[j];
-            } else {
-                st_words<NR>(st(cur, g - 1, col[c] + 1) + lane * NR, Lout);
-            }
-        };
-        uint32_t Lb[2][NR];
-        if (xs[0] < W) run_dir(0, 2, Lb[0]);
-        if (warp == 0 && has_left && !last) ll_send_u32<NR>(p.ring + ((size_t)(strip * 2 + 0) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[0]);
-        if (xs[1] < W) run_dir(1, 1, Lb[1]);
-        if (warp == 0 && has_right && !last) ll_send_u32<NR>(p.ring + ((size_t)(strip * 2 + 1) * 2 + cur) * VS, lane, (uint32_t)(i + 1), Lb[1]);
+            for (int j = 0; j < NR; ++j) cc[c][j] = c16[c][j] & ~NANBITS;
+        uint32_t Lb[2][NR], Lp[NR];
+        // outgoing border diagonals first: column slot 0 (strip column `warp`) dx = -1, slot 1 dx = +1
+        lds_words<NR>(pred[0][1] + prvb, Lp);
+        nstep<NR>(cc[0], Lp, Lb[0], lane, p.p1p1, p.p2p2);
+        sts_words<NR>(own[0][1] + curb, Lb[0]);
+        if (send_l && !last) ll_send_u32<NR>(ring_sl + (i & 1) * VS, lane, (uint32_t)(i + 1), Lb[0]);
+        lds_words<NR>(pred[1][0] + prvb, Lp);
+        nstep<NR>(cc[1], Lp, Lb[1], lane, p.p1p1, p.p2p2);
+        sts_words<NR>(own[1][0] + curb, Lb[1]);
+        if (send_r && !last) ll_send_u32<NR>(ring_sr + (i & 1) * VS, lane, (uint32_t)(i + 1), Lb[1]);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int x = xs[c];
-            if (x >= W) continue;
             uint32_t L0[NR], Lo[NR], tot[NR];
-            run_dir(c, 0, L0);
-            run_dir(c, c == 0 ? 1 : 2, Lo);
+            nstep<NR>(cc[c], Lv[c], L0, lane, p.p1p1, p.p2p2);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) Lv[c][j] = L0[j];
+            const int od = (c == 0) ? 0 : 1;               // the diagonal not done above: slot 0 -> dx = +1, slot 1 -> dx = -1
+            lds_words<NR>(pred[c][od] + prvb, Lp);
+            nstep<NR>(cc[c], Lp, Lo, lane, p.p1p1, p.p2p2);
+            sts_words<NR>(own[c][od] + curb, Lo);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] = p16[c][j] + L0[j] + Lo[j] + Lb[c][j];
-            uint32_t *b = p.buf + ((size_t)y * W + x) * D + lane * NR;
-            if (!FINAL) {
-                st_words<NR>(b + VS, tot);
-            } else {
-                // total -> float32 (exact), overcounting, NaN restore, in place: this lane overwrites the bytes it loaded
-                float fa[NR], fb[NR];
-                uint32_t best = 0xFFFFFFFFu;
+            if (valid[c]) {
+                if (!FINAL) {
+                    st_words<NR>(gp[c] + VS, tot);
+                } else {
+                    // total -> float32 (exact), overcounting, NaN restore, in place: this lane overwrites the bytes it loaded
+                    float fa[NR], fb[NR];
+                    uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    uint32_t t = tot[j];
-                    if (p.overcounting) t = t - 7u * cc[c][j];       // S >= 8 C in every half: no borrow
-                    const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                    const bool nlo = (c16[c][j] & 0x8000u) != 0, nhi = (c16[c][j] & 0x80000000u) != 0;
-                    fa[j] = nlo ? nan_f() : small_int_to_float(lo);
-                    fb[j] = nhi ? nan_f() : small_int_to_float(hi);
-                    if (WTA) {
-                        const uint32_t ka = (lo << 16) | (uint32_t)(lane * NR + j);
-                        const uint32_t kb = (hi << 16) | (uint32_t)(D / 2 + lane * NR + j);
-                        best = min(best, nlo ? 0xFFFFFFFFu : ka);
-                        best = min(best, nhi ? 0xFFFFFFFFu : kb);
+                    for (int j = 0; j < NR; ++j) {
+                        uint32_t t = tot[j];
+                        if (p.overcounting) t = t - 7u * cc[c][j];   // S >= 8 C in every half: no borrow
+                        const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                        const bool nlo = (c16[c][j] & 0x8000u) != 0, nhi = (c16[c][j] & 0x80000000u) != 0;
+                        fa[j] = nlo ? nan_f() : small_int_to_float(lo);
+                        fb[j] = nhi ? nan_f() : small_int_to_float(hi);
+                        if (WTA) {
+                            const uint32_t ka = (lo << 16) | (uint32_t)(lane * NR + j);
+                            const uint32_t kb = (hi << 16) | (uint32_t)(D / 2 + lane * NR + j);
+                            best = min(best, nlo ? 0xFFFFFFFFu : ka);
+                            best = min(best, nhi ? 0xFFFFFFFFu : kb);
+                        }
                     }
-                }
-                float *o = reinterpret_cast<float *>(b);
-                st_floats<NR>(o, fa);
-                st_floats<NR>(o + D / 2, fb);
-                if (WTA) {
-                    best = __reduce_min_sync(0xffffffffu, best);
-                    if (lane == 0) {
-                        const size_t pix = (size_t)y * W + x;
-                        const bool none = (best == 0xFFFFFFFFu);
-                        p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
-                        if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                    float *o = reinterpret_cast<float *>(gp[c]);
+                    st_floats<NR>(o, fa);
+                    st_floats<NR>(o + D / 2, fb);
+                    if (WTA) {
+                        best = __reduce_min_sync(0xffffffffu, best);
+                        if (lane == 0) {
+                            const size_t pix = (size_t)(y0 + i * dy) * W + xs[c];
+                            const bool none = (best == 0xFFFFFFFFu);
+                            p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
+                            if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                        }
                     }
                 }
             }
+            gp[c] += row_stride;
         }
         __syncthreads();
+    };
+#pragma unroll 1
+    for (int i = 0; i < H; i += 2) {
+        row(i, cA, pA, cB, pB);
+        if (i + 1 < H) row(i + 1, cB, pB, cA, pA);
     }
 }
 
