@@ -302,9 +302,17 @@ def run_ours(args):
         sgm_alg = 8.0 * D * H * W          # SGM must read C (4D) and write S (4D) bytes per pixel
         census_alg = (4.0 * D + 8.0) * H * W
         sgm_gbs = sgm_alg / (stage["sgm_ms"] * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "sgm_path_kernel (one SGM stage = 8 direction launches)", "achieved": sgm_gbs,
-                            "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "sgm_stage_traffic.json")) as fh:
+                traffic = float(json.load(fh)["dram_bytes_per_stage"])
+        except Exception:
+            pass
+        line["roofline"] = {"bound": "hbm",
+                            "kernel": "SGM stage = sgm_narrow_h_kernel x2 (E, W) + sgm_narrow_vsweep_kernel x2 (S/SE/SW, N/NE/NW + WTA); "
+                                      "4 launches timed as one unit (8*D algorithmic bytes per pixel belong to the stage)",
+                            "achieved": sgm_gbs, "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": traffic,
+                            "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
         cen_gbs = census_alg / (stage["census_ms"] * 1e-3) / 1e9
         line["stages"] = {"census_fill": {"ms": stage["census_ms"], "algorithmic_bytes": census_alg, "achieved_gbs": cen_gbs, "frac": cen_gbs / peak},
                           "sgm_8path_wta": {"ms": stage["sgm_ms"], "algorithmic_bytes": sgm_alg, "achieved_gbs": sgm_gbs, "frac": sgm_gbs / peak},

@@ -21,6 +21,8 @@
 // The data condition (integer costs in [0, 8191 - P2]) is verified by pass E on every cell; a violation raises a
 // device flag, the remaining narrow kernels return at once and the float kernels, enqueued behind them and gated
 // on the same flag, redo the whole stage.  No host synchronisation is involved.
+#include <cstdlib>
+
 #include "sgm_common.cuh"
 
 namespace pb200 {
@@ -45,6 +47,7 @@ struct NarrowParams {
     int dmin;
     float invalid_disparity;
     unsigned long long *ring;
+    int debug;                // PB200_SGM_DEBUG bit 0: no strip exchange (timing experiments only, wrong results)
 };
 
 template <int NR> struct Words;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     const uint32_t sbase = smem_u32(nsweep_smem) + (uint32_t)(lane * NR) * 4u;
     for (int i = threadIdx.x; i < 2 * 2 * (K + 2) * VS; i += blockDim.x) nsweep_smem[i] = 0u;
     __syncthreads();
-    const bool has_left = strip > 0, has_right = strip + 1 < nstrips;
+    const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
 
     if (warp == nwarp) {                                  // exchange warp: neighbours' border states of row i -> halo columns
         const unsigned long long *ring_l = p.ring + (size_t)((strip - 1) * 2 + 1) * 2 * VS;
@@ -425,11 +428,8 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     int K = ceil_div(W, nsm);
     if (K < 4) K = 4;
     K = (K + 1) / 2 * 2;
-    const int nwarp = K / 2;
-    if (nwarp > 15) return PB200_OK;
-    const int nstrips = ceil_div(W, K);
+    if (K / 2 > 15) return PB200_OK;
     const int NR = D / 64;
-    const size_t ring_bytes = (size_t)nstrips * 2 * 2 * NR * 32 * sizeof(unsigned long long);
     const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
     if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
 
@@ -442,8 +442,14 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.dy = 1; p.overcounting = overcounting;
     p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
     p.ring = nullptr;
+    p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
+    int kdiv = getenv("PB200_SGM_KDIV") ? atoi(getenv("PB200_SGM_KDIV")) : 1;
+    if (kdiv > 1) { K = (K / kdiv + 1) / 2 * 2; if (K < 4) K = 4; }
     bool done = false;
     int rc;
+    const int nwarp = K / 2;
+    const int nstrips = ceil_div(W, K);
+    const size_t ring_bytes = (size_t)nstrips * 2 * 2 * NR * 32 * sizeof(unsigned long long);
     if (NR == 4) rc = launch_narrow<4>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
     else if (NR == 2) rc = launch_narrow<2>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
     else rc = launch_narrow<1>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
