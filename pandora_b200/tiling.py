@@ -97,19 +97,17 @@ def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down
     """
     order = group_order(rank, world) if order is None else order
     has_up_nb, has_down_nb = rank > 0, rank < world - 1
-    recv_bufs, recv_work, send_work, keep = {}, {}, [], []
-    if world > 1:
-        for g in order:                                   # pre-post both receives: they depend on nothing local
-            src = rank - 1 if g == 0 else rank + 1
-            if (g == 0 and has_up_nb) or (g == 1 and has_down_nb):
-                recv_bufs[g] = backend.new_halo()
-                recv_work[g] = dist.irecv(recv_bufs[g], src=src, group=pg_down if g == 0 else pg_up)
+    send_work, keep = [], []
     backend.run_horizontal(True)
     for i, g in enumerate(order):
+        # The receive is posted only now, never ahead of local work: an NCCL receive kernel that sits on the GPU
+        # waiting for its peer would keep the cooperative strip-sweep launch of the OTHER group from becoming
+        # resident, and two ranks doing that to each other deadlock.  Posted here, the only kernel ordered behind
+        # the receive is the sweep that needs its data anyway.
         halo_in = None
-        if g in recv_work:
-            recv_work[g].wait()
-            halo_in = recv_bufs[g]
+        if world > 1 and ((g == 0 and has_up_nb) or (g == 1 and has_down_nb)):
+            halo_in = backend.new_halo()
+            dist.irecv(halo_in, src=rank - 1 if g == 0 else rank + 1, group=pg_down if g == 0 else pg_up).wait()
         send_to = None
         if world > 1 and ((g == 0 and has_down_nb) or (g == 1 and has_up_nb)):
             send_to = rank + 1 if g == 0 else rank - 1
@@ -121,6 +119,31 @@ def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down
     for w in send_work:
         w.wait()
     return order
+
+
+def warm_up_links(rank: int, world: int, dist, pg_down, pg_up, device=None) -> None:
+    """Establish the neighbour connections of both wave groups with one batched (grouped) dummy exchange each.
+
+    The first send / receive between two ranks on an NCCL communicator sets the transport up and BLOCKS THE HOST
+    until the peer makes the matching call.  In ``run_tiled_sgm`` the first calls of two neighbours are on
+    different groups (rank r sends "down" while rank r+1 sends "up"), so without this warm-up both hosts would
+    sit in their first send forever.  A batched exchange posts each rank's send and receive together."""
+    import torch  # noqa: PLC0415
+
+    if world == 1:
+        return
+    for pg, to, frm in ((pg_down, rank + 1, rank - 1), (pg_up, rank - 1, rank + 1)):
+        ops, bufs = [], []
+        if 0 <= to < world:
+            bufs.append(torch.zeros(4, dtype=torch.float32, device=device))
+            ops.append(dist.P2POp(dist.isend, bufs[-1], to, pg))
+        if 0 <= frm < world:
+            bufs.append(torch.zeros(4, dtype=torch.float32, device=device))
+            ops.append(dist.P2POp(dist.irecv, bufs[-1], frm, pg))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if device is not None and torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 def exchange_image_halo(tile, half: int, rank: int, world: int, dist, group=None):
@@ -171,6 +194,7 @@ class TiledStereoPipeline:
         self.flags = self.eng.empty((tile_rows, W), torch.uint8)
         self.pg_down = dist.new_group(list(range(world))) if world > 1 else None
         self.pg_up = dist.new_group(list(range(world))) if world > 1 else None
+        warm_up_links(rank, world, dist, self.pg_down, self.pg_up, self.eng.device)
 
     def run(self, left_tile, right_tile):
         """``left_tile`` / ``right_tile``: this rank's (rows, W) float32 device tensors.  Returns the disparity tile."""

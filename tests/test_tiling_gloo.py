@@ -83,6 +83,7 @@ def _worker(rank, world, port, H, W, D, tmpdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pg_down = dist.new_group(list(range(world)))
     pg_up = dist.new_group(list(range(world)))
+    tiling.warm_up_links(rank, world, dist, pg_down, pg_up)
     g = np.random.default_rng(5)
     C = g.integers(0, 26, (H, W, D)).astype(np.float32)          # every rank draws the same full volume
     rows = tiling.split_rows(H, world)[rank]
