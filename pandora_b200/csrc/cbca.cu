@@ -199,6 +199,175 @@ __global__ void __launch_bounds__(32 * CBCA_TX) cbca_aggregate_kernel(const floa
     }
 }
 
+// ---- aggregation, pipelined version (MA <= 8) -------------------------------------------------------------
+// Same arithmetic as cbca_aggregate_kernel, but every global read of the row loop (cost row incl. its halo
+// columns, both support rows) is staged PF rows ahead into a shared-memory ring with cp.async (LDGSTS), so the
+// march down the rows never waits for HBM, the centre cost is taken from the ring instead of being re-read, and
+// one __syncthreads per row is enough.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, bool pred) {
+    const int n = pred ? 4 : 0;                                  // src-size 0: zero fill, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, bool pred) {
+    const int n = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MA, bool RAW>
+__global__ void __launch_bounds__(32 * CBCA_TX) cbca_aggregate_pipe_kernel(const float *__restrict__ cv_in, float *__restrict__ cv_out,
+                                                                           float *__restrict__ out_n, int H, int W, int D, int dmin,
+                                                                           int off, const short4 *__restrict__ crossL,
+                                                                           const short4 *__restrict__ crossR) {
+    constexpr int TX = CBCA_TX;
+    constexpr int RING = 4 * MA;                 // prefix rings: >= 2*MA + 2 rows
+    constexpr int NS = 16;                       // staged rows: MA + 2 + PF
+    constexpr int PF = NS - MA - 2;              // prefetch distance in rows
+    constexpr int CW = TX + 2 * MA;              // staged columns per row
+    constexpr int NL = (CW + TX - 1) / TX;       // staged cells per thread and row
+    constexpr int XRN = TX + 31;                 // right-image supports a CTA can meet per row
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *crow = reinterpret_cast<float *>(smem_raw);                       // [NS][CW][32]  staged costs, then NaN -> 0
+    float *hpre = crow + NS * CW * 32;                                       // [CW + 1][32]   row prefix of the current row
+    float *PE = hpre + (CW + 1) * 32;                                        // [RING][TX][32]
+    int *PN = reinterpret_cast<int *>(PE + RING * TX * 32);                  // [RING][TX][32]
+    short4 *XL = reinterpret_cast<short4 *>(PN + RING * TX * 32);            // [NS][TX]
+    short4 *XR = XL + NS * TX;                                               // [NS][XRN]
+    unsigned char *isn = reinterpret_cast<unsigned char *>(XR + NS * XRN);   // [NS][TX][32]  centre cost was NaN
+
+    const int Hi = H - 2 * off, Wi = W - 2 * off;
+    const int lane = threadIdx.x, cx = threadIdx.y, tid = cx * 32 + lane;
+    const int k0 = blockIdx.y * 32, k = k0 + lane;
+    const int x0 = blockIdx.x * TX;
+    const int x = x0 + cx;
+    const int d = dmin + k;
+    const int xr = x + d;
+    const bool active = (k < D) && (x < Wi);
+    const bool valid_col = active && xr >= 0 && xr < Wi;
+    const int ring_idx = cx * 32 + lane;
+    const int xr0 = x0 + dmin + k0;               // right column of XR entry 0
+    const size_t row_elems = (size_t)W * D;
+
+    // per-thread staging sources (row 0), advanced by one row per staged row
+    const float *src[NL];
+    bool src_ok[NL];
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+        const int jj = cx + q * TX, xx = x0 - MA + jj;
+        src_ok[q] = (jj < CW) && (k < D) && xx >= 0 && xx < Wi;
+        src[q] = src_ok[q] ? cv_in + ((size_t)off * W + (xx + off)) * D + k : cv_in;
+    }
+    const bool xl_ok = tid < TX && x0 + tid < Wi;
+    const short4 *xl_src = xl_ok ? crossL + x0 + tid : crossL;
+    const int xre = tid - 32;
+    const bool xr_ok = tid >= 32 && xre < XRN && xr0 + xre >= 0 && xr0 + xre < Wi;
+    const short4 *xr_src = xr_ok ? crossR + xr0 + xre : crossR;
+    float *out_ptr = cv_out + ((size_t)off * W + (x + off)) * D + k;       // row yo = 0
+    float *outn_ptr = RAW ? out_n + ((size_t)off * W + (x + off)) * D + k : nullptr;
+
+    auto stage_row = [&](int r) {                 // enqueue the copies of row r (r < Hi) into ring stage r % NS
+        const int sg = r & (NS - 1);
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int jj = cx + q * TX;
+            if (jj < CW) cp_async4(crow + (sg * CW + jj) * 32 + lane, src[q], src_ok[q]);
+            if (src_ok[q]) src[q] += row_elems;
+        }
+        if (tid < TX) cp_async8(XL + sg * TX + tid, xl_src, xl_ok);
+        if (tid >= 32 && xre < XRN) cp_async8(XR + sg * XRN + xre, xr_src, xr_ok);
+        if (xl_ok) xl_src += Wi;
+        if (xr_ok) xr_src += Wi;
+    };
+
+    for (int r = 0; r < PF; ++r) {
+        if (r < Hi) stage_row(r);
+        cp_async_commit();
+    }
+    float pe_run = 0.f;
+    int pn_run = 0;
+    for (int i = 0; i < Hi + MA; ++i) {
+        if (i + PF < Hi) stage_row(i + PF);
+        cp_async_commit();
+        cp_async_wait<PF>();                      // this thread's copies of row i have landed
+        const int sgi = i & (NS - 1);
+        if (i < Hi) {
+            // clean the cells this thread staged: NaN -> 0 (step 1 does not propagate NaN), remember the centre NaNs
+#pragma unroll
+            for (int q = 0; q < NL; ++q) {
+                const int jj = cx + q * TX;
+                if (jj < CW) {
+                    float *cellp = crow + (sgi * CW + jj) * 32 + lane;
+                    const float v = *cellp;
+                    const bool nn = (v != v);
+                    if (nn) *cellp = 0.f;
+                    if (jj >= MA && jj < MA + TX) isn[(sgi * TX + jj - MA) * 32 + lane] = nn ? 1 : 0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- row prefix over the staged columns (warp 0: lane k scans its CW cells) ------------------------
+        if (i < Hi && cx == 0) {
+            float v[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = crow[(sgi * CW + j) * 32 + lane];
+            float run = 0.f;
+            hpre[lane] = 0.f;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                run = run + v[j];
+                hpre[(j + 1) * 32 + lane] = run;
+            }
+        }
+        __syncthreads();
+        // ---- stage 1: horizontal arm sums of row i ---------------------------------------------------
+        if (i < Hi) {
+            float eh = 0.f;
+            int nh = 0;
+            if (valid_col) {
+                const short4 a = XL[sgi * TX + cx];
+                const short4 b = XR[sgi * XRN + cx + lane];
+                const int l = min(min((int)a.x, (int)b.x), MA), r = min(min((int)a.y, (int)b.y), MA);
+                eh = hpre[(cx + MA + r + 1) * 32 + lane] - hpre[(cx + MA - l) * 32 + lane];
+                nh = l + r;
+            }
+            pe_run = pe_run + eh;                                           // the reference's step-3 column prefix
+            pn_run += nh;
+            PE[(i & (RING - 1)) * TX * 32 + ring_idx] = pe_run;
+            PN[(i & (RING - 1)) * TX * 32 + ring_idx] = pn_run;
+        }
+        // ---- stage 2: vertical arm sums of row yo = i - MA (its staged supports are still in the ring) --------
+        const int yo = i - MA;
+        if (yo >= 0 && active) {
+            const int sg = yo & (NS - 1);
+            float e = 0.f;
+            int n = 1;
+            if (valid_col) {
+                const short4 a = XL[sg * TX + cx];
+                const short4 b = XR[sg * XRN + cx + lane];
+                const int t = min(min((int)a.z, (int)b.z), MA), bo = min(min((int)a.w, (int)b.w), MA);
+                const int r1 = yo + bo, r0 = yo - t - 1;
+                const float e1 = PE[(r1 & (RING - 1)) * TX * 32 + ring_idx];
+                const int n1 = PN[(r1 & (RING - 1)) * TX * 32 + ring_idx];
+                const float e0 = (r0 >= 0) ? PE[(r0 & (RING - 1)) * TX * 32 + ring_idx] : 0.f;
+                const int n0 = (r0 >= 0) ? PN[(r0 & (RING - 1)) * TX * 32 + ring_idx] : 0;
+                e = e1 - e0;
+                n = n1 - n0 + t + bo + 1;
+            }
+            const bool cnan = isn[(sg * TX + cx) * 32 + lane] != 0;
+            if (RAW) {
+                *out_ptr = e;
+                *outn_ptr = (float)(n - 1);
+                outn_ptr += row_elems;
+            } else {
+                *out_ptr = cnan ? nan_f() : e / (float)n;                   // (0*c + E) / N
+            }
+            out_ptr += row_elems;
+        }
+    }
+}
+
 // copy of the `off`-wide border ring (cells the aggregation leaves untouched, cbca.py:173-177)
 __global__ void __launch_bounds__(256) cbca_border_kernel(const float *__restrict__ cv_in, float *__restrict__ cv_out, int H, int W,
                                                           int D, int off) {
@@ -223,8 +392,23 @@ __global__ void __launch_bounds__(256) cbca_border_kernel(const float *__restric
 }
 
 template <int MA, bool RAW>
+static int launch_cbca_pipe(const float *in, float *out, float *out_n, int H, int W, int D, int dmin, int off, const int16_t *cl,
+                            const int16_t *cr, cudaStream_t s) {
+    constexpr int RING = 4 * MA, NS = 16;
+    const size_t smem = (size_t)NS * (CBCA_TX + 2 * MA) * 32 * 4 + (size_t)(CBCA_TX + 2 * MA + 1) * 32 * 4 + 2 * (size_t)RING * CBCA_TX * 32 * 4 +
+                        (size_t)NS * (CBCA_TX + CBCA_TX + 31) * 8 + (size_t)NS * CBCA_TX * 32;
+    PB200_CUDA(cudaFuncSetAttribute(cbca_aggregate_pipe_kernel<MA, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, CBCA_TX), grid(ceil_div(W - 2 * off, CBCA_TX), ceil_div(D, 32));
+    cbca_aggregate_pipe_kernel<MA, RAW><<<grid, block, smem, s>>>(in, out, out_n, H, W, D, dmin, off, (const short4 *)cl,
+                                                                   (const short4 *)cr);
+    PB200_LAUNCH_CHECK("cbca_aggregate_pipe_kernel");
+    return PB200_OK;
+}
+
+template <int MA, bool RAW>
 static int launch_cbca(const float *in, float *out, float *out_n, int H, int W, int D, int dmin, int off, const int16_t *cl,
                        const int16_t *cr, cudaStream_t s) {
+    if constexpr (MA <= 8) return launch_cbca_pipe<MA, RAW>(in, out, out_n, H, W, D, dmin, off, cl, cr, s);
     constexpr int RING = 4 * MA;
     const size_t smem = (size_t)(CBCA_TX + 2 * MA) * 32 * 4 + 2 * (size_t)RING * CBCA_TX * 32 * 4;
     PB200_CUDA(cudaFuncSetAttribute(cbca_aggregate_kernel<MA, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
