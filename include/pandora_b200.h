@@ -118,7 +118,17 @@ PB200_API size_t pb200_sgm_workspace_bytes(int H, int W, int D);
  * (otherwise it accumulates into it); bit 1: the last direction of this call finalises it (NaN restore,
  * overcounting, fused WTA).  A single-GPU call uses dir_mask = 0xFF, init_final = 3; a tiled run splits
  * the directions over several calls (pandora_b200/tiling.py).  Halo planes are indexed by the direction's
- * rank inside its group: (S, SE, SW) for the top/bottom-out pair, (N, NE, NW) for the other. */
+ * rank inside its group: (S, SE, SW) for the top/bottom-out pair, (N, NE, NW) for the other.
+ * `init_final` bit 2 (value 4), split calls only: the caller allows PACKED intermediates -- between the calls
+ * d_cv_out and the halo buffers may hold the 16-bit representation of the exact integer fast path instead of
+ * float32 (same sizes, opaque contents).  Call sequence, all on the same workspace:
+ *   1. dir_mask 0x03, init_final 1|4      packed E + W (verifies the data; raises the int flag at
+ *                                         d_workspace + pb200_sgm_flag_offset(W, D) when it does not qualify)
+ *   2. (ranks that exchange halos max-reduce the flag among themselves)
+ *   3. dir_mask 0x03, init_final 1|4|8    float E + W, executed only where the flag is raised
+ *   4. dir_mask 0x1C and 0xE0 (any order), init_final 4, the last one 2|4: packed sweep, or float sweep when flagged.
+ * When the shape / penalties are not eligible for the packed path the same sequence runs the float kernels. */
+PB200_API size_t pb200_sgm_flag_offset(int W, int D);
 PB200_API int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
               int overcounting, int dir_mask, int init_final, const float *d_halo_in_top, const float *d_halo_in_bottom,
               float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "pb200_cross_support": (_ci, [_vp, _ci, _ci, _ci, _ci, _cf, _ci, _vp, _vp]),
     "pb200_cbca_aggregate": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _ci, _vp]),
     "pb200_sgm_workspace_bytes": (_sz, [_ci, _ci, _ci]),
+    "pb200_sgm_flag_offset": (_sz, [_ci, _ci]),
     "pb200_sgm": (_ci, [_vp, _vp, _ci, _ci, _ci, _cf, _cf, _cf, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _ci, _cf, _vp, _vp, _sz, _vp]),
     "pb200_wta": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _cf, _vp, _vp, _vp]),
     "pb200_validity_mask_init": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp]),

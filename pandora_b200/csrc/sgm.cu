@@ -507,7 +507,7 @@ static int launch_sweep(SweepParams p, void *workspace, size_t workspace_bytes, 
 
 int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, float p2, float invalid_value, int overcounting,
                    float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
-                   cudaStream_t s, const int **gate);   // sgm_narrow.cu
+                   cudaStream_t s, const int **gate, int phase, int dy, int final, const float *halo_in, float *halo_out);   // sgm_narrow.cu
 
 }  // namespace pb200
 
@@ -519,6 +519,8 @@ extern "C" size_t pb200_sgm_workspace_bytes(int H, int W, int D) {
     if (W <= 0 || D <= 0) return 16;
     return sgm_ring_max_bytes(W, D) + 512;
 }
+
+extern "C" size_t pb200_sgm_flag_offset(int W, int D) { return (W <= 0 || D <= 0) ? 0 : sgm_ring_max_bytes(W, D) + 256; }
 
 extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
                          int overcounting, int dir_mask, int init_final, const float *d_halo_in_top, const float *d_halo_in_bottom,
@@ -537,9 +539,36 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
     // verifies the data while it runs and raises a device flag when a cost is not a small integer; the float
     // kernels below are then enqueued gated on that flag (they return at once when the fast path succeeded).
     const int *gate = nullptr;
+    const bool packed_ok = (init_final & 4) != 0, float_only = (init_final & 8) != 0;
+    init_final &= 3;
     if (dir_mask == 0xFF && init_final == 3 && !d_halo_in_top && !d_halo_in_bottom && !d_halo_out_bottom && !d_halo_out_top) {
         int rc = sgm_narrow_try(d_cv_in, d_cv_out, H, W, D, p1, p2, invalid_value, overcounting, d_disp, dmin, invalid_disparity,
-                                d_all_nan, d_workspace, workspace_bytes, s, &gate);
+                                d_all_nan, d_workspace, workspace_bytes, s, &gate, 0, 1, 1, nullptr, nullptr);
+        if (rc != PB200_OK) return rc;
+    } else if (packed_ok) {
+        // split calls of a row-tiled run (pandora_b200/tiling.py): horizontal pair first, then one vertical group per call
+        int rc = PB200_OK;
+        if (dir_mask == 0x03 && init_final == 1) {
+            // first call: packed E + W only (they also verify the data).  The float E + W are NOT enqueued here: ranks
+            // must first agree on the flag; the caller then repeats the call with bit 3 set, which enqueues only the
+            // float kernels, gated on the (agreed) flag.
+            rc = sgm_narrow_try(d_cv_in, d_cv_out, H, W, D, p1, p2, invalid_value, overcounting, nullptr, dmin, invalid_disparity, nullptr,
+                                d_workspace, workspace_bytes, s, &gate, float_only ? 3 : 1, 1, 0, nullptr, nullptr);
+            if (rc != PB200_OK) return rc;
+            if (!float_only && gate != nullptr) return PB200_OK;
+            if (float_only && gate == nullptr) return PB200_OK;     // not eligible: the first call already ran the float kernels
+        } else if (dir_mask == 0x1C && !(init_final & 1))
+            rc = sgm_narrow_try(d_cv_in, d_cv_out, H, W, D, p1, p2, invalid_value, overcounting, (init_final & 2) ? d_disp : nullptr, dmin,
+                                invalid_disparity, (init_final & 2) ? d_all_nan : nullptr, d_workspace, workspace_bytes, s, &gate, 2, 1,
+                                init_final & 2, d_halo_in_top, d_halo_out_bottom);
+        else if (dir_mask == 0xE0 && !(init_final & 1))
+            rc = sgm_narrow_try(d_cv_in, d_cv_out, H, W, D, p1, p2, invalid_value, overcounting, (init_final & 2) ? d_disp : nullptr, dmin,
+                                invalid_disparity, (init_final & 2) ? d_all_nan : nullptr, d_workspace, workspace_bytes, s, &gate, 2, -1,
+                                init_final & 2, d_halo_in_bottom, d_halo_out_top);
+        else {
+            set_error("pb200_sgm: packed intermediates (init_final bit 2) need dir_mask 0x03 (init), 0x1C or 0xE0");
+            return PB200_ERR_BAD_ARG;
+        }
         if (rc != PB200_OK) return rc;
     }
     // direction table in accumulation order; group 0 horizontal, 1 downward, 2 upward

@@ -47,6 +47,8 @@ struct NarrowParams {
     int dmin;
     float invalid_disparity;
     unsigned long long *ring;
+    const uint32_t *halo_in;  // packed (3, W, D/2 words) states of the row just outside the tile (order dx = 0, +1, -1) or NULL
+    uint32_t *halo_out;       // packed states of this tile's last row in travel direction or NULL
     int debug;                // PB200_SGM_DEBUG bit 0: no strip exchange (timing experiments only, wrong results)
 };
 
@@ -236,6 +238,38 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     for (int i = threadIdx.x; i < 2 * 2 * (K + 2) * VS; i += blockDim.x) nsweep_smem[i] = 0u;
     __syncthreads();
     const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
+    const size_t hplane = (size_t)W * VS;                 // words per halo plane
+    if (p.halo_in != nullptr) {
+        // row-tiled run: the previous row lives in the neighbouring tile; its diagonal states go where row 0 will
+        // look for them (buffer 1 is "previous" for row 0), the vertical ones into Lv below
+        if (warp < nwarp) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int cl = c == 0 ? warp : K - 1 - warp, x = strip * K + cl;
+                if (x < W) {
+#pragma unroll
+                    for (int dg = 0; dg < 2; ++dg) {
+                        uint32_t v[NR];
+                        ld_words<NR>(p.halo_in + (size_t)(dg + 1) * hplane + (size_t)x * VS + lane * NR, v);
+                        sts_words<NR>(sbase + (uint32_t)dg * DIAGB + (uint32_t)((cl + 1) * VS) * 4u + BUFB, v);
+                    }
+                }
+            }
+        } else {
+            const int xl = strip * K - 1, xr = strip * K + K;
+            if (xl >= 0) {
+                uint32_t v[NR];
+                ld_words<NR>(p.halo_in + 1 * hplane + (size_t)xl * VS + lane * NR, v);
+                sts_words<NR>(sbase + BUFB, v);
+            }
+            if (xr < W) {
+                uint32_t v[NR];
+                ld_words<NR>(p.halo_in + 2 * hplane + (size_t)xr * VS + lane * NR, v);
+                sts_words<NR>(sbase + DIAGB + (uint32_t)((K + 1) * VS) * 4u + BUFB, v);
+            }
+        }
+        __syncthreads();
+    }
 
     if (warp == nwarp) {                                  // exchange warp: neighbours' border states of row i -> halo columns
         const unsigned long long *ring_l = p.ring + (size_t)((strip - 1) * 2 + 1) * 2 * VS;
@@ -288,7 +322,11 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
         for (int j = 0; j < NR; ++j) { Lv[c][j] = 0u; cA[c][j] = 0u; pA[c][j] = 0u; cB[c][j] = 0u; pB[c][j] = 0u; }
 #pragma unroll
     for (int c = 0; c < 2; ++c)
-        if (valid[c]) { ld_words<NR>(gp[c], cA[c]); ld_words<NR>(gp[c] + VS, pA[c]); }
+        if (valid[c]) {
+            ld_words<NR>(gp[c], cA[c]);
+            ld_words<NR>(gp[c] + VS, pA[c]);
+            if (p.halo_in != nullptr) ld_words<NR>(p.halo_in + (size_t)xs[c] * VS + lane * NR, Lv[c]);
+        }
 
     // one row: uses (c16, p16), prefetches the next row into (c16n, p16n)
     auto row = [&](const int i, const uint32_t (&c16)[2][NR], const uint32_t (&p16)[2][NR], uint32_t (&c16n)[2][NR], uint32_t (&p16n)[2][NR]) {
@@ -326,6 +364,12 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
             sts_words<NR>(own[c][od] + curb, Lo);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] = p16[c][j] + L0[j] + Lo[j] + Lb[c][j];
+            if (last && p.halo_out != nullptr && valid[c]) {
+                uint32_t *ho = p.halo_out + (size_t)xs[c] * VS + lane * NR;
+                st_words<NR>(ho, L0);
+                st_words<NR>(ho + hplane, c == 0 ? Lo : Lb[1]);             // dx = +1
+                st_words<NR>(ho + 2 * hplane, c == 0 ? Lb[0] : Lo);         // dx = -1
+            }
             if (valid[c]) {
                 if (!FINAL) {
                     st_words<NR>(gp[c] + VS, tot);
@@ -373,8 +417,11 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     }
 }
 
+enum { NARROW_ALL = 0, NARROW_H = 1, NARROW_V = 2 };
+
 template <int NR>
-int launch_narrow(NarrowParams p, int nstrips, int nwarp, void *workspace, size_t ring_bytes, cudaStream_t s, bool *done) {
+int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, void *workspace, size_t ring_bytes, cudaStream_t s,
+                  bool *done) {
     *done = false;
     const int nsm = sm_count();
     const int K = nwarp * 2;
@@ -391,19 +438,25 @@ int launch_narrow(NarrowParams p, int nstrips, int nwarp, void *workspace, size_
     PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fin, threads, smem));
     if ((long)per_sm * nsm < nstrips) return PB200_OK;
 
-    PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
-    const int hgrid = ceil_div(p.H, 4);
-    sgm_narrow_h_kernel<NR, true><<<hgrid, 128, 0, s>>>(p);
-    PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<E>");
-    sgm_narrow_h_kernel<NR, false><<<hgrid, 128, 0, s>>>(p);
-    PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<W>");
-    p.ring = reinterpret_cast<unsigned long long *>(workspace);
-    for (int pass = 0; pass < 2; ++pass) {
-        p.dy = pass == 0 ? 1 : -1;
-        PB200_CUDA(cudaMemsetAsync(p.ring, 0, ring_bytes, s));
-        void *args[] = {(void *)&p};
-        PB200_CUDA(cudaLaunchCooperativeKernel((const void *)(pass == 0 ? mid : fin), dim3(nstrips), dim3(threads), args, smem, s));
-        PB200_LAUNCH_CHECK("sgm_narrow_vsweep_kernel");
+    if (phase != NARROW_V) {
+        PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
+        const int hgrid = ceil_div(p.H, 4);
+        sgm_narrow_h_kernel<NR, true><<<hgrid, 128, 0, s>>>(p);
+        PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<E>");
+        sgm_narrow_h_kernel<NR, false><<<hgrid, 128, 0, s>>>(p);
+        PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<W>");
+    }
+    if (phase != NARROW_H) {
+        p.ring = reinterpret_cast<unsigned long long *>(workspace);
+        const int npass = (phase == NARROW_ALL) ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            const bool is_final = (phase == NARROW_ALL) ? (pass == 1) : (final != 0);
+            if (phase == NARROW_ALL) p.dy = pass == 0 ? 1 : -1;
+            PB200_CUDA(cudaMemsetAsync(p.ring, 0, ring_bytes, s));
+            void *args[] = {(void *)&p};
+            PB200_CUDA(cudaLaunchCooperativeKernel((const void *)(is_final ? fin : mid), dim3(nstrips), dim3(threads), args, smem, s));
+            PB200_LAUNCH_CHECK("sgm_narrow_vsweep_kernel");
+        }
     }
     *done = true;
     return PB200_OK;
@@ -415,9 +468,12 @@ bool is_small_int(float v, int lo, int hi) { return v >= (float)lo && v <= (floa
 
 // Try the packed-integer path.  On return *gate is NULL when nothing was launched (the caller runs the float
 // kernels unconditionally) or points to the device flag the float kernels must be gated on.
+// phase 0: the whole stage in one call; 1: the horizontal pair only (data check, C16 / P16 left in `out`);
+// 2: one vertical group (dy, final) with optional packed halos -- the split used by row-tiled multi-GPU runs;
+// 3: launch nothing, only report the flag when the shape / parameters are eligible.
 int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, float p2, float invalid_value, int overcounting,
                    float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
-                   cudaStream_t s, const int **gate) {
+                   cudaStream_t s, const int **gate, int phase, int dy, int final, const float *halo_in, float *halo_out) {
     *gate = nullptr;
     if (D != 64 && D != 128 && D != 256) return PB200_OK;
     if (!is_small_int(p1, 1, NARROW_MAX) || !is_small_int(p2, 1, NARROW_MAX) || p1 > p2 || !is_small_int(invalid_value, 0, NARROW_MAX) ||
@@ -439,20 +495,27 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.inv = (uint32_t)invalid_value;
     p.cost_ok_max = (float)(NARROW_MAX - (int)p2);
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
-    p.dy = 1; p.overcounting = overcounting;
+    p.dy = dy; p.overcounting = overcounting;
     p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
     p.ring = nullptr;
+    p.halo_in = reinterpret_cast<const uint32_t *>(halo_in);
+    p.halo_out = reinterpret_cast<uint32_t *>(halo_out);
+    if ((reinterpret_cast<uintptr_t>(halo_in) & 15) || (reinterpret_cast<uintptr_t>(halo_out) & 15)) return PB200_OK;
     p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
     int kdiv = getenv("PB200_SGM_KDIV") ? atoi(getenv("PB200_SGM_KDIV")) : 1;
     if (kdiv > 1) { K = (K / kdiv + 1) / 2 * 2; if (K < 4) K = 4; }
+    if (phase == 3) {                 // query only: eligible -> the caller gates its float kernels on the flag
+        *gate = p.flag;
+        return PB200_OK;
+    }
     bool done = false;
     int rc;
     const int nwarp = K / 2;
     const int nstrips = ceil_div(W, K);
     const size_t ring_bytes = (size_t)nstrips * 2 * 2 * NR * 32 * sizeof(unsigned long long);
-    if (NR == 4) rc = launch_narrow<4>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
-    else if (NR == 2) rc = launch_narrow<2>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
-    else rc = launch_narrow<1>(p, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    if (NR == 4) rc = launch_narrow<4>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else if (NR == 2) rc = launch_narrow<2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else rc = launch_narrow<1>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
     if (rc != PB200_OK) return rc;
     if (done) *gate = p.flag;
     return PB200_OK;

@@ -147,8 +147,15 @@ class Engine:
     def sgm(self, cv: torch.Tensor, p1: float, p2: float, invalid_value: float, overcounting: bool = False,
             out: Optional[torch.Tensor] = None, fuse_wta: bool = False, dmin: int = 0, invalid_disparity: float = -9999.0,
             dir_mask: int = 0xFF, init_final: int = 3, halo_in_top=None, halo_in_bottom=None, halo_out_bottom=None, halo_out_top=None,
-            disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
+            disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, packed: bool = False,
+            float_only: bool = False):
+        """8-path SGM (or the directions in ``dir_mask``).  ``packed``: split calls may leave the exact 16-bit
+        intermediate representation in ``out`` / the halo buffers (include/pandora_b200.h, init_final bit 2)."""
         H, W, D = (int(s) for s in cv.shape)
+        if packed:
+            init_final |= 4
+        if float_only:
+            init_final |= 8
         res = torch.empty_like(cv) if out is None else out
         if fuse_wta and disp is None:
             disp = self.empty((H, W))
@@ -161,6 +168,13 @@ class Engine:
                 _ptr(disp) if fuse_wta else None, int(dmin), float(invalid_disparity), _ptr(flags) if fuse_wta else None,
                 _ptr(ws), ws.numel(), self._stream()))
         return (res, disp, flags) if fuse_wta else res
+
+    def sgm_path_flag(self, W: int, D: int) -> torch.Tensor:
+        """int32 view (1 element) of the fast-path flag inside the SGM workspace: 0 = the packed integer path ran."""
+        H = 1
+        ws = self._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, W, D))
+        off = int(self.lib.pb200_sgm_flag_offset(W, D))
+        return ws[off: off + 4].view(torch.int32)
 
     # ---- disparity ----------------------------------------------------------------------------------
     def wta(self, cv: torch.Tensor, dmin: int, is_max: bool = False, invalid_disparity: float = -9999.0):

@@ -58,6 +58,9 @@ class SgmBackend:
     def run_horizontal(self, init: bool) -> None:
         raise NotImplementedError
 
+    def agree_on_path(self, dist) -> None:
+        """Make every rank take the same numeric path for the vertical groups (no-op for backends with one path)."""
+
     def run_group(self, group: int, final: bool, halo_in, halo_out) -> None:
         raise NotImplementedError
 
@@ -76,7 +79,15 @@ class EngineSgmBackend(SgmBackend):
         return self.eng.empty((3, W, D))
 
     def run_horizontal(self, init: bool) -> None:
-        self.eng.sgm(self.cv, *self.args, out=self.out, dir_mask=0x03, init_final=1 if init else 0)
+        self.eng.sgm(self.cv, *self.args, out=self.out, dir_mask=0x03, init_final=1 if init else 0, packed=init)
+
+    def agree_on_path(self, dist) -> None:
+        # the packed integer path qualifies per tile (device flag); halos are only compatible when all ranks agree
+        if dist is not None:
+            _, W, D = self.cv.shape
+            dist.all_reduce(self.eng.sgm_path_flag(W, D), op=dist.ReduceOp.MAX)
+        # float E + W, executed on the device only where the (agreed) flag says the packed path is off
+        self.eng.sgm(self.cv, *self.args, out=self.out, dir_mask=0x03, init_final=1, packed=True, float_only=True)
 
     def run_group(self, group, final, halo_in, halo_out) -> None:
         if group == 0:
@@ -85,7 +96,8 @@ class EngineSgmBackend(SgmBackend):
             kw = {"halo_in_bottom": halo_in, "halo_out_top": halo_out}
         fuse = final and self.disp is not None
         self.eng.sgm(self.cv, *self.args, out=self.out, fuse_wta=fuse, dmin=self.dmin, invalid_disparity=self.invalid_disparity,
-                     dir_mask=0x1C if group == 0 else 0xE0, init_final=2 if final else 0, disp=self.disp, flags=self.flags, **kw)
+                     dir_mask=0x1C if group == 0 else 0xE0, init_final=2 if final else 0, disp=self.disp, flags=self.flags,
+                     packed=True, **kw)
 
 
 def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down=None, pg_up=None, order: Optional[List[int]] = None):
@@ -99,6 +111,7 @@ def run_tiled_sgm(backend: SgmBackend, rank: int, world: int, dist=None, pg_down
     has_up_nb, has_down_nb = rank > 0, rank < world - 1
     send_work, keep = [], []
     backend.run_horizontal(True)
+    backend.agree_on_path(dist if world > 1 else None)
     for i, g in enumerate(order):
         # The receive is posted only now, never ahead of local work: an NCCL receive kernel that sits on the GPU
         # waiting for its peer would keep the cooperative strip-sweep launch of the OTHER group from becoming

@@ -388,6 +388,52 @@ def test_sgm_row_tiles_with_halo_equal_whole_image(eng, oracle):
     np.testing.assert_array_equal(whole, oracle.sgm_cost_volume(host(cv), 8, 32, cmax=25))
 
 
+@pytest.mark.parametrize("kind", ["integer", "float"])
+@pytest.mark.parametrize("shape", [(40, 96, 64), (37, 333, 128), (30, 200, 256)])
+def test_sgm_row_tiles_packed_split_calls(eng, oracle, kind, shape):
+    """The split-call sequence of a row-tiled run with packed intermediates (include/pandora_b200.h, init_final
+    bits 2 and 3): bit-identical to the whole-image run, on the packed path (integer costs) and on the gated
+    float fallback (float costs)."""
+    import torch
+
+    g = np.random.default_rng(shape[1])
+    H, W, D = shape
+    if kind == "integer":
+        cvh = g.integers(0, 26, shape).astype(np.float32)
+        p1, p2, inv = 8.0, 32.0, 58.0
+    else:
+        cvh = (g.random(shape) * 25).astype(np.float32)
+        p1, p2, inv = 8.0, 32.0, 58.0
+    cvh[g.random(shape) < 0.1] = np.nan
+    cv = dev(eng, cvh)
+    dmin = -(D - 1)
+    whole, wdisp, wflags = eng.sgm(cv, p1, p2, inv, fuse_wta=True, dmin=dmin)
+    whole, wdisp = host(whole), host(wdisp)
+    np.testing.assert_array_equal(whole, oracle.sgm_cost_volume(cvh, p1, p2, cmax=25))
+    cuts = [0, H // 3, 2 * H // 3 + 1, H]
+    tiles = [cv[a:b].contiguous() for a, b in zip(cuts[:-1], cuts[1:])]
+    outs = [torch.empty_like(t) for t in tiles]
+    disps = [torch.empty(t.shape[:2], device=cv.device) for t in tiles]
+    flags = [torch.empty(t.shape[:2], dtype=torch.uint8, device=cv.device) for t in tiles]
+    n = len(tiles)
+    for t, o in zip(tiles, outs):
+        eng.sgm(t, p1, p2, inv, out=o, dir_mask=0x03, init_final=1, packed=True)
+        eng.sgm(t, p1, p2, inv, out=o, dir_mask=0x03, init_final=1, packed=True, float_only=True)
+    halo = None
+    for i in range(n):                                   # downward wave, top tile first
+        nxt = torch.empty((3, W, D), device=cv.device)
+        eng.sgm(tiles[i], p1, p2, inv, out=outs[i], dir_mask=0x1C, init_final=0, halo_in_top=halo, halo_out_bottom=nxt, packed=True)
+        halo = nxt
+    halo = None
+    for i in reversed(range(n)):                         # upward wave, bottom tile first, final + fused WTA
+        nxt = torch.empty((3, W, D), device=cv.device)
+        eng.sgm(tiles[i], p1, p2, inv, out=outs[i], dir_mask=0xE0, init_final=2, halo_in_bottom=halo, halo_out_top=nxt, packed=True,
+                fuse_wta=True, dmin=dmin, disp=disps[i], flags=flags[i])
+        halo = nxt
+    np.testing.assert_array_equal(np.concatenate([host(o) for o in outs]), whole)
+    np.testing.assert_array_equal(np.concatenate([host(d) for d in disps]), wdisp)
+
+
 # ------------------------------------------------------------------------------------------------
 # host-buffer C-ABI entry points (what a reference-side binding calls)
 # ------------------------------------------------------------------------------------------------
