@@ -30,7 +30,6 @@ namespace pb200 {
 namespace {
 
 constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger than any state, INF + P cannot wrap
-constexpr uint32_t NANBITS = 0x80008000u;    // bit 15 of a C16 half: the original cost was NaN
 constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
 
 struct NarrowParams {
@@ -83,6 +82,48 @@ __device__ __forceinline__ void st_floats(float *p, const float (&v)[NR]) {
     else *p = v[0];
 }
 
+// ---- storage tiers ------------------------------------------------------------------------------------------
+// CB = bytes per stored cost.  CB == 2: C16 words [0, D/2), P16 words [D/2, D) of a pixel's D-word region.
+// CB == 1 (cost + P2 <= 127): C8 words [0, D/4), P16 words [D/4, 3D/4), and the E -> W hand-over P8 (L_E <= 255)
+// in words [3D/4, D).  In registers a cost is always one 16-bit half; the NaN flag sits in bit 15 (CB 2) or 7 (CB 1).
+template <int CB> struct Tier;
+template <> struct Tier<2> { static constexpr uint32_t FLAGS = 0x80008000u, VALUES = 0x7FFF7FFFu, FLAG1 = 0x8000u; };
+template <> struct Tier<1> { static constexpr uint32_t FLAGS = 0x00800080u, VALUES = 0x007F007Fu, FLAG1 = 0x80u; };
+
+// raw words of a lane's costs (NR * CB / 2 words) and their expansion to one 16-bit half per cost; kept apart so a
+// prefetch can leave the raw words in flight and unpack them only when the row is consumed
+template <int NR, int CB>
+__device__ __forceinline__ void ld_cost_raw(const uint32_t *pix, int lane, uint32_t (&w)[NR * CB / 2]) {
+    ld_words<NR * CB / 2>(pix + lane * (NR * CB / 2), w);
+}
+template <int NR, int CB>
+__device__ __forceinline__ void unpack_cost(const uint32_t (&w)[NR * CB / 2], uint32_t (&c)[NR]) {
+    if constexpr (CB == 2) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) c[j] = w[j];
+    } else {
+#pragma unroll
+        for (int q = 0; q < NR / 2; ++q) {
+            c[2 * q] = __byte_perm(w[q], 0u, 0x4140);            // bytes (b0, 0, b1, 0)
+            c[2 * q + 1] = __byte_perm(w[q], 0u, 0x4342);        // bytes (b2, 0, b3, 0)
+        }
+    }
+}
+template <int NR, int CB>
+__device__ __forceinline__ void st_cost(uint32_t *pix, int lane, const uint32_t (&c)[NR]) {
+    if constexpr (CB == 2) {
+        st_words<NR>(pix + lane * NR, c);
+    } else {
+        uint32_t w[NR / 2];
+#pragma unroll
+        for (int q = 0; q < NR / 2; ++q) w[q] = __byte_perm(c[2 * q], c[2 * q + 1], 0x6420);
+        st_words<NR / 2>(pix + lane * (NR / 2), w);
+    }
+}
+// word offsets of the partial sums inside a pixel region
+template <int CB> __device__ __forceinline__ int p16_off(int D) { return CB == 2 ? D / 2 : D / 4; }
+__device__ __forceinline__ int p8_off(int D) { return 3 * (D / 4); }
+
 // One recurrence step on packed states: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m).
 // Register j of a lane holds disparity NR*lane + j (low half) and D/2 + NR*lane + j (high half).
 template <int NR>
@@ -111,18 +152,19 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
 }
 
 // float32 cost -> 16-bit code (value, or invalid_value | 0x8000 for NaN); `bad` is raised for anything else
+template <int CB>
 __device__ __forceinline__ uint32_t encode_cost(float v, uint32_t inv, float ok_max, bool &bad) {
     const float t = v + 8388608.0f;                       // exact integer extraction for 0 <= v < 2^23
     const bool isn = (v != v);
     const bool ok = (t - 8388608.0f == v) && (v >= 0.f) && (v <= ok_max);
     bad = bad || !(ok || isn);
-    return isn ? (inv | 0x8000u) : (__float_as_uint(t) & 0xFFFFu);
+    return isn ? (inv | Tier<CB>::FLAG1) : (__float_as_uint(t) & 0xFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------------
 // horizontal passes: one warp per row
 // ------------------------------------------------------------------------------------------------
-template <int NR, bool FIRST>
+template <int NR, int CB, bool FIRST>
 __global__ void __launch_bounds__(128) sgm_narrow_h_kernel(const NarrowParams p) {
     if (!FIRST && *p.flag != 0) return;
     const int lane = threadIdx.x & 31;
@@ -130,34 +172,37 @@ __global__ void __launch_bounds__(128) sgm_narrow_h_kernel(const NarrowParams p)
     if (path >= p.H) return;
     const int W = p.W, D = p.D;
     const int dx = FIRST ? 1 : -1;
-    int x = FIRST ? 0 : W - 1;
+    const int x = FIRST ? 0 : W - 1;
     const size_t pix0 = (size_t)path * W + x;
     const long step = (long)dx * D;
-    uint32_t *b_ptr = p.buf + pix0 * D + lane * NR;         // this lane's C16 words; its P16 words are NR*32 further
+    uint32_t *b_ptr = p.buf + pix0 * D;                     // this pixel's D-word region
     const float *c_ptr = p.cv + pix0 * D + lane * NR;       // FIRST: low-half costs; high-half costs D/2 further
+    const int poff = p16_off<CB>(D) + lane * NR;            // P16 words of this lane
+    const int qoff = (CB == 2) ? poff : p8_off(D) + lane * (NR / 2);   // what E hands to W: P16, or P8 in the byte tier
     uint32_t Lp[NR];
     bool bad = false;
     // prefetch registers for the next pixel
     float fa[NR], fb[NR];
-    uint32_t c16n[NR], p16n[NR];
+    constexpr int RW = NR * CB / 2;                         // raw words per lane (costs, and the E -> W hand-over)
+    uint32_t cn[RW], pn[RW];
     if (FIRST) { ld_floats<NR>(c_ptr, fa); ld_floats<NR>(c_ptr + D / 2, fb); }
-    else { ld_words<NR>(b_ptr, c16n); ld_words<NR>(b_ptr + NR * 32, p16n); }
+    else { ld_cost_raw<NR, CB>(b_ptr, lane, cn); ld_words<RW>(b_ptr + qoff, pn); }
     for (int i = 0; i < W; ++i) {
-        uint32_t c16[NR], p16[NR], cc[NR];
+        uint32_t c[NR], ps[NR], cc[NR];
         if (FIRST) {
 #pragma unroll
             for (int j = 0; j < NR; ++j)
-                c16[j] = encode_cost(fa[j], p.inv, p.cost_ok_max, bad) | (encode_cost(fb[j], p.inv, p.cost_ok_max, bad) << 16);
+                c[j] = encode_cost<CB>(fa[j], p.inv, p.cost_ok_max, bad) | (encode_cost<CB>(fb[j], p.inv, p.cost_ok_max, bad) << 16);
         } else {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) { c16[j] = c16n[j]; p16[j] = p16n[j]; }
+            unpack_cost<NR, CB>(cn, c);
+            unpack_cost<NR, CB>(pn, ps);                    // the hand-over uses the same packing as the costs
         }
         if (i + 1 < W) {
             if (FIRST) { ld_floats<NR>(c_ptr + step, fa); ld_floats<NR>(c_ptr + step + D / 2, fb); }
-            else { ld_words<NR>(b_ptr + step, c16n); ld_words<NR>(b_ptr + step + NR * 32, p16n); }
+            else { ld_cost_raw<NR, CB>(b_ptr + step, lane, cn); ld_words<RW>(b_ptr + step + qoff, pn); }
         }
 #pragma unroll
-        for (int j = 0; j < NR; ++j) cc[j] = c16[j] & ~NANBITS;
+        for (int j = 0; j < NR; ++j) cc[j] = c[j] & Tier<CB>::VALUES;
         uint32_t L[NR];
         if (i == 0) {
 #pragma unroll
@@ -168,10 +213,15 @@ __global__ void __launch_bounds__(128) sgm_narrow_h_kernel(const NarrowParams p)
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             Lp[j] = L[j];
-            p16[j] = FIRST ? L[j] : p16[j] + L[j];
+            ps[j] = FIRST ? L[j] : ps[j] + L[j];
         }
-        if (FIRST) st_words<NR>(b_ptr, c16);
-        st_words<NR>(b_ptr + NR * 32, p16);
+        if (FIRST) {
+            st_cost<NR, CB>(b_ptr, lane, c);
+            if constexpr (CB == 2) st_words<NR>(b_ptr + qoff, ps);
+            else st_cost<NR, 1>(b_ptr + p8_off(D), lane, ps);               // L_E <= 255: one byte each
+        } else {
+            st_words<NR>(b_ptr + poff, ps);
+        }
         b_ptr += step;
         c_ptr += step;
     }
@@ -222,7 +272,7 @@ __device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&v)[NR]
 // t - m = 0).  The state buffers therefore start as zeros and image-border halo columns simply stay zero: the row
 // loop has no "first row" / "no predecessor" cases.  Columns right of the image (last strip) run on zero costs,
 // which keeps their leftward diagonal state flat, and have their loads / stores predicated off.
-template <int NR, bool FINAL, bool WTA>
+template <int NR, int CB, bool FINAL, bool WTA>
 __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowParams p) {
     if (*p.flag != 0) return;
     extern __shared__ __align__(16) uint32_t nsweep_smem[];
@@ -311,37 +361,44 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     }
     const long row_stride = (long)dy * W * D;              // words
     const int y0 = dy > 0 ? 0 : H - 1;
-    uint32_t *gp[2];                                       // this lane's C16 words of the current row; P16 words are VS further
+    uint32_t *gp[2];                                       // pixel regions of the current row
 #pragma unroll
-    for (int c = 0; c < 2; ++c) gp[c] = p.buf + ((size_t)y0 * W + (valid[c] ? xs[c] : 0)) * D + lane * NR;
+    for (int c = 0; c < 2; ++c) gp[c] = p.buf + ((size_t)y0 * W + (valid[c] ? xs[c] : 0)) * D;
+    const int poff = p16_off<CB>(D) + lane * NR;
 
-    uint32_t Lv[2][NR], cA[2][NR], pA[2][NR], cB[2][NR], pB[2][NR];
+    constexpr int RW = NR * CB / 2;                        // raw cost words per lane
+    uint32_t Lv[2][NR], cA[2][RW], pA[2][NR], cB[2][RW], pB[2][NR];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 2; ++c) {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { Lv[c][j] = 0u; cA[c][j] = 0u; pA[c][j] = 0u; cB[c][j] = 0u; pB[c][j] = 0u; }
+        for (int j = 0; j < NR; ++j) { Lv[c][j] = 0u; pA[c][j] = 0u; pB[c][j] = 0u; }
+#pragma unroll
+        for (int j = 0; j < RW; ++j) { cA[c][j] = 0u; cB[c][j] = 0u; }
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c)
         if (valid[c]) {
-            ld_words<NR>(gp[c], cA[c]);
-            ld_words<NR>(gp[c] + VS, pA[c]);
+            ld_cost_raw<NR, CB>(gp[c], lane, cA[c]);
+            ld_words<NR>(gp[c] + poff, pA[c]);
             if (p.halo_in != nullptr) ld_words<NR>(p.halo_in + (size_t)xs[c] * VS + lane * NR, Lv[c]);
         }
 
     // one row: uses (c16, p16), prefetches the next row into (c16n, p16n)
-    auto row = [&](const int i, const uint32_t (&c16)[2][NR], const uint32_t (&p16)[2][NR], uint32_t (&c16n)[2][NR], uint32_t (&p16n)[2][NR]) {
+    auto row = [&](const int i, const uint32_t (&craw)[2][RW], const uint32_t (&p16)[2][NR], uint32_t (&c16n)[2][RW], uint32_t (&p16n)[2][NR]) {
         const bool last = (i == H - 1);
         const uint32_t curb = (uint32_t)(i & 1) * BUFB, prvb = BUFB - curb;
         if (!last) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-                if (valid[c]) { ld_words<NR>(gp[c] + row_stride, c16n[c]); ld_words<NR>(gp[c] + row_stride + VS, p16n[c]); }
+                if (valid[c]) { ld_cost_raw<NR, CB>(gp[c] + row_stride, lane, c16n[c]); ld_words<NR>(gp[c] + row_stride + poff, p16n[c]); }
         }
-        uint32_t cc[2][NR];
+        uint32_t c16[2][NR], cc[2][NR];
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 2; ++c) {
+            unpack_cost<NR, CB>(craw[c], c16[c]);
 #pragma unroll
-            for (int j = 0; j < NR; ++j) cc[c][j] = c16[c][j] & ~NANBITS;
+            for (int j = 0; j < NR; ++j) cc[c][j] = c16[c][j] & Tier<CB>::VALUES;
+        }
         uint32_t Lb[2][NR], Lp[NR];
         // outgoing border diagonals first: column slot 0 (strip column `warp`) dx = -1, slot 1 dx = +1
         lds_words<NR>(pred[0][1] + prvb, Lp);
@@ -372,7 +429,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
             }
             if (valid[c]) {
                 if (!FINAL) {
-                    st_words<NR>(gp[c] + VS, tot);
+                    st_words<NR>(gp[c] + poff, tot);
                 } else {
                     // total -> float32 (exact), overcounting, NaN restore, in place: this lane overwrites the bytes it loaded
                     float fa[NR], fb[NR];
@@ -382,7 +439,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
                         uint32_t t = tot[j];
                         if (p.overcounting) t = t - 7u * cc[c][j];   // S >= 8 C in every half: no borrow
                         const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                        const bool nlo = (c16[c][j] & 0x8000u) != 0, nhi = (c16[c][j] & 0x80000000u) != 0;
+                        const bool nlo = (c16[c][j] & Tier<CB>::FLAG1) != 0, nhi = (c16[c][j] & (Tier<CB>::FLAG1 << 16)) != 0;
                         fa[j] = nlo ? nan_f() : small_int_to_float(lo);
                         fb[j] = nhi ? nan_f() : small_int_to_float(hi);
                         if (WTA) {
@@ -392,7 +449,8 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
                             best = min(best, nhi ? 0xFFFFFFFFu : kb);
                         }
                     }
-                    float *o = reinterpret_cast<float *>(gp[c]);
+                    // in place: the stores depend on registers the whole warp's loads of this pixel have filled
+                    float *o = reinterpret_cast<float *>(gp[c]) + lane * NR;
                     st_floats<NR>(o, fa);
                     st_floats<NR>(o + D / 2, fb);
                     if (WTA) {
@@ -419,7 +477,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
 
 enum { NARROW_ALL = 0, NARROW_H = 1, NARROW_V = 2 };
 
-template <int NR>
+template <int NR, int CB>
 int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, void *workspace, size_t ring_bytes, cudaStream_t s,
                   bool *done) {
     *done = false;
@@ -428,8 +486,8 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     const size_t smem = (size_t)2 * 2 * (K + 2) * NR * 32 * sizeof(uint32_t);
     const int threads = (nwarp + 1) * 32;
     const bool wta = p.disp != nullptr;
-    void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, false, false>;
-    void (*fin)(const NarrowParams) = wta ? sgm_narrow_vsweep_kernel<NR, true, true> : sgm_narrow_vsweep_kernel<NR, true, false>;
+    void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, CB, false, false>;
+    void (*fin)(const NarrowParams) = wta ? sgm_narrow_vsweep_kernel<NR, CB, true, true> : sgm_narrow_vsweep_kernel<NR, CB, true, false>;
     int per_sm = 0;
     PB200_CUDA(cudaFuncSetAttribute((const void *)mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PB200_CUDA(cudaFuncSetAttribute((const void *)fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -441,9 +499,9 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     if (phase != NARROW_V) {
         PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
         const int hgrid = ceil_div(p.H, 4);
-        sgm_narrow_h_kernel<NR, true><<<hgrid, 128, 0, s>>>(p);
+        sgm_narrow_h_kernel<NR, CB, true><<<hgrid, 128, 0, s>>>(p);
         PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<E>");
-        sgm_narrow_h_kernel<NR, false><<<hgrid, 128, 0, s>>>(p);
+        sgm_narrow_h_kernel<NR, CB, false><<<hgrid, 128, 0, s>>>(p);
         PB200_LAUNCH_CHECK("sgm_narrow_h_kernel<W>");
     }
     if (phase != NARROW_H) {
@@ -493,7 +551,9 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.cv = cv; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
-    p.cost_ok_max = (float)(NARROW_MAX - (int)p2);
+    // byte tier (C8, and P8 between E and W) when cost + P2 fits 7 bits; else 16-bit storage
+    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && !getenv("PB200_SGM_NO_BYTE_TIER");
+    p.cost_ok_max = (float)((bytes ? 127 : NARROW_MAX) - (int)p2);
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
     p.dy = dy; p.overcounting = overcounting;
     p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
@@ -513,9 +573,11 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     const int nwarp = K / 2;
     const int nstrips = ceil_div(W, K);
     const size_t ring_bytes = (size_t)nstrips * 2 * 2 * NR * 32 * sizeof(unsigned long long);
-    if (NR == 4) rc = launch_narrow<4>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
-    else if (NR == 2) rc = launch_narrow<2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
-    else rc = launch_narrow<1>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    if (NR == 4) rc = bytes ? launch_narrow<4, 1>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done)
+                            : launch_narrow<4, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else if (NR == 2) rc = bytes ? launch_narrow<2, 1>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done)
+                                 : launch_narrow<2, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else rc = launch_narrow<1, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
     if (rc != PB200_OK) return rc;
     if (done) *gate = p.flag;
     return PB200_OK;

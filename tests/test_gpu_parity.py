@@ -307,17 +307,17 @@ def test_sgm_strip_sweep_float_costs_repeatable(eng, oracle):
 
 
 @pytest.mark.parametrize("shape", [(9, 21, 64), (31, 333, 128), (16, 600, 256), (3, 4, 64), (1, 50, 128), (40, 1, 64)])
-@pytest.mark.parametrize("over", [False, True])
-def test_sgm_packed_integer_path(eng, oracle, shape, over):
+@pytest.mark.parametrize("over,p1,p2", [(False, 8, 32), (True, 8, 32), (False, 10, 120), (True, 3, 200)])
+def test_sgm_packed_integer_path(eng, oracle, shape, over, p1, p2):
     """D in {64, 128, 256} with integer costs takes the packed 16-bit path (sgm_narrow.cu): bit-identical to the
     oracle, including NaN cells, all-NaN pixels, overcounting and the fused WTA."""
-    g = np.random.default_rng(shape[0] * 1000 + shape[2])
+    g = np.random.default_rng(shape[0] * 1000 + shape[2] + p2)
     cv = g.integers(0, 26, shape).astype(np.float32)
     cv[g.random(shape) < 0.15] = np.nan
     cv[g.random(shape[:2]) < 0.1] = np.nan                   # whole pixels without any valid cost
-    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25, overcounting=over)
+    ref = oracle.sgm_cost_volume(cv, p1, p2, cmax=25, overcounting=over)   # P2 = 32: byte storage tier; larger: 16-bit tier
     dmin = -(shape[2] - 1)
-    got, disp, flags = eng.sgm(dev(eng, cv), 8, 32, 58.0, overcounting=over, fuse_wta=True, dmin=dmin)
+    got, disp, flags = eng.sgm(dev(eng, cv), p1, p2, oracle.sgm_invalid_value(25, p2), overcounting=over, fuse_wta=True, dmin=dmin)
     np.testing.assert_array_equal(host(got), ref)
     exp_disp, exp_inv = oracle.wta(ref, np.arange(dmin, 1))
     np.testing.assert_array_equal(host(disp), exp_disp)
