@@ -254,6 +254,14 @@ __device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int 
     for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
 }
 
+template <int NWORDS>
+__device__ __forceinline__ void cp_async_words(uint32_t smem_addr, const uint32_t *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(gsrc), "n"(NWORDS * 4) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // shared-memory access by 32-bit shared address (no generic-pointer conversion in the row loop)
 template <int NR>
 __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&v)[NR]) {
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     const uint32_t BUFB = (uint32_t)(2 * (K + 2) * VS) * 4u;            // bytes per buffer
     const uint32_t DIAGB = (uint32_t)((K + 2) * VS) * 4u;               // bytes per diagonal plane
     const uint32_t sbase = smem_u32(nsweep_smem) + (uint32_t)(lane * NR) * 4u;
-    for (int i = threadIdx.x; i < 2 * 2 * (K + 2) * VS; i += blockDim.x) nsweep_smem[i] = 0u;
+    for (int i = threadIdx.x; i < 2 * 2 * (K + 2) * VS + 4 * nwarp * 2 * 32 * (NR * CB / 2 + NR); i += blockDim.x) nsweep_smem[i] = 0u;
     __syncthreads();
     const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
     const size_t hplane = (size_t)W * VS;                 // words per halo plane
@@ -367,35 +375,52 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     const int poff = p16_off<CB>(D) + lane * NR;
 
     constexpr int RW = NR * CB / 2;                        // raw cost words per lane
-    uint32_t Lv[2][NR], cA[2][RW], pA[2][NR], cB[2][RW], pB[2][NR];
+    // Input staging: the C / P16 words of the next PFD rows travel global -> shared with cp.async (LDGSTS), one
+    // private slot per (stage, warp, column slot, lane): no register prefetch sets, no barrier (a lane only reads
+    // what it copied itself), and deep enough to cover the HBM latency of a row step that takes ~1.3 us.
+    constexpr int NSTG = 4, PFD = NSTG - 1;
+    uint32_t *stg_c = nsweep_smem + 2 * 2 * (K + 2) * VS;                       // [NSTG][nwarp][2][32][RW]
+    uint32_t *stg_p = stg_c + (size_t)NSTG * nwarp * 2 * 32 * RW;               // [NSTG][nwarp][2][32][NR]
+    const uint32_t stgc_base = smem_u32(stg_c) + (uint32_t)(((warp * 2) * 32 + lane) * RW) * 4u;
+    const uint32_t stgp_base = smem_u32(stg_p) + (uint32_t)(((warp * 2) * 32 + lane) * NR) * 4u;
+    const uint32_t stgc_stage = (uint32_t)(nwarp * 2 * 32 * RW) * 4u, stgp_stage = (uint32_t)(nwarp * 2 * 32 * NR) * 4u;
+    uint32_t Lv[2][NR];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { Lv[c][j] = 0u; pA[c][j] = 0u; pB[c][j] = 0u; }
-#pragma unroll
-        for (int j = 0; j < RW; ++j) { cA[c][j] = 0u; cB[c][j] = 0u; }
+        for (int j = 0; j < NR; ++j) Lv[c][j] = 0u;
+        if (valid[c] && p.halo_in != nullptr) ld_words<NR>(p.halo_in + (size_t)xs[c] * VS + lane * NR, Lv[c]);
     }
+    auto stage_in = [&](int r) {                           // enqueue row r (travel order) of both column slots
+        const uint32_t sg = (uint32_t)(r & (NSTG - 1));
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-        if (valid[c]) {
-            ld_cost_raw<NR, CB>(gp[c], lane, cA[c]);
-            ld_words<NR>(gp[c] + poff, pA[c]);
-            if (p.halo_in != nullptr) ld_words<NR>(p.halo_in + (size_t)xs[c] * VS + lane * NR, Lv[c]);
-        }
+        for (int c = 0; c < 2; ++c)
+            if (valid[c]) {
+                const uint32_t *src = gp[c] + (long)r * row_stride;
+                cp_async_words<RW>(stgc_base + sg * stgc_stage + (uint32_t)(c * 32 * RW) * 4u, src + lane * RW);
+                cp_async_words<NR>(stgp_base + sg * stgp_stage + (uint32_t)(c * 32 * NR) * 4u, src + poff);
+            }
+    };
+    for (int r = 0; r < PFD; ++r) {
+        if (r < H) stage_in(r);
+        cp_async_commit();
+    }
 
-    // one row: uses (c16, p16), prefetches the next row into (c16n, p16n)
-    auto row = [&](const int i, const uint32_t (&craw)[2][RW], const uint32_t (&p16)[2][NR], uint32_t (&c16n)[2][RW], uint32_t (&p16n)[2][NR]) {
+    // one row of the sweep
+    auto row = [&](const int i) {
         const bool last = (i == H - 1);
         const uint32_t curb = (uint32_t)(i & 1) * BUFB, prvb = BUFB - curb;
-        if (!last) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-                if (valid[c]) { ld_cost_raw<NR, CB>(gp[c] + row_stride, lane, c16n[c]); ld_words<NR>(gp[c] + row_stride + poff, p16n[c]); }
-        }
-        uint32_t c16[2][NR], cc[2][NR];
+        if (i + PFD < H) stage_in(i + PFD);
+        cp_async_commit();
+        cp_async_wait<PFD>();                              // this lane's copies of row i have landed
+        uint32_t c16[2][NR], p16[2][NR], cc[2][NR];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            unpack_cost<NR, CB>(craw[c], c16[c]);
+            uint32_t craw[RW];
+            const uint32_t sg = (uint32_t)(i & (NSTG - 1));
+            lds_words<RW>(stgc_base + sg * stgc_stage + (uint32_t)(c * 32 * RW) * 4u, craw);
+            lds_words<NR>(stgp_base + sg * stgp_stage + (uint32_t)(c * 32 * NR) * 4u, p16[c]);
+            unpack_cost<NR, CB>(craw, c16[c]);
 #pragma unroll
             for (int j = 0; j < NR; ++j) cc[c][j] = c16[c][j] & Tier<CB>::VALUES;
         }
@@ -428,8 +453,9 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
                 st_words<NR>(ho + 2 * hplane, c == 0 ? Lb[0] : Lo);         // dx = -1
             }
             if (valid[c]) {
+                uint32_t *gpix = gp[c] + (long)i * row_stride;
                 if (!FINAL) {
-                    st_words<NR>(gp[c] + poff, tot);
+                    st_words<NR>(gpix + poff, tot);
                 } else {
                     // total -> float32 (exact), overcounting, NaN restore, in place: this lane overwrites the bytes it loaded
                     float fa[NR], fb[NR];
@@ -450,7 +476,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
                         }
                     }
                     // in place: the stores depend on registers the whole warp's loads of this pixel have filled
-                    float *o = reinterpret_cast<float *>(gp[c]) + lane * NR;
+                    float *o = reinterpret_cast<float *>(gpix) + lane * NR;
                     st_floats<NR>(o, fa);
                     st_floats<NR>(o + D / 2, fb);
                     if (WTA) {
@@ -464,15 +490,11 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
                     }
                 }
             }
-            gp[c] += row_stride;
         }
         __syncthreads();
     };
 #pragma unroll 1
-    for (int i = 0; i < H; i += 2) {
-        row(i, cA, pA, cB, pB);
-        if (i + 1 < H) row(i + 1, cB, pB, cA, pA);
-    }
+    for (int i = 0; i < H; ++i) row(i);
 }
 
 enum { NARROW_ALL = 0, NARROW_H = 1, NARROW_V = 2 };
@@ -483,7 +505,9 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     *done = false;
     const int nsm = sm_count();
     const int K = nwarp * 2;
-    const size_t smem = (size_t)2 * 2 * (K + 2) * NR * 32 * sizeof(uint32_t);
+    const size_t smem = (size_t)2 * 2 * (K + 2) * NR * 32 * sizeof(uint32_t) +                 // state buffers
+                        (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);    // input staging ring
+    if (smem > 220 * 1024) return PB200_OK;
     const int threads = (nwarp + 1) * 32;
     const bool wta = p.disp != nullptr;
     void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, CB, false, false>;
