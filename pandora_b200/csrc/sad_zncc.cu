@@ -101,6 +101,137 @@ __global__ void __launch_bounds__(256) zncc_kernel(const float *__restrict__ L, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled versions (window <= 13): a CTA owns one image row x TX pixels x all disparities.  The WIN image rows it
+// needs are staged once in shared memory (left: TX + 2*half columns, right: the TX + 2*half + D - 1 columns the
+// disparity range can reach); a thread owns 4 consecutive disparities of one pixel and keeps, per window row, a
+// 4-wide register window of right pixels that slides by one column per window column -- one shared-memory read
+// per (window row, window column) for four cells -- exactly the tap order of the plain kernels above
+// (column offset outer, row offset inner), so the float results are unchanged bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int MC_TX = 32;
+
+template <int WIN, int MODE>   // MODE 0: SAD, 1: SSD, 2: ZNCC (float64 accumulation of float32 products)
+__global__ void __launch_bounds__(256) window_cost_tiled_kernel(const float *__restrict__ L, const float *__restrict__ R, int H, int W,
+                                                                int dmin, int D, float *__restrict__ cv,
+                                                                const double *__restrict__ meanL, const double *__restrict__ stdL,
+                                                                const double *__restrict__ meanR, const double *__restrict__ stdR) {
+    constexpr int HALF = WIN / 2;
+    constexpr int LW = MC_TX + 2 * HALF;
+    extern __shared__ __align__(16) float mc_smem[];
+    const int RW = MC_TX + 2 * HALF + D + 3;          // right columns staged per window row
+    float *sL = mc_smem;                              // [WIN][LW]
+    float *sR = mc_smem + WIN * LW;                   // [WIN][RW]
+    const int y = blockIdx.y, x0 = blockIdx.x * MC_TX;
+    const int tid = threadIdx.x;
+    const bool row_ok = (y >= HALF && y < H - HALF);
+    const int npx = min(MC_TX, W - x0);
+    const int G = (D + 3) >> 2;
+    float *out_row = cv + ((size_t)y * W + x0) * D;
+    if (!row_ok) {
+        for (int i = tid; i < npx * D; i += blockDim.x) out_row[i] = nan_f();
+        return;
+    }
+    const int xr0 = x0 - HALF + dmin;                 // image column of sR[.][0]
+    for (int i = tid; i < WIN * LW; i += blockDim.x) {
+        const int wy = i / LW, j = i % LW;
+        const int xx = x0 - HALF + j;
+        sL[i] = (xx >= 0 && xx < W) ? __ldg(L + (size_t)(y - HALF + wy) * W + xx) : 0.f;
+    }
+    for (int i = tid; i < WIN * RW; i += blockDim.x) {
+        const int wy = i / RW, j = i % RW;
+        const int xx = xr0 + j;
+        sR[i] = (xx >= 0 && xx < W) ? __ldg(R + (size_t)(y - HALF + wy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    for (int item = tid; item < npx * G; item += blockDim.x) {
+        const int pp = item / G, g = item - pp * G;
+        const int k0 = g * 4;
+        const int x = x0 + pp;
+        float res[4] = {nan_f(), nan_f(), nan_f(), nan_f()};
+        if (x >= HALF && x < W - HALF) {
+            // right window: win[wy][q] = R[y - HALF + wy][x - HALF + dxi + dmin + k0 + q] for the current dxi
+            float win[WIN][4];
+            const float *rbase = sR + pp + k0;        // column (x - HALF + dmin + k0) - xr0 = pp + k0
+#pragma unroll
+            for (int wy = 0; wy < WIN; ++wy)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) win[wy][q + 1] = rbase[wy * RW + q];
+            float accf[4];
+            double accd[4];
+#pragma unroll
+            for (int dxi = 0; dxi < WIN; ++dxi) {
+#pragma unroll
+                for (int wy = 0; wy < WIN; ++wy) {
+                    win[wy][0] = win[wy][1];
+                    win[wy][1] = win[wy][2];
+                    win[wy][2] = win[wy][3];
+                    win[wy][3] = rbase[wy * RW + dxi + 3];
+                    const float a = sL[wy * LW + pp + dxi];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (MODE == 2) {
+                            const double t = (double)(a * win[wy][q]);           // float32 product, float64 sum
+                            accd[q] = (dxi == 0 && wy == 0) ? t : accd[q] + t;
+                        } else {
+                            const float df = a - win[wy][q];
+                            const float t = (MODE == 1) ? df * df : fabsf(df);
+                            accf[q] = (dxi == 0 && wy == 0) ? t : accf[q] + t;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int d = dmin + k0 + q;
+                if (x - HALF + d >= 0 && x + HALF + d < W) {
+                    if (MODE == 2) {
+                        const size_t pix = (size_t)y * W + x;
+                        double z = accd[q] / (double)(WIN * WIN) - meanL[pix] * meanR[pix + d];
+                        const double den = stdL[pix] * stdR[pix + d];
+                        z = (den > 0.0) ? z / den : 0.0;
+                        res[q] = (float)z;
+                    } else {
+                        res[q] = accf[q];
+                    }
+                }
+            }
+        }
+        float *dst = out_row + (size_t)pp * D + k0;
+        if ((D & 3) == 0) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (k0 + q < D) dst[q] = res[q];
+        }
+    }
+}
+
+template <int MODE>
+static int launch_window_cost(const float *L, const float *R, int H, int W, int win, int dmin, int D, float *cv, const double *mL,
+                              const double *sL, const double *mR, const double *sR, cudaStream_t s, bool *done) {
+    *done = false;
+    if (win > 13 || (reinterpret_cast<uintptr_t>(cv) & 15)) return PB200_OK;
+    const int half = win / 2;
+    const size_t smem = (size_t)win * ((MC_TX + 2 * half) + (MC_TX + 2 * half + D + 3)) * sizeof(float);
+    if (smem > 160 * 1024) return PB200_OK;
+    dim3 grid(ceil_div(W, MC_TX), H);
+#define PB200_W(WIN)                                                                                                         \
+    case WIN:                                                                                                                \
+        PB200_CUDA(cudaFuncSetAttribute(window_cost_tiled_kernel<WIN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        window_cost_tiled_kernel<WIN, MODE><<<grid, 256, smem, s>>>(L, R, H, W, dmin, D, cv, mL, sL, mR, sR);               \
+        break;
+    switch (win) {
+        PB200_W(1) PB200_W(3) PB200_W(5) PB200_W(7) PB200_W(9) PB200_W(11) PB200_W(13)
+        default: return PB200_OK;
+    }
+#undef PB200_W
+    PB200_LAUNCH_CHECK("window_cost_tiled_kernel");
+    *done = true;
+    return PB200_OK;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -115,6 +246,10 @@ extern "C" int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_rig
         set_error("pb200_sad_ssd_cost_volume: window_size %d must be odd and >= 1", window);
         return PB200_ERR_UNSUPPORTED;
     }
+    bool done = false;
+    int rc = squared ? launch_window_cost<1>(d_left, d_right, H, W, window, dmin, D, d_cv, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, &done)
+                     : launch_window_cost<0>(d_left, d_right, H, W, window, dmin, D, d_cv, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream, &done);
+    if (rc != PB200_OK || done) return rc;
     dim3 block(32, 8);
     const int grid = ceil_div((long)H * W, 8);
     if (squared) sad_ssd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(d_left, d_right, H, W, window, dmin, D, d_cv);
@@ -150,6 +285,9 @@ extern "C" int pb200_zncc_cost_volume(const float *d_left, const float *d_right,
     PB200_LAUNCH_CHECK("zncc_stats_kernel");
     zncc_stats_kernel<<<g1, 256, 0, s>>>(d_right, H, W, window, mR, sR);
     PB200_LAUNCH_CHECK("zncc_stats_kernel");
+    bool done = false;
+    int rc = launch_window_cost<2>(d_left, d_right, H, W, window, dmin, D, d_cv, mL, sL, mR, sR, s, &done);
+    if (rc != PB200_OK || done) return rc;
     dim3 block(32, 8);
     zncc_kernel<<<ceil_div((long)n, 8), block, 0, s>>>(d_left, d_right, mL, sL, mR, sR, H, W, window, dmin, D, d_cv);
     PB200_LAUNCH_CHECK("zncc_kernel");
