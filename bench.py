@@ -200,7 +200,7 @@ def run_ours(args):
             return pipe.run_device(d_left, d_right)
 
         def step_host():
-            return pipe.run_host(h_left.numpy(), h_right.numpy())
+            return pipe.run_host(h_left, h_right)
     else:
         from pandora_b200.tiling import TiledStereoPipeline  # noqa: PLC0415
 

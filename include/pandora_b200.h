@@ -75,6 +75,13 @@ PB200_API int pb200_census_cost_volume(const float *d_left, const float *d_right
                              float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
                              float invalid_disparity, uint8_t *d_all_nan, void *stream);
 
+/* Same, restricted to the rows [row_begin, row_end) of the volume (and of d_disp / d_all_nan).  Only the image rows
+ * [row_begin - window/2, row_end + window/2) need to be resident when the call runs: used to overlap the host-to-
+ * device copy of the images with the fill, row band by row band. */
+PB200_API int pb200_census_cost_volume_rows(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
+                                  float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
+                                  float invalid_disparity, uint8_t *d_all_nan, int row_begin, int row_end, void *stream);
+
 /* SAD (squared == 0) / SSD (squared != 0) cost volume, window odd >= 1 (sad_ssd.py:180-206). */
 PB200_API int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
                               int squared, float *d_cv, void *stream);

@@ -36,12 +36,12 @@ static inline int census_pitch(int W) { return ((W + 3) & ~3) + 4; }
 // ------------------------------------------------------------------------------------------------
 template <int WIN>
 __global__ void __launch_bounds__(256) census_transform_kernel(const float *__restrict__ img, int H, int W, int pitch,
-                                                               uint32_t *__restrict__ desc) {
+                                                               uint32_t *__restrict__ desc, int row0, int row1) {
     constexpr int HALF = WIN / 2;
     constexpr int NW = (WIN * WIN + 31) / 32;
     constexpr int TW = 32, TH = 8;
     __shared__ float tile[TH + 2 * HALF][TW + 2 * HALF + 1];
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = blockIdx.x * TW, y0 = row0 + blockIdx.y * TH;
     for (int i = threadIdx.y * TW + threadIdx.x; i < (TH + 2 * HALF) * (TW + 2 * HALF); i += TW * TH) {
         const int ty = i / (TW + 2 * HALF), tx = i % (TW + 2 * HALF);
         const int gy = y0 + ty - HALF, gx = x0 + tx - HALF;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) census_transform_kernel(const float *__re
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= pitch || y >= H) return;
+    if (x >= pitch || y >= row1) return;
     uint32_t words[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) words[i] = 0u;
@@ -82,6 +82,7 @@ struct FillParams {
     float *disp;        // optional fused WTA output
     uint8_t *all_nan;   // optional
     int H, W, D, dmin, half, pitch;
+    int row0;           // first row of the range this launch fills
     int TX;             // pixels per tile (multiple of 4)
     int CH;             // consecutive pixels per work item
     int tiles_x;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p)
     uint32_t parity = 0;
     int it = 0;
     for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int y = (int)(tile / p.tiles_x);
+        const int y = p.row0 + (int)(tile / p.tiles_x);
         const int x0 = (int)(tile % p.tiles_x) * p.TX;
         const int npx = min(p.TX, p.W - x0);
         float *out = sOut + (size_t)(it & 1) * ((tile_elems + 3) & ~3);
@@ -249,9 +250,9 @@ __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p)
 }
 
 template <int WIN>
-static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, cudaStream_t s) {
-    dim3 block(32, 8), grid(ceil_div(pitch, 32), ceil_div(H, 8));
-    census_transform_kernel<WIN><<<grid, block, 0, s>>>(img, H, W, pitch, desc);
+static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, int row0, int row1, cudaStream_t s) {
+    dim3 block(32, 8), grid(ceil_div(pitch, 32), ceil_div(row1 - row0, 8));
+    census_transform_kernel<WIN><<<grid, block, 0, s>>>(img, H, W, pitch, desc, row0, row1);
     PB200_LAUNCH_CHECK("census_transform_kernel");
     return PB200_OK;
 }
@@ -281,7 +282,14 @@ extern "C" size_t pb200_census_workspace_bytes(int H, int W, int window) {
 extern "C" int pb200_census_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin,
                                         int D, float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
                                         float invalid_disparity, uint8_t *d_all_nan, void *stream) {
-    if (!d_left || !d_right || !d_cv || !d_workspace || H <= 0 || W <= 0 || D <= 0) {
+    return pb200_census_cost_volume_rows(d_left, d_right, H, W, window, dmin, D, d_cv, d_workspace, workspace_bytes, d_disp,
+                                         invalid_disparity, d_all_nan, 0, H, stream);
+}
+
+extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d_right, int H, int W, int window, int dmin,
+                                             int D, float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
+                                             float invalid_disparity, uint8_t *d_all_nan, int row_begin, int row_end, void *stream) {
+    if (!d_left || !d_right || !d_cv || !d_workspace || H <= 0 || W <= 0 || D <= 0 || row_begin < 0 || row_end > H || row_begin >= row_end) {
         set_error("pb200_census_cost_volume: bad argument");
         return PB200_ERR_BAD_ARG;
     }
@@ -304,8 +312,8 @@ extern "C" int pb200_census_cost_volume(const float *d_left, const float *d_righ
     int rc;
 #define PB200_T(WIN)                                                       \
     case WIN:                                                              \
-        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, s);         \
-        if (rc == PB200_OK) rc = launch_transform<WIN>(d_right, H, W, pitch, descR, s); \
+        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, row_begin, row_end, s);         \
+        if (rc == PB200_OK) rc = launch_transform<WIN>(d_right, H, W, pitch, descR, row_begin, row_end, s); \
         break;
     switch (window) {
         PB200_T(3) PB200_T(5) PB200_T(7) PB200_T(9) PB200_T(11) PB200_T(13)
@@ -329,7 +337,8 @@ extern "C" int pb200_census_cost_volume(const float *d_left, const float *d_righ
     while (TX % CH) CH >>= 1;
     p.CH = CH;
     p.tiles_x = ceil_div(W, TX);
-    p.n_tiles = (long)p.tiles_x * H;
+    p.row0 = row_begin;
+    p.n_tiles = (long)p.tiles_x * (row_end - row_begin);
     p.r_len = (TX + D + 3 + 3 + 3) & ~3;            // shift (<=3) + TX + D - 1 + window slack, rounded to 4
     p.invalid_disparity = invalid_disparity;
     // the left-descriptor bulk copy reads TX words from x0: keep it inside the pitch
@@ -342,7 +351,7 @@ extern "C" int pb200_census_cost_volume(const float *d_left, const float *d_righ
         while (TX % CH) CH >>= 1;
         p.CH = CH;
         p.tiles_x = ceil_div(W, TX);
-        p.n_tiles = (long)p.tiles_x * H;
+        p.n_tiles = (long)p.tiles_x * (row_end - row_begin);
         p.r_len = (TX + D + 9) & ~3;
     }
     const size_t tile_elems = ((size_t)TX * D + 3) & ~(size_t)3;

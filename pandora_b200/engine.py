@@ -58,19 +58,25 @@ class Engine:
 
     # ---- matching cost ------------------------------------------------------------------------------
     def census(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int,
-               out: Optional[torch.Tensor] = None, fuse_wta: bool = False, invalid_disparity: float = -9999.0):
-        """Census cost volume; with ``fuse_wta`` also returns (disparity map, all-NaN flags)."""
+               out: Optional[torch.Tensor] = None, fuse_wta: bool = False, invalid_disparity: float = -9999.0,
+               rows: Optional[Tuple[int, int]] = None, disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
+        """Census cost volume; with ``fuse_wta`` also returns (disparity map, all-NaN flags).  ``rows`` = (begin, end)
+        restricts the call to a band of rows of the volume (only the image rows within half a window of the band need
+        to be resident yet -- see ``StereoPipeline.run_host``)."""
         H, W = self._hw(left)
         D = dmax - dmin + 1
         cv = self.empty((H, W, D)) if out is None else out
         nbytes = self.lib.pb200_census_workspace_bytes(H, W, window)
         ws = self._workspace("census", nbytes)
-        disp = self.empty((H, W)) if fuse_wta else None
-        flags = self.empty((H, W), torch.uint8) if fuse_wta else None
+        if fuse_wta and disp is None:
+            disp = self.empty((H, W))
+            flags = self.empty((H, W), torch.uint8)
+        r0, r1 = (0, H) if rows is None else rows
         with torch.cuda.device(self.device):
-            _native.check(self.lib.pb200_census_cost_volume(
+            _native.check(self.lib.pb200_census_cost_volume_rows(
                 _ptr(left), _ptr(right), H, W, window, dmin, D, _ptr(cv), _ptr(ws), ws.numel(),
-                _ptr(disp), float(invalid_disparity), _ptr(flags), self._stream()))
+                _ptr(disp) if fuse_wta else None, float(invalid_disparity), _ptr(flags) if fuse_wta else None, int(r0), int(r1),
+                self._stream()))
         return (cv, disp, flags) if fuse_wta else cv
 
     def sad_ssd(self, left, right, window: int, dmin: int, dmax: int, squared: bool = False, out=None) -> torch.Tensor:

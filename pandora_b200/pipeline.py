@@ -81,6 +81,7 @@ class StereoPipeline:
         self.h_right = torch.empty((H, W), dtype=torch.float32, pin_memory=True)
         self.h_disp = torch.empty((H, W), dtype=torch.float32, pin_memory=True)
         self.final_cv = None
+        self._copy_stream = None
         if method == "census":
             self.cmax = float(window * window)
         elif method == "zncc":
@@ -90,22 +91,28 @@ class StereoPipeline:
 
     def run_device(self, left, right):
         """``left`` / ``right``: float32 (H, W) device tensors.  Returns the disparity tensor (device)."""
+        have_disp, cmax = self._matching_cost(left, right)
+        return self._after_cost(left, right, have_disp, cmax)
+
+    def _matching_cost(self, left, right, rows=None):
+        """Matching-cost step into ``cv_a`` (optionally one band of rows, Census only); returns (have_disp, cmax)."""
         e = self.eng
-        cur, other = self.cv_a, self.cv_b
-        have_disp = False
+        cur = self.cv_a
         cmax = self.cmax
         if self.method == "census":
             fuse = not self.cbca and not self.sgm
-            if fuse:
-                _, self.disp, self.flags = self._census_fused(left, right, cur)
-                have_disp = True
-            else:
-                e.census(left, right, self.window, self.dmin, self.dmax, out=cur)
-        else:
-            e.matching_cost(self.method, left, right, self.window, self.dmin, self.dmax, out=cur)
-            if cmax is None:
-                mx = self.torch.maximum((left.max() - right.min()).abs(), (right.max() - left.min()).abs()).item()
-                cmax = float(int((mx if self.method == "sad" else mx * mx) * self.window**2))
+            e.census(left, right, self.window, self.dmin, self.dmax, out=cur, fuse_wta=fuse, invalid_disparity=self.invalid_disparity,
+                     rows=rows, disp=self.disp, flags=self.flags)
+            return fuse, cmax
+        e.matching_cost(self.method, left, right, self.window, self.dmin, self.dmax, out=cur)
+        if cmax is None:
+            mx = self.torch.maximum((left.max() - right.min()).abs(), (right.max() - left.min()).abs()).item()
+            cmax = float(int((mx if self.method == "sad" else mx * mx) * self.window**2))
+        return False, cmax
+
+    def _after_cost(self, left, right, have_disp, cmax):
+        e = self.eng
+        cur, other = self.cv_a, self.cv_b
         if self.cbca:
             dist, inten = self.cbca
             e.cbca(left, right, cur, self.offset, self.dmin, dist, inten, out=other)
@@ -127,28 +134,52 @@ class StereoPipeline:
         self.final_cv = cur
         return self.disp
 
-    def _census_fused(self, left, right, out):
-        from . import _native  # noqa: PLC0415
-
-        e = self.eng
-        ws = e._workspace("census", e.lib.pb200_census_workspace_bytes(self.H, self.W, self.window))
-        with self.torch.cuda.device(e.device):
-            _native.check(e.lib.pb200_census_cost_volume(
-                left.data_ptr(), right.data_ptr(), self.H, self.W, self.window, self.dmin, self.D, out.data_ptr(),
-                ws.data_ptr(), ws.numel(), self.disp.data_ptr(), self.invalid_disparity, self.flags.data_ptr(), e._stream()))
-        return out, self.disp, self.flags
-
     def run_host(self, left: np.ndarray, right: np.ndarray) -> np.ndarray:
-        """Host images in, host disparity map out: pinned staging, H2D + kernels + D2H on one stream."""
+        """Host images in, host disparity map out (the end-to-end call).  Images that are not already in pinned
+        memory are staged through the pipeline's pinned buffers.  For Census the upload is cut into row bands on a
+        copy stream and the cost-volume fill of a band starts as soon as its rows (plus half a window) have
+        arrived, so most of the host-to-device copy hides behind the fill."""
         t = self.torch
-        self.h_left.copy_(t.from_numpy(np.ascontiguousarray(left, dtype=np.float32)))
-        self.h_right.copy_(t.from_numpy(np.ascontiguousarray(right, dtype=np.float32)))
-        self.d_left.copy_(self.h_left, non_blocking=True)
-        self.d_right.copy_(self.h_right, non_blocking=True)
-        disp = self.run_device(self.d_left, self.d_right)
+        dev = self.eng.device
+        hl, hr = self._pinned(left, self.h_left), self._pinned(right, self.h_right)
+        cur = t.cuda.current_stream(dev)
+        bands = max(1, min(8, self.H // 256)) if self.method == "census" else 1
+        if bands == 1:
+            self.d_left.copy_(hl, non_blocking=True)
+            self.d_right.copy_(hr, non_blocking=True)
+            have_disp, cmax = self._matching_cost(self.d_left, self.d_right)
+        else:
+            if self._copy_stream is None:
+                self._copy_stream = t.cuda.Stream(device=dev)
+            cs = self._copy_stream
+            cs.wait_stream(cur)                                   # the previous step may still read d_left / d_right
+            edges = [self.H * b // bands for b in range(bands + 1)]
+            copied = 0
+            have_disp, cmax = False, self.cmax
+            for b in range(bands):
+                r0, r1 = edges[b], edges[b + 1]
+                upto = self.H if b == bands - 1 else min(self.H, r1 + self.offset)
+                with t.cuda.stream(cs):
+                    self.d_left[copied:upto].copy_(hl[copied:upto], non_blocking=True)
+                    self.d_right[copied:upto].copy_(hr[copied:upto], non_blocking=True)
+                    ev = t.cuda.Event()
+                    ev.record(cs)
+                copied = upto
+                cur.wait_event(ev)
+                have_disp, cmax = self._matching_cost(self.d_left, self.d_right, rows=(r0, r1))
+        disp = self._after_cost(self.d_left, self.d_right, have_disp, cmax)
         self.h_disp.copy_(disp, non_blocking=True)
-        t.cuda.current_stream(self.eng.device).synchronize()
+        cur.synchronize()
         return self.h_disp.numpy()
+
+    def _pinned(self, arr, staging):
+        """``arr`` as a pinned float32 host tensor: itself when it already is one, else a copy into ``staging``."""
+        t = self.torch
+        src = arr if isinstance(arr, t.Tensor) else t.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        if src.dtype == t.float32 and src.is_contiguous() and src.is_pinned():
+            return src
+        staging.copy_(src)
+        return staging
 
     def validity_mask(self):
         """uint16 validity mask of the last run (criteria + WTA rules), as a device tensor (int16 storage)."""

@@ -130,3 +130,25 @@ def test_baseline_sizes_properties(pb, oracle, cfg):
         np.testing.assert_array_equal(disp[band][2:-2], exp[2:-2])
     # (5) determinism / idempotence: a second run gives the identical map
     assert np.array_equal(pipe.run_host(left, right), disp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(sgm=(8, 32)), dict(), dict(cbca=(5, 30.0))])
+def test_run_host_banded_upload_equals_device_run(pb, oracle, cfg):
+    """run_host uploads the images in row bands and starts the Census fill of a band as soon as it has arrived:
+    same disparity map and volume as the single-shot device run, from pinned and from pageable host images."""
+    import torch
+
+    H, W, D = 1300, 257, 64
+    left, right, _ = oracle.synthetic_pair(H, W, D)
+    pipe = pb.StereoPipeline(H, W, -(D - 1), 0, "census", 5, **cfg)
+    ref = pipe.run_device(pipe.eng.to_device(left), pipe.eng.to_device(right)).cpu().numpy()
+    ref_cv = pipe.final_cv.clone()
+    pipe.cv_a.fill_(-1.0)
+    got = pipe.run_host(left, right).copy()                                # pageable numpy input
+    np.testing.assert_array_equal(got, ref)
+    assert torch.equal(torch.nan_to_num(pipe.final_cv, nan=-7.0), torch.nan_to_num(ref_cv, nan=-7.0))
+    hl, hr = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
+    pipe.cv_a.fill_(-1.0)
+    got = pipe.run_host(hl, hr).copy()                                     # pinned tensors: no staging copy
+    np.testing.assert_array_equal(got, ref)
