@@ -26,6 +26,15 @@ build matching_cost_cpp "$REF/matching_cost/cpp/includes" \
   "$REF/matching_cost/cpp/src/bindings.cpp" "$REF/matching_cost/cpp/src/census.cpp" "$REF/matching_cost/cpp/src/matching_cost.cpp" &
 build aggregation_cpp "$REF/aggregation/cpp/includes" \
   "$REF/aggregation/cpp/src/bindings.cpp" "$REF/aggregation/cpp/src/aggregation.cpp" &
+# the "next" rows of SURVEY.md 8(f): sub-pixel refinement, cost-volume confidence, criteria
+build refinement_cpp "$REF/refinement/cpp/includes" \
+  "$REF/refinement/cpp/src/bindings.cpp" "$REF/refinement/cpp/src/refinement.cpp" "$REF/refinement/cpp/src/refinement_tools.cpp" \
+  "$REF/refinement/cpp/src/vfit.cpp" "$REF/refinement/cpp/src/quadratic.cpp" &
+build cost_volume_confidence_cpp "$REF/cost_volume_confidence/cpp/includes" \
+  "$REF/cost_volume_confidence/cpp/src/bindings.cpp" "$REF/cost_volume_confidence/cpp/src/ambiguity.cpp" \
+  "$REF/cost_volume_confidence/cpp/src/risk.cpp" "$REF/cost_volume_confidence/cpp/src/interval_bounds.cpp" \
+  "$REF/cost_volume_confidence/cpp/src/cost_volume_confidence_tools.cpp" &
+build criteria_cpp "$REF/cpp/includes" "$REF/cpp/src/bindings_criteria.cpp" "$REF/cpp/src/criteria.cpp" &
 wait
 touch "$OUT/__init__.py"
 ls -la "$OUT"

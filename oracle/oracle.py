@@ -38,6 +38,12 @@ MSK_INVALID = 0b01111000011
 MSK_LEFT_NODATA_OR_BORDER = 1 << 0
 MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING = 1 << 1
 MSK_RIGHT_INCOMPLETE_DISPARITY_RANGE = 1 << 2
+MSK_STOPPED_INTERPOLATION = 1 << 3
+MSK_IN_VALIDITY_MASK_LEFT = 1 << 6
+MSK_IN_VALIDITY_MASK_RIGHT = 1 << 7
+MSK_OCCLUSION = 1 << 8
+MSK_MISMATCH = 1 << 9
+MSK_INCOMPLETE_VARIABLE_DISPARITY_RANGE = 1 << 12
 
 
 def build(force: bool = False) -> str:
@@ -74,6 +80,13 @@ def lib() -> ctypes.CDLL:
         _LIB.pbo_sgm_direction.restype = ci
         _LIB.pbo_wta.argtypes = [f32p, ci, ci, ci, f32p, ci, cf, f32p, u8p]
         _LIB.pbo_wta.restype = None
+        u16p, i32p, f64p, cd = ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double), ctypes.c_double
+        _LIB.pbo_refinement.argtypes = [f32p, ci, ci, ci, cd, cd, ci, ci, ci, ci, f32p, u16p, f32p]
+        _LIB.pbo_refinement.restype = None
+        _LIB.pbo_ambiguity.argtypes = [f32p, ci, ci, ci, f32p, ci, i32p, f32p, f32p, f32p]
+        _LIB.pbo_ambiguity.restype = None
+        _LIB.pbo_risk.argtypes = [f32p, f32p, ci, ci, ci, f64p, ci, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
+        _LIB.pbo_risk.restype = None
     return _LIB
 
 
@@ -418,6 +431,222 @@ def reverse_cost_volume(left_cv: np.ndarray, min_disp: int) -> np.ndarray:
     out = np.empty_like(left_cv)
     lib().pbo_reverse_cost_volume(_p(left_cv, ctypes.c_float), H, W, D, int(min_disp), _p(out, ctypes.c_float))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# input masks and variable disparity grids.
+# criteria.py:36-63, 66-288 ; matching_cost/matching_cost.py:484-602, 770-872 ; cpp/src/criteria.cpp:27-110
+# --------------------------------------------------------------------------------------------
+def binary_dilation_nodata(msk: np.ndarray, no_data: int, window: int) -> np.ndarray:
+    """criteria.py:36-63: scipy.ndimage.binary_dilation of ``msk == no_data`` with a full window x window structure
+    (odd window: the centred square neighbourhood; outside the image counts as background)."""
+    nd = np.asarray(msk) == no_data
+    H, W = nd.shape
+    half = (window - 1) // 2
+    pad = np.zeros((H + 2 * half, W + 2 * half), dtype=bool)
+    pad[half : half + H, half : half + W] = nd
+    out = np.zeros((H, W), dtype=bool)
+    for dy in range(window):
+        for dx in range(window):
+            out |= pad[dy : dy + H, dx : dx + W]
+    return out
+
+
+def partially_missing_variable_ranges(grid_min, grid_max, right_invalid: np.ndarray) -> np.ndarray:
+    """cpp/src/criteria.cpp:27-110: True where [col + dmin, col + dmax] is not inside one run of unmasked right pixels."""
+    right_invalid = np.asarray(right_invalid, dtype=bool)
+    H, W = right_invalid.shape
+    out = np.ones((H, W), dtype=bool)
+    for r in range(H):
+        runs, last = [], True
+        for c in range(W):
+            if right_invalid[r, c] != last:
+                runs.append(c)
+                last = bool(right_invalid[r, c])
+        if not last:
+            runs.append(W)
+        for c in range(W):
+            lo, hi = int(grid_min[r, c]) + c, int(grid_max[r, c]) + c
+            out[r, c] = not any(runs[i] <= lo and hi < runs[i + 1] for i in range(0, len(runs) - 1, 2))
+    return out
+
+
+def validity_mask_with_masks(H: int, W: int, dmin: int, dmax: int, offset: int, window: int, left_msk=None, right_msk=None,
+                             valid_pixels: int = 0, no_data: int = 1, grid_min=None, grid_max=None) -> np.ndarray:
+    """criteria.validity_mask (criteria.py:66-158) with optional left / right ``msk`` (allocate_left_mask :178-213,
+    allocate_right_mask :216-288) and, with a right mask and disparity grids, mask_partially_missing_variable_ranges
+    (:161-175).  ``dmin`` / ``dmax`` are the cost volume's global range."""
+    vm = validity_mask(H, W, dmin, dmax, offset)
+    col = np.arange(W)
+    if dmax < 0:
+        bit_1 = np.where((col + dmax) < offset)[0]
+    elif dmin > 0:
+        bit_1 = np.where((col + dmin) > (W - 1 - offset))[0]
+    else:
+        bit_1 = np.array([], dtype=int)
+    if left_msk is not None:
+        left_msk = np.asarray(left_msk)
+        vm += binary_dilation_nodata(left_msk, no_data, window).astype(np.uint16) * np.uint16(MSK_LEFT_NODATA_OR_BORDER)
+        vm += np.where((left_msk != no_data) & (left_msk != valid_pixels), MSK_IN_VALIDITY_MASK_LEFT, 0).astype(np.uint16)
+    if right_msk is not None:
+        right_msk = np.asarray(right_msk)
+        dil = binary_dilation_nodata(right_msk, no_data, window)
+        r_mask = ((right_msk != no_data) & (right_msk != valid_pixels)).astype(np.int64)
+        b_2_7 = np.zeros((H, W), dtype=np.int64)
+        no_data_right = np.zeros((H, W), dtype=np.int64)
+        nd = dmax - dmin + 1
+        for dsp in range(dmin, dmax + 1):
+            col_d = col + dsp
+            ok = (col_d >= offset) & (col_d <= W - 1 - offset)
+            b_2_7[:, col[ok]] += r_mask[:, col_d[ok]]
+            b_2_7[:, col[~ok]] += 1
+            no_data_right[:, col[ok]] += dil[:, col_d[ok]]
+            no_data_right[:, col[~ok]] += 1
+            b_2_7[:, bit_1] = 0
+            no_data_right[:, bit_1] = 0
+            vm[b_2_7 == nd] += MSK_IN_VALIDITY_MASK_RIGHT
+            vm[no_data_right == nd] += MSK_RIGHT_NODATA_OR_DISPARITY_RANGE_MISSING
+        if grid_min is not None:
+            miss = partially_missing_variable_ranges(grid_min, grid_max, right_msk != valid_pixels)
+            vm[miss] |= MSK_INCOMPLETE_VARIABLE_DISPARITY_RANGE
+    return vm
+
+
+def cv_masked_full(cv: np.ndarray, vm: np.ndarray, offset: int, window: int, dmin: int, left_msk=None, right_msk=None,
+                   valid_pixels: int = 0, no_data: int = 1, grid_min=None, grid_max=None) -> None:
+    """matching_cost.py:770-872 for subpix == 1, step == 1, in place on ``cv`` and ``vm``: NaN for cells whose left pixel
+    or right pixel (col + d) is invalid or has a no_data in its window (masks_dilatation :484-602), NaN outside the
+    per-pixel [grid_min, grid_max], then mask_invalid_variable_disparity_range and mask_border."""
+    H, W, D = cv.shape
+
+    def dilated(msk):
+        out = np.zeros((H, W), dtype=np.float64)
+        if msk is not None:
+            msk = np.asarray(msk)
+            out[(msk != valid_pixels) & (msk != no_data)] = np.nan
+            out[binary_dilation_nodata(msk, no_data, window)] = np.nan
+        return out
+
+    m_left, m_right = dilated(left_msk), dilated(right_msk)
+    for k in range(D):
+        d = dmin + k
+        p0, p1 = max(0 - d, 0), min(W - 1 - d, W - 1)                  # mask_column_interval_without_step :655-708
+        if p0 > p1:
+            continue
+        cv[:, p0 : p1 + 1, k] = (cv[:, p0 : p1 + 1, k] + m_right[:, p0 + d : p1 + d + 1] + m_left[:, p0 : p1 + 1]).astype(np.float32)
+    if grid_min is not None:
+        gmin, gmax = np.asarray(grid_min)[:H, :W], np.asarray(grid_max)[:H, :W]
+        for k in range(D):
+            d = dmin + k
+            cv[:, :, k][(d < gmin) | (d > gmax)] = np.nan
+    cv_masked(cv, vm, offset)
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) rank 2: right disparity map of the fast cross-checking + the consistency check
+# state_machine.py:436-448 ; validation/validation.py:226-371
+# --------------------------------------------------------------------------------------------
+def right_disparity_fast(left_cv: np.ndarray, dmin: int, dmax: int, type_measure: str = "min", invalid_disparity: float = -9999.0):
+    """state_machine.py:438-448: reverse_cost_volume(left_cv, -dmax) followed by WTA on the right disparity range."""
+    right_cv = reverse_cost_volume(left_cv, -dmax)
+    return wta(right_cv, np.arange(-dmax, -dmin + 1), type_measure, invalid_disparity)
+
+
+def cross_checking(disp_left, mask_left, disp_right, threshold: float, dmin: int, dmax: int, offset: int = 0):
+    """CrossCheckingAccurate.disparity_checking, validation/validation.py:226-371, restated line by line (row loop and
+    fancy indexing included).  Returns (updated validity mask, left-right distance map).  ``dmin`` / ``dmax`` = the
+    left map's disparity interval (disparity.py:334-347).  Like the reference it assumes that a pixel whose disparity
+    is NaN is flagged invalid; its "outside the right image" branch (validation.py:355-357) can never fire
+    (``(col_right < 0) & (col_right >= nb_col)``) and is restated as such."""
+    disp_left = np.asarray(disp_left, dtype=np.float32)
+    disp_right = np.asarray(disp_right, dtype=np.float32)
+    vm = np.array(mask_left, dtype=np.uint16, copy=True)
+    nb_row, nb_col = disp_left.shape
+    disparity_range = np.arange(dmin, dmax + 1)
+    conf = np.full((nb_row, nb_col), np.nan, dtype=np.float32)
+    thr = np.float32(threshold)
+    for row in range(nb_row):
+        valid_pixel = np.where((vm[row, :] & MSK_INVALID) == 0)
+        col_left = np.arange(nb_col, dtype=np.int64)[valid_pixel]
+        col_right = col_left + disp_left[row, col_left]
+        col_right = col_right[np.logical_not(np.isnan(col_right))]
+        col_right = np.rint(col_right).astype(int)
+        inside_right = np.where((col_right >= 0) & (col_right < nb_col))
+        right_disp = disp_right[row, col_right[inside_right]]
+        right_disp[np.isnan(right_disp)] = np.inf
+        left_disp = disp_left[row, col_left[inside_right]]
+        left_disp[np.isnan(left_disp)] = np.inf
+        conf[row, col_left[inside_right]] = np.abs(right_disp + left_disp)
+        invalid = np.abs(right_disp + left_disp) > thr
+        cols_inv = col_left[inside_right][invalid]
+        index = np.tile(disparity_range, (len(cols_inv), 1)).astype(np.float32) + np.tile(cols_inv, (len(disparity_range), 1)).transpose()
+        inside_col_disp = np.where((index >= 0) & (index < nb_col))
+        dr = np.full(index.shape, np.inf, dtype=np.float32)
+        dr[inside_col_disp] = disp_right[row, index[inside_col_disp].astype(int)]
+        comp = np.rint(dr) == np.tile(-1 * disparity_range, (len(cols_inv), 1)).astype(np.float32)
+        comp = np.sum(comp, axis=1)
+        comp[comp > 1] = 1
+        vm[row, cols_inv] += np.uint16(MSK_OCCLUSION)
+        vm[row, cols_inv] += (MSK_MISMATCH * comp).astype(np.uint16)
+        vm[row, cols_inv] -= (MSK_OCCLUSION * comp).astype(np.uint16)
+    if offset > 0:
+        vm[:offset, :] = MSK_LEFT_NODATA_OR_BORDER
+        vm[-offset:, :] = MSK_LEFT_NODATA_OR_BORDER
+        vm[offset:-offset, :offset] = MSK_LEFT_NODATA_OR_BORDER
+        vm[offset:-offset, -offset:] = MSK_LEFT_NODATA_OR_BORDER
+    return vm, conf
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) rank 3: sub-pixel refinement (refinement/refinement.py:78-181 + refinement/cpp/src/*.cpp)
+# --------------------------------------------------------------------------------------------
+def refinement(cv, disp, mask, d_min: float, d_max: float, subpix: int = 1, type_measure: str = "min", method: str = "vfit",
+               approximate: bool = False):
+    """loop_refinement / loop_approximate_refinement with vfit or quadratic.  Returns (itp_coeff, disp, mask) like the
+    reference's C++ (refinement.cpp:29-181); inputs are not modified."""
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    disp = np.array(disp, dtype=np.float32, copy=True)
+    mask = np.array(mask, dtype=np.uint16, copy=True)
+    itp = np.empty((H, W), dtype=np.float32)
+    lib().pbo_refinement(_p(cv, ctypes.c_float), H, W, D, float(d_min), float(d_max), int(subpix), int(type_measure == "max"),
+                         {"vfit": 0, "quadratic": 1}[method], int(bool(approximate)), _p(disp, ctypes.c_float),
+                         _p(mask, ctypes.c_uint16), _p(itp, ctypes.c_float))
+    return itp, disp, mask
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) rank 4: cost-volume confidence (cost_volume_confidence/cpp/src/{ambiguity,risk}.cpp)
+# --------------------------------------------------------------------------------------------
+def ambiguity(cv, etas, grids, disparity_range_, sampled: bool = False):
+    """compute_ambiguity_and_sampled_ambiguity (ambiguity.cpp:28-142) on a min-type volume; etas are cast to float32
+    like the pybind11 signature does.  grids = (2, H, W) integer [disp_min, disp_max] per pixel."""
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    et = _f32(etas)
+    gr = np.ascontiguousarray(grids, dtype=np.int32)
+    dr = _f32(disparity_range_)
+    amb = np.empty((H, W), dtype=np.float32)
+    samp = np.empty((H, W, len(et)), dtype=np.float32) if sampled else None
+    lib().pbo_ambiguity(_p(cv, ctypes.c_float), H, W, D, _p(et, ctypes.c_float), len(et), _p(gr, ctypes.c_int32), _p(dr, ctypes.c_float),
+                        _p(amb, ctypes.c_float), _p(samp, ctypes.c_float) if sampled else None)
+    return (amb, samp) if sampled else amb
+
+
+def risk(cv, sampled_ambiguity, etas, grids, disparity_range_, sampled: bool = False):
+    """compute_risk_and_sampled_risk (risk.cpp:28-197): returns (risk_max, risk_min, disp_sup, disp_inf[, samp_max, samp_min])."""
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    sa = _f32(sampled_ambiguity)
+    et = np.ascontiguousarray(etas, dtype=np.float64)
+    gr = np.ascontiguousarray(grids, dtype=np.int32)
+    dr = _f32(disparity_range_)
+    outs = [np.empty((H, W), dtype=np.float32) for _ in range(4)]
+    samp = [np.empty((H, W, len(et)), dtype=np.float32) for _ in range(2)] if sampled else [None, None]
+    lib().pbo_risk(_p(cv, ctypes.c_float), _p(sa, ctypes.c_float), H, W, D, _p(et, ctypes.c_double), len(et), _p(gr, ctypes.c_int32),
+                   _p(dr, ctypes.c_float), *[_p(o, ctypes.c_float) for o in outs],
+                   *[(_p(o, ctypes.c_float) if o is not None else None) for o in samp])
+    return tuple(outs) + (tuple(samp) if sampled else ())
 
 
 # --------------------------------------------------------------------------------------------

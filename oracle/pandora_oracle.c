@@ -340,3 +340,203 @@ PBO_API void pbo_wta(const float *cv, int H, int W, int D, const float *disp_coo
         if (all_nan) all_nan[p] = (uint8_t)!any;
     }
 }
+
+/* ========================================================================================== */
+/* SURVEY.md 8(f) "next" rows: sub-pixel refinement, cost-volume confidence                     */
+/* All pinned to the reference's golden vectors (tests/test_refinement.py, tests/test_confidence) */
+/* and to the compiled reference C++ (oracle/_ref: refinement_cpp, cost_volume_confidence_cpp). */
+/* ========================================================================================== */
+
+#define PBO_MSK_INVALID 0x3C3               /* src/pandora/constants.py:28 */
+#define PBO_MSK_STOPPED_INTERPOLATION 8     /* src/pandora/constants.py:36 */
+
+/* validate_costs_and_get_variables: src/pandora/refinement/cpp/src/refinement_tools.cpp:25-56 */
+static int refine_valid(float c0, float c1, float c2, int is_max, float *ic0, float *ic2) {
+    if (isnan(c0) || isnan(c2)) return 0;
+    const float inverse = is_max ? -1.f : 1.f;
+    const float i0 = inverse * c0, i1 = inverse * c1, i2 = inverse * c2;
+    if (i1 > i0 || i1 > i2) return 0;
+    *ic0 = i0;
+    *ic2 = i2;
+    return 1;
+}
+
+/* vfit_refinement_method: refinement/cpp/src/vfit.cpp:28-55;  quadratic_refinement_method:
+ * refinement/cpp/src/quadratic.cpp:28-49.  method 0 = vfit, 1 = quadratic.  Returns the mask increment. */
+static int refine_method(int method, float c0, float c1, float c2, int is_max, float *sub_disp, float *sub_cost) {
+    float ic0 = 0.f, ic2 = 0.f;
+    if (!refine_valid(c0, c1, c2, is_max, &ic0, &ic2)) {
+        *sub_disp = 0.f;
+        *sub_cost = c1;
+        return PBO_MSK_STOPPED_INTERPOLATION;
+    }
+    if (method == 0) {
+        const float a = ic0 > ic2 ? c0 - c1 : c2 - c1;
+        if (fabs((double)a) < 1.0e-15) {
+            *sub_disp = 0.f;
+            *sub_cost = c1;
+            return 0;
+        }
+        const float sd = (c0 - c2) / (2 * a);
+        *sub_disp = sd;
+        *sub_cost = a * (sd - 1) + c2;
+        return 0;
+    }
+    const float alpha = (c0 - 2.f * c1 + c2) / 2.f;
+    const float beta = (c2 - c0) / 2.f;
+    const float q = -beta / (2.f * alpha);
+    const float lo = (-1.f < q) ? q : -1.f;          /* std::max(-1.f, q) */
+    const float sd = (lo < 1.f) ? lo : 1.f;          /* std::min(1.f, lo) */
+    *sub_disp = sd;
+    *sub_cost = (alpha * sd * sd) + (beta * sd) + c1;
+    return 0;
+}
+
+/* loop_refinement (approx == 0): refinement/cpp/src/refinement.cpp:29-106;
+ * loop_approximate_refinement (approx != 0): refinement.cpp:109-181.
+ * disp (H, W) float32 and mask (H, W) uint16 are updated in place, itp (H, W) receives the interpolated costs.
+ * Cells the reference would read out of bounds (undefined behaviour there) give itp = NaN and leave the pixel. */
+PBO_API void pbo_refinement(const float *cv, int H, int W, int D, double d_min, double d_max, int subpix, int is_max,
+                            int method, int approx, float *disp, uint16_t *mask, float *itp) {
+    for (int row = 0; row < H; ++row)
+        for (int col = 0; col < W; ++col) {
+            const size_t i = (size_t)row * W + col;
+            if ((mask[i] & PBO_MSK_INVALID) != 0) { itp[i] = NAN; continue; }
+            const float raw = disp[i];
+            int dsp, diag = col;
+            if (!approx) dsp = (int)((raw - d_min) * subpix);
+            else { dsp = (int)((-raw - d_min) * subpix); diag = (int)((float)col + raw); }
+            if (dsp < 0 || dsp >= D || diag < 0 || diag >= W) { itp[i] = NAN; continue; }
+            const float *pc = cv + ((size_t)row * W + diag) * D;
+            const float c1 = pc[dsp];
+            if (isnan(c1)) { itp[i] = c1; continue; }
+            if (raw == d_min || raw == d_max || (approx && (diag == 0 || diag == W - 1))) {
+                itp[i] = c1;
+                mask[i] = (uint16_t)(mask[i] + PBO_MSK_STOPPED_INTERPOLATION);
+                continue;
+            }
+            float c0, c2;
+            if (!approx) {
+                if (dsp - 1 < 0 || dsp + 1 >= D) { itp[i] = NAN; continue; }
+                c0 = pc[dsp - 1]; c2 = pc[dsp + 1];
+            } else {
+                if (dsp + subpix >= D || dsp - subpix < 0) { itp[i] = NAN; continue; }
+                c0 = pc[-D + dsp + subpix]; c2 = pc[D + dsp - subpix];
+            }
+            float sd, sc;
+            const int flag = refine_method(method, c0, c1, c2, is_max, &sd, &sc);
+            disp[i] = raw + sd / (float)subpix;
+            itp[i] = sc;
+            mask[i] = (uint16_t)(mask[i] + flag);
+        }
+}
+
+/* searchsorted: cost_volume_confidence/cpp/src/cost_volume_confidence_tools.cpp:22-38 */
+static size_t pbo_searchsorted(const float *arr, int n, float value) {
+    size_t left = 0, right = (size_t)n - 1;
+    while (left < right) {
+        const size_t mid = left + (right - left) / 2;
+        if (arr[mid] < value) left = mid + 1; else right = mid;
+    }
+    return left;
+}
+
+/* min_max_cost: cost_volume_confidence_tools.cpp:40-87 (per-pixel minimum image + global extrema) */
+static void pbo_min_max(const float *cv, int H, int W, int D, float *min_img, float *gmin, float *gmax) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t p = 0; p < (size_t)H * W; ++p) {
+        float pmin = INFINITY, pmax = -INFINITY;
+        int all_nan = 1;
+        for (int k = 0; k < D; ++k) {
+            const float v = cv[p * D + k];
+            if (!isnan(v)) { all_nan = 0; if (v < pmin) pmin = v; if (v > pmax) pmax = v; }
+        }
+        if (all_nan) { min_img[p] = NAN; continue; }
+        min_img[p] = pmin;
+        if (pmin < mn) mn = pmin;
+        if (pmax > mx) mx = pmax;
+    }
+    *gmin = mn; *gmax = mx;
+}
+
+/* normalised costs of one pixel with the +-inf convention of ambiguity.cpp:97-116 / risk.cpp:113-126 */
+static void pbo_normalise(const float *pc, int D, float gmin, float diff, size_t imin, size_t imax, float *out) {
+    for (int k = 0; k < D; ++k) {
+        const float v = pc[k];
+        if (isnan(v)) out[k] = ((size_t)k >= imin && (size_t)k < imax) ? -INFINITY : INFINITY;
+        else out[k] = (v - gmin) / diff;
+    }
+}
+
+/* compute_ambiguity_and_sampled_ambiguity: cost_volume_confidence/cpp/src/ambiguity.cpp:28-142.
+ * grids (2, H, W) int32 = per-pixel [disp_min, disp_max]; etas float32; samp (H, W, n_etas) may be NULL. */
+PBO_API void pbo_ambiguity(const float *cv, int H, int W, int D, const float *etas, int n_etas, const int32_t *grids,
+                           const float *disparity_range, float *amb, float *samp) {
+    float *min_img = (float *)malloc((size_t)H * W * sizeof(float));
+    float *norm = (float *)malloc((size_t)D * sizeof(float));
+    float gmin, gmax;
+    pbo_min_max(cv, H, W, D, min_img, &gmin, &gmax);
+    const float diff = gmax - gmin;
+    for (size_t p = 0; p < (size_t)H * W; ++p) {
+        const float ext = (min_img[p] - gmin) / diff;
+        if (isnan(ext)) {
+            amb[p] = (float)(n_etas * D);
+            if (samp) for (int e = 0; e < n_etas; ++e) samp[p * n_etas + e] = (float)D;
+            continue;
+        }
+        const size_t imin = pbo_searchsorted(disparity_range, D, (float)grids[p]);
+        const size_t imax = pbo_searchsorted(disparity_range, D, (float)grids[(size_t)H * W + p]) + 1;
+        pbo_normalise(cv + p * D, D, gmin, diff, imin, imax, norm);
+        float amb_sum = 0;
+        for (int e = 0; e < n_etas; ++e) {
+            float s = 0;
+            for (int k = 0; k < D; ++k) s += (norm[k] <= (ext + etas[e])) ? 1.f : 0.f;
+            amb_sum += s;
+            if (samp) samp[p * n_etas + e] = s;
+        }
+        amb[p] = amb_sum;
+    }
+    free(min_img);
+    free(norm);
+}
+
+/* compute_risk_and_sampled_risk: cost_volume_confidence/cpp/src/risk.cpp:28-197.  etas are DOUBLE here
+ * (risk.hpp takes array_t<double>), so the threshold comparison happens in double precision. */
+PBO_API void pbo_risk(const float *cv, const float *samp_amb, int H, int W, int D, const double *etas, int n_etas,
+                      const int32_t *grids, const float *disparity_range, float *risk_max, float *risk_min,
+                      float *disp_sup, float *disp_inf, float *samp_risk_max, float *samp_risk_min) {
+    float *min_img = (float *)malloc((size_t)H * W * sizeof(float));
+    float *norm = (float *)malloc((size_t)D * sizeof(float));
+    float gmin, gmax;
+    pbo_min_max(cv, H, W, D, min_img, &gmin, &gmax);
+    const float diff = gmax - gmin;
+    for (size_t p = 0; p < (size_t)H * W; ++p) {
+        const float ext = (min_img[p] - gmin) / diff;
+        if (isnan(ext)) {
+            risk_min[p] = risk_max[p] = disp_inf[p] = disp_sup[p] = NAN;
+            if (samp_risk_max) for (int e = 0; e < n_etas; ++e) samp_risk_min[p * n_etas + e] = samp_risk_max[p * n_etas + e] = NAN;
+            continue;
+        }
+        const size_t imin = pbo_searchsorted(disparity_range, D, (float)grids[p]);
+        const size_t imax = pbo_searchsorted(disparity_range, D, (float)grids[(size_t)H * W + p]) + 1;
+        pbo_normalise(cv + p * D, D, gmin, diff, imin, imax, norm);
+        float s_min = 0, s_max = 0, s_inf = 0, s_sup = 0;
+        for (int e = 0; e < n_etas; ++e) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int k = 0; k < D; ++k) {
+                if (norm[k] > (ext + etas[e])) continue;
+                if ((float)k < lo) lo = (float)k;
+                if ((float)k > hi) hi = (float)k;
+            }
+            const float dlo = disparity_range[(int)lo], dhi = disparity_range[(int)hi];
+            const float e_max = hi - lo;
+            const float e_min = 1 + e_max - samp_amb[p * n_etas + e];
+            s_sup += dhi; s_inf += dlo; s_min += e_min; s_max += e_max;
+            if (samp_risk_max) { samp_risk_min[p * n_etas + e] = e_min; samp_risk_max[p * n_etas + e] = e_max; }
+        }
+        risk_min[p] = s_min / n_etas; risk_max[p] = s_max / n_etas;
+        disp_sup[p] = s_sup / n_etas; disp_inf[p] = s_inf / n_etas;
+    }
+    free(min_img);
+    free(norm);
+}

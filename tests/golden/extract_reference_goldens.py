@@ -10,7 +10,9 @@ the file:line provenance of every key) and is what ``tests/test_oracle_goldens.p
 oracle against.
 
 Key format:  ``<relative test file>::<function or Class.method>::<variable>[#n]``
-(``#n`` = n-th re-assignment of the same name inside the function, 0-based, omitted for the first),
+(``#n`` = n-th re-assignment of the same name inside the function, 0-based, omitted for the first;
+``@k`` = k-th numpy literal nested inside a right-hand side that is not itself a pure literal, e.g. the arrays
+inside an ``xr.Dataset(...)`` call, in ``ast.walk`` order),
 and for parametrised tests ``<file>::<function>[<case index>]::<argname>``.
 """
 from __future__ import annotations
@@ -39,6 +41,12 @@ TARGETS = [
     ("test_disparity.py", "*"),
     ("test_filter.py", "*"),
     ("test_criteria.py", "*"),
+    # SURVEY.md 8(f) "next" rows: refinement, cross-checking, confidence
+    ("test_refinement.py", "*"),
+    ("test_validation.py", "*"),
+    ("test_confidence/conftest.py", "*"),
+    ("test_confidence/test_ambiguity.py", "*"),
+    ("test_confidence/test_risk.py", "*"),
 ]
 
 
@@ -99,6 +107,23 @@ def _walk_function(fn, qual, relfile, out, prov, module_env):
                 try:
                     val = _eval(st.value, env)
                 except Exception:
+                    # not a pure literal (e.g. ``xr.Dataset({... np.array([...]) ...})``): keep the numpy literals
+                    # nested inside it, in source order, as ``<name>@<k>``
+                    k = 0
+                    for sub in ast.walk(st.value):
+                        if isinstance(sub, ast.Call) and ast.unparse(sub.func) in ("np.array", "np.asarray", "np.full", "np.arange"):
+                            try:
+                                sval = _eval(sub, env)
+                            except Exception:
+                                continue
+                            if _storable(sval):
+                                n = seen.get(name, 0)
+                                key = f"{relfile}::{qual}::{name}" + (f"#{n}" if n else "") + f"@{k}"
+                                out[key] = np.asarray(sval)
+                                prov[key] = f"tests/{relfile}:{sub.lineno}"
+                                k += 1
+                    if k:
+                        seen[name] = seen.get(name, 0) + 1
                     continue
                 env[name.replace("self.", "self_")] = val
                 if isinstance(st.targets[0], ast.Name):
@@ -140,6 +165,22 @@ def _parametrize(fn, qual, relfile, out, prov, module_env):
                     key = f"{relfile}::{qual}[{i}]::{nm}"
                     out[key] = np.asarray(val)
                     prov[key] = f"tests/{relfile}:{dec.lineno}"
+                elif isinstance(val, dict):
+                    # a parameter dictionary (e.g. the masks of TestCvMasked): ``<argname>.<key>[.<subkey>]``
+                    def store(prefix, dic):
+                        for dk, dv in dic.items():
+                            if isinstance(dv, dict):
+                                store(f"{prefix}.{dk}", dv)
+                            elif _storable(dv):
+                                key = f"{relfile}::{qual}[{i}]::{prefix}.{dk}"
+                                out[key] = np.asarray(dv)
+                                prov[key] = f"tests/{relfile}:{dec.lineno}"
+                            elif isinstance(dv, str):
+                                key = f"{relfile}::{qual}[{i}]::{prefix}.{dk}"
+                                out[key] = np.frombuffer(dv.encode(), dtype=np.uint8)
+                                prov[key] = f"tests/{relfile}:{dec.lineno}"
+
+                    store(nm, val)
 
 
 def _reference_constants():
@@ -162,7 +203,7 @@ def main():
     for relfile, want in TARGETS:
         path = os.path.join(REF_TESTS, relfile)
         tree = ast.parse(open(path).read())
-        module_env = {"np": np, "pytest": _FakePytest, "n": np.nan, "cst": cst}
+        module_env = {"np": np, "pytest": _FakePytest, "n": np.nan, "cst": cst, "Affine": lambda *a, **k: None}
         # module-level simple constants (e.g. ``n = np.nan``)
         for st in tree.body:
             if isinstance(st, ast.Assign) and len(st.targets) == 1 and isinstance(st.targets[0], ast.Name):
