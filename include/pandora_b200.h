@@ -158,6 +158,75 @@ PB200_API int pb200_validity_mask_init(uint16_t *d_mask, int H, int W, int dmin,
 PB200_API int pb200_validity_mask(uint16_t *d_mask, const uint8_t *d_all_nan, int H, int W, int offset, int wta_invalidate,
                         void *stream);
 
+/* ---- input masks and per-pixel disparity grids ---------------------------- */
+/* One byte of flags per pixel from an image mask `msk` (int16, (H, W)): bit 0 = a no_data pixel lies inside the
+ * window x window neighbourhood (binary_dilation_msk, criteria.py:36-63), bit 1 = neither valid_pixels nor no_data
+ * (masks_dilatation, matching_cost/matching_cost.py:527-553), bit 2 = msk != valid_pixels (criteria.py:171). */
+PB200_API int pb200_mask_flags(const int16_t *d_msk, int H, int W, int valid_pixels, int no_data, int window, uint8_t *d_flags,
+                     void *stream);
+
+/* criteria.validity_mask with image masks: adds to a mask initialised by pb200_validity_mask_init the bits of
+ * allocate_left_mask (criteria.py:178-213; d_flags_left may be NULL), allocate_right_mask (criteria.py:216-288;
+ * d_flags_right may be NULL) and, when a right mask and the (H, W) float32 disparity grids are given,
+ * mask_partially_missing_variable_ranges (criteria.py:161-175, cpp/src/criteria.cpp:27-110; needs grid_min <= grid_max). */
+PB200_API int pb200_validity_mask_masks(uint16_t *d_mask, int H, int W, int dmin, int dmax, int offset, const uint8_t *d_flags_left,
+                              const uint8_t *d_flags_right, const float *d_grid_min, const float *d_grid_max, void *stream);
+
+/* The masking part of cv_masked (matching_cost/matching_cost.py:815-856, subpix 1, step 1), in place: cell (y, x, k)
+ * becomes NaN when the left pixel or the right pixel x + dmin + k carries flag bit 0 or 1 (only where that column is
+ * inside the image), or when dmin + k lies outside [grid_min(y,x), grid_max(y,x)].  Flags / grids may be NULL.
+ * d_all_nan (optional) receives 1 for pixels whose whole vector is NaN afterwards -- the input of
+ * pb200_validity_mask(..., wta_invalidate = 0), which finishes cv_masked (criteria.py:291-353). */
+PB200_API int pb200_cv_masked(float *d_cv, int H, int W, int D, int dmin, const uint8_t *d_flags_left, const uint8_t *d_flags_right,
+                    const float *d_grid_min, const float *d_grid_max, uint8_t *d_all_nan, void *stream);
+
+/* ---- fast cross-checking -------------------------------------------------- */
+/* Right disparity map straight from the LEFT volume: WTA over right(i, j, k) = left(i, j + k + min_disp_right, D-1-k)
+ * without materialising the right volume (replaces reverse_cost_volume, matching_cost.cpp:26-57, followed by
+ * WinnerTakesAll.to_disp as run by state_machine.py:436-448).  d_disp[i, j] = min_disp_right + argmin_k (argmax when
+ * is_max), first index on ties, invalid_disparity when every k is NaN (d_all_nan, optional, flags those).
+ * Needs D % 4 == 0, D <= 992 and a 16-byte aligned volume; otherwise PB200_ERR_UNSUPPORTED (use
+ * pb200_reverse_cost_volume + pb200_wta). */
+PB200_API int pb200_wta_right(const float *d_left_cv, int H, int W, int D, int min_disp_right, int is_max, float invalid_disparity,
+                    float *d_disp, uint8_t *d_all_nan, void *stream);
+
+/* CrossCheckingAccurate.disparity_checking (validation/validation.py:226-371): for every valid left pixel whose match
+ * rint(x + disp_left) lies inside the right map, distance = abs(disp_right + disp_left) goes to d_conf (NaN elsewhere;
+ * d_conf may be NULL) and, when distance > threshold, the pixel gets PANDORA_MSK_PIXEL_MISMATCH if some d in
+ * [dmin, dmax] has rint(disp_right(x + d)) == -d, else PANDORA_MSK_PIXEL_OCCLUSION.  offset > 0 re-applies
+ * mask_border (criteria.py:325-353).  d_mask_left is updated in place. */
+PB200_API int pb200_cross_checking(const float *d_disp_left, uint16_t *d_mask_left, const float *d_disp_right, int H, int W,
+                         float threshold, int dmin, int dmax, int offset, float *d_conf, void *stream);
+
+/* ---- sub-pixel refinement -------------------------------------------------- */
+/* loop_refinement (approximate == 0) / loop_approximate_refinement (approximate != 0), refinement/cpp/src/
+ * refinement.cpp:29-181, with method 0 = vfit (vfit.cpp:28-55) or 1 = quadratic (quadratic.cpp:28-49).
+ * d_min / d_max = first / last disparity coordinate of the volume, subpix = cv.attrs["subpixel"].
+ * approximate == 2: loop_refinement of a RIGHT disparity map on the reversed volume right(i, j, k) =
+ * left(i, j + k + d_min, D-1-k) read straight from the LEFT volume d_cv (the right refinement of the
+ * cross_checking_fast mode, state_machine.py:488-490, without the right volume); d_min / d_max are then the right
+ * coordinates (-dmax_left, -dmin_left) and subpix must be 1.
+ * d_disp (H, W) float32 and d_mask (H, W) uint16 are updated in place; d_itp_coeff (H, W) gets the interpolated cost. */
+PB200_API int pb200_refinement(const float *d_cv, int H, int W, int D, double d_min, double d_max, int subpix, int is_max, int method,
+                     int approximate, float *d_disp, uint16_t *d_mask, float *d_itp_coeff, void *stream);
+
+/* ---- cost-volume confidence ------------------------------------------------ */
+PB200_API size_t pb200_confidence_workspace_bytes(int H, int W, int n_etas);
+
+/* Ambiguity (cost_volume_confidence/cpp/src/ambiguity.cpp:28-142) and risk (risk.cpp:28-197) in one pass over the
+ * volume (plus one pass for the global extrema, cost_volume_confidence_tools.cpp:40-87).  `etas` is a HOST array
+ * (np.arange(eta_min, eta_max, eta_step): non-negative, non-decreasing; ambiguity compares in float32, risk in
+ * float64 like the reference).  d_grids: (2, H, W) int32 per-pixel [disp_min, disp_max] or NULL (whole range);
+ * d_disparity_range: (D) float32 device array.  is_max negates the volume on the fly (ambiguity.py:135-137).
+ * Outputs, each optional: d_ambiguity (H, W); d_sampled_ambiguity (H, W, n_etas); the four risk maps (together);
+ * sampled risks (H, W, n_etas, together).  d_sampled_ambiguity_in: the sampled ambiguity risk.cpp takes as input,
+ * NULL = the one computed by this call (what Risk.confidence_prediction does, risk.py:141-153). */
+PB200_API int pb200_confidence(const float *d_cv, int H, int W, int D, int is_max, const double *etas, int n_etas,
+                     const int32_t *d_grids, const float *d_disparity_range, float *d_ambiguity, float *d_sampled_ambiguity,
+                     const float *d_sampled_ambiguity_in, float *d_risk_max, float *d_risk_min, float *d_disp_sup,
+                     float *d_disp_inf, float *d_sampled_risk_max, float *d_sampled_risk_min, void *d_workspace,
+                     size_t workspace_bytes, void *stream);
+
 /* ---- host-buffer entry points (what a reference-side binding calls; synchronous) --------------- */
 /* compute_matching_costs(img_left, [img_right], cv, disps, w, w): dmin = lround(disps[0]) (census.cpp:109). */
 PB200_API int pb200_census_cost_volume_host(const float *left, const float *right, int H, int W, int window,

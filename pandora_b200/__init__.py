@@ -15,5 +15,9 @@ from .disparity import AbstractDisparity, WinnerTakesAll  # noqa: F401
 from .matching_cost import AbstractMatchingCost, Census, SadSsd, Zncc  # noqa: F401
 from .optimization import AbstractOptimization, Sgm  # noqa: F401
 from .pipeline import StereoPipeline, run  # noqa: F401
+from .refinement import AbstractRefinement, Quadratic, Vfit  # noqa: F401
+from .validation import AbstractValidation, CrossCheckingAccurate, right_disparity_fast  # noqa: F401
+from .cost_volume_confidence import AbstractCostVolumeConfidence, Ambiguity, Risk  # noqa: F401
+from .criteria import validity_mask  # noqa: F401
 
 __version__ = "0.1.0"

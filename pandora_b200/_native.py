@@ -37,7 +37,7 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
-_vp, _ci, _cf, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_vp, _ci, _cf, _sz, _cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/pandora_b200.h one to one
 PROTOTYPES = {
@@ -61,6 +61,14 @@ PROTOTYPES = {
     "pb200_wta": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _cf, _vp, _vp, _vp]),
     "pb200_validity_mask_init": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp]),
     "pb200_validity_mask": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _vp]),
+    "pb200_mask_flags": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp]),
+    "pb200_validity_mask_masks": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp]),
+    "pb200_cv_masked": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pb200_wta_right": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _cf, _vp, _vp, _vp]),
+    "pb200_cross_checking": (_ci, [_vp, _vp, _vp, _ci, _ci, _cf, _ci, _ci, _ci, _vp, _vp]),
+    "pb200_refinement": (_ci, [_vp, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp]),
+    "pb200_confidence_workspace_bytes": (_sz, [_ci, _ci, _ci]),
+    "pb200_confidence": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb200_census_cost_volume_host": (_ci, [_vp, _vp, _ci, _ci, _ci, _vp, _ci, _vp]),
     "pb200_reverse_cost_volume_host": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp]),
     "pb200_cross_support_host": (_ci, [_vp, _ci, _ci, _ci, _cf, _vp]),

@@ -68,6 +68,7 @@ class WinnerTakesAll(AbstractDisparity):
         disp = disp_t.cpu().numpy()
         out = Dataset({"disparity_map": (("row", "col"), disp)},
                       coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=cv.attrs)
+        out["disparity_interval"] = (("disparity",), np.asarray(disps)[[0, -1]])                # disparity.py:301-315, 456
         cv["disp_indices"] = (("row", "col"), disp.copy())
         if "validity_mask" in cv:
             mask_t = eng.to_device(np.ascontiguousarray(cv["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)

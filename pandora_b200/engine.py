@@ -192,6 +192,13 @@ class Engine:
                                              _ptr(flags), self._stream()))
         return disp, flags
 
+    def validity_mask_init(self, H: int, W: int, dmin: int, dmax: int, offset: int) -> torch.Tensor:
+        """criteria.validity_mask without image masks (criteria.py:106-147): the per-column disparity-range bits."""
+        mask = self.empty((H, W), torch.int16)           # uint16 bit flags stored in an int16 tensor
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_validity_mask_init(_ptr(mask), H, W, int(dmin), int(dmax), int(offset), self._stream()))
+        return mask
+
     def validity_mask(self, H: int, W: int, dmin: int, dmax: int, offset: int, flags: Optional[torch.Tensor] = None,
                       wta_invalidate: bool = False, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         with torch.cuda.device(self.device):
@@ -201,3 +208,107 @@ class Engine:
             _native.check(self.lib.pb200_validity_mask(_ptr(mask), _ptr(flags), H, W, int(offset), int(wta_invalidate),
                                                        self._stream()))
         return mask
+
+    # ---- input masks / disparity grids -------------------------------------------
+    def mask_flags(self, msk, valid_pixels: int, no_data: int, window: int) -> torch.Tensor:
+        """Per-pixel flag byte of an image mask (dilated no_data | invalid | not valid), criteria.py:36-63."""
+        host = np.ascontiguousarray(np.asarray(msk), dtype=np.int16)
+        H, W = host.shape
+        d_msk = torch.from_numpy(host).to(self.device)
+        flags = self.empty((H, W), torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_mask_flags(_ptr(d_msk), H, W, int(valid_pixels), int(no_data), int(window), _ptr(flags), self._stream()))
+        return flags
+
+    def validity_mask_masks(self, mask: torch.Tensor, dmin: int, dmax: int, offset: int, flags_left=None, flags_right=None,
+                            grid_min=None, grid_max=None) -> torch.Tensor:
+        H, W = (int(s) for s in mask.shape)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_validity_mask_masks(_ptr(mask), H, W, int(dmin), int(dmax), int(offset), _ptr(flags_left),
+                                                             _ptr(flags_right), _ptr(grid_min), _ptr(grid_max), self._stream()))
+        return mask
+
+    def cv_masked(self, cv: torch.Tensor, dmin: int, flags_left=None, flags_right=None, grid_min=None, grid_max=None) -> torch.Tensor:
+        """In-place masking of the volume (matching_cost.py:815-856); returns the all-NaN flags (H, W) uint8."""
+        H, W, D = (int(s) for s in cv.shape)
+        all_nan = self.empty((H, W), torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_cv_masked(_ptr(cv), H, W, D, int(dmin), _ptr(flags_left), _ptr(flags_right), _ptr(grid_min),
+                                                   _ptr(grid_max), _ptr(all_nan), self._stream()))
+        return all_nan
+
+    # ---- fast cross-checking (SURVEY.md 8f rank 2) --------------------------------------------------------
+    def wta_right(self, left_cv: torch.Tensor, min_disp_right: int, is_max: bool = False, invalid_disparity: float = -9999.0):
+        """Right disparity map from the LEFT volume (no right volume is materialised); falls back to
+        reverse_cost_volume + wta only for shapes the fused kernel does not take (D % 4 != 0, D > 992)."""
+        H, W, D = (int(s) for s in left_cv.shape)
+        if D % 4 != 0 or D > 992 or left_cv.data_ptr() % 16 != 0:
+            return self.wta(self.reverse_cost_volume(left_cv, min_disp_right), min_disp_right, is_max, invalid_disparity)
+        disp = self.empty((H, W))
+        flags = self.empty((H, W), torch.uint8)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_wta_right(_ptr(left_cv), H, W, D, int(min_disp_right), int(is_max), float(invalid_disparity),
+                                                   _ptr(disp), _ptr(flags), self._stream()))
+        return disp, flags
+
+    def cross_checking(self, disp_left: torch.Tensor, mask_left: torch.Tensor, disp_right: torch.Tensor, threshold: float, dmin: int,
+                       dmax: int, offset: int = 0):
+        """validation.py:226-371; ``mask_left`` (int16 storage of the uint16 flags) is updated in place; returns the
+        left-right distance map."""
+        H, W = (int(s) for s in disp_left.shape)
+        conf = self.empty((H, W))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_cross_checking(_ptr(disp_left), _ptr(mask_left), _ptr(disp_right), H, W,
+                                                        float(np.float32(threshold)), int(dmin), int(dmax), int(offset), _ptr(conf),
+                                                        self._stream()))
+        return conf
+
+    # ---- sub-pixel refinement (SURVEY.md 8f rank 3) --------------------------------------------------------
+    def refinement(self, cv: torch.Tensor, disp: torch.Tensor, mask: torch.Tensor, d_min: float, d_max: float, subpix: int = 1,
+                   is_max: bool = False, method: str = "vfit", approximate=False) -> torch.Tensor:
+        """``disp`` (float32) and ``mask`` (int16 storage) are refined in place; returns the interpolated coefficients.
+        ``approximate``: False / 0 = the volume's own map, True / 1 = loop_approximate_refinement, 2 = right map refined
+        on the reversed volume read from the LEFT one (d_min / d_max = right coordinates)."""
+        H, W, D = (int(s) for s in cv.shape)
+        itp = self.empty((H, W))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_refinement(_ptr(cv), H, W, D, float(d_min), float(d_max), int(subpix), int(is_max),
+                                                    {"vfit": 0, "quadratic": 1}[method], int(approximate), _ptr(disp), _ptr(mask),
+                                                    _ptr(itp), self._stream()))
+        return itp
+
+    # ---- cost-volume confidence (SURVEY.md 8f rank 4) -------------------------------------------------------
+    def confidence(self, cv: torch.Tensor, etas, grids=None, disparity_range=None, is_max: bool = False, ambiguity: bool = True,
+                   sampled_ambiguity: bool = False, risk: bool = False, sampled_risk: bool = False, sampled_ambiguity_in=None) -> dict:
+        """Ambiguity and / or risk of a volume in one pass (ambiguity.cpp:28-142, risk.cpp:28-197).  ``grids``: (2, H, W)
+        integer [disp_min, disp_max] per pixel (host or device) or None; ``disparity_range``: the disp coordinates."""
+        import ctypes  # noqa: PLC0415
+
+        H, W, D = (int(s) for s in cv.shape)
+        et = np.ascontiguousarray(etas, dtype=np.float64)
+        n = int(et.shape[0])
+        dr = torch.as_tensor(np.ascontiguousarray(disparity_range, dtype=np.float32)).to(self.device)
+        g = None
+        if grids is not None:
+            g = grids if isinstance(grids, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(grids, dtype=np.int32))
+            g = g.to(device=self.device, dtype=torch.int32).contiguous()
+        out = {}
+        if ambiguity:
+            out["ambiguity"] = self.empty((H, W))
+        if sampled_ambiguity:
+            out["sampled_ambiguity"] = self.empty((H, W, n))
+        if risk:
+            for k in ("risk_max", "risk_min", "disp_sup", "disp_inf"):
+                out[k] = self.empty((H, W))
+        if sampled_risk:
+            out["sampled_risk_max"] = self.empty((H, W, n))
+            out["sampled_risk_min"] = self.empty((H, W, n))
+        sa_in = None if sampled_ambiguity_in is None else self.to_device(sampled_ambiguity_in)
+        ws = self._workspace("confidence", self.lib.pb200_confidence_workspace_bytes(H, W, n))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_confidence(
+                _ptr(cv), H, W, D, int(is_max), et.ctypes.data_as(ctypes.c_void_p), n, _ptr(g), _ptr(dr), _ptr(out.get("ambiguity")),
+                _ptr(out.get("sampled_ambiguity")), _ptr(sa_in), _ptr(out.get("risk_max")), _ptr(out.get("risk_min")),
+                _ptr(out.get("disp_sup")), _ptr(out.get("disp_inf")), _ptr(out.get("sampled_risk_max")), _ptr(out.get("sampled_risk_min")),
+                _ptr(ws), ws.numel(), self._stream()))
+        return out

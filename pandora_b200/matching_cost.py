@@ -130,21 +130,30 @@ class AbstractMatchingCost:
         return int(round(float(disps[0]))), int(round(float(disps[-1])))
 
     def cv_masked(self, img_left, img_right, cost_volume, disp_min, disp_max) -> None:
-        """matching_cost.py:770-872, no-mask / fixed-range branch: the cost values are unchanged, the
-        validity mask gets ``mask_invalid_variable_disparity_range`` and ``mask_border`` on the device."""
-        if "msk" in getattr(img_left, "data_vars", {}) or "msk" in getattr(img_right, "data_vars", {}):
-            raise NotImplementedError("input masks are not on the B200 hot path yet (SURVEY.md 8f rank 1)")
-        dmin_g, dmax_g = self.get_min_max_from_grid(disp_min, disp_max)
-        dmin, dmax = self._disp_bounds(cost_volume)
-        if np.nanmax(disp_min) != dmin_g or np.nanmin(disp_max) != dmax_g or dmin_g != dmin or dmax_g != dmax:
-            raise NotImplementedError("variable disparity grids are not on the B200 hot path yet (SURVEY.md 8f rank 1)")
+        """matching_cost.py:770-872 on the device: cells whose left / right pixel is invalid or sees a no_data in its
+        window, and cells outside the per-pixel [disp_min, disp_max], become NaN in ONE pass over the volume (the
+        reference loops over the disparities in Python twice); then ``mask_invalid_variable_disparity_range`` and
+        ``mask_border`` update the validity mask.  Without masks and with a fixed range the volume is only read."""
+        from .criteria import image_mask_flags  # noqa: PLC0415
+
         eng = get_engine()
+        dmin, dmax = self._disp_bounds(cost_volume)
         cv_t = device_volume(eng, cost_volume)
         H, W, _ = (int(s) for s in cv_t.shape)
         off = int(cost_volume.attrs["offset_row_col"])
-        is_max = cost_volume.attrs.get("type_measure") == "max"
-        _, flags = eng.wta(cv_t, dmin, is_max)                        # all-NaN detection pass
-        mask = eng.validity_mask(H, W, dmin, dmax, off, flags)
+        fl, fr = image_mask_flags(eng, img_left, self._window_size), image_mask_flags(eng, img_right, self._window_size)
+        gmin_h, gmax_h = np.asarray(disp_min, dtype=np.float32)[:H, :W], np.asarray(disp_max, dtype=np.float32)[:H, :W]
+        variable = bool(np.nanmax(gmin_h) != np.nanmin(gmin_h) or np.nanmax(gmax_h) != np.nanmin(gmax_h)
+                        or int(np.nanmin(gmin_h)) != dmin or int(np.nanmax(gmax_h)) != dmax)
+        gmin = eng.to_device(gmin_h) if variable else None
+        gmax = eng.to_device(gmax_h) if variable else None
+        flags = eng.cv_masked(cv_t, dmin, fl, fr, gmin, gmax)                # masks the volume, reports all-NaN pixels
+        store_volume(cost_volume, cv_t)
+        if "validity_mask" in cost_volume:
+            mask = eng.to_device(np.ascontiguousarray(cost_volume["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+        else:
+            mask = eng.validity_mask_init(H, W, dmin, dmax, off)
+        mask = eng.validity_mask(H, W, dmin, dmax, off, flags, mask=mask)
         cost_volume["validity_mask"] = (("row", "col"), mask.cpu().numpy().view(np.uint16))
 
 

@@ -18,19 +18,29 @@ from .disparity import AbstractDisparity
 from .matching_cost import AbstractMatchingCost
 from .optimization import AbstractOptimization
 
-HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity")
+HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity", "refinement", "validation", "cost_volume_confidence")
 
 
 def run(img_left, img_right, cfg: dict):
     """Run the hot-path steps named in ``cfg["pipeline"]`` in order; returns (left disparity dataset, cost volume).
 
-    ``cfg`` is a Pandora user configuration (``{"pipeline": {"matching_cost": {...}, ...}}``); steps outside
-    the hot path (refinement, filter, validation, ...) are rejected -- they belong to Pandora itself.
+    ``cfg`` is a Pandora user configuration (``{"pipeline": {"matching_cost": {...}, ...}}``).  Implemented steps:
+    matching_cost, aggregation, optimization, disparity, and the adjacent rows refinement, validation
+    (``cross_checking_fast``: the right map comes from the left volume) and cost_volume_confidence; anything else
+    (filter, multiscale, semantic_segmentation, ``cross_checking_accurate`` ...) is rejected -- it stays Pandora's.
     """
+    from .cost_volume_confidence import AbstractCostVolumeConfidence  # noqa: PLC0415
+    from .criteria import validity_mask  # noqa: PLC0415
+    from .refinement import AbstractRefinement  # noqa: PLC0415
+    from .validation import AbstractValidation, right_disparity_fast  # noqa: PLC0415
+
     pipeline = cfg["pipeline"]
     disp_grids = (img_left["disparity"].data[0], img_left["disparity"].data[1])
+    right_mode = pipeline.get("validation", {}).get("validation_method")          # state_machine.py:600-640
+    if right_mode not in (None, "cross_checking_fast"):
+        raise NotImplementedError(f"validation method {right_mode!r} is outside the B200 hot path (only cross_checking_fast)")
     cv = None
-    disp = None
+    disp = right_disp = None
     for step, step_cfg in pipeline.items():
         name = step.split(".")[0]
         if name not in HOT_PATH_STEPS:
@@ -38,6 +48,7 @@ def run(img_left, img_right, cfg: dict):
         if name == "matching_cost":                               # state_machine.py:292-364
             mc = AbstractMatchingCost(**step_cfg)
             cv = mc.allocate_cost_volume(img_left, disp_grids, cfg)
+            cv = validity_mask(img_left, img_right, cv)
             cv = mc.compute_cost_volume(img_left, img_right, cv)
             mc.cv_masked(img_left, img_right, cv, *disp_grids)
         elif name == "aggregation":                               # state_machine.py:366-380
@@ -45,7 +56,23 @@ def run(img_left, img_right, cfg: dict):
         elif name == "optimization":                              # state_machine.py:404-419
             cv = AbstractOptimization(img_left, **step_cfg).optimize_cv(cv, img_left, img_right)
         elif name == "disparity":                                 # state_machine.py:421-448
-            disp = AbstractDisparity(**step_cfg).to_disp(cv, img_left, img_right)
+            disparity_ = AbstractDisparity(**step_cfg)
+            disp = disparity_.to_disp(cv, img_left, img_right)
+            if right_mode == "cross_checking_fast":
+                right_disp = right_disparity_fast(cv, disparity_.cfg["invalid_disparity"])
+        elif name == "cost_volume_confidence":                    # state_machine.py:566-587
+            step_cfg = dict(step_cfg)
+            if len(step.split(".")) == 2:
+                step_cfg["indicator"] = "." + step.split(".")[1]
+            disp, cv = AbstractCostVolumeConfidence(**step_cfg).confidence_prediction(disp, img_left, img_right, cv)
+        elif name == "refinement":                                # state_machine.py:474-490
+            refinement_ = AbstractRefinement(**step_cfg)
+            refinement_.subpixel_refinement(cv, disp)
+            if right_disp is not None:
+                refinement_.right_subpixel_refinement(cv, right_disp)
+        elif name == "validation":                                # state_machine.py:492-519
+            disp = AbstractValidation(**step_cfg).disparity_checking(disp, right_disp, img_left, img_right, cv)
+            right_disp = None
     return disp, cv
 
 

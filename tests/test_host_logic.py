@@ -153,4 +153,46 @@ def test_dataset_shim_lazy_volume():
 def test_run_rejects_steps_outside_the_hot_path():
     img = pb.create_image_dataset(np.zeros((6, 9), np.float32), disparity=[-1, 1])
     with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
-        pb.run(img, img, {"pipeline": {"refinement": {"refinement_method": "vfit"}}})
+        pb.run(img, img, {"pipeline": {"filter": {"filter_method": "median"}}})
+    with pytest.raises(NotImplementedError, match="only cross_checking_fast"):
+        pb.run(img, img, {"pipeline": {"validation": {"validation_method": "cross_checking_accurate"}}})
+
+
+def test_next_row_registries_and_config_errors():
+    """refinement / validation / cost_volume_confidence mirrors: same factories and error behaviour as the reference
+    (refinement.py:52-74, validation.py:59-84, cost_volume_confidence.py:52-75)."""
+    import pandora_b200 as pb
+
+    assert isinstance(pb.AbstractRefinement(refinement_method="vfit"), pb.Vfit)
+    assert isinstance(pb.AbstractRefinement(refinement_method="quadratic"), pb.Quadratic)
+    with pytest.raises(KeyError):
+        pb.AbstractRefinement(refinement_method="cubic")
+    for name in ("cross_checking_fast", "cross_checking_accurate"):                    # tests/test_validation.py:92-103
+        assert isinstance(pb.AbstractValidation(validation_method=name), pb.CrossCheckingAccurate)
+    with pytest.raises(KeyError):
+        pb.AbstractValidation(**{"something's wrong": "blue"})                         # tests/test_validation.py:78-83
+    with pytest.raises(KeyError):
+        pb.AbstractValidation(validation_method="hello")
+    assert pb.AbstractValidation(validation_method="cross_checking_fast").cfg["cross_checking_threshold"] == 1.0
+    amb = pb.AbstractCostVolumeConfidence(confidence_method="ambiguity")
+    assert isinstance(amb, pb.Ambiguity) and amb._nbr_etas == 70 and amb.cfg["normalization"] is True
+    risk = pb.AbstractCostVolumeConfidence(confidence_method="risk", eta_max=0.5, eta_step=0.3)
+    assert isinstance(risk, pb.Risk) and list(risk._etas) == [0.0, 0.3]
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractCostVolumeConfidence(confidence_method="ambiguity", eta_max=1.5)
+    with pytest.raises(KeyError):
+        pb.AbstractCostVolumeConfidence(confidence_method="variance")
+
+
+def test_allocate_confidence_map_appends_indicators():
+    import pandora_b200 as pb
+
+    cv = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3)})
+    disp = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3)})
+    first, second = np.ones((2, 3), np.float32), np.full((2, 3), 2, np.float32)
+    disp, cv = pb.AbstractCostVolumeConfidence.allocate_confidence_map("ambiguity", first, disp, cv)
+    disp, cv = pb.AbstractCostVolumeConfidence.allocate_confidence_map("risk_max", second, disp, cv)
+    for ds in (disp, cv):
+        assert ds["confidence_measure"].data.shape == (2, 3, 2)
+        assert list(ds.coords["indicator"].data) == ["confidence_from_ambiguity", "confidence_from_risk_max"]
+        np.testing.assert_array_equal(ds["confidence_measure"].data[:, :, 1], second)
