@@ -497,6 +497,281 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
     for (int i = 0; i < H; ++i) row(i);
 }
 
+// ------------------------------------------------------------------------------------------------
+// wavefront sweeps: FOUR directions per pass, two passes for the whole stage
+// ------------------------------------------------------------------------------------------------
+// A pixel's E, SE, S and SW predecessors are (y, x-1), (y-1, x-1), (y-1, x), (y-1, x+1): all of them are finished
+// when the image is walked in the order t = 2y + x.  sgm_wave_kernel runs that wavefront as DATAFLOW instead of a
+// row barrier: a warp owns two adjacent columns and walks them downwards; what it needs from its neighbours travels
+// through small shared-memory mailboxes guarded by progress counters (the left warp's E / SE states of its right
+// column, the right warp's SW state of its left column), and across strips through the L2-resident flag-in-data
+// ring.  The vertical state, the pair's inner E / SE / SW hand-overs and the partial sums never leave registers.
+// Pass 1 (top-down: E, SE, S, SW) reads the float32 costs, verifies + packs them and writes C (8 or 16 bit) and the
+// 16-bit partial sum; pass 2 runs the same code on the image flipped in both axes (bottom-up: W, NW, N, NE), adds
+// its four directions and emits float32 S (+ NaN restore, overcounting, WTA) in place:
+//      pass 1   4D read + D (or 2D) + 2D written        pass 2   D (or 2D) + 2D read + 4D written
+// = 14D bytes per pixel (16D with 16-bit costs) instead of 22D / 28D, in two launches instead of four.
+//
+// Mailbox discipline (i = row in travel order, w = warp, A / B = its left / right column):
+//   phase 1 (no neighbour needed)  SW_A(i) from the pair's own SW_B(i-1) -> mailbox sw[i&1][w], counter fs[w] = i+1;
+//                                  S_A, S_B; SE_B(i) from the pair's own SE_A(i-1) -> mailbox se[i&3][w]
+//   phase 2                        wait fe[w-1] >= i+1: E_in = e[i&1][w-1], SE_in = se[(i-1)&3][w-1];
+//                                  wait fs[w+1] >= i:   SW_in = sw[(i-1)&1][w+1]   (loaded BEFORE the next publish)
+//                                  E_A, E_B -> mailbox e[i&1][w], counter fe[w] = i+1;  SE_A
+//   phase 3                        SW_B(i) from SW_in
+// A mailbox slot is overwritten only after its reader is known to be done with it: e / sw have two slots because the
+// writer's own wait for row i proves the reader finished row i-2; se is written one phase earlier and has four.
+__device__ __forceinline__ void flag_publish(uint32_t addr, uint32_t v, bool relaxed) {
+    if (relaxed) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    else asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t target) {
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    } while (v < target);
+}
+// first (speculative) poll of a ring slot: loads only; ll_finish_u32 checks the tags and re-polls until they match
+template <int NR>
+__device__ __forceinline__ void ll_peek_u32(const unsigned long long *slot, int lane, unsigned long long (&w)[NR]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
+}
+template <int NR>
+__device__ __forceinline__ void ll_finish_u32(const unsigned long long *slot, int lane, uint32_t tag, unsigned long long (&w)[NR], uint32_t (&v)[NR]) {
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
+        if (__all_sync(0xffffffffu, ok)) break;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
+}
+
+template <int NR, int CB, bool FINAL, bool WTA>
+__global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) {
+    if (FINAL && *p.flag != 0) return;
+    extern __shared__ __align__(16) uint32_t wave_smem[];
+    constexpr int VS = NR * 32;                          // words per packed state vector
+    constexpr int RW = NR * CB / 2;                      // raw cost words per lane
+    constexpr int SIN = FINAL ? (RW + NR) : 2 * NR;      // staged input words per lane and pixel
+    constexpr int NSTG = 4, PFD = NSTG - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int K = nwarp * 2;
+    const int strip = blockIdx.x, nstrips = gridDim.x;
+    const int H = p.H, W = p.W, D = p.D;
+    const bool relaxed = (p.debug & 2) != 0;
+    // shared: e[2][nwarp][VS] | se[4][nwarp][VS] | sw[2][nwarp][VS] | fe[nwarp] fs[nwarp] (64 words) | staging
+    const int state_words = 8 * nwarp * VS + 64;
+    // mailboxes, counters AND the staging ring start as zeros (columns right of the image are never staged and must
+    // read as zero costs, which also pass the data check)
+    for (int i = threadIdx.x; i < state_words + NSTG * nwarp * 2 * 32 * SIN; i += blockDim.x) wave_smem[i] = 0u;
+    __syncthreads();
+    const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
+    const uint32_t e_base = smem_u32(wave_smem) + lane_b;
+    const uint32_t se_base = e_base + (uint32_t)(2 * nwarp * VS) * 4u;
+    const uint32_t sw_base = se_base + (uint32_t)(4 * nwarp * VS) * 4u;
+    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(8 * nwarp * VS) * 4u, fs_base = fe_base + 128u;
+    const uint32_t SLOT = (uint32_t)(nwarp * VS) * 4u, VB = (uint32_t)VS * 4u;   // bytes per mailbox slot / per vector
+    uint32_t *stg = wave_smem + state_words;                                    // [NSTG][nwarp][2][32][SIN]
+    // a pixel's staging block holds two lane-major parts so that every lane's vectors stay naturally aligned:
+    // pass 1: [32][NR] low-half floats | [32][NR] high-half floats;  pass 2: [32][RW] cost words | [32][NR] partial sums
+    constexpr int P0 = FINAL ? RW : NR;
+    const uint32_t stg_pix = (uint32_t)(32 * SIN) * 4u, stg_stage = (uint32_t)(nwarp * 2) * stg_pix;
+    const uint32_t stg_base = smem_u32(stg) + (uint32_t)(warp * 2) * stg_pix;
+    const uint32_t off0 = (uint32_t)(lane * P0) * 4u, off1 = (uint32_t)(32 * P0 + lane * NR) * 4u;
+
+    // logical columns of this warp (travel frame: pass 2 sees the image flipped in both axes)
+    const int xl[2] = {strip * K + 2 * warp, strip * K + 2 * warp + 1};
+    const bool valid[2] = {xl[0] < W, xl[1] < W};
+    const bool left_warp = warp > 0, right_warp = warp + 1 < nwarp;
+    // p.debug (PB200_SGM_DEBUG, timing experiments only, wrong results): bit 0 = no strip exchange, bit 2 = no mailbox waits
+    const bool left_ring = !left_warp && strip > 0 && !(p.debug & 1), right_ring = !right_warp && strip + 1 < nstrips && !(p.debug & 1);
+    const bool nowait = (p.debug & 4) != 0;
+    // ring, per strip boundary b (between strips b and b + 1): 8 vectors of VS 64-bit words: e[2] | se[4] | sw[2]
+    unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 8 * VS;          // boundary on our left (valid when left_ring)
+    unsigned long long *ring_r = p.ring + (size_t)strip * 8 * VS;                // boundary on our right
+    const int y0 = FINAL ? H - 1 : 0;
+    const long row_stride = (FINAL ? -1L : 1L) * W * D;                          // words (== floats)
+    size_t pix0[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) pix0[c] = ((size_t)y0 * W + (valid[c] ? (FINAL ? W - 1 - xl[c] : xl[c]) : 0)) * D;
+    const int poff = p16_off<CB>(D) + lane * NR;
+
+    auto stage_in = [&](int r) {
+        const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (valid[c]) {
+                if (!FINAL) {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cv) + pix0[c] + (long)r * row_stride + lane * NR;
+                    cp_async_words<NR>(sg + c * stg_pix + off0, src);
+                    cp_async_words<NR>(sg + c * stg_pix + off1, src + D / 2);
+                } else {
+                    const uint32_t *src = p.buf + pix0[c] + (long)r * row_stride;
+                    cp_async_words<RW>(sg + c * stg_pix + off0, src + lane * RW);
+                    cp_async_words<NR>(sg + c * stg_pix + off1, src + poff);
+                }
+            }
+    };
+    for (int r = 0; r < PFD; ++r) {
+        if (r < H) stage_in(r);
+        cp_async_commit();
+    }
+
+    uint32_t Sv[2][NR], SEA_prev[NR], SWB_prev[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = SWB_prev[j] = 0u;
+    bool bad = false;
+
+#pragma unroll 1
+    for (int i = 0; i < H; ++i) {
+        const uint32_t tag = (uint32_t)(i + 1);
+        // speculative first polls of the ring slots this row needs (their latency hides behind phase 1)
+        unsigned long long wE[NR], wSE[NR], wSW[NR];
+        if (left_ring) {
+            ll_peek_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, wE);
+            if (i > 0) ll_peek_u32<NR>(ring_l + (size_t)(2 + ((i - 1) & 3)) * VS, lane, wSE);
+        }
+        if (right_ring && i > 0) ll_peek_u32<NR>(ring_r + (size_t)(6 + ((i - 1) & 1)) * VS, lane, wSW);
+
+        if (i + PFD < H) stage_in(i + PFD);
+        cp_async_commit();
+        cp_async_wait<PFD>();
+        uint32_t c16[2][NR], p16[2][NR], cc[2][NR];
+        const uint32_t sg = stg_base + (uint32_t)(i & (NSTG - 1)) * stg_stage;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!FINAL) {
+                uint32_t fa[NR], fb[NR];
+                lds_words<NR>(sg + c * stg_pix + off0, fa);
+                lds_words<NR>(sg + c * stg_pix + off1, fb);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    c16[c][j] = encode_cost<CB>(__uint_as_float(fa[j]), p.inv, p.cost_ok_max, bad) |
+                                (encode_cost<CB>(__uint_as_float(fb[j]), p.inv, p.cost_ok_max, bad) << 16);
+                    p16[c][j] = 0u;
+                }
+                if (valid[c]) st_cost<NR, CB>(p.buf + pix0[c] + (long)i * row_stride, lane, c16[c]);
+            } else {
+                uint32_t craw[RW];
+                lds_words<RW>(sg + c * stg_pix + off0, craw);
+                lds_words<NR>(sg + c * stg_pix + off1, p16[c]);
+                unpack_cost<NR, CB>(craw, c16[c]);
+            }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                if (!valid[c]) { c16[c][j] = 0u; p16[c][j] = 0u; }          // columns right of the image: zero costs, flat states
+                cc[c][j] = c16[c][j] & Tier<CB>::VALUES;
+            }
+        }
+
+        // ---- phase 1: everything that needs no neighbour ------------------------------------------------
+        uint32_t L_SW_A[NR], L_SE_B[NR], L0[NR];
+        nstep<NR>(cc[0], SWB_prev, L_SW_A, lane, p.p1p1, p.p2p2);
+        if (left_warp) {
+            sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + (uint32_t)warp * VB, L_SW_A);
+            __syncwarp();
+            if (lane == 0) flag_publish(fs_base + (uint32_t)warp * 4u, tag, relaxed);
+        } else if (left_ring) {
+            ll_send_u32<NR>(ring_l + (size_t)(6 + (i & 1)) * VS, lane, tag, L_SW_A);
+        }
+        nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p.p1p1, p.p2p2);
+        if (right_warp) sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + (uint32_t)warp * VB, L_SE_B);
+        else if (right_ring) ll_send_u32<NR>(ring_r + (size_t)(2 + (i & 3)) * VS, lane, tag, L_SE_B);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            nstep<NR>(cc[c], Sv[c], L0, lane, p.p1p1, p.p2p2);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) Sv[c][j] = L0[j];
+        }
+
+        // ---- phase 2: the E chain ---------------------------------------------------------------------------
+        uint32_t E_in[NR], SE_in[NR], SW_in[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) E_in[j] = SE_in[j] = SW_in[j] = 0u;
+        if (left_warp) {
+            if (!nowait) flag_wait(fe_base + (uint32_t)(warp - 1) * 4u, tag);
+            lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)(warp - 1) * VB, E_in);
+            if (i > 0) lds_words<NR>(se_base + (uint32_t)((i - 1) & 3) * SLOT + (uint32_t)(warp - 1) * VB, SE_in);
+        } else if (left_ring) {
+            ll_finish_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, tag, wE, E_in);
+            if (i > 0) ll_finish_u32<NR>(ring_l + (size_t)(2 + ((i - 1) & 3)) * VS, lane, tag - 1, wSE, SE_in);
+        }
+        if (i > 0) {                                       // loaded before E_B(i) is published (slot discipline above)
+            if (right_warp) {
+                if (!nowait) flag_wait(fs_base + (uint32_t)(warp + 1) * 4u, tag - 1);
+                lds_words<NR>(sw_base + (uint32_t)((i - 1) & 1) * SLOT + (uint32_t)(warp + 1) * VB, SW_in);
+            } else if (right_ring) {
+                ll_finish_u32<NR>(ring_r + (size_t)(6 + ((i - 1) & 1)) * VS, lane, tag - 1, wSW, SW_in);
+            }
+        }
+        uint32_t L_E_A[NR], L_E_B[NR], L_SE_A[NR], L_SW_B[NR];
+        nstep<NR>(cc[0], E_in, L_E_A, lane, p.p1p1, p.p2p2);
+        nstep<NR>(cc[1], L_E_A, L_E_B, lane, p.p1p1, p.p2p2);
+        if (right_warp) {
+            sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)warp * VB, L_E_B);
+            __syncwarp();
+            if (lane == 0) flag_publish(fe_base + (uint32_t)warp * 4u, tag, relaxed);
+        } else if (right_ring) {
+            ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 1)) * VS, lane, tag, L_E_B);
+        }
+        nstep<NR>(cc[0], SE_in, L_SE_A, lane, p.p1p1, p.p2p2);
+        // ---- phase 3 ------------------------------------------------------------------------------------------
+        nstep<NR>(cc[1], SW_in, L_SW_B, lane, p.p1p1, p.p2p2);
+
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t tot[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                tot[j] = p16[c][j] + Sv[c][j] + (c == 0 ? (L_E_A[j] + L_SE_A[j] + L_SW_A[j]) : (L_E_B[j] + L_SE_B[j] + L_SW_B[j]));
+            if (valid[c]) {
+                uint32_t *gpix = p.buf + pix0[c] + (long)i * row_stride;
+                if (!FINAL) {
+                    st_words<NR>(gpix + poff, tot);
+                } else {
+                    float fa[NR], fb[NR];
+                    uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        uint32_t t = tot[j];
+                        if (p.overcounting) t = t - 7u * cc[c][j];
+                        const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                        const bool nlo = (c16[c][j] & Tier<CB>::FLAG1) != 0, nhi = (c16[c][j] & (Tier<CB>::FLAG1 << 16)) != 0;
+                        fa[j] = nlo ? nan_f() : small_int_to_float(lo);
+                        fb[j] = nhi ? nan_f() : small_int_to_float(hi);
+                        if (WTA) {
+                            const uint32_t ka = (lo << 16) | (uint32_t)(lane * NR + j);
+                            const uint32_t kb = (hi << 16) | (uint32_t)(D / 2 + lane * NR + j);
+                            best = min(best, nlo ? 0xFFFFFFFFu : ka);
+                            best = min(best, nhi ? 0xFFFFFFFFu : kb);
+                        }
+                    }
+                    float *o = reinterpret_cast<float *>(gpix) + lane * NR;
+                    st_floats<NR>(o, fa);
+                    st_floats<NR>(o + D / 2, fb);
+                    if (WTA) {
+                        best = __reduce_min_sync(0xffffffffu, best);
+                        if (lane == 0) {
+                            const size_t pix = (pix0[c] + (long)i * row_stride) / D;
+                            const bool none = (best == 0xFFFFFFFFu);
+                            p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
+                            if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { SEA_prev[j] = L_SE_A[j]; SWB_prev[j] = L_SW_B[j]; }
+    }
+    if (!FINAL && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
+}
+
 enum { NARROW_ALL = 0, NARROW_H = 1, NARROW_V = 2 };
 
 template <int NR, int CB>
@@ -508,8 +783,38 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     const size_t smem = (size_t)2 * 2 * (K + 2) * NR * 32 * sizeof(uint32_t) +                 // state buffers
                         (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);    // input staging ring
     if (smem > 220 * 1024) return PB200_OK;
-    const int threads = (nwarp + 1) * 32;
     const bool wta = p.disp != nullptr;
+    // wavefront path: the whole stage in two 4-direction passes (single-call runs without tile halos)
+    if (phase == NARROW_ALL && p.halo_in == nullptr && p.halo_out == nullptr && !getenv("PB200_SGM_NO_WAVE")) {
+        void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false>;
+        void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
+        const int wthreads = nwarp * 32;
+        const size_t state = ((size_t)8 * nwarp * NR * 32 + 64) * sizeof(uint32_t);
+        const size_t smem1 = state + (size_t)4 * nwarp * 2 * 32 * (2 * NR) * sizeof(uint32_t);
+        const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
+        int occ1 = 0, occ2 = 0;
+        if (wthreads <= 512 && smem1 <= 220 * 1024) {
+            PB200_CUDA(cudaFuncSetAttribute((const void *)w1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            PB200_CUDA(cudaFuncSetAttribute((const void *)w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, (const void *)w1, wthreads, smem1));
+            PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void *)w2, wthreads, smem2));
+        }
+        if ((long)occ1 * nsm >= nstrips && (long)occ2 * nsm >= nstrips) {
+            p.ring = reinterpret_cast<unsigned long long *>(workspace);
+            const size_t wring = (size_t)nstrips * 8 * NR * 32 * sizeof(unsigned long long);
+            PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
+            void *args[] = {(void *)&p};
+            PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+            PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(wthreads), args, smem1, s));
+            PB200_LAUNCH_CHECK("sgm_wave_kernel<down>");
+            PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+            PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(wthreads), args, smem2, s));
+            PB200_LAUNCH_CHECK("sgm_wave_kernel<up>");
+            *done = true;
+            return PB200_OK;
+        }
+    }
+    const int threads = (nwarp + 1) * 32;
     void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, CB, false, false>;
     void (*fin)(const NarrowParams) = wta ? sgm_narrow_vsweep_kernel<NR, CB, true, true> : sgm_narrow_vsweep_kernel<NR, CB, true, false>;
     int per_sm = 0;

@@ -324,6 +324,22 @@ def test_sgm_packed_integer_path(eng, oracle, shape, over, p1, p2):
     np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
 
 
+@pytest.mark.parametrize("shape", [(5, 4096, 256), (7, 3000, 128), (4, 4095, 64), (33, 1500, 256), (2, 4736, 64)])
+def test_sgm_wavefront_wide_images(eng, oracle, shape):
+    """Wide images: strips of many warps (K = 2 * warps columns), partial last strips, odd widths -- the 4-direction
+    wavefront passes (sgm_wave_kernel) against the oracle, bit-exact, with the fused WTA."""
+    g = np.random.default_rng(shape[1])
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.1] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25)
+    dmin = -(shape[2] - 1)
+    got, disp, flags = eng.sgm(dev(eng, cv), 8, 32, oracle.sgm_invalid_value(25, 32), fuse_wta=True, dmin=dmin)
+    np.testing.assert_array_equal(host(got), ref)
+    exp_disp, exp_inv = oracle.wta(ref, np.arange(dmin, 1))
+    np.testing.assert_array_equal(host(disp), exp_disp)
+    np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
+
+
 @pytest.mark.parametrize("kind", ["float", "one_fraction", "negative", "too_large", "big_penalty"])
 def test_sgm_packed_path_falls_back_exactly(eng, oracle, kind):
     """Volumes that do not qualify for the packed path (checked on the device while it runs) are redone by the

@@ -9,7 +9,8 @@ rep = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+vals = rows[2 + (int(sys.argv[3]) if len(sys.argv) > 3 else 0)]
 keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "sm__warps_active.avg.per_cycle_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum", "lts__t_sector_hit_rate.pct",
@@ -23,9 +24,15 @@ for i, h in enumerate(hdr):
         print(f"  {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]}: {float(vals[i]):.2f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]
+# one block per profiled kernel: a "Kernel Name" row, a header row, then the SASS lines; argv[3] picks the block
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+b0 = starts[kidx]
+b1 = starts[kidx + 1] if kidx + 1 < len(starts) else len(rows)
+print("source block:", rows[b0][1][:100])
+hdr = rows[b0 + 1]
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-data = rows[2:]
+data = [r for r in rows[b0 + 2:b1] if len(r) > max(isamp, iex)]
 tot = sum(int(r[isamp]) for r in data)
 texec = sum(int(r[iex]) for r in data)
 print(f"total samples {tot}, SASS instructions {len(data)}, warp-instructions executed {texec}")

@@ -87,6 +87,25 @@ timeit("C3 sgm 8-path + fused WTA", lambda: eng.sgm(p3.cv_a, 8.0, 32.0, 58.0, ou
 timeit("C3 pipeline census+sgm+wta", lambda: p3.run_device(l, r), (12 * D + 12) * H * W)
 timeit("C3 wta standalone 4096x4096x256", lambda: eng.wta(p3.cv_b, -(D - 1)), (4 * D + 6) * H * W)
 timeit("C3 reverse_cost_volume", lambda: eng.reverse_cost_volume(p3.cv_a, 0), 8 * D * H * W, reps=2)
+# next rows on the C3 SGM result: algorithmic bytes = one read of the volume (+ O(H*W) maps)
+dmin3 = -(D - 1)
+timeit("C3 wta_right (right map from the left volume)", lambda: eng.wta_right(p3.cv_b, 0), (4 * D + 5) * H * W)
+timeit("C3 reverse_cost_volume + wta (what wta_right replaces)", lambda: eng.wta(eng.reverse_cost_volume(p3.cv_b, 0), 0), (4 * D + 5) * H * W, reps=2)
+timeit("C3 cv_masked pass (all-NaN detection, no masks)", lambda: eng.cv_masked(p3.cv_b, dmin3), (4 * D + 1) * H * W)
+msk = (torch.rand((H, W), device="cuda") < 0.02).to(torch.int16).cpu().numpy()
+fl3 = eng.mask_flags(msk, 0, 1, 5)
+timeit("C3 mask_flags (5x5 no_data dilation)", lambda: eng.mask_flags(msk, 0, 1, 5), 3 * H * W, reps=2)
+vm3 = eng.validity_mask_init(H, W, dmin3, 0, 2)
+timeit("C3 validity_mask_masks (left + right msk)", lambda: eng.validity_mask_masks(vm3, dmin3, 0, 2, fl3, fl3), 6 * H * W)
+disp3, flags3 = eng.wta(p3.cv_b, dmin3)
+mask3 = eng.validity_mask(H, W, dmin3, 0, 2, flags3, wta_invalidate=True, mask=eng.validity_mask(H, W, dmin3, 0, 2, flags3))
+rdisp3, _ = eng.wta_right(p3.cv_b, 0)
+timeit("C3 refinement vfit", lambda: eng.refinement(p3.cv_b, disp3.clone(), mask3.clone(), dmin3, 0, 1, False, "vfit"), (3 * 32 + 4 + 2 + 4 + 2 + 4) * H * W)
+timeit("C3 cross_checking", lambda: eng.cross_checking(disp3, mask3.clone(), rdisp3, 1.0, dmin3, 0, 2), (4 + 4 + 2 + 2 + 4) * H * W)
+etas3 = np.arange(0.0, 0.7, 0.01)
+dr3 = np.arange(dmin3, 1).astype(np.float32)
+timeit("C3 ambiguity (70 etas; 2 reads of the volume)", lambda: eng.confidence(p3.cv_b, etas3, None, dr3), (8 * D + 8) * H * W, reps=2)
+timeit("C3 ambiguity + risk (70 etas)", lambda: eng.confidence(p3.cv_b, etas3, None, dr3, risk=True), (8 * D + 24) * H * W, reps=2)
 # float costs: the float SGM kernels (no packed path)
 p3.cv_a.mul_(0.37)
 timeit("C3 sgm float costs (float kernels)", lambda: eng.sgm(p3.cv_a, 0.3, 1.7, 12.0, out=p3.cv_b), 8 * D * H * W, reps=2)
