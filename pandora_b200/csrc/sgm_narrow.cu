@@ -161,6 +161,18 @@ __device__ __forceinline__ uint32_t encode_cost(float v, uint32_t inv, float ok_
     return isn ? (inv | Tier<CB>::FLAG1) : (__float_as_uint(t) & 0xFFFFu);
 }
 
+// Two float32 costs -> one packed word of 16-bit codes (6.5 instructions per cost): NaN is first replaced by the float
+// whose integer code is invalid_value | flag, t = v + 2^23 carries the integer in its low mantissa bits (one PRMT packs
+// both), and the data condition "v is an integer in [0, ok_max]" is the single ordered comparison
+// min(|t - 2^23|, ok_max) <> v  (false for NaN, true for fractions, negatives, too large values and infinities).
+__device__ __forceinline__ uint32_t encode_pair(float vlo, float vhi, float nan_code, float ok_max, bool &bad) {
+    const float alo = (vlo != vlo) ? nan_code : vlo, ahi = (vhi != vhi) ? nan_code : vhi;
+    const float tlo = alo + 8388608.0f, thi = ahi + 8388608.0f;
+    const float clo = fminf(fabsf(tlo - 8388608.0f), ok_max), chi = fminf(fabsf(thi - 8388608.0f), ok_max);
+    bad = bad || (clo < vlo) || (clo > vlo) || (chi < vhi) || (chi > vhi);      // ordered <>: false for NaN
+    return __byte_perm(__float_as_uint(tlo), __float_as_uint(thi), 0x5410);
+}
+
 // ------------------------------------------------------------------------------------------------
 // horizontal passes: one warp per row
 // ------------------------------------------------------------------------------------------------
@@ -505,7 +517,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
 // row barrier: a warp owns two adjacent columns and walks them downwards; what it needs from its neighbours travels
 // through small shared-memory mailboxes guarded by progress counters (the left warp's E / SE states of its right
 // column, the right warp's SW state of its left column), and across strips through the L2-resident flag-in-data
-// ring.  The vertical state, the pair's inner E / SE / SW hand-overs and the partial sums never leave registers.
+// ring, served by two relay warps per CTA so that the compute warps only ever see mailboxes.  The vertical state, the pair's inner E / SE / SW hand-overs and the partial sums never leave registers.
 // Pass 1 (top-down: E, SE, S, SW) reads the float32 costs, verifies + packs them and writes C (8 or 16 bit) and the
 // 16-bit partial sum; pass 2 runs the same code on the image flipped in both axes (bottom-up: W, NW, N, NE), adds
 // its four directions and emits float32 S (+ NaN restore, overcounting, WTA) in place:
@@ -531,26 +543,6 @@ __device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t target) {
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     } while (v < target);
 }
-// first (speculative) poll of a ring slot: loads only; ll_finish_u32 checks the tags and re-polls until they match
-template <int NR>
-__device__ __forceinline__ void ll_peek_u32(const unsigned long long *slot, int lane, unsigned long long (&w)[NR]) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
-}
-template <int NR>
-__device__ __forceinline__ void ll_finish_u32(const unsigned long long *slot, int lane, uint32_t tag, unsigned long long (&w)[NR], uint32_t (&v)[NR]) {
-    for (;;) {
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
-        if (__all_sync(0xffffffffu, ok)) break;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
-}
-
 template <int NR, int CB, bool FINAL, bool WTA>
 __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) {
     if (FINAL && *p.flag != 0) return;
@@ -559,41 +551,89 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     constexpr int RW = NR * CB / 2;                      // raw cost words per lane
     constexpr int SIN = FINAL ? (RW + NR) : 2 * NR;      // staged input words per lane and pixel
     constexpr int NSTG = 4, PFD = NSTG - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int K = nwarp * 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nc = (blockDim.x >> 5) - 2;                // compute warps; warps nc / nc + 1 relay to the left / right strip
+    const int NV = nc + 2;                               // mailbox columns: 0 = left strip, 1 .. nc = compute warps, nc + 1 = right strip
+    const int K = nc * 2;
     const int strip = blockIdx.x, nstrips = gridDim.x;
     const int H = p.H, W = p.W, D = p.D;
-    const bool relaxed = (p.debug & 2) != 0;
-    // shared: e[2][nwarp][VS] | se[4][nwarp][VS] | sw[2][nwarp][VS] | fe[nwarp] fs[nwarp] (64 words) | staging
-    const int state_words = 8 * nwarp * VS + 64;
+    const bool relaxed = (p.debug & 2) != 0, nowait = (p.debug & 4) != 0;
+    // p.debug (PB200_SGM_DEBUG, timing experiments only, wrong results): bit 0 = no strip exchange, bit 2 = no mailbox waits
+    const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
+    // shared: e[2][NV][VS] | se[4][NV][VS] | sw[2][NV][VS] | fe[32] fs[32] | staging
+    const int state_words = 8 * NV * VS + 64;
     // mailboxes, counters AND the staging ring start as zeros (columns right of the image are never staged and must
-    // read as zero costs, which also pass the data check)
-    for (int i = threadIdx.x; i < state_words + NSTG * nwarp * 2 * 32 * SIN; i += blockDim.x) wave_smem[i] = 0u;
+    // read as zero costs, which also pass the data check; a strip without a neighbour reads flat zero states)
+    for (int i = threadIdx.x; i < state_words + NSTG * nc * 2 * 32 * SIN; i += blockDim.x) wave_smem[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!has_left) wave_smem[8 * NV * VS + 0] = 0xFFFFFFFFu;                 // fe[0]: the image border never makes anyone wait
+        if (!has_right) wave_smem[8 * NV * VS + 32 + NV - 1] = 0xFFFFFFFFu;       // fs[nc + 1]
+    }
     __syncthreads();
     const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
     const uint32_t e_base = smem_u32(wave_smem) + lane_b;
-    const uint32_t se_base = e_base + (uint32_t)(2 * nwarp * VS) * 4u;
-    const uint32_t sw_base = se_base + (uint32_t)(4 * nwarp * VS) * 4u;
-    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(8 * nwarp * VS) * 4u, fs_base = fe_base + 128u;
-    const uint32_t SLOT = (uint32_t)(nwarp * VS) * 4u, VB = (uint32_t)VS * 4u;   // bytes per mailbox slot / per vector
-    uint32_t *stg = wave_smem + state_words;                                    // [NSTG][nwarp][2][32][SIN]
+    const uint32_t se_base = e_base + (uint32_t)(2 * NV * VS) * 4u;
+    const uint32_t sw_base = se_base + (uint32_t)(4 * NV * VS) * 4u;
+    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(8 * NV * VS) * 4u, fs_base = fe_base + 128u;
+    const uint32_t SLOT = (uint32_t)(NV * VS) * 4u, VB = (uint32_t)VS * 4u;      // bytes per mailbox slot / per vector
+    // ring, per strip boundary b (between strips b and b + 1): 8 vectors of VS 64-bit words: e[2] | se[4] | sw[2]
+    unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 8 * VS;          // boundary on our left (used when has_left)
+    unsigned long long *ring_r = p.ring + (size_t)strip * 8 * VS;                // boundary on our right
+
+    // ---- relay warps: mailbox <-> L2 ring, so that no compute warp ever touches the ring -----------------------
+    if (warp == nc) {                                     // left relay
+        if (!has_left) return;
+        for (int i = 0; i < H; ++i) {
+            const uint32_t tag = (uint32_t)(i + 1);
+            uint32_t v[NR];
+            // outbound: SW_A(i) of the first compute warp
+            if (!nowait) flag_wait(fs_base + 1u * 4u, tag);
+            lds_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + 1u * VB, v);
+            ll_send_u32<NR>(ring_l + (size_t)(6 + (i & 1)) * VS, lane, tag, v);
+            // inbound: E(i), then SE(i), of the left strip's last column
+            ll_recv_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, tag, v);
+            sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT, v);
+            __syncwarp();
+            if (lane == 0) flag_publish(fe_base, tag, relaxed);
+            ll_recv_u32<NR>(ring_l + (size_t)(2 + (i & 3)) * VS, lane, tag, v);
+            sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT, v);                 // visible with the next E flag
+        }
+        return;
+    }
+    if (warp == nc + 1) {                                 // right relay
+        if (!has_right) return;
+        for (int i = 0; i < H; ++i) {
+            const uint32_t tag = (uint32_t)(i + 1);
+            uint32_t v[NR];
+            // outbound: E_B(i), SE_B(i) of the last compute warp
+            if (!nowait) flag_wait(fe_base + (uint32_t)nc * 4u, tag);
+            lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)nc * VB, v);
+            ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 1)) * VS, lane, tag, v);
+            lds_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + (uint32_t)nc * VB, v);
+            ll_send_u32<NR>(ring_r + (size_t)(2 + (i & 3)) * VS, lane, tag, v);
+            // inbound: SW_A(i) of the right strip's first column
+            ll_recv_u32<NR>(ring_r + (size_t)(6 + (i & 1)) * VS, lane, tag, v);
+            sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + (uint32_t)(nc + 1) * VB, v);
+            __syncwarp();
+            if (lane == 0) flag_publish(fs_base + (uint32_t)(nc + 1) * 4u, tag, relaxed);
+        }
+        return;
+    }
+
+    // ---- compute warps -------------------------------------------------------------------------------------------
+    const uint32_t vme = (uint32_t)(warp + 1);            // this warp's mailbox column
+    uint32_t *stg = wave_smem + state_words;              // [NSTG][nc][2 pixels][32 * SIN]
     // a pixel's staging block holds two lane-major parts so that every lane's vectors stay naturally aligned:
     // pass 1: [32][NR] low-half floats | [32][NR] high-half floats;  pass 2: [32][RW] cost words | [32][NR] partial sums
     constexpr int P0 = FINAL ? RW : NR;
-    const uint32_t stg_pix = (uint32_t)(32 * SIN) * 4u, stg_stage = (uint32_t)(nwarp * 2) * stg_pix;
+    const uint32_t stg_pix = (uint32_t)(32 * SIN) * 4u, stg_stage = (uint32_t)(nc * 2) * stg_pix;
     const uint32_t stg_base = smem_u32(stg) + (uint32_t)(warp * 2) * stg_pix;
     const uint32_t off0 = (uint32_t)(lane * P0) * 4u, off1 = (uint32_t)(32 * P0 + lane * NR) * 4u;
 
     // logical columns of this warp (travel frame: pass 2 sees the image flipped in both axes)
     const int xl[2] = {strip * K + 2 * warp, strip * K + 2 * warp + 1};
     const bool valid[2] = {xl[0] < W, xl[1] < W};
-    const bool left_warp = warp > 0, right_warp = warp + 1 < nwarp;
-    // p.debug (PB200_SGM_DEBUG, timing experiments only, wrong results): bit 0 = no strip exchange, bit 2 = no mailbox waits
-    const bool left_ring = !left_warp && strip > 0 && !(p.debug & 1), right_ring = !right_warp && strip + 1 < nstrips && !(p.debug & 1);
-    const bool nowait = (p.debug & 4) != 0;
-    // ring, per strip boundary b (between strips b and b + 1): 8 vectors of VS 64-bit words: e[2] | se[4] | sw[2]
-    unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 8 * VS;          // boundary on our left (valid when left_ring)
-    unsigned long long *ring_r = p.ring + (size_t)strip * 8 * VS;                // boundary on our right
     const int y0 = FINAL ? H - 1 : 0;
     const long row_stride = (FINAL ? -1L : 1L) * W * D;                          // words (== floats)
     size_t pix0[2];
@@ -622,6 +662,8 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         cp_async_commit();
     }
 
+    const float nan_code = (float)(p.inv | Tier<CB>::FLAG1);
+    const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
     uint32_t Sv[2][NR], SEA_prev[NR], SWB_prev[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = SWB_prev[j] = 0u;
@@ -630,14 +672,6 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll 1
     for (int i = 0; i < H; ++i) {
         const uint32_t tag = (uint32_t)(i + 1);
-        // speculative first polls of the ring slots this row needs (their latency hides behind phase 1)
-        unsigned long long wE[NR], wSE[NR], wSW[NR];
-        if (left_ring) {
-            ll_peek_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, wE);
-            if (i > 0) ll_peek_u32<NR>(ring_l + (size_t)(2 + ((i - 1) & 3)) * VS, lane, wSE);
-        }
-        if (right_ring && i > 0) ll_peek_u32<NR>(ring_r + (size_t)(6 + ((i - 1) & 1)) * VS, lane, wSW);
-
         if (i + PFD < H) stage_in(i + PFD);
         cp_async_commit();
         cp_async_wait<PFD>();
@@ -651,8 +685,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
                 lds_words<NR>(sg + c * stg_pix + off1, fb);
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
-                    c16[c][j] = encode_cost<CB>(__uint_as_float(fa[j]), p.inv, p.cost_ok_max, bad) |
-                                (encode_cost<CB>(__uint_as_float(fb[j]), p.inv, p.cost_ok_max, bad) << 16);
+                    c16[c][j] = encode_pair(__uint_as_float(fa[j]), __uint_as_float(fb[j]), nan_code, p.cost_ok_max, bad);
                     p16[c][j] = 0u;
                 }
                 if (valid[c]) st_cost<NR, CB>(p.buf + pix0[c] + (long)i * row_stride, lane, c16[c]);
@@ -669,59 +702,44 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             }
         }
 
-        // ---- phase 1: everything that needs no neighbour ------------------------------------------------
-        uint32_t L_SW_A[NR], L_SE_B[NR], L0[NR];
-        nstep<NR>(cc[0], SWB_prev, L_SW_A, lane, p.p1p1, p.p2p2);
-        if (left_warp) {
-            sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + (uint32_t)warp * VB, L_SW_A);
-            __syncwarp();
-            if (lane == 0) flag_publish(fs_base + (uint32_t)warp * 4u, tag, relaxed);
-        } else if (left_ring) {
-            ll_send_u32<NR>(ring_l + (size_t)(6 + (i & 1)) * VS, lane, tag, L_SW_A);
-        }
-        nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p.p1p1, p.p2p2);
-        if (right_warp) sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + (uint32_t)warp * VB, L_SE_B);
-        else if (right_ring) ll_send_u32<NR>(ring_r + (size_t)(2 + (i & 3)) * VS, lane, tag, L_SE_B);
+        // ---- phase 1: everything that does not need this row's E chain ----------------------------------
+        uint32_t L_SW_A[NR], L_SE_B[NR], L0[NR], SW_in[NR], L_SW_B[NR];
+        nstep<NR>(cc[0], SWB_prev, L_SW_A, lane, p1p1, p2p2);
+        sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + vme * VB, L_SW_A);
+        __syncwarp();
+        if (lane == 0) flag_publish(fs_base + vme * 4u, tag, relaxed);
+        nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p1p1, p2p2);
+        sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            nstep<NR>(cc[c], Sv[c], L0, lane, p.p1p1, p.p2p2);
+            nstep<NR>(cc[c], Sv[c], L0, lane, p1p1, p2p2);
 #pragma unroll
             for (int j = 0; j < NR; ++j) Sv[c][j] = L0[j];
         }
-
-        // ---- phase 2: the E chain ---------------------------------------------------------------------------
-        uint32_t E_in[NR], SE_in[NR], SW_in[NR];
+        // the right neighbour's SW state of the previous row (published a whole row ago): loaded BEFORE E_B(i) is
+        // published (slot discipline above), and off the E chain
 #pragma unroll
-        for (int j = 0; j < NR; ++j) E_in[j] = SE_in[j] = SW_in[j] = 0u;
-        if (left_warp) {
-            if (!nowait) flag_wait(fe_base + (uint32_t)(warp - 1) * 4u, tag);
-            lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)(warp - 1) * VB, E_in);
-            if (i > 0) lds_words<NR>(se_base + (uint32_t)((i - 1) & 3) * SLOT + (uint32_t)(warp - 1) * VB, SE_in);
-        } else if (left_ring) {
-            ll_finish_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, tag, wE, E_in);
-            if (i > 0) ll_finish_u32<NR>(ring_l + (size_t)(2 + ((i - 1) & 3)) * VS, lane, tag - 1, wSE, SE_in);
+        for (int j = 0; j < NR; ++j) SW_in[j] = 0u;
+        if (i > 0) {
+            if (!nowait) flag_wait(fs_base + (vme + 1u) * 4u, tag - 1);
+            lds_words<NR>(sw_base + (uint32_t)((i - 1) & 1) * SLOT + (vme + 1u) * VB, SW_in);
         }
-        if (i > 0) {                                       // loaded before E_B(i) is published (slot discipline above)
-            if (right_warp) {
-                if (!nowait) flag_wait(fs_base + (uint32_t)(warp + 1) * 4u, tag - 1);
-                lds_words<NR>(sw_base + (uint32_t)((i - 1) & 1) * SLOT + (uint32_t)(warp + 1) * VB, SW_in);
-            } else if (right_ring) {
-                ll_finish_u32<NR>(ring_r + (size_t)(6 + ((i - 1) & 1)) * VS, lane, tag - 1, wSW, SW_in);
-            }
-        }
-        uint32_t L_E_A[NR], L_E_B[NR], L_SE_A[NR], L_SW_B[NR];
-        nstep<NR>(cc[0], E_in, L_E_A, lane, p.p1p1, p.p2p2);
-        nstep<NR>(cc[1], L_E_A, L_E_B, lane, p.p1p1, p.p2p2);
-        if (right_warp) {
-            sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)warp * VB, L_E_B);
-            __syncwarp();
-            if (lane == 0) flag_publish(fe_base + (uint32_t)warp * 4u, tag, relaxed);
-        } else if (right_ring) {
-            ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 1)) * VS, lane, tag, L_E_B);
-        }
-        nstep<NR>(cc[0], SE_in, L_SE_A, lane, p.p1p1, p.p2p2);
-        // ---- phase 3 ------------------------------------------------------------------------------------------
-        nstep<NR>(cc[1], SW_in, L_SW_B, lane, p.p1p1, p.p2p2);
+        nstep<NR>(cc[1], SW_in, L_SW_B, lane, p1p1, p2p2);
+
+        // ---- phase 2: the E chain -- wait, two steps, publish -------------------------------------------------
+        uint32_t E_in[NR], SE_in[NR], L_E_A[NR], L_E_B[NR], L_SE_A[NR];
+        if (!nowait) flag_wait(fe_base + (vme - 1u) * 4u, tag);
+        lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (vme - 1u) * VB, E_in);
+        nstep<NR>(cc[0], E_in, L_E_A, lane, p1p1, p2p2);
+        nstep<NR>(cc[1], L_E_A, L_E_B, lane, p1p1, p2p2);
+        sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + vme * VB, L_E_B);
+        __syncwarp();
+        if (lane == 0) flag_publish(fe_base + vme * 4u, tag, relaxed);
+        // ---- phase 3: the left neighbour's SE state of the previous row (visible since its E flag of this row) ----
+#pragma unroll
+        for (int j = 0; j < NR; ++j) SE_in[j] = 0u;
+        if (i > 0) lds_words<NR>(se_base + (uint32_t)((i - 1) & 3) * SLOT + (vme - 1u) * VB, SE_in);
+        nstep<NR>(cc[0], SE_in, L_SE_A, lane, p1p1, p2p2);
 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -735,30 +753,35 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
                     st_words<NR>(gpix + poff, tot);
                 } else {
                     float fa[NR], fb[NR];
-                    uint32_t best = 0xFFFFFFFFu;
+                    uint32_t bl = 0xFFFFFFFFu, bh = 0xFFFFFFFFu;
 #pragma unroll
                     for (int j = 0; j < NR; ++j) {
                         uint32_t t = tot[j];
-                        if (p.overcounting) t = t - 7u * cc[c][j];
-                        const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                        const bool nlo = (c16[c][j] & Tier<CB>::FLAG1) != 0, nhi = (c16[c][j] & (Tier<CB>::FLAG1 << 16)) != 0;
-                        fa[j] = nlo ? nan_f() : small_int_to_float(lo);
-                        fb[j] = nhi ? nan_f() : small_int_to_float(hi);
+                        if (p.overcounting) t = t - 7u * cc[c][j];   // S >= 8 C in every half: no borrow
+                        // 16-bit integer -> float32: PRMT builds 0x4B00'nnnn, one FADD removes the 2^23
+                        const float vlo = __uint_as_float(__byte_perm(t, 0x4B00u, 0x5410)) - 8388608.0f;
+                        const float vhi = __uint_as_float(__byte_perm(t, 0x4B00u, 0x5432)) - 8388608.0f;
+                        const uint32_t fl = c16[c][j] & Tier<CB>::FLAGS;
+                        fa[j] = (fl & 0xFFFFu) ? nan_f() : vlo;
+                        fb[j] = (fl >> 16) ? nan_f() : vhi;
                         if (WTA) {
-                            const uint32_t ka = (lo << 16) | (uint32_t)(lane * NR + j);
-                            const uint32_t kb = (hi << 16) | (uint32_t)(D / 2 + lane * NR + j);
-                            best = min(best, nlo ? 0xFFFFFFFFu : ka);
-                            best = min(best, nhi ? 0xFFFFFFFFu : kb);
+                            // NaN cells saturate their half (no valid sum reaches the sentinel), then one 32-bit key per
+                            // half: (sum << 16) | register index; the lane offset of the disparity is added once below
+                            const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;
+                            const uint32_t tk = t | sat;
+                            bl = min(bl, (tk << 16) | (uint32_t)j);
+                            bh = min(bh, (tk & 0xFFFF0000u) | (uint32_t)j);
                         }
                     }
                     float *o = reinterpret_cast<float *>(gpix) + lane * NR;
                     st_floats<NR>(o, fa);
                     st_floats<NR>(o + D / 2, fb);
                     if (WTA) {
+                        uint32_t best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
                         best = __reduce_min_sync(0xffffffffu, best);
                         if (lane == 0) {
                             const size_t pix = (pix0[c] + (long)i * row_stride) / D;
-                            const bool none = (best == 0xFFFFFFFFu);
+                            const bool none = (best >> 16) >= ((CB == 1) ? 0xFF80u : 0xFFFFu);
                             p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
                             if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
                         }
@@ -788,8 +811,8 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     if (phase == NARROW_ALL && p.halo_in == nullptr && p.halo_out == nullptr && !getenv("PB200_SGM_NO_WAVE")) {
         void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false>;
         void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
-        const int wthreads = nwarp * 32;
-        const size_t state = ((size_t)8 * nwarp * NR * 32 + 64) * sizeof(uint32_t);
+        const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
+        const size_t state = ((size_t)8 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
         const size_t smem1 = state + (size_t)4 * nwarp * 2 * 32 * (2 * NR) * sizeof(uint32_t);
         const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
         int occ1 = 0, occ2 = 0;
