@@ -524,15 +524,16 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
 //      pass 1   4D read + D (or 2D) + 2D written        pass 2   D (or 2D) + 2D read + 4D written
 // = 14D bytes per pixel (16D with 16-bit costs) instead of 22D / 28D, in two launches instead of four.
 //
-// Mailbox discipline (i = row in travel order, w = warp, A / B = its left / right column):
-//   phase 1 (no neighbour needed)  SW_A(i) from the pair's own SW_B(i-1) -> mailbox sw[i&1][w], counter fs[w] = i+1;
-//                                  S_A, S_B; SE_B(i) from the pair's own SE_A(i-1) -> mailbox se[i&3][w]
-//   phase 2                        wait fe[w-1] >= i+1: E_in = e[i&1][w-1], SE_in = se[(i-1)&3][w-1];
-//                                  wait fs[w+1] >= i:   SW_in = sw[(i-1)&1][w+1]   (loaded BEFORE the next publish)
-//                                  E_A, E_B -> mailbox e[i&1][w], counter fe[w] = i+1;  SE_A
-//   phase 3                        SW_B(i) from SW_in
-// A mailbox slot is overwritten only after its reader is known to be done with it: e / sw have two slots because the
-// writer's own wait for row i proves the reader finished row i-2; se is written one phase earlier and has four.
+// Mailbox discipline (i = row in travel order, w = warp, A / B = its left / right column; every mailbox has four slots):
+//   phase 1 (no E needed)   wait fs[w+1] >= i: SW_in = sw[(i-1)&3][w+1];  SW_B(i);  SW_A(i+1) from it, ONE ROW AHEAD
+//                           -> mailbox sw[(i+1)&3][w], counter fs[w] = i+2;  S_A, S_B;  SE_B(i) from the pair's own
+//                           SE_A(i-1) -> mailbox se[i&3][w]
+//   phase 2 (the E chain)   wait fe[w-1] >= i+1: E_in = e[i&3][w-1];  E_A, E_B -> mailbox e[i&3][w], counter fe[w] = i+1
+//   phase 3                 SE_in = se[(i-1)&3][w-1] (visible since that E flag);  SE_A(i)
+// A slot is overwritten four rows later, and a writer that reaches row i+4 has -- through its own waits of rows
+// i+3 / i+4 -- proof that its reader finished row i+1, the last row that looks at the slot.  Column 0 / nc+1 of every
+// mailbox belong to the relay warps (the neighbouring strips); at an image border their counters start at "infinity"
+// and the slots stay zero: a flat state, i.e. a path start.
 __device__ __forceinline__ void flag_publish(uint32_t addr, uint32_t v, bool relaxed) {
     if (relaxed) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
     else asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -560,26 +561,26 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     const bool relaxed = (p.debug & 2) != 0, nowait = (p.debug & 4) != 0;
     // p.debug (PB200_SGM_DEBUG, timing experiments only, wrong results): bit 0 = no strip exchange, bit 2 = no mailbox waits
     const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
-    // shared: e[2][NV][VS] | se[4][NV][VS] | sw[2][NV][VS] | fe[32] fs[32] | staging
-    const int state_words = 8 * NV * VS + 64;
+    // shared: e[4][NV][VS] | se[4][NV][VS] | sw[4][NV][VS] | fe[32] fs[32] | staging
+    const int state_words = 12 * NV * VS + 64;
     // mailboxes, counters AND the staging ring start as zeros (columns right of the image are never staged and must
     // read as zero costs, which also pass the data check; a strip without a neighbour reads flat zero states)
     for (int i = threadIdx.x; i < state_words + NSTG * nc * 2 * 32 * SIN; i += blockDim.x) wave_smem[i] = 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (!has_left) wave_smem[8 * NV * VS + 0] = 0xFFFFFFFFu;                 // fe[0]: the image border never makes anyone wait
-        if (!has_right) wave_smem[8 * NV * VS + 32 + NV - 1] = 0xFFFFFFFFu;       // fs[nc + 1]
+        if (!has_left) wave_smem[12 * NV * VS + 0] = 0xFFFFFFFFu;                // fe[0]: the image border never makes anyone wait
+        if (!has_right) wave_smem[12 * NV * VS + 32 + NV - 1] = 0xFFFFFFFFu;      // fs[nc + 1]
     }
     __syncthreads();
     const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
     const uint32_t e_base = smem_u32(wave_smem) + lane_b;
-    const uint32_t se_base = e_base + (uint32_t)(2 * NV * VS) * 4u;
+    const uint32_t se_base = e_base + (uint32_t)(4 * NV * VS) * 4u;
     const uint32_t sw_base = se_base + (uint32_t)(4 * NV * VS) * 4u;
-    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(8 * NV * VS) * 4u, fs_base = fe_base + 128u;
+    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(12 * NV * VS) * 4u, fs_base = fe_base + 128u;
     const uint32_t SLOT = (uint32_t)(NV * VS) * 4u, VB = (uint32_t)VS * 4u;      // bytes per mailbox slot / per vector
-    // ring, per strip boundary b (between strips b and b + 1): 8 vectors of VS 64-bit words: e[2] | se[4] | sw[2]
-    unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 8 * VS;          // boundary on our left (used when has_left)
-    unsigned long long *ring_r = p.ring + (size_t)strip * 8 * VS;                // boundary on our right
+    // ring, per strip boundary b (between strips b and b + 1): 12 vectors of VS 64-bit words: e[4] | se[4] | sw[4]
+    unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 12 * VS;         // boundary on our left (used when has_left)
+    unsigned long long *ring_r = p.ring + (size_t)strip * 12 * VS;               // boundary on our right
 
     // ---- relay warps: mailbox <-> L2 ring, so that no compute warp ever touches the ring -----------------------
     if (warp == nc) {                                     // left relay
@@ -587,16 +588,16 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         for (int i = 0; i < H; ++i) {
             const uint32_t tag = (uint32_t)(i + 1);
             uint32_t v[NR];
-            // outbound: SW_A(i) of the first compute warp
+            // outbound: SW_A(i) of the first compute warp (published one row early, see phase 1)
             if (!nowait) flag_wait(fs_base + 1u * 4u, tag);
-            lds_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + 1u * VB, v);
-            ll_send_u32<NR>(ring_l + (size_t)(6 + (i & 1)) * VS, lane, tag, v);
+            lds_words<NR>(sw_base + (uint32_t)(i & 3) * SLOT + 1u * VB, v);
+            ll_send_u32<NR>(ring_l + (size_t)(8 + (i & 3)) * VS, lane, tag, v);
             // inbound: E(i), then SE(i), of the left strip's last column
-            ll_recv_u32<NR>(ring_l + (size_t)(0 + (i & 1)) * VS, lane, tag, v);
-            sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT, v);
+            ll_recv_u32<NR>(ring_l + (size_t)(0 + (i & 3)) * VS, lane, tag, v);
+            sts_words<NR>(e_base + (uint32_t)(i & 3) * SLOT, v);
             __syncwarp();
             if (lane == 0) flag_publish(fe_base, tag, relaxed);
-            ll_recv_u32<NR>(ring_l + (size_t)(2 + (i & 3)) * VS, lane, tag, v);
+            ll_recv_u32<NR>(ring_l + (size_t)(4 + (i & 3)) * VS, lane, tag, v);
             sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT, v);                 // visible with the next E flag
         }
         return;
@@ -608,13 +609,13 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             uint32_t v[NR];
             // outbound: E_B(i), SE_B(i) of the last compute warp
             if (!nowait) flag_wait(fe_base + (uint32_t)nc * 4u, tag);
-            lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (uint32_t)nc * VB, v);
-            ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 1)) * VS, lane, tag, v);
+            lds_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + (uint32_t)nc * VB, v);
+            ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 3)) * VS, lane, tag, v);
             lds_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + (uint32_t)nc * VB, v);
-            ll_send_u32<NR>(ring_r + (size_t)(2 + (i & 3)) * VS, lane, tag, v);
+            ll_send_u32<NR>(ring_r + (size_t)(4 + (i & 3)) * VS, lane, tag, v);
             // inbound: SW_A(i) of the right strip's first column
-            ll_recv_u32<NR>(ring_r + (size_t)(6 + (i & 1)) * VS, lane, tag, v);
-            sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + (uint32_t)(nc + 1) * VB, v);
+            ll_recv_u32<NR>(ring_r + (size_t)(8 + (i & 3)) * VS, lane, tag, v);
+            sts_words<NR>(sw_base + (uint32_t)(i & 3) * SLOT + (uint32_t)(nc + 1) * VB, v);
             __syncwarp();
             if (lane == 0) flag_publish(fs_base + (uint32_t)(nc + 1) * 4u, tag, relaxed);
         }
@@ -641,73 +642,106 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     for (int c = 0; c < 2; ++c) pix0[c] = ((size_t)y0 * W + (valid[c] ? (FINAL ? W - 1 - xl[c] : xl[c]) : 0)) * D;
     const int poff = p16_off<CB>(D) + lane * NR;
 
-    auto stage_in = [&](int r) {
-        const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-            if (valid[c]) {
-                if (!FINAL) {
-                    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cv) + pix0[c] + (long)r * row_stride + lane * NR;
-                    cp_async_words<NR>(sg + c * stg_pix + off0, src);
-                    cp_async_words<NR>(sg + c * stg_pix + off1, src + D / 2);
-                } else {
-                    const uint32_t *src = p.buf + pix0[c] + (long)r * row_stride;
-                    cp_async_words<RW>(sg + c * stg_pix + off0, src + lane * RW);
-                    cp_async_words<NR>(sg + c * stg_pix + off1, src + poff);
-                }
-            }
+    // Pixel A (the left column) is staged, unpacked and -- for its SW direction -- computed ONE ROW AHEAD of pixel B:
+    // SW_A(i + 1) only needs the pair's own SW_B(i), so it is published a whole row before the left neighbour uses it.
+    // That takes the program-order coupling "E wait of row i -> SW publish of row i + 1" out of the border cycle
+    // (E hop -> remainder of the row -> SW hop back), which otherwise limits the row rate to ~1.4 ring round trips.
+    auto stage_pix = [&](int c, int r) {
+        if (!valid[c] || r >= H) return;
+        const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage + c * stg_pix;
+        if (!FINAL) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(p.cv) + pix0[c] + (long)r * row_stride + lane * NR;
+            cp_async_words<NR>(sg + off0, src);
+            cp_async_words<NR>(sg + off1, src + D / 2);
+        } else {
+            const uint32_t *src = p.buf + pix0[c] + (long)r * row_stride;
+            cp_async_words<RW>(sg + off0, src + lane * RW);
+            cp_async_words<NR>(sg + off1, src + poff);
+        }
     };
+    const float nan_code = (float)(p.inv | Tier<CB>::FLAG1);
+    const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
+    bool bad = false;
+    // unpack pixel c of row r from its staging slot (pass 1: verify + pack + write the cost code; zeros outside the image)
+    auto load_pix = [&](int c, int r, uint32_t (&c16)[NR], uint32_t (&p16)[NR]) {
+        const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage + c * stg_pix;
+        if (!FINAL) {
+            uint32_t fa[NR], fb[NR];
+            lds_words<NR>(sg + off0, fa);
+            lds_words<NR>(sg + off1, fb);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                c16[j] = encode_pair(__uint_as_float(fa[j]), __uint_as_float(fb[j]), nan_code, p.cost_ok_max, bad);
+                p16[j] = 0u;
+            }
+            if (valid[c] && r < H) st_cost<NR, CB>(p.buf + pix0[c] + (long)r * row_stride, lane, c16);
+        } else {
+            uint32_t craw[RW];
+            lds_words<RW>(sg + off0, craw);
+            lds_words<NR>(sg + off1, p16);
+            unpack_cost<NR, CB>(craw, c16);
+        }
+        if (!valid[c] || r >= H) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) c16[j] = p16[j] = 0u;              // outside the image: zero costs, flat states
+        }
+    };
+    stage_pix(0, 0);
+    cp_async_commit();
     for (int r = 0; r < PFD; ++r) {
-        if (r < H) stage_in(r);
+        stage_pix(0, r + 1);
+        stage_pix(1, r);
         cp_async_commit();
     }
 
-    const float nan_code = (float)(p.inv | Tier<CB>::FLAG1);
-    const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
-    uint32_t Sv[2][NR], SEA_prev[NR], SWB_prev[NR];
+    uint32_t Sv[2][NR], SEA_prev[NR], c16A[NR], p16A[NR], SWA_cur[NR], zero[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = SWB_prev[j] = 0u;
-    bool bad = false;
+    for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = zero[j] = 0u;
+    cp_async_wait<PFD>();                                  // pixel A of row 0
+    load_pix(0, 0, c16A, p16A);
+    {
+        uint32_t ccA[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) ccA[j] = c16A[j] & Tier<CB>::VALUES;
+        nstep<NR>(ccA, zero, SWA_cur, lane, p1p1, p2p2);     // SW_A(0): a path start
+        sts_words<NR>(sw_base + vme * VB, SWA_cur);
+        __syncwarp();
+        if (lane == 0) flag_publish(fs_base + vme * 4u, 1u, relaxed);
+    }
 
 #pragma unroll 1
     for (int i = 0; i < H; ++i) {
         const uint32_t tag = (uint32_t)(i + 1);
-        if (i + PFD < H) stage_in(i + PFD);
+        stage_pix(0, i + PFD + 1);
+        stage_pix(1, i + PFD);
         cp_async_commit();
-        cp_async_wait<PFD>();
-        uint32_t c16[2][NR], p16[2][NR], cc[2][NR];
-        const uint32_t sg = stg_base + (uint32_t)(i & (NSTG - 1)) * stg_stage;
+        cp_async_wait<PFD>();                              // pixel A of row i + 1 and pixel B of row i have landed
+        uint32_t c16[2][NR], p16[2][NR], cc[2][NR], c16An[NR], p16An[NR], ccAn[NR];
+        load_pix(0, i + 1, c16An, p16An);
+        load_pix(1, i, c16[1], p16[1]);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            if (!FINAL) {
-                uint32_t fa[NR], fb[NR];
-                lds_words<NR>(sg + c * stg_pix + off0, fa);
-                lds_words<NR>(sg + c * stg_pix + off1, fb);
-#pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    c16[c][j] = encode_pair(__uint_as_float(fa[j]), __uint_as_float(fb[j]), nan_code, p.cost_ok_max, bad);
-                    p16[c][j] = 0u;
-                }
-                if (valid[c]) st_cost<NR, CB>(p.buf + pix0[c] + (long)i * row_stride, lane, c16[c]);
-            } else {
-                uint32_t craw[RW];
-                lds_words<RW>(sg + c * stg_pix + off0, craw);
-                lds_words<NR>(sg + c * stg_pix + off1, p16[c]);
-                unpack_cost<NR, CB>(craw, c16[c]);
-            }
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                if (!valid[c]) { c16[c][j] = 0u; p16[c][j] = 0u; }          // columns right of the image: zero costs, flat states
-                cc[c][j] = c16[c][j] & Tier<CB>::VALUES;
-            }
+        for (int j = 0; j < NR; ++j) {
+            c16[0][j] = c16A[j];
+            p16[0][j] = p16A[j];
+            cc[0][j] = c16A[j] & Tier<CB>::VALUES;
+            cc[1][j] = c16[1][j] & Tier<CB>::VALUES;
+            ccAn[j] = c16An[j] & Tier<CB>::VALUES;
         }
 
         // ---- phase 1: everything that does not need this row's E chain ----------------------------------
-        uint32_t L_SW_A[NR], L_SE_B[NR], L0[NR], SW_in[NR], L_SW_B[NR];
-        nstep<NR>(cc[0], SWB_prev, L_SW_A, lane, p1p1, p2p2);
-        sts_words<NR>(sw_base + (uint32_t)(i & 1) * SLOT + vme * VB, L_SW_A);
+        uint32_t L_SE_B[NR], L0[NR], SW_in[NR], L_SW_B[NR], SWA_next[NR];
+        // the right neighbour's SW_A(i - 1): published two of its rows ago
+#pragma unroll
+        for (int j = 0; j < NR; ++j) SW_in[j] = 0u;
+        if (i > 0) {
+            if (!nowait) flag_wait(fs_base + (vme + 1u) * 4u, tag - 1);
+            lds_words<NR>(sw_base + (uint32_t)((i - 1) & 3) * SLOT + (vme + 1u) * VB, SW_in);
+        }
+        nstep<NR>(cc[1], SW_in, L_SW_B, lane, p1p1, p2p2);                   // SW_B(i)
+        nstep<NR>(ccAn, L_SW_B, SWA_next, lane, p1p1, p2p2);                 // SW_A(i + 1), one row ahead
+        sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, SWA_next);
         __syncwarp();
-        if (lane == 0) flag_publish(fs_base + vme * 4u, tag, relaxed);
+        if (lane == 0) flag_publish(fs_base + vme * 4u, tag + 1, relaxed);
         nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p1p1, p2p2);
         sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
 #pragma unroll
@@ -716,23 +750,14 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
             for (int j = 0; j < NR; ++j) Sv[c][j] = L0[j];
         }
-        // the right neighbour's SW state of the previous row (published a whole row ago): loaded BEFORE E_B(i) is
-        // published (slot discipline above), and off the E chain
-#pragma unroll
-        for (int j = 0; j < NR; ++j) SW_in[j] = 0u;
-        if (i > 0) {
-            if (!nowait) flag_wait(fs_base + (vme + 1u) * 4u, tag - 1);
-            lds_words<NR>(sw_base + (uint32_t)((i - 1) & 1) * SLOT + (vme + 1u) * VB, SW_in);
-        }
-        nstep<NR>(cc[1], SW_in, L_SW_B, lane, p1p1, p2p2);
 
         // ---- phase 2: the E chain -- wait, two steps, publish -------------------------------------------------
         uint32_t E_in[NR], SE_in[NR], L_E_A[NR], L_E_B[NR], L_SE_A[NR];
         if (!nowait) flag_wait(fe_base + (vme - 1u) * 4u, tag);
-        lds_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + (vme - 1u) * VB, E_in);
+        lds_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + (vme - 1u) * VB, E_in);
         nstep<NR>(cc[0], E_in, L_E_A, lane, p1p1, p2p2);
         nstep<NR>(cc[1], L_E_A, L_E_B, lane, p1p1, p2p2);
-        sts_words<NR>(e_base + (uint32_t)(i & 1) * SLOT + vme * VB, L_E_B);
+        sts_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_E_B);
         __syncwarp();
         if (lane == 0) flag_publish(fe_base + vme * 4u, tag, relaxed);
         // ---- phase 3: the left neighbour's SE state of the previous row (visible since its E flag of this row) ----
@@ -746,7 +771,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             uint32_t tot[NR];
 #pragma unroll
             for (int j = 0; j < NR; ++j)
-                tot[j] = p16[c][j] + Sv[c][j] + (c == 0 ? (L_E_A[j] + L_SE_A[j] + L_SW_A[j]) : (L_E_B[j] + L_SE_B[j] + L_SW_B[j]));
+                tot[j] = p16[c][j] + Sv[c][j] + (c == 0 ? (L_E_A[j] + L_SE_A[j] + SWA_cur[j]) : (L_E_B[j] + L_SE_B[j] + L_SW_B[j]));
             if (valid[c]) {
                 uint32_t *gpix = p.buf + pix0[c] + (long)i * row_stride;
                 if (!FINAL) {
@@ -790,7 +815,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             }
         }
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { SEA_prev[j] = L_SE_A[j]; SWB_prev[j] = L_SW_B[j]; }
+        for (int j = 0; j < NR; ++j) { SEA_prev[j] = L_SE_A[j]; SWA_cur[j] = SWA_next[j]; c16A[j] = c16An[j]; p16A[j] = p16An[j]; }
     }
     if (!FINAL && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
 }
@@ -812,7 +837,7 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
         void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false>;
         void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
         const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
-        const size_t state = ((size_t)8 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
+        const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
         const size_t smem1 = state + (size_t)4 * nwarp * 2 * 32 * (2 * NR) * sizeof(uint32_t);
         const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
         int occ1 = 0, occ2 = 0;
@@ -824,7 +849,7 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
         }
         if ((long)occ1 * nsm >= nstrips && (long)occ2 * nsm >= nstrips) {
             p.ring = reinterpret_cast<unsigned long long *>(workspace);
-            const size_t wring = (size_t)nstrips * 8 * NR * 32 * sizeof(unsigned long long);
+            const size_t wring = (size_t)nstrips * 12 * NR * 32 * sizeof(unsigned long long);
             PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
             void *args[] = {(void *)&p};
             PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
