@@ -309,8 +309,9 @@ def run_ours(args):
         except Exception:
             pass
         line["roofline"] = {"bound": "hbm",
-                            "kernel": "SGM stage = sgm_narrow_h_kernel x2 (E, W) + sgm_narrow_vsweep_kernel x2 (S/SE/SW, N/NE/NW + WTA); "
-                                      "4 launches timed as one unit (8*D algorithmic bytes per pixel belong to the stage)",
+                            "kernel": "SGM stage = sgm_wave_kernel x2 (pass 1: E/SE/S/SW reading float C; pass 2: W/NW/N/NE writing "
+                                      "float S + WTA); 2 launches timed as one unit (the stage's 8*D algorithmic bytes per pixel "
+                                      "= 4*D read by pass 1 + 4*D written by pass 2)",
                             "achieved": sgm_gbs, "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": traffic,
                             "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
         cen_gbs = census_alg / (stage["census_ms"] * 1e-3) / 1e9

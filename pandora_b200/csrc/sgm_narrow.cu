@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
     for (int c = 0; c < 2; ++c) pix0[c] = ((size_t)y0 * W + (valid[c] ? (FINAL ? W - 1 - xl[c] : xl[c]) : 0)) * D;
     const int poff = p16_off<CB>(D) + lane * NR;
+    const size_t pixi0[2] = {pix0[0] / D, pix0[1] / D};                           // pixel indices of the first row (WTA outputs)
 
     // Pixel A (the left column) is staged, unpacked and -- for its SW direction -- computed ONE ROW AHEAD of pixel B:
     // SW_A(i + 1) only needs the pair's own SW_B(i), so it is published a whole row before the left neighbour uses it.
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         if (lane == 0) flag_publish(fs_base + vme * 4u, 1u, relaxed);
     }
 
-#pragma unroll 1
+#pragma unroll 2
     for (int i = 0; i < H; ++i) {
         const uint32_t tag = (uint32_t)(i + 1);
         stage_pix(0, i + PFD + 1);
@@ -794,8 +795,8 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
                             // half: (sum << 16) | register index; the lane offset of the disparity is added once below
                             const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;
                             const uint32_t tk = t | sat;
-                            bl = min(bl, (tk << 16) | (uint32_t)j);
-                            bh = min(bh, (tk & 0xFFFF0000u) | (uint32_t)j);
+                            bl = min(bl, __byte_perm(tk, (uint32_t)j, 0x1054));      // (low sum << 16) | j
+                            bh = min(bh, __byte_perm(tk, (uint32_t)j, 0x3254));      // (high sum << 16) | j
                         }
                     }
                     float *o = reinterpret_cast<float *>(gpix) + lane * NR;
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
                         uint32_t best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
                         best = __reduce_min_sync(0xffffffffu, best);
                         if (lane == 0) {
-                            const size_t pix = (pix0[c] + (long)i * row_stride) / D;
+                            const size_t pix = pixi0[c] + (long)i * (FINAL ? -(long)W : (long)W);
                             const bool none = (best >> 16) >= ((CB == 1) ? 0xFF80u : 0xFFFFu);
                             p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
                             if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
