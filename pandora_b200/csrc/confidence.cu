@@ -8,12 +8,17 @@
 // n_etas thresholds and over the D costs (n_etas * D comparisons per pixel, twice when risk follows ambiguity).
 // Here: pass 1 (cv_extrema_kernel) reads the volume once for the per-pixel minimum and the global extrema; pass 2
 // (confidence_kernel) reads it once more, one warp per pixel, and -- because ext + eta is non-decreasing in eta --
-// finds for every cost the FIRST threshold it passes with a binary search (log2 n_etas comparisons instead of
-// n_etas), which gives the ambiguity integral directly and the per-eta samples / disparity extents through small
-// per-warp shared-memory histograms followed by a prefix scan.  Ambiguity and risk share that single pass.
-// The float32 / float64 comparison types are the reference's (ambiguity takes float etas, risk double etas), the
-// normalisation is the same float32 expression, counts are exact integers, and the risk sums are accumulated in eta
-// order in float32 like the reference, so all outputs are bit-identical.
+// finds for every cost the FIRST threshold it passes (index guessed from the even spacing of np.arange etas, then
+// corrected against the true thresholds: one or two comparisons instead of n_etas), which gives the ambiguity integral
+// directly and the per-eta samples / disparity extents through small per-warp shared-memory histograms followed by a
+// prefix scan.  Ambiguity and risk share that single pass.  The comparison semantics are the reference's (ambiguity
+// compares with float32 thresholds; risk with float64 ones, reproduced exactly by float32 thresholds rounded down),
+// the normalisation is the same float32 expression, counts are exact integers, and the risk sums are either provably
+// order-independent (integer counts, dyadic disparities) or accumulated in eta order like the reference, so all
+// outputs are bit-identical.
+#include <cmath>
+#include <vector>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -84,6 +89,7 @@ struct ConfParams {
     float *amb, *samp_amb;          // outputs (optional)
     const float *samp_amb_in;       // risk input; NULL = the samples computed by this pass
     float *risk_max, *risk_min, *disp_sup, *disp_inf, *samp_risk_max, *samp_risk_min;
+    int exact_sums, vec4;                 // the risk sums are exact in any order (integer counts, dyadic disparities): reduce in parallel
 };
 
 // searchsorted of cost_volume_confidence_tools.cpp:22-38 (lower bound, clamped to n - 1)
@@ -96,8 +102,8 @@ __device__ __forceinline__ int searchsorted_dev(const float *arr, int n, float v
     return left;
 }
 
-// per warp in shared memory: thr_d[n] doubles | thr_f[n] floats | hist[n + 1] | lo[n + 1] | hi[n + 1] ints
-__host__ __device__ inline size_t conf_warp_bytes(int n) { return (size_t)n * 8 + (size_t)((n + 1) / 2 * 2) * 4 + (size_t)3 * (n + 2) * 4; }
+// per warp in shared memory: thr_r[-2 .. n+1] | thr_f[-2 .. n+1] floats (sentinels -inf, -inf | +inf, +inf) | hist | lo | hi ints
+__host__ __device__ inline size_t conf_warp_bytes(int n) { return (size_t)2 * ((n + 4 + 3) / 4 * 4) * 4 + (size_t)3 * (n + 2) * 4; }
 
 template <bool RISK>
 __global__ void __launch_bounds__(256) confidence_kernel(const ConfParams p) {
@@ -105,9 +111,12 @@ __global__ void __launch_bounds__(256) confidence_kernel(const ConfParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = p.n_etas, D = p.D;
     unsigned char *base = conf_smem + (size_t)warp * ((conf_warp_bytes(n) + 15) / 16 * 16);
-    double *thr_d = reinterpret_cast<double *>(base);
-    float *thr_f = reinterpret_cast<float *>(thr_d + n);
-    int *hist = reinterpret_cast<int *>(thr_f + (n + 1) / 2 * 2);
+    // thr_r[e] = the double threshold of risk.cpp rounded DOWN to float: for a float x, x > T  <=>  x > rd(T), so the
+    // inner loop never touches float64 (stored in the first half of the 8-byte slots the layout reserves)
+    const int npad = (n + 4 + 3) / 4 * 4;                  // floats per threshold array incl. the four sentinels
+    float *thr_r = reinterpret_cast<float *>(base) + 2;
+    float *thr_f = thr_r + npad;
+    int *hist = reinterpret_cast<int *>(thr_f - 2 + npad);
     int *lo = hist + (n + 2), *hi = lo + (n + 2);
     const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -136,32 +145,55 @@ __global__ void __launch_bounds__(256) confidence_kernel(const ConfParams p) {
         __syncwarp();
         for (int e = lane; e < n; e += 32) {
             thr_f[e] = ext + p.etas_f[e];
-            if (RISK) thr_d[e] = (double)ext + p.etas_d[e];
+            if (RISK) thr_r[e] = __double2float_rd((double)ext + p.etas_d[e]);
+        }
+        if (lane < 2) {
+            thr_f[lane - 2] = thr_r[lane - 2] = -CUDART_INF_F;
+            thr_f[n + lane] = thr_r[n + lane] = CUDART_INF_F;
         }
         for (int e = lane; e < n + 1; e += 32) { hist[e] = 0; lo[e] = 0x7fffffff; hi[e] = -1; }
         __syncwarp();
         int cnt = 0;
         const float *pc = p.cv + pix * D;
-        for (int k = lane; k < D; k += 32) {
-            float v = pc[k];
+        // first threshold a cost passes: the thresholds are non-decreasing and (for np.arange etas) evenly spaced, so the
+        // index is guessed from the spacing and then corrected against the true thresholds -- exact for any spacing,
+        // one or two comparisons instead of a log2(n) search when the guess is good
+        const float t0 = thr_f[0], tn = thr_f[n - 1];
+        const float inv_step = (tn > t0) ? (float)(n - 1) / (tn - t0) : 0.f;
+        // thr[-2], thr[-1] hold -inf and thr[n], thr[n+1] hold +inf (see the layout), so a 4-wide window around the
+        // guess can be read without bounds checks.  first index = (thresholds below the window, assumed not passed) +
+        // (not passed inside it); the assumption is verified on the window's ends and a plain loop handles the rest.
+        auto first_pass = [&](const float *thr, float nv, int guess) -> int {
+            const int w0 = guess - 2;                         // window = thr[w0 .. w0 + 3], w0 in [-2, n - 2]
+            const bool q0 = nv <= thr[w0], q1 = nv <= thr[w0 + 1], q2 = nv <= thr[w0 + 2], q3 = nv <= thr[w0 + 3];
+            int e = max(w0, 0) + (int)(w0 >= 0 && !q0) + (int)(w0 + 1 >= 0 && !q1) + (int)!q2 + (int)(w0 + 3 < n && !q3);
+            const bool ok = (w0 <= 0 || !q0) && (w0 + 3 >= n - 1 || q3);
+            if (!ok) {                                        // guess off by more than the window: exact search
+                e = min(max(guess, 0), n);
+                while (e > 0 && nv <= thr[e - 1]) --e;
+                while (e < n && !(nv <= thr[e])) ++e;
+            }
+            return e;
+        };
+        auto one_cost = [&](float v, int k) {
             if (p.is_max) v = -v;
             const float nv = (v != v) ? ((k >= imin && k < imax) ? -CUDART_INF_F : CUDART_INF_F) : (v - gmin) / diff;
-            int a = 0, b = n;                               // first e with nv <= thr_f[e]
-            while (a < b) {
-                const int mid = (a + b) >> 1;
-                if (nv <= thr_f[mid]) b = mid; else a = mid + 1;
-            }
+            const int guess = (int)fminf(fmaxf((nv - t0) * inv_step, 0.f), (float)n);
+            const int a = first_pass(thr_f, nv, guess);
             cnt += n - a;
-            if (want_samples) atomicAdd(&hist[a], 1);
+            if (want_samples && a < n) atomicAdd(&hist[a], 1);
             if (RISK) {
-                int c = 0, d = n;                           // first e with (double)nv <= thr_d[e]  (risk.cpp:137: not >)
-                const double nd = (double)nv;
-                while (c < d) {
-                    const int mid = (c + d) >> 1;
-                    if (!(nd > thr_d[mid])) d = mid; else c = mid + 1;
-                }
+                const int c = RISK ? first_pass(thr_r, nv, a) : 0;   // risk.cpp:137 (not >): the float64 comparison, see thr_r
                 if (c < n) { atomicMin(&lo[c], k); atomicMax(&hi[c], k); }
             }
+        };
+        if (p.vec4) {
+            for (int k = lane * 4; k < D; k += 128) {
+                const float4 v = *reinterpret_cast<const float4 *>(pc + k);
+                one_cost(v.x, k); one_cost(v.y, k + 1); one_cost(v.z, k + 2); one_cost(v.w, k + 3);
+            }
+        } else {
+            for (int k = lane; k < D; k += 32) one_cost(pc[k], k);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0 && p.amb) p.amb[pix] = (float)cnt;
@@ -197,7 +229,31 @@ __global__ void __launch_bounds__(256) confidence_kernel(const ConfParams p) {
                     p.samp_risk_min[pix * n + e] = 1.f + e_max - sa;
                 }
             }
-            if (lane == 0) {                                // float32 sums in eta order, like risk.cpp:128-175
+            if (p.exact_sums && p.samp_amb_in == nullptr) {
+                // every term is a small integer or a dyadic disparity: float32 addition is exact in any order, so the
+                // eta-ordered sums of risk.cpp:128-175 can be reduced across the lanes
+                float s_min = 0.f, s_max = 0.f, s_inf = 0.f, s_sup = 0.f;
+                for (int e = lane; e < n; e += 32) {
+                    const float e_max = (float)hi[e] - (float)lo[e];
+                    s_sup += p.disparity_range[hi[e]];
+                    s_inf += p.disparity_range[lo[e]];
+                    s_min += 1.f + e_max - (float)hist[e];
+                    s_max += e_max;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s_min += __shfl_xor_sync(0xffffffffu, s_min, o);
+                    s_max += __shfl_xor_sync(0xffffffffu, s_max, o);
+                    s_inf += __shfl_xor_sync(0xffffffffu, s_inf, o);
+                    s_sup += __shfl_xor_sync(0xffffffffu, s_sup, o);
+                }
+                if (lane == 0) {
+                    p.risk_min[pix] = s_min / (float)n;
+                    p.risk_max[pix] = s_max / (float)n;
+                    p.disp_sup[pix] = s_sup / (float)n;
+                    p.disp_inf[pix] = s_inf / (float)n;
+                }
+            } else if (lane == 0) {                         // float32 sums in eta order, like risk.cpp:128-175
                 float s_min = 0.f, s_max = 0.f, s_inf = 0.f, s_sup = 0.f;
                 for (int e = 0; e < n; ++e) {
                     const float e_max = (float)hi[e] - (float)lo[e];
@@ -278,6 +334,16 @@ extern "C" int pb200_confidence(const float *d_cv, int H, int W, int D, int is_m
     PB200_CUDA(cudaMemcpyAsync(etas_f, etas_host_f, (size_t)n_etas * sizeof(float), cudaMemcpyHostToDevice, s));
     PB200_CUDA(cudaStreamSynchronize(s));                 // etas_host_f lives on this stack frame
 
+    // are the risk sums order-independent?  counts are integers <= D <= 2^12; disparities must be multiples of 1/16 below
+    // 2^12 (then every partial sum of <= 128 terms is an integer multiple of 1/16 below 2^23 / 16: exact in float32)
+    bool exact_sums = risk && n_etas <= 128 && D <= 4096;
+    if (exact_sums) {
+        std::vector<float> dr((size_t)D);
+        PB200_CUDA(cudaMemcpyAsync(dr.data(), d_disparity_range, (size_t)D * sizeof(float), cudaMemcpyDeviceToHost, s));
+        PB200_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < D && exact_sums; ++k)
+            exact_sums = std::fabs(dr[k]) < 4096.f && dr[k] * 16.f == std::floor(dr[k] * 16.f);
+    }
     const long n_pix = (long)H * W;
     long blocks = (n_pix + 7) / 8;
     const long cap = (long)sm_count() * 8;
@@ -296,6 +362,8 @@ extern "C" int pb200_confidence(const float *d_cv, int H, int W, int D, int is_m
     p.amb = d_ambiguity; p.samp_amb = d_sampled_ambiguity; p.samp_amb_in = d_sampled_ambiguity_in;
     p.risk_max = d_risk_max; p.risk_min = d_risk_min; p.disp_sup = d_disp_sup; p.disp_inf = d_disp_inf;
     p.samp_risk_max = d_sampled_risk_max; p.samp_risk_min = d_sampled_risk_min;
+    p.vec4 = vec ? 1 : 0;
+    p.exact_sums = exact_sums ? 1 : 0;
     const size_t smem = 8 * ((conf_warp_bytes(n_etas) + 15) / 16 * 16);
     if (smem > 200 * 1024) {
         set_error("pb200_confidence: too many etas for the shared-memory histograms");

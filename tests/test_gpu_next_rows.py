@@ -319,3 +319,28 @@ def test_run_with_next_rows(eng, oracle):
     assert list(disp.coords["indicator"].data) == ["confidence_from_ambiguity", "confidence_from_left_right_consistency"]
     np.testing.assert_array_equal(conf[:, :, 0], 1 - amb)
     np.testing.assert_array_equal(conf[:, :, 1], exp_conf)
+
+
+def test_confidence_generic_inputs_sequential_sums(eng, oracle):
+    """Non-dyadic disparity coordinates and an external sampled ambiguity take the eta-ordered float32 sums of
+    risk.cpp:128-175 (no parallel reduction); unevenly spaced etas exercise the threshold search's correction loops."""
+    gen = np.random.default_rng(11)
+    H, W, D = 17, 29, 20
+    cv = random_volume(11, H, W, D, nan_frac=0.1, integer=False, hi=30)
+    dr = (np.arange(D) * 0.3 - 2.1).astype(np.float32)                      # not multiples of 1/16
+    grids = np.array([np.full((H, W), -2), np.full((H, W), 3)], dtype=np.int64)
+    etas = np.sort(gen.random(37) * 0.6)
+    etas[0] = 0.0
+    exp_amb, exp_samp = oracle.ambiguity(cv, etas, grids, dr, sampled=True)
+    fake_samp = (exp_samp + gen.random(exp_samp.shape).astype(np.float32)).astype(np.float32)
+    exp_risk = oracle.risk(cv, fake_samp, etas, grids, dr, sampled=True)
+    out = eng.confidence(dev(eng, cv), etas, grids, dr, sampled_ambiguity=True, risk=True, sampled_risk=True, sampled_ambiguity_in=fake_samp)
+    np.testing.assert_array_equal(host(out["ambiguity"]), exp_amb)
+    np.testing.assert_array_equal(host(out["sampled_ambiguity"]), exp_samp)
+    for key, exp in zip(["risk_max", "risk_min", "disp_sup", "disp_inf", "sampled_risk_max", "sampled_risk_min"], exp_risk):
+        np.testing.assert_array_equal(host(out[key]), exp)
+    # internal samples + non-dyadic disparities: still the sequential sums
+    exp_risk2 = oracle.risk(cv, exp_samp, etas, grids, dr)
+    out2 = eng.confidence(dev(eng, cv), etas, grids, dr, ambiguity=False, risk=True)
+    for key, exp in zip(["risk_max", "risk_min", "disp_sup", "disp_inf"], exp_risk2):
+        np.testing.assert_array_equal(host(out2[key]), exp)
