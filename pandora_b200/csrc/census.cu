@@ -103,25 +103,65 @@ __device__ __forceinline__ uint32_t hamming_flagged(const uint32_t (&a)[NW], con
 template <int NW, bool VEC4>
 __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [2][TX*D] float out tiles | [NW][r_len] right words | [NW][TX] left words | mbarrier
+    // layout: [2][TX*D] float out tiles | 2 x ([NW][r_len] right words | [NW][TX] left words) | 2 mbarriers.
+    // The descriptors of the NEXT tile are requested (TMA) before the current tile is computed, so their HBM / L2
+    // latency hides behind the compute instead of being paid once per tile.
     float *sOut = reinterpret_cast<float *>(smem_raw);
     const int tile_elems = p.TX * p.D;
-    uint32_t *sR = reinterpret_cast<uint32_t *>(sOut + 2 * (size_t)((tile_elems + 3) & ~3));
-    uint32_t *sL = sR + NW * p.r_len;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sL + NW * p.TX);
+    uint32_t *sR0 = reinterpret_cast<uint32_t *>(sOut + 2 * (size_t)((tile_elems + 3) & ~3));
+    const int desc_words = NW * p.r_len + NW * p.TX;          // one staging buffer
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR0 + 2 * desc_words);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
+    // request the descriptors of `tile` into staging buffer `buf` (all threads call it; thread 0 drives the TMA)
+    auto request = [&](long tile, int buf) {
+        const int y = p.row0 + (int)(tile / p.tiles_x);
+        if (!(y >= p.half && y < p.H - p.half)) return;        // border rows are all NaN: nothing to stage
+        const int x0 = (int)(tile % p.tiles_x) * p.TX;
+        uint32_t *sR = sR0 + buf * desc_words, *sL = sR + NW * p.r_len;
+        const int lo = x0 + p.dmin;                 // right position of (pixel 0, k = 0)
+        const int base = lo & ~3;                   // smem index j <-> right column base + j (floor to 4, also for lo < 0)
+        const int clo = max(base, 0);
+        const int chi = min(base + p.r_len, p.pitch);
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            if (chi > clo) bytes += (uint32_t)NW * (uint32_t)(chi - clo) * 4u;
+            bytes += (uint32_t)NW * (uint32_t)p.TX * 4u;
+            mbar_expect_tx(bars + buf, bytes);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (chi > clo)
+                    tma_load_1d(sR + w * p.r_len + (clo - base), p.descR + ((size_t)w * p.H + y) * p.pitch + clo,
+                                (uint32_t)(chi - clo) * 4u, bars + buf);
+                // pitch >= roundup4(W) + 4 and x0 + TX <= roundup(W, TX): clamp the tail to the pitch
+                tma_load_1d(sL + w * p.TX, p.descL + ((size_t)w * p.H + y) * p.pitch + x0, (uint32_t)p.TX * 4u, bars + buf);
+            }
+        }
+        // right columns outside the stored row: flag as invalid by hand (disjoint from the TMA range)
+        for (int j = tid; j < p.r_len; j += blockDim.x) {
+            const int c = base + j;
+            if (c < clo || c >= chi) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sR[w * p.r_len + j] = (w == NW - 1) ? 0x80000000u : 0u;
+            }
+        }
+    };
+
     const int G = (p.D + 3) >> 2;             // groups of 4 disparities
     const int n_chunks = p.TX / p.CH;
-    uint32_t parity = 0;
+    uint32_t parity = 0u;                       // bit b = phase parity of staging buffer b
     int it = 0;
+    if ((long)blockIdx.x < p.n_tiles) request(blockIdx.x, 0);
     for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        uint32_t *sR = sR0 + buf * desc_words, *sL = sR + NW * p.r_len;
         const int y = p.row0 + (int)(tile / p.tiles_x);
         const int x0 = (int)(tile % p.tiles_x) * p.TX;
         const int npx = min(p.TX, p.W - x0);
@@ -130,37 +170,14 @@ __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p)
         if (tid == 0) tma_store_wait_read<1>();
         __syncthreads();
 
+        // the other staging buffer was last read while computing the previous tile (a barrier ago): refill it now
+        if (tile + gridDim.x < p.n_tiles) request(tile + gridDim.x, buf ^ 1);
         const bool row_ok = (y >= p.half && y < p.H - p.half);
         if (row_ok) {
-            // ---- stage descriptors through TMA --------------------------------------------------
-            const int lo = x0 + p.dmin;                 // right position of (pixel 0, k = 0)
-            const int base = lo & ~3;                   // smem index j <-> right column base + j (floor to 4, also for lo < 0)
-            const int clo = max(base, 0);
-            const int chi = min(base + p.r_len, p.pitch);
-            if (tid == 0) {
-                uint32_t bytes = 0;
-                if (chi > clo) bytes += (uint32_t)NW * (uint32_t)(chi - clo) * 4u;
-                bytes += (uint32_t)NW * (uint32_t)p.TX * 4u;
-                mbar_expect_tx(bar, bytes);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    if (chi > clo)
-                        tma_load_1d(sR + w * p.r_len + (clo - base), p.descR + ((size_t)w * p.H + y) * p.pitch + clo,
-                                    (uint32_t)(chi - clo) * 4u, bar);
-                    // pitch >= roundup4(W) + 4 and x0 + TX <= roundup(W, TX): clamp the tail to the pitch
-                    tma_load_1d(sL + w * p.TX, p.descL + ((size_t)w * p.H + y) * p.pitch + x0, (uint32_t)p.TX * 4u, bar);
-                }
-            }
-            // right columns outside the stored row: flag as invalid by hand (disjoint from the TMA range)
-            for (int j = tid; j < p.r_len; j += blockDim.x) {
-                const int c = base + j;
-                if (c < clo || c >= chi) {
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) sR[w * p.r_len + j] = (w == NW - 1) ? 0x80000000u : 0u;
-                }
-            }
-            mbar_wait(bar, parity);
-            parity ^= 1u;
+            const int lo = x0 + p.dmin;
+            const int base = lo & ~3;
+            mbar_wait(bars + buf, (parity >> buf) & 1u);
+            parity ^= 1u << buf;
             __syncthreads();
 
             // ---- compute: work item = (chunk of CH consecutive pixels, group of 4 disparities) -----
@@ -355,7 +372,7 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
         p.r_len = (TX + D + 9) & ~3;
     }
     const size_t tile_elems = ((size_t)TX * D + 3) & ~(size_t)3;
-    const size_t smem = 2 * tile_elems * 4 + (size_t)nw * p.r_len * 4 + (size_t)nw * TX * 4 + 16;
+    const size_t smem = 2 * tile_elems * 4 + 2 * ((size_t)nw * p.r_len * 4 + (size_t)nw * TX * 4) + 32;
     int per_sm = (int)(200 * 1024 / smem);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 3) per_sm = 3;
