@@ -24,6 +24,8 @@
 //   [TX][D] float tile in shared memory (conflict-free 16-byte STS) which one elected thread
 //   hands to the TMA store engine (cp.async.bulk.global.shared::cta) as a single contiguous span,
 //   double-buffered so the next tile is computed while the previous one drains to HBM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -343,6 +345,7 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
     p.descL = descL; p.descR = descR; p.cv = d_cv; p.disp = d_disp; p.all_nan = d_all_nan;
     p.H = H; p.W = W; p.D = D; p.dmin = dmin; p.half = window / 2; p.pitch = pitch;
     int TX = (8192 / D) & ~3;                       // <= 32 KB of float per tile
+    if (getenv("PB200_CENSUS_TILE")) TX = (atoi(getenv("PB200_CENSUS_TILE")) / D) & ~3;
     if (TX < 4) TX = 4;
     if (TX > 128) TX = 128;
     while (TX > 4 && TX >= 2 * (((W + 3) & ~3))) TX >>= 1;   // do not make tiles much wider than the image

@@ -340,6 +340,29 @@ def test_sgm_wavefront_wide_images(eng, oracle, shape):
     np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
 
 
+def test_sgm_wavefront_repeatable_under_load(eng, oracle):
+    """The wavefront passes synchronise through mailboxes and progress counters, not barriers: the same input must give
+    the same bits every time, also while another stream keeps the SMs busy (different warp interleavings)."""
+    import torch
+
+    shape = (48, 4096, 256)
+    g = np.random.default_rng(5)
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.05] = np.nan
+    ref = oracle.sgm_cost_volume(cv, 8, 32, cmax=25)
+    d_cv = dev(eng, cv)
+    side = torch.cuda.Stream()
+    junk = torch.empty(64 << 20, device="cuda")
+    for rep in range(6):
+        if rep >= 3:
+            with torch.cuda.stream(side):                         # memory traffic next to the sweep
+                for _ in range(20):
+                    junk.add_(1.0)
+        got = host(eng.sgm(d_cv, 8, 32, oracle.sgm_invalid_value(25, 32)))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(got, ref)
+
+
 @pytest.mark.parametrize("kind", ["float", "one_fraction", "negative", "too_large", "big_penalty"])
 def test_sgm_packed_path_falls_back_exactly(eng, oracle, kind):
     """Volumes that do not qualify for the packed path (checked on the device while it runs) are redone by the
