@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p)
                 for (int q = 0; q < 3; ++q)
 #pragma unroll
                     for (int w = 0; w < NW; ++w) win[q + 1][w] = sR[w * p.r_len + shift + p0 + k0 + q];
+#pragma unroll 4
                 for (int pp = p0; pp < p0 + p.CH; ++pp) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
