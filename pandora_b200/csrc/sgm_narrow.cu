@@ -130,11 +130,18 @@ template <int NR>
 __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (&Lp)[NR], uint32_t (&L)[NR], int lane, uint32_t p1p1,
                                       uint32_t p2p2) {
     uint32_t mn = Lp[0];
+    if constexpr (NR >= 3) {
+        mn = __vimin3_u16x2(Lp[0], Lp[1], Lp[2]);
 #pragma unroll
-    for (int j = 1; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
-    uint32_t m16 = min(mn & 0xFFFFu, mn >> 16);
-    m16 = __reduce_min_sync(0xffffffffu, m16);
-    const uint32_t mm = m16 * 0x10001u;
+        for (int j = 3; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
+    } else {
+#pragma unroll
+        for (int j = 1; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
+    }
+    // both halves := min(low, high); a 32-bit minimum over words of the form (v << 16) | v is the minimum of the v's
+    // replicated in both halves, i.e. the word the step needs -- no mask, no multiply
+    mn = __vminu2(mn, __byte_perm(mn, 0u, 0x1032));
+    const uint32_t mm = __reduce_min_sync(0xffffffffu, mn);
     const uint32_t mp2 = mm + p2p2;
     const uint32_t up = __shfl_sync(0xffffffffu, Lp[NR - 1], (lane + 31) & 31);
     const uint32_t dn = __shfl_sync(0xffffffffu, Lp[0], (lane + 1) & 31);
