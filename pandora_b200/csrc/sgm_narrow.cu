@@ -145,10 +145,11 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
     const uint32_t mp2 = mm + p2p2;
     const uint32_t up = __shfl_sync(0xffffffffu, Lp[NR - 1], (lane + 31) & 31);
     const uint32_t dn = __shfl_sync(0xffffffffu, Lp[0], (lane + 1) & 31);
-    // lane 0: d-1 of its low half does not exist, d-1 of its high half (D/2 - 1) is lane 31's last LOW half
-    const uint32_t lo0 = (lane == 0) ? ((up << 16) | INF16) : up;
-    // lane 31: d+1 of its low half (D/2) is lane 0's first HIGH half, d+1 of its high half does not exist
-    const uint32_t hiN = (lane == 31) ? ((dn >> 16) | (INF16 << 16)) : dn;
+    // lane 0: d-1 of its low half does not exist, d-1 of its high half (D/2 - 1) is lane 31's last LOW half:
+    // (up << 16) | INF16.  lane 31: d+1 of its low half (D/2) is lane 0's first HIGH half, d+1 of its high half does
+    // not exist: (dn >> 16) | (INF16 << 16).  One PRMT each, with a per-lane (loop-invariant) selector.
+    const uint32_t lo0 = __byte_perm(up, INF16 * 0x10001u, lane == 0 ? 0x1054u : 0x3210u);
+    const uint32_t hiN = __byte_perm(dn, INF16 * 0x10001u, lane == 31 ? 0x5432u : 0x3210u);
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
         const uint32_t lo = (j == 0) ? lo0 : Lp[j - 1];
