@@ -269,6 +269,103 @@ __global__ void __launch_bounds__(256, 3) census_fill_kernel(const FillParams p)
     if (tid == 0) tma_store_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// fill, barrier-free variant (D % 4 == 0): one warp per (row, 4 consecutive pixels)
+// ------------------------------------------------------------------------------------------------
+// The tiled kernel above pays three CTA barriers and a TMA round trip per 32-pixel tile.  Here a warp owns a span of
+// 4 pixels x D disparities (4*D*4 contiguous bytes of the volume): a lane takes groups of 4 consecutive disparities,
+// loads the 7 right descriptors those meet over the 4 pixels straight from global memory (L1 / L2 resident: a
+// descriptor row is 16 KB and is reused by every warp of the row), and writes its float4 results with streaming
+// 16-byte stores -- a warp instruction covers 512 contiguous bytes.  No shared memory, no barrier, every warp
+// independent; the store stream is the only thing left to wait for.
+template <int NW, bool WTA>
+__global__ void __launch_bounds__(256) census_fill_direct_kernel(const FillParams p) {
+    const int lane = threadIdx.x & 31;
+    const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int G = p.D >> 2;
+    const int spans_x = (p.W + 3) >> 2;
+    const long n_items = (long)spans_x * (p.tiles_x /* rows of this launch */);
+    for (long item = gw; item < n_items; item += nwarps) {
+        const int y = p.row0 + (int)(item / spans_x);
+        const int x0 = (int)(item % spans_x) << 2;
+        const int npx = min(4, p.W - x0);
+        const bool row_ok = (y >= p.half && y < p.H - p.half);
+        float *dst_row = p.cv + ((size_t)y * p.W + x0) * p.D;
+        uint32_t best[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (row_ok) {
+            uint32_t a[4][NW];                           // left descriptors of the 4 pixels (same for every lane)
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) a[pp][w] = p.descL[((size_t)w * p.H + y) * p.pitch + x0 + pp];   // x0 + 3 < pitch
+            for (int g = lane; g < G; g += 32) {
+                const int k0 = g << 2;
+                const int c0 = x0 + p.dmin + k0;         // right column of (pixel 0, disparity k0)
+                uint32_t rw[7][NW];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    const int c = c0 + q;
+                    const bool in = (c >= 0 && c < p.pitch);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w)
+                        rw[q][w] = in ? __ldg(p.descR + ((size_t)w * p.H + y) * p.pitch + c) : ((w == NW - 1) ? 0x80000000u : 0u);
+                }
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    if (pp < npx) {
+                        float4 r;
+                        if ((int32_t)a[pp][NW - 1] < 0) {   // left window leaves the image: whole pixel NaN
+                            r = make_float4(nan_f(), nan_f(), nan_f(), nan_f());
+                        } else {
+                            const uint32_t h0 = hamming_flagged<NW>(a[pp], rw[pp]), h1 = hamming_flagged<NW>(a[pp], rw[pp + 1]),
+                                           h2 = hamming_flagged<NW>(a[pp], rw[pp + 2]), h3 = hamming_flagged<NW>(a[pp], rw[pp + 3]);
+                            r = make_float4(small_int_to_float(h0), small_int_to_float(h1), small_int_to_float(h2), small_int_to_float(h3));
+                            if (WTA) {
+                                // a flagged cost has all ones above bit 8: it can never win, and a pixel with nothing but
+                                // flagged costs keeps the sentinel
+                                best[pp] = min(best[pp], (h0 & 0x80000000u) ? 0xFFFFFFFFu : ((h0 << 16) | (uint32_t)k0));
+                                best[pp] = min(best[pp], (h1 & 0x80000000u) ? 0xFFFFFFFFu : ((h1 << 16) | (uint32_t)(k0 + 1)));
+                                best[pp] = min(best[pp], (h2 & 0x80000000u) ? 0xFFFFFFFFu : ((h2 << 16) | (uint32_t)(k0 + 2)));
+                                best[pp] = min(best[pp], (h3 & 0x80000000u) ? 0xFFFFFFFFu : ((h3 << 16) | (uint32_t)(k0 + 3)));
+                            }
+                        }
+                        *reinterpret_cast<float4 *>(dst_row + (size_t)pp * p.D + k0) = r;
+                    }
+                }
+            }
+        } else {
+            const float4 r = make_float4(nan_f(), nan_f(), nan_f(), nan_f());
+            for (int i = lane; i < npx * G; i += 32) st_cs_f4(dst_row + (size_t)i * 4, r);
+        }
+        if (WTA) {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                const uint32_t b = __reduce_min_sync(0xffffffffu, best[pp]);
+                if (lane == pp && pp < npx) {
+                    const size_t pix = (size_t)y * p.W + x0 + pp;
+                    const bool none = (b == 0xFFFFFFFFu);
+                    p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(b & 0xFFFFu));
+                    if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
+template <int NW>
+static int launch_fill_direct(FillParams p, int rows, cudaStream_t s) {
+    p.tiles_x = rows;                                    // reused as "rows of this launch" by the direct kernel
+    const long items = (long)((p.W + 3) >> 2) * rows;
+    long blocks = (items + 7) / 8;
+    const long cap = (long)sm_count() * 8;               // 8 CTAs x 8 warps per SM
+    if (blocks > cap) blocks = cap;
+    if (p.disp != nullptr) census_fill_direct_kernel<NW, true><<<(int)blocks, 256, 0, s>>>(p);
+    else census_fill_direct_kernel<NW, false><<<(int)blocks, 256, 0, s>>>(p);
+    PB200_LAUNCH_CHECK("census_fill_direct_kernel");
+    return PB200_OK;
+}
+
 template <int WIN>
 static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, int row0, int row1, cudaStream_t s) {
     dim3 block(32, 8), grid(ceil_div(pitch, 32), ceil_div(row1 - row0, 8));
@@ -345,6 +442,24 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
     FillParams p;
     p.descL = descL; p.descR = descR; p.cv = d_cv; p.disp = d_disp; p.all_nan = d_all_nan;
     p.H = H; p.W = W; p.D = D; p.dmin = dmin; p.half = window / 2; p.pitch = pitch;
+    // Two fill kernels, same results: the TMA-tiled one (shared-memory staging, bulk stores) and the barrier-free
+    // direct one.  Measured (profiles/r1_stage_bench_final2.json): equal at 4096x4096x256 (3.1 ms), the direct one
+    // ahead for smaller volumes and whenever the WTA is fused (C1 pipeline 0.25 -> 0.19 ms).
+    const bool direct_ok = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(d_cv) & 15) == 0;
+    const bool want_direct = getenv("PB200_CENSUS_DIRECT") ? atoi(getenv("PB200_CENSUS_DIRECT")) != 0 : (d_disp != nullptr || D < 256);
+    if (direct_ok && want_direct) {
+        p.TX = 4; p.CH = 4; p.tiles_x = 0; p.n_tiles = 0; p.r_len = 0;
+        p.row0 = row_begin;
+        p.invalid_disparity = invalid_disparity;
+        switch (nw) {
+            case 1: return launch_fill_direct<1>(p, row_end - row_begin, s);
+            case 2: return launch_fill_direct<2>(p, row_end - row_begin, s);
+            case 3: return launch_fill_direct<3>(p, row_end - row_begin, s);
+            case 4: return launch_fill_direct<4>(p, row_end - row_begin, s);
+            case 6: return launch_fill_direct<6>(p, row_end - row_begin, s);
+            default: set_error("census: unexpected descriptor size"); return PB200_ERR_UNSUPPORTED;
+        }
+    }
     int TX = (8192 / D) & ~3;                       // <= 32 KB of float per tile
     if (getenv("PB200_CENSUS_TILE")) TX = (atoi(getenv("PB200_CENSUS_TILE")) / D) & ~3;
     if (TX < 4) TX = 4;
