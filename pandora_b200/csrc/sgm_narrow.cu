@@ -7,6 +7,9 @@
 // VIADDMNMX.U16x2, the DPX dynamic-programming instructions) and kept in 16-bit storage between the passes.
 // The result is bit-identical to the float path; only the traffic and the instruction count change:
 //
+// Single-call runs (one GPU) take the two 4-direction WAVEFRONT passes further down (sgm_wave_kernel: 14D bytes per
+// pixel, two launches).  Row-tiled multi-GPU runs, whose vertical groups must be split around the halo exchange, and
+// images wider than 28 columns per SM keep the four-launch schedule:
 //   pass E   read C float32 (4D B/pixel), check + pack it to C16, write C16 and P16 = L_E        (2D + 2D)
 //   pass W   read C16, read P16, P16 += L_W, write P16                                           (2D + 2D + 2D)
 //   sweep S  read C16, read P16, P16 += L_S + L_SE + L_SW, write P16                              (6D)
