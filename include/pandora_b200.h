@@ -198,6 +198,12 @@ PB200_API int pb200_wta_right(const float *d_left_cv, int H, int W, int D, int m
 PB200_API int pb200_cross_checking(const float *d_disp_left, uint16_t *d_mask_left, const float *d_disp_right, int H, int W,
                          float threshold, int dmin, int dmax, int offset, float *d_conf, void *stream);
 
+/* ---- disparity filter ------------------------------------------------------------------------------ */
+/* MedianFilter.filter_disparity with filter_size 3 (filter/median.py:96-179): invalid pixels (validity mask &
+ * PANDORA_MSK_PIXEL_INVALID) are ignored by the 3x3 NaN-median and left untouched, every finite valid pixel is replaced
+ * by the median of its valid neighbourhood (border ring unchanged).  d_scratch: 2 * H * W floats. */
+PB200_API int pb200_filter_median3(float *d_disp, const uint16_t *d_mask, int H, int W, float *d_scratch, void *stream);
+
 /* ---- sub-pixel refinement -------------------------------------------------- */
 /* loop_refinement (approximate == 0) / loop_approximate_refinement (approximate != 0), refinement/cpp/src/
  * refinement.cpp:29-181, with method 0 = vfit (vfit.cpp:28-55) or 1 = quadratic (quadratic.cpp:28-49).

@@ -19,5 +19,6 @@ from .refinement import AbstractRefinement, Quadratic, Vfit  # noqa: F401
 from .validation import AbstractValidation, CrossCheckingAccurate, right_disparity_fast  # noqa: F401
 from .cost_volume_confidence import AbstractCostVolumeConfidence, Ambiguity, Risk  # noqa: F401
 from .criteria import validity_mask  # noqa: F401
+from .filter import AbstractFilter, MedianFilter  # noqa: F401
 
 __version__ = "0.1.0"

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "pb200_wta_right": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _cf, _vp, _vp, _vp]),
     "pb200_cross_checking": (_ci, [_vp, _vp, _vp, _ci, _ci, _cf, _ci, _ci, _ci, _vp, _vp]),
     "pb200_refinement": (_ci, [_vp, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp]),
+    "pb200_filter_median3": (_ci, [_vp, _vp, _ci, _ci, _vp, _vp]),
     "pb200_confidence_workspace_bytes": (_sz, [_ci, _ci, _ci]),
     "pb200_confidence": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb200_census_cost_volume_host": (_ci, [_vp, _vp, _ci, _ci, _ci, _vp, _ci, _vp]),

@@ -108,9 +108,41 @@ __global__ void __launch_bounds__(256) reverse_cv_kernel(const float *__restrict
     }
 }
 
+// MedianFilter.filter_disparity (filter/median.py:96-132), the two element-wise halves around the 3x3 NaN-median:
+// (a) masked = invalid pixel ? NaN : disparity; (b) disparity = isfinite(masked) ? median(masked) : disparity.
+__global__ void __launch_bounds__(256) filter_mask_kernel(const float *__restrict__ disp, const uint16_t *__restrict__ mask, long n,
+                                                          float *__restrict__ masked) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) masked[i] = (mask[i] & 0x3C3) ? nan_f() : disp[i];
+}
+__global__ void __launch_bounds__(256) filter_select_kernel(float *__restrict__ disp, const float *__restrict__ masked,
+                                                            const float *__restrict__ med, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float m = masked[i];
+    if (m == m && fabsf(m) != CUDART_INF_F) disp[i] = med[i];      // np.isfinite(masked_data)
+}
+
 }  // namespace pb200
 
 using namespace pb200;
+
+extern "C" int pb200_filter_median3(float *d_disp, const uint16_t *d_mask, int H, int W, float *d_scratch, void *stream) {
+    if (!d_disp || !d_mask || !d_scratch || H <= 0 || W <= 0) {
+        set_error("pb200_filter_median3: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    const long n = (long)H * W;
+    float *masked = d_scratch, *med = d_scratch + n;
+    cudaStream_t s = (cudaStream_t)stream;
+    filter_mask_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_disp, d_mask, n, masked);
+    PB200_LAUNCH_CHECK("filter_mask_kernel");
+    const int rc = pb200_median3(masked, H, W, med, stream);
+    if (rc != PB200_OK) return rc;
+    filter_select_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_disp, masked, med, n);
+    PB200_LAUNCH_CHECK("filter_select_kernel");
+    return PB200_OK;
+}
 
 extern "C" int pb200_wta(const float *d_cv, int H, int W, int D, int dmin, int is_max, float invalid_disparity,
                          float *d_disp, uint8_t *d_all_nan, void *stream) {

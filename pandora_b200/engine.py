@@ -312,3 +312,12 @@ class Engine:
                 _ptr(out.get("disp_sup")), _ptr(out.get("disp_inf")), _ptr(out.get("sampled_risk_max")), _ptr(out.get("sampled_risk_min")),
                 _ptr(ws), ws.numel(), self._stream()))
         return out
+
+    # ---- disparity filter ------------------------------------------------------------------------------------
+    def filter_median3(self, disp: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """3x3 median of the valid pixels of a disparity map, in place (filter/median.py:96-179)."""
+        H, W = (int(s) for s in disp.shape)
+        scratch = self.empty((2, H, W))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_filter_median3(_ptr(disp), _ptr(mask), H, W, _ptr(scratch), self._stream()))
+        return disp

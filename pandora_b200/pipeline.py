@@ -18,28 +18,42 @@ from .disparity import AbstractDisparity
 from .matching_cost import AbstractMatchingCost
 from .optimization import AbstractOptimization
 
-HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity", "refinement", "validation", "cost_volume_confidence")
+HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity", "refinement", "filter", "validation",
+                  "cost_volume_confidence")
 
 
-def run(img_left, img_right, cfg: dict):
-    """Run the hot-path steps named in ``cfg["pipeline"]`` in order; returns (left disparity dataset, cost volume).
+def run(img_left, img_right, cfg: dict, return_right: bool = False):
+    """Run the steps named in ``cfg["pipeline"]`` in order, like ``PandoraMachine`` does (state_machine.py:292-590);
+    returns (left disparity dataset, left cost volume) -- plus the right disparity dataset with ``return_right``.
 
     ``cfg`` is a Pandora user configuration (``{"pipeline": {"matching_cost": {...}, ...}}``).  Implemented steps:
-    matching_cost, aggregation, optimization, disparity, and the adjacent rows refinement, validation
-    (``cross_checking_fast``: the right map comes from the left volume) and cost_volume_confidence; anything else
-    (filter, multiscale, semantic_segmentation, ``cross_checking_accurate`` ...) is rejected -- it stays Pandora's.
+    matching_cost, aggregation, optimization, disparity, cost_volume_confidence, refinement, filter (3x3 median) and
+    validation -- ``cross_checking_accurate`` (every step also runs on the right image with the roles swapped,
+    state_machine.py:316-331) and ``cross_checking_fast`` (the right map comes from the left volume).  Anything else
+    (multiscale, semantic_segmentation, disparity interpolation ...) is rejected: it stays Pandora's.
     """
     from .cost_volume_confidence import AbstractCostVolumeConfidence  # noqa: PLC0415
     from .criteria import validity_mask  # noqa: PLC0415
+    from .dataset import add_disparity  # noqa: PLC0415
+    from .filter import AbstractFilter  # noqa: PLC0415
     from .refinement import AbstractRefinement  # noqa: PLC0415
     from .validation import AbstractValidation, right_disparity_fast  # noqa: PLC0415
 
     pipeline = cfg["pipeline"]
     disp_grids = (img_left["disparity"].data[0], img_left["disparity"].data[1])
     right_mode = pipeline.get("validation", {}).get("validation_method")          # state_machine.py:600-640
-    if right_mode not in (None, "cross_checking_fast"):
-        raise NotImplementedError(f"validation method {right_mode!r} is outside the B200 hot path (only cross_checking_fast)")
-    cv = None
+    if right_mode not in (None, "cross_checking_fast", "cross_checking_accurate"):
+        raise NotImplementedError(f"validation method {right_mode!r} is outside the B200 hot path")
+    if "interpolated_disparity" in pipeline.get("validation", {}):
+        raise NotImplementedError("interpolated_disparity is outside the B200 hot path (use Pandora's own implementation)")
+    accurate = right_mode == "cross_checking_accurate"
+    right_grids = None
+    if accurate:
+        if "disparity" not in getattr(img_right, "data_vars", {}):                # state_machine.py:651-657
+            img_right = img_right.copy(deep=False)
+            add_disparity(img_right, (-int(np.nanmax(disp_grids[1])), -int(np.nanmin(disp_grids[0]))))
+        right_grids = (img_right["disparity"].data[0], img_right["disparity"].data[1])
+    cv = right_cv = None
     disp = right_disp = None
     for step, step_cfg in pipeline.items():
         name = step.split(".")[0]
@@ -51,29 +65,55 @@ def run(img_left, img_right, cfg: dict):
             cv = validity_mask(img_left, img_right, cv)
             cv = mc.compute_cost_volume(img_left, img_right, cv)
             mc.cv_masked(img_left, img_right, cv, *disp_grids)
+            if accurate:
+                right_cv = mc.allocate_cost_volume(img_right, right_grids, cfg)
+                right_cv = validity_mask(img_right, img_left, right_cv)
+                right_cv = mc.compute_cost_volume(img_right, img_left, right_cv)
+                mc.cv_masked(img_right, img_left, right_cv, *right_grids)
         elif name == "aggregation":                               # state_machine.py:366-380
-            AbstractAggregation(**step_cfg).cost_volume_aggregation(img_left, img_right, cv)
+            agg = AbstractAggregation(**step_cfg)
+            agg.cost_volume_aggregation(img_left, img_right, cv)
+            if accurate:
+                agg.cost_volume_aggregation(img_right, img_left, right_cv)
         elif name == "optimization":                              # state_machine.py:404-419
-            cv = AbstractOptimization(img_left, **step_cfg).optimize_cv(cv, img_left, img_right)
+            opt = AbstractOptimization(img_left, **step_cfg)
+            cv = opt.optimize_cv(cv, img_left, img_right)
+            if accurate:
+                right_cv = opt.optimize_cv(right_cv, img_right, img_left)
         elif name == "disparity":                                 # state_machine.py:421-448
             disparity_ = AbstractDisparity(**step_cfg)
             disp = disparity_.to_disp(cv, img_left, img_right)
-            if right_mode == "cross_checking_fast":
+            if accurate:
+                right_disp = disparity_.to_disp(right_cv, img_right, img_left)
+            elif right_mode == "cross_checking_fast":
                 right_disp = right_disparity_fast(cv, disparity_.cfg["invalid_disparity"])
         elif name == "cost_volume_confidence":                    # state_machine.py:566-587
             step_cfg = dict(step_cfg)
             if len(step.split(".")) == 2:
                 step_cfg["indicator"] = "." + step.split(".")[1]
-            disp, cv = AbstractCostVolumeConfidence(**step_cfg).confidence_prediction(disp, img_left, img_right, cv)
+            confidence_ = AbstractCostVolumeConfidence(**step_cfg)
+            disp, cv = confidence_.confidence_prediction(disp, img_left, img_right, cv)
+            if accurate:
+                right_disp, right_cv = confidence_.confidence_prediction(right_disp, img_right, img_left, right_cv)
         elif name == "refinement":                                # state_machine.py:474-490
             refinement_ = AbstractRefinement(**step_cfg)
             refinement_.subpixel_refinement(cv, disp)
-            if right_disp is not None:
+            if accurate:
+                refinement_.subpixel_refinement(right_cv, right_disp)
+            elif right_disp is not None:
                 refinement_.right_subpixel_refinement(cv, right_disp)
+        elif name == "filter":                                    # state_machine.py:450-473
+            filter_ = AbstractFilter(dict(step_cfg))
+            filter_.filter_disparity(disp, img_left)
+            if right_disp is not None:
+                filter_.filter_disparity(right_disp, img_right)
         elif name == "validation":                                # state_machine.py:492-519
-            disp = AbstractValidation(**step_cfg).disparity_checking(disp, right_disp, img_left, img_right, cv)
-            right_disp = None
-    return disp, cv
+            validation_ = AbstractValidation(**step_cfg)
+            disp = validation_.disparity_checking(disp, right_disp, img_left, img_right, cv)
+            right_disp = validation_.disparity_checking(right_disp, disp, img_right, img_left, right_cv)
+            if right_mode == "cross_checking_fast":
+                right_disp = None                                 # state_machine.py:514-519
+    return (disp, cv, right_disp) if return_right else (disp, cv)
 
 
 class StereoPipeline:

@@ -152,3 +152,64 @@ def test_run_host_banded_upload_equals_device_run(pb, oracle, cfg):
     pipe.cv_a.fill_(-1.0)
     got = pipe.run_host(hl, hr).copy()                                     # pinned tensors: no staging copy
     np.testing.assert_array_equal(got, ref)
+
+
+def _oracle_median_filter(oracle, disp, mask):
+    """MedianFilter.filter_disparity, filter/median.py:96-132."""
+    masked = disp.copy()
+    masked[(mask & oracle.MSK_INVALID) != 0] = np.nan
+    valid = np.isfinite(masked)
+    med = oracle.median_filter3(masked)
+    out = disp.copy()
+    out[valid] = med[valid]
+    return out
+
+
+def test_reference_sample_config_a_semi_global_matching(pb, oracle):
+    """The reference's flagship sample pipeline (data_samples/json_conf_files/a_semi_global_matching.json: census 5x5 ->
+    SGM P1=8 P2=32 -> WTA (invalid = NaN) -> vfit -> 3x3 median -> cross_checking_accurate (threshold 1) -> 3x3 median) on
+    cones through run(), every step on the device for the left AND the right image, against the same chain of oracle
+    functions -- bit-exact -- and against the reference's functional gate (tests/functional_tests/test_basic.py:135-166)."""
+    left, right, gt = cones()
+    H, W = left.shape
+    cfg = {"pipeline": {
+        "matching_cost": {"matching_cost_method": "census", "window_size": 5, "subpix": 1},
+        "optimization": {"optimization_method": "sgm", "overcounting": False,
+                         "penalty": {"penalty_method": "sgm_penalty", "P1": 8, "P2": 32, "p2_method": "constant"}},
+        "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"},
+        "refinement": {"refinement_method": "vfit"},
+        "filter": {"filter_method": "median", "filter_size": 3},
+        "validation": {"validation_method": "cross_checking_accurate", "cross_checking_threshold": 1},
+        "filter.this_time_after_validation": {"filter_method": "median", "filter_size": 3}}}
+    dl = pb.create_image_dataset(left, disparity=[-60, 0])
+    dr = pb.create_image_dataset(right)
+    disp, cv, rdisp = pb.run(dl, dr, cfg, return_right=True)
+
+    def side(a, b, dmin, dmax):
+        ccv, attrs = oracle.census_cost_volume(a, b, 5, dmin, dmax)
+        vm = oracle.validity_mask(H, W, dmin, dmax, 2)
+        oracle.cv_masked(ccv, vm, 2)
+        scv = oracle.sgm_cost_volume(ccv, 8, 32, cmax=attrs["cmax"])
+        d, inv = oracle.wta(scv, np.arange(dmin, dmax + 1), invalid_disparity=np.nan)
+        m = oracle.wta_validity_mask(vm, inv)
+        itp, d, m = oracle.refinement(scv, d, m, dmin, dmax, 1, "min", "vfit")
+        return scv, _oracle_median_filter(oracle, d, m), m, itp
+
+    scv_l, d_l, m_l, itp_l = side(left, right, -60, 0)
+    _, d_r, m_r, _ = side(right, left, 0, 60)
+    m_l2, conf_l = oracle.cross_checking(d_l, m_l, d_r, 1, -60, 0, 2)
+    m_r2, _ = oracle.cross_checking(d_r, m_r, d_l, 1, 0, 60, 2)
+    d_l2 = _oracle_median_filter(oracle, d_l, m_l2)
+    d_r2 = _oracle_median_filter(oracle, d_r, m_r2)
+    np.testing.assert_array_equal(cv["cost_volume"].data, scv_l)
+    np.testing.assert_array_equal(disp["validity_mask"].data, m_l2)
+    np.testing.assert_array_equal(disp["disparity_map"].data, d_l2)
+    np.testing.assert_array_equal(disp["interpolated_coeff"].data, itp_l)
+    np.testing.assert_array_equal(np.asarray(disp["confidence_measure"].data)[:, :, 0], conf_l)
+    np.testing.assert_array_equal(rdisp["validity_mask"].data, m_r2)
+    np.testing.assert_array_equal(rdisp["disparity_map"].data, d_r2)
+    assert disp.attrs["filter"] == "median" and disp.attrs["validation"] == "cross_checking_accurate"
+    # functional gate of the reference on the valid pixels of the final map
+    ok = (disp["validity_mask"].data & oracle.MSK_INVALID) == 0
+    sel = ok & (gt > 0)
+    assert float(np.mean(np.abs(disp["disparity_map"].data[sel] + gt[sel]) > 1.0)) <= 0.20

@@ -153,9 +153,14 @@ def test_dataset_shim_lazy_volume():
 def test_run_rejects_steps_outside_the_hot_path():
     img = pb.create_image_dataset(np.zeros((6, 9), np.float32), disparity=[-1, 1])
     with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
-        pb.run(img, img, {"pipeline": {"filter": {"filter_method": "median"}}})
-    with pytest.raises(NotImplementedError, match="only cross_checking_fast"):
-        pb.run(img, img, {"pipeline": {"validation": {"validation_method": "cross_checking_accurate"}}})
+        pb.run(img, img, {"pipeline": {"multiscale": {"multiscale_method": "fixed_zoom_pyramid"}}})
+    with pytest.raises(NotImplementedError, match="interpolated_disparity"):
+        pb.run(img, img, {"pipeline": {"validation": {"validation_method": "cross_checking_accurate", "interpolated_disparity": "sgm"}}})
+    with pytest.raises(KeyError):
+        pb.AbstractFilter({"filter_method": "bilateral_b200"})
+    with pytest.raises(pb.ConfigError):
+        pb.AbstractFilter({"filter_method": "median", "filter_size": 5})
+    assert pb.AbstractFilter({"filter_method": "median"}).cfg["filter_size"] == 3
 
 
 def test_next_row_registries_and_config_errors():
