@@ -269,6 +269,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage["census_ms"] = float(np.mean([a.elapsed_time(b) for a, b, _ in evs]))
         stage["sgm_ms"] = float(np.mean([b.elapsed_time(c) for _, b, c in evs]))
+        if pipe.fused_ran:
+            # the stage the pipeline actually runs: census transforms + the two wavefront passes, Census costs computed
+            # inside pass 1 (pb200_census_sgm)
+            fev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+            torch.cuda.synchronize()
+            for i in range(args.steps):
+                fev[i][0].record()
+                e.census_descriptors(d_left, d_right, WINDOW)
+                fev[i][1].record()
+                e.census_sgm(d_left, d_right, WINDOW, dmin, dmax, P1, P2, False, out=pipe.cv_b, fuse_wta=True, invalid_disparity=-9999.0,
+                             disp=pipe.disp, flags=pipe.flags, descriptors_ready=True)
+                fev[i][2].record()
+            torch.cuda.synchronize()
+            stage["transform_ms"] = float(np.mean([a.elapsed_time(b) for a, b, _ in fev]))
+            stage["fused_ms"] = float(np.mean([b.elapsed_time(c) for _, b, c in fev]))
 
     for _ in range(2):
         step_host()
@@ -292,7 +307,7 @@ def run_ours(args):
         "config": {"workload": "C3: 4096x4096 synthetic pair per GPU, Census 5x5 + SGM 8-path P1=8 P2=32 + WTA, D=256, disp [-255, 0]",
                    "rows_per_gpu": H, "cols": W, "total_rows": H * world,
                    "parallelism": "1 GPU" if world == 1 else f"row tiles x{world}, SGM path-state halo over NCCL p2p",
-                   "l2": "cost volumes (17.2 GB in, 17.2 GB out per GPU) exceed the 126 MB L2; no flush needed"},
+                   "l2": "the cost volume (17.2 GB per GPU, plus 12.9 GB of packed intermediates) exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * H * W * 4 * world, "d2h_bytes_per_step": H * W * 4 * world,
                 "ms_per_step": e2e_ms / args.steps},
@@ -302,23 +317,45 @@ def run_ours(args):
         sgm_alg = 8.0 * D * H * W          # SGM must read C (4D) and write S (4D) bytes per pixel
         census_alg = (4.0 * D + 8.0) * H * W
         sgm_gbs = sgm_alg / (stage["sgm_ms"] * 1e-3) / 1e9
+        fused = "fused_ms" in stage
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "sgm_stage_traffic.json")) as fh:
-                traffic = float(json.load(fh)["dram_bytes_per_stage"])
+                traffic = json.load(fh).get("dram_bytes_per_fused_stage" if fused else "dram_bytes_per_stage")
+                traffic = None if traffic is None else float(traffic)
         except Exception:
             pass
-        line["roofline"] = {"bound": "hbm",
-                            "kernel": "SGM stage = sgm_wave_kernel x2 (pass 1: E/SE/S/SW reading float C; pass 2: W/NW/N/NE writing "
-                                      "float S + WTA); 2 launches timed as one unit (the stage's 8*D algorithmic bytes per pixel "
-                                      "= 4*D read by pass 1 + 4*D written by pass 2)",
-                            "achieved": sgm_gbs, "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": traffic,
-                            "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
+        if fused:
+            # the dominant kernel pair of the step that was timed: the SGM row of SURVEY 8(d) (8*D bytes per pixel: the
+            # cost C and the result S) is kept as its algorithmic figure although pass 1 no longer reads a float C --
+            # it computes the Census costs from the descriptors -- so the fraction stays comparable with earlier lines
+            f_gbs = sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm",
+                                "kernel": "fused Census+SGM stage = sgm_wave_kernel x2 (pass 1: Hamming costs from the census "
+                                          "descriptors + E/SE/S/SW, writes C8 + P16; pass 2: W/NW/N/NE, writes float S + WTA); 2 launches "
+                                          "timed as one unit against the SGM row's 8*D algorithmic bytes per pixel",
+                                "achieved": f_gbs, "peak": peak, "unit": "GB/s", "frac": f_gbs / peak, "traffic": traffic,
+                                "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["fused_ms"]}
+        else:
+            line["roofline"] = {"bound": "hbm",
+                                "kernel": "SGM stage = sgm_wave_kernel x2 (pass 1: E/SE/S/SW reading float C; pass 2: W/NW/N/NE writing "
+                                          "float S + WTA); 2 launches timed as one unit (the stage's 8*D algorithmic bytes per pixel "
+                                          "= 4*D read by pass 1 + 4*D written by pass 2)",
+                                "achieved": sgm_gbs, "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": traffic,
+                                "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
         cen_gbs = census_alg / (stage["census_ms"] * 1e-3) / 1e9
-        line["stages"] = {"census_fill": {"ms": stage["census_ms"], "algorithmic_bytes": census_alg, "achieved_gbs": cen_gbs, "frac": cen_gbs / peak},
-                          "sgm_8path_wta": {"ms": stage["sgm_ms"], "algorithmic_bytes": sgm_alg, "achieved_gbs": sgm_gbs, "frac": sgm_gbs / peak},
+        line["stages"] = {"census_fill": {"ms": stage["census_ms"], "algorithmic_bytes": census_alg, "achieved_gbs": cen_gbs, "frac": cen_gbs / peak,
+                                          "in_step": not fused},
+                          "sgm_8path_wta": {"ms": stage["sgm_ms"], "algorithmic_bytes": sgm_alg, "achieved_gbs": sgm_gbs, "frac": sgm_gbs / peak,
+                                            "in_step": not fused},
                           "pipeline_algorithmic_bytes": (12.0 * D + 12.0) * H * W,
                           "pipeline_frac": (12.0 * D + 12.0) * H * W / (ms_per_step * 1e-3) / 1e9 / peak}
+        if fused:
+            line["stages"]["census_transform_x2"] = {"ms": stage["transform_ms"], "in_step": True}
+            line["stages"]["census_sgm_fused_wta"] = {"ms": stage["fused_ms"], "algorithmic_bytes": sgm_alg, "in_step": True,
+                                                      "achieved_gbs": sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9,
+                                                      "frac": sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9 / peak}
+        line["config"]["fused_census_sgm"] = bool(fused)
         # CPU baseline on a bounded row band of the same pair, same run
         rows = 32
         cl, cr = np.ascontiguousarray(left[:rows]), np.ascontiguousarray(right[:rows])

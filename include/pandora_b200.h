@@ -82,6 +82,24 @@ PB200_API int pb200_census_cost_volume_rows(const float *d_left, const float *d_
                                   float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
                                   float invalid_disparity, uint8_t *d_all_nan, int row_begin, int row_end, void *stream);
 
+/* Census transform only: the planar descriptors of rows [row_begin, row_end) of both images into d_workspace
+ * (census_transform, matching_cost/cpp/src/census.cpp:45-95).  Feeds pb200_census_sgm(descriptors_ready = 1). */
+PB200_API int pb200_census_descriptors_rows(const float *d_left, const float *d_right, int H, int W, int window, void *d_workspace,
+                                  size_t workspace_bytes, int row_begin, int row_end, void *stream);
+
+/* Fused matching-cost + optimisation steps for a pipeline with nothing in between (state_machine.py:292-364 followed
+ * by :404-419): Census (census.cpp:45-180) -> 8-path SGM (P1, P2, invalid value = window^2 + P2 + 1) [-> WTA], the
+ * Hamming costs going from the descriptors straight into the first SGM pass -- the float32 Census volume is never
+ * written.  d_cv_out receives the SGM volume (bit-identical to pb200_census_cost_volume + pb200_sgm), d_disp /
+ * d_all_nan the optional fused WTA.  *ran = 1 when the fused kernels were launched, 0 when the configuration is not
+ * eligible (window not in {3, 5}, D not in {64, 128, 256}, non-integer or large penalties, image wider than one
+ * co-resident wave): nothing has been computed then and the caller runs the two steps separately.
+ * Workspaces: pb200_census_workspace_bytes / pb200_sgm_workspace_bytes. */
+PB200_API int pb200_census_sgm(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1, float p2,
+                     int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
+                     void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
+                     uint8_t *d_all_nan, int descriptors_ready, int *ran, void *stream);
+
 /* SAD (squared == 0) / SSD (squared != 0) cost volume, window odd >= 1 (sad_ssd.py:180-206). */
 PB200_API int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
                               int squared, float *d_cv, void *stream);

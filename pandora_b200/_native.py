@@ -48,6 +48,8 @@ PROTOTYPES = {
     "pb200_census_workspace_bytes": (_sz, [_ci, _ci, _ci]),
     "pb200_census_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _vp]),
     "pb200_census_cost_volume_rows": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _ci, _ci, _vp]),
+    "pb200_census_descriptors_rows": (_ci, [_vp, _vp, _ci, _ci, _ci, _vp, _sz, _ci, _ci, _vp]),
+    "pb200_census_sgm": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _ci, _vp, _vp]),
     "pb200_sad_ssd_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _vp, _vp]),
     "pb200_zncc_workspace_bytes": (_sz, [_ci, _ci]),
     "pb200_zncc_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp]),

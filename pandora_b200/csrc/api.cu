@@ -165,6 +165,10 @@ extern "C" int pb200_cbca_host(const float *input, int H, int W, const int16_t *
     return PB200_OK;
 }
 
+#ifndef PB200_FUSE_CENSUS_SGM_DEFAULT
+#define PB200_FUSE_CENSUS_SGM_DEFAULT 0
+#endif
+
 // Whole pipeline on host images (the end-to-end path bench.py reports as `e2e`).
 extern "C" int pb200_disparity_host(const float *left, const float *right, int H, int W, int method, int window, int dmin,
                                     int dmax, int cbca_distance, float cbca_intensity, float sgm_p1, float sgm_p2,
@@ -189,14 +193,35 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
     bool have_disp = false;
     float cmax = 0.f;
     // ---- matching cost ----
+    bool sgm_done = false;
+    DevBuf sws;
     if (method == 0) {
         const size_t wsb = pb200_census_workspace_bytes(H, W, window);
         PB200_RC(ws.alloc(wsb));
-        const bool fuse = !do_cbca && !do_sgm;
-        PB200_RC(pb200_census_cost_volume(dl.as<float>(), dr.as<float>(), H, W, window, dmin, D, cur, ws.p, wsb,
-                                          fuse ? ddisp.as<float>() : nullptr, invalid_disparity,
-                                          fuse ? dnan.as<uint8_t>() : nullptr, nullptr));
-        have_disp = fuse;
+        // Census directly followed by SGM: one fused stage when eligible (the Census volume is never written)
+        const char *fenv = getenv("PB200_FUSE_CENSUS_SGM");
+        if (do_sgm && !do_cbca && (fenv ? atoi(fenv) != 0 : PB200_FUSE_CENSUS_SGM_DEFAULT)) {
+            const size_t swsb = pb200_sgm_workspace_bytes(H, W, D);
+            PB200_RC(sws.alloc(swsb));
+            int ran = 0;
+            PB200_RC(pb200_census_sgm(dl.as<float>(), dr.as<float>(), H, W, window, dmin, D, sgm_p1, sgm_p2, sgm_overcounting, other, ws.p,
+                                      wsb, sws.p, swsb, ddisp.as<float>(), invalid_disparity, dnan.as<uint8_t>(), 0, &ran, nullptr));
+            if (ran) {
+                PB200_CUDA(cudaDeviceSynchronize());
+                float *t = cur; cur = other; other = t;
+                sgm_done = have_disp = true;
+            }
+        }
+    }
+    if (method == 0) {
+        if (!sgm_done) {
+            const size_t wsb = pb200_census_workspace_bytes(H, W, window);
+            const bool fuse = !do_cbca && !do_sgm;
+            PB200_RC(pb200_census_cost_volume(dl.as<float>(), dr.as<float>(), H, W, window, dmin, D, cur, ws.p, wsb,
+                                              fuse ? ddisp.as<float>() : nullptr, invalid_disparity,
+                                              fuse ? dnan.as<uint8_t>() : nullptr, nullptr));
+            have_disp = fuse;
+        }
         cmax = (float)(window * window);
     } else if (method == 1 || method == 2) {
         PB200_RC(pb200_sad_ssd_cost_volume(dl.as<float>(), dr.as<float>(), H, W, window, dmin, D, method == 2, cur, nullptr));
@@ -231,14 +256,13 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
         cmax *= (float)((2 * cbca_distance - 1) * (2 * cbca_distance - 1));
     }
     // ---- optimisation ----
-    if (do_sgm) {
+    if (do_sgm && !sgm_done) {
         if (is_max) {
             set_error("pb200_disparity_host: SGM on a max-type measure is not wired in the host pipeline");
             return PB200_ERR_UNSUPPORTED;
         }
-        DevBuf sws;
         const size_t swsb = pb200_sgm_workspace_bytes(H, W, D);
-        PB200_RC(sws.alloc(swsb));
+        if (!sws.p) PB200_RC(sws.alloc(swsb));
         PB200_RC(pb200_sgm(cur, other, H, W, D, sgm_p1, sgm_p2, cmax + sgm_p2 + 1.f, sgm_overcounting, 0xFF, 3, nullptr, nullptr, nullptr,
                            nullptr, ddisp.as<float>(), dmin, invalid_disparity, dnan.as<uint8_t>(), sws.p, swsb, nullptr));
         PB200_CUDA(cudaDeviceSynchronize());          // the workspace must outlive the sweeps

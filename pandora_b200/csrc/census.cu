@@ -387,9 +387,83 @@ static int launch_fill(const FillParams &p, size_t smem, int grid, cudaStream_t 
     return PB200_OK;
 }
 
+int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch, int window, float *out, int H, int W, int D, float p1,
+                        float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
+                        size_t workspace_bytes, cudaStream_t s, bool *done);   // sgm_narrow.cu
+
+static int census_transform_pair(const float *d_left, const float *d_right, int H, int W, int window, uint32_t *descL, uint32_t *descR,
+                                 int row_begin, int row_end, cudaStream_t s) {
+    const int pitch = census_pitch(W);
+    int rc;
+#define PB200_T(WIN)                                                       \
+    case WIN:                                                              \
+        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, row_begin, row_end, s);         \
+        if (rc == PB200_OK) rc = launch_transform<WIN>(d_right, H, W, pitch, descR, row_begin, row_end, s); \
+        break;
+    switch (window) {
+        PB200_T(3) PB200_T(5) PB200_T(7) PB200_T(9) PB200_T(11) PB200_T(13)
+        default: rc = PB200_ERR_UNSUPPORTED;
+    }
+#undef PB200_T
+    return rc;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
+
+extern "C" int pb200_census_descriptors_rows(const float *d_left, const float *d_right, int H, int W, int window, void *d_workspace,
+                                             size_t workspace_bytes, int row_begin, int row_end, void *stream) {
+    if (!d_left || !d_right || !d_workspace || H <= 0 || W <= 0 || row_begin < 0 || row_end > H || row_begin >= row_end) {
+        set_error("pb200_census_descriptors_rows: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (window != 3 && window != 5 && window != 7 && window != 9 && window != 11 && window != 13) {
+        set_error("pb200_census_descriptors_rows: window_size %d not in {3,5,7,9,11,13}", window);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < pb200_census_workspace_bytes(H, W, window)) {
+        set_error("pb200_census_descriptors_rows: workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    uint32_t *descL = (uint32_t *)d_workspace;
+    uint32_t *descR = descL + (size_t)census_nwords(window) * H * census_pitch(W);
+    return census_transform_pair(d_left, d_right, H, W, window, descL, descR, row_begin, row_end, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_census_sgm(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1, float p2,
+                                int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
+                                void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
+                                uint8_t *d_all_nan, int descriptors_ready, int *ran, void *stream) {
+    if (!ran) {
+        set_error("pb200_census_sgm: ran must not be NULL");
+        return PB200_ERR_BAD_ARG;
+    }
+    *ran = 0;
+    if (!d_left || !d_right || !d_cv_out || !d_census_workspace || !d_sgm_workspace || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_census_sgm: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (window != 3 && window != 5) return PB200_OK;                 // not eligible: the caller runs the two steps separately
+    if (census_workspace_bytes < pb200_census_workspace_bytes(H, W, window)) {
+        set_error("pb200_census_sgm: census workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int pitch = census_pitch(W);
+    uint32_t *descL = (uint32_t *)d_census_workspace;
+    uint32_t *descR = descL + (size_t)H * pitch;
+    if (!descriptors_ready) {
+        const int rc = census_transform_pair(d_left, d_right, H, W, window, descL, descR, 0, H, s);
+        if (rc != PB200_OK) return rc;
+    }
+    bool done = false;
+    const int rc = sgm_census_wave_try(descL, descR, pitch, window, d_cv_out, H, W, D, p1, p2, overcounting, d_disp, dmin, invalid_disparity,
+                                       d_all_nan, d_sgm_workspace, sgm_workspace_bytes, s, &done);
+    if (rc != PB200_OK) return rc;
+    *ran = done ? 1 : 0;
+    return PB200_OK;
+}
 
 extern "C" size_t pb200_census_workspace_bytes(int H, int W, int window) {
     if (H <= 0 || W <= 0 || window < 3) return 0;
@@ -426,17 +500,7 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
     const int nw = census_nwords(window), pitch = census_pitch(W);
     uint32_t *descL = (uint32_t *)d_workspace;
     uint32_t *descR = descL + (size_t)nw * H * pitch;
-    int rc;
-#define PB200_T(WIN)                                                       \
-    case WIN:                                                              \
-        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, row_begin, row_end, s);         \
-        if (rc == PB200_OK) rc = launch_transform<WIN>(d_right, H, W, pitch, descR, row_begin, row_end, s); \
-        break;
-    switch (window) {
-        PB200_T(3) PB200_T(5) PB200_T(7) PB200_T(9) PB200_T(11) PB200_T(13)
-        default: rc = PB200_ERR_UNSUPPORTED;
-    }
-#undef PB200_T
+    const int rc = census_transform_pair(d_left, d_right, H, W, window, descL, descR, row_begin, row_end, s);
     if (rc != PB200_OK) return rc;
 
     FillParams p;

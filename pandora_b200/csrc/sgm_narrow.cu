@@ -52,6 +52,9 @@ struct NarrowParams {
     const uint32_t *halo_in;  // packed (3, W, D/2 words) states of the row just outside the tile (order dx = 0, +1, -1) or NULL
     uint32_t *halo_out;       // packed states of this tile's last row in travel direction or NULL
     int debug;                // PB200_SGM_DEBUG bit 0: no strip exchange (timing experiments only, wrong results)
+    // fused Census source of the first wavefront pass (CENSUS = true): planar one-word descriptors (census.cu)
+    const uint32_t *descL, *descR;
+    int pitch, half;
 };
 
 template <int NR> struct Words;
@@ -298,6 +301,8 @@ __device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&v)[NR]
     else if constexpr (NR == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
     else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
 }
+
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // A path start (L = C) is the same as a step from a FLAT previous state (all disparities equal: m = Lp[d], so
 // t - m = 0).  The state buffers therefore start as zeros and image-border halo columns simply stay zero: the row
@@ -555,14 +560,18 @@ __device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t target) {
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     } while (v < target);
 }
-template <int NR, int CB, bool FINAL, bool WTA>
+template <int NR, int CB, bool FINAL, bool WTA, bool CENSUS = false>
 __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) {
+    static_assert(!(CENSUS && FINAL), "the Census source only exists for the first pass");
     if (FINAL && *p.flag != 0) return;
     extern __shared__ __align__(16) uint32_t wave_smem[];
     constexpr int VS = NR * 32;                          // words per packed state vector
     constexpr int RW = NR * CB / 2;                      // raw cost words per lane
     constexpr int SIN = FINAL ? (RW + NR) : 2 * NR;      // staged input words per lane and pixel
-    constexpr int NSTG = 4, PFD = NSTG - 1;
+    // CENSUS: a staged row of a warp is D + 1 right descriptors (columns xA + dmin ... xB + dmax), the two left ones and
+    // padding: CW words.  Pixel A reads row i + 1 while pixel B still reads row i and PFD + 1 rows are in flight: 8 slots.
+    constexpr int CW = 2 * VS + 8;
+    constexpr int PFD = 3, NSTG = CENSUS ? 8 : 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = (blockDim.x >> 5) - 2;                // compute warps; warps nc / nc + 1 relay to the left / right strip
     const int NV = nc + 2;                               // mailbox columns: 0 = left strip, 1 .. nc = compute warps, nc + 1 = right strip
@@ -576,7 +585,8 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     const int state_words = 12 * NV * VS + 64;
     // mailboxes, counters AND the staging ring start as zeros (columns right of the image are never staged and must
     // read as zero costs, which also pass the data check; a strip without a neighbour reads flat zero states)
-    for (int i = threadIdx.x; i < state_words + NSTG * nc * 2 * 32 * SIN; i += blockDim.x) wave_smem[i] = 0u;
+    const int stage_words = CENSUS ? NSTG * nc * CW : NSTG * nc * 2 * 32 * SIN;
+    for (int i = threadIdx.x; i < state_words + stage_words; i += blockDim.x) wave_smem[i] = 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (!has_left) wave_smem[12 * NV * VS + 0] = 0xFFFFFFFFu;                // fe[0]: the image border never makes anyone wait
@@ -658,7 +668,35 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     // SW_A(i + 1) only needs the pair's own SW_B(i), so it is published a whole row before the left neighbour uses it.
     // That takes the program-order coupling "E wait of row i -> SW publish of row i + 1" out of the border cycle
     // (E hop -> remainder of the row -> SW hop back), which otherwise limits the row rate to ~1.4 ring round trips.
+    // CENSUS staging: the warp's private block of a row, [0, D] = right descriptors of columns xA + dmin + s (a column
+    // outside the descriptor row reads as "window leaves the image"), [D + 1], [D + 2] = left descriptors of A and B
+    const uint32_t cstg_base = smem_u32(stg) + (uint32_t)(warp * CW) * 4u, cstg_stage = (uint32_t)(nc * CW) * 4u;
     auto stage_pix = [&](int c, int r) {
+        if (CENSUS) {
+            if (c != 0 || !valid[0] || r >= H) return;        // one request per row, issued with pixel A (one row ahead)
+            const uint32_t sg = cstg_base + (uint32_t)(r & (NSTG - 1)) * cstg_stage;
+            const uint32_t *rowR = p.descR + (size_t)r * p.pitch, *rowL = p.descL + (size_t)r * p.pitch;
+            const int col0 = xl[0] + p.dmin;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const int sidx = h * VS + lane * NR + j;
+                    const int col = col0 + sidx;
+                    if (col >= 0 && col < p.pitch) cp_async_words<1>(sg + (uint32_t)sidx * 4u, rowR + col);
+                    else sts_u32(sg + (uint32_t)sidx * 4u, 0x80000000u);
+                }
+            }
+            if (lane < 3) {
+                const int sidx = 2 * VS + lane;
+                const int col = (lane == 0) ? col0 + 2 * VS : xl[0] + lane - 1;
+                const bool ok = (lane == 0) ? (col >= 0 && col < p.pitch) : (col < W);
+                const uint32_t *src = (lane == 0 ? rowR : rowL) + col;
+                if (ok) cp_async_words<1>(sg + (uint32_t)sidx * 4u, src);
+                else sts_u32(sg + (uint32_t)sidx * 4u, 0x80000000u);
+            }
+            return;
+        }
         if (!valid[c] || r >= H) return;
         const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage + c * stg_pix;
         if (!FINAL) {
@@ -677,7 +715,43 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     // unpack pixel c of row r from its staging slot (pass 1: verify + pack + write the cost code; zeros outside the image)
     auto load_pix = [&](int c, int r, uint32_t (&c16)[NR], uint32_t (&p16)[NR]) {
         const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage + c * stg_pix;
-        if (!FINAL) {
+        if (CENSUS) {
+            // Hamming costs straight from the descriptors (census.cpp:97-180): popcount(left ^ right), NaN code when either
+            // window leaves the image.  B's window is A's shifted by one column.
+            const uint32_t cg = cstg_base + (uint32_t)(r & (NSTG - 1)) * cstg_stage;
+            uint32_t lw[1], ra[NR], rb[NR];
+            lds_words<1>(cg + (uint32_t)(2 * VS + 1 + c) * 4u, lw);
+            if (c == 0) {
+                lds_words<NR>(cg + lane_b, ra);
+                lds_words<NR>(cg + (uint32_t)VS * 4u + lane_b, rb);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    uint32_t t[1];
+                    lds_words<1>(cg + lane_b + (uint32_t)(1 + j) * 4u, t);
+                    ra[j] = t[0];
+                    lds_words<1>(cg + (uint32_t)VS * 4u + lane_b + (uint32_t)(1 + j) * 4u, t);
+                    rb[j] = t[0];
+                }
+            }
+            const int xr0 = xl[c] + p.dmin;                    // right column of disparity index 0
+            const bool full = !(lw[0] >> 31) && xr0 >= p.half && xr0 + 2 * VS - 1 < W - p.half;    // warp-uniform
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) c16[j] = __byte_perm(__popc(lw[0] ^ ra[j]), __popc(lw[0] ^ rb[j]), 0x5410);
+            } else {
+                const uint32_t nanc = p.inv | Tier<CB>::FLAG1;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const uint32_t lo = ((int32_t)(lw[0] | ra[j]) < 0) ? nanc : (uint32_t)__popc(lw[0] ^ ra[j]);
+                    const uint32_t hi = ((int32_t)(lw[0] | rb[j]) < 0) ? nanc : (uint32_t)__popc(lw[0] ^ rb[j]);
+                    c16[j] = lo | (hi << 16);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) p16[j] = 0u;
+            if (valid[c] && r < H) st_cost<NR, CB>(p.buf + pix0[c] + (long)r * row_stride, lane, c16);
+        } else if (!FINAL) {
             uint32_t fa[NR], fb[NR];
             lds_words<NR>(sg + off0, fa);
             lds_words<NR>(sg + off1, fb);
@@ -710,6 +784,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
     for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = zero[j] = 0u;
     cp_async_wait<PFD>();                                  // pixel A of row 0
+    if (CENSUS) __syncwarp();                              // a lane reads descriptors its neighbours copied
     load_pix(0, 0, c16A, p16A);
     {
         uint32_t ccA[NR];
@@ -728,6 +803,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         stage_pix(1, i + PFD);
         cp_async_commit();
         cp_async_wait<PFD>();                              // pixel A of row i + 1 and pixel B of row i have landed
+        if (CENSUS) __syncwarp();
         uint32_t c16[2][NR], p16[2][NR], cc[2][NR], c16An[NR], p16An[NR], ccAn[NR];
         load_pix(0, i + 1, c16An, p16An);
         load_pix(1, i, c16[1], p16[1]);
@@ -829,7 +905,41 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
         for (int j = 0; j < NR; ++j) { SEA_prev[j] = L_SE_A[j]; SWA_cur[j] = SWA_next[j]; c16A[j] = c16An[j]; p16A[j] = p16An[j]; }
     }
-    if (!FINAL && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
+    if (!FINAL && !CENSUS && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// the two wavefront passes; CENSUS: the first one computes its costs from census descriptors (p.descL / p.descR)
+template <int NR, int CB, bool CENSUS>
+int launch_wave(NarrowParams p, int nstrips, int nwarp, void *workspace, cudaStream_t s, bool *done) {
+    *done = false;
+    const int nsm = sm_count();
+    const bool wta = p.disp != nullptr;
+    void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false, CENSUS>;
+    void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
+    const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
+    const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
+    const size_t smem1 = state + (CENSUS ? (size_t)8 * nwarp * (2 * NR * 32 + 8) : (size_t)4 * nwarp * 2 * 32 * (2 * NR)) * sizeof(uint32_t);
+    const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
+    int occ1 = 0, occ2 = 0;
+    if (wthreads <= 512 && smem1 <= 220 * 1024 && smem2 <= 220 * 1024) {
+        PB200_CUDA(cudaFuncSetAttribute((const void *)w1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        PB200_CUDA(cudaFuncSetAttribute((const void *)w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, (const void *)w1, wthreads, smem1));
+        PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void *)w2, wthreads, smem2));
+    }
+    if ((long)occ1 * nsm < nstrips || (long)occ2 * nsm < nstrips) return PB200_OK;
+    p.ring = reinterpret_cast<unsigned long long *>(workspace);
+    const size_t wring = (size_t)nstrips * 12 * NR * 32 * sizeof(unsigned long long);
+    PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
+    void *args[] = {(void *)&p};
+    PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(wthreads), args, smem1, s));
+    PB200_LAUNCH_CHECK(CENSUS ? "sgm_wave_kernel<down, census>" : "sgm_wave_kernel<down>");
+    PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(wthreads), args, smem2, s));
+    PB200_LAUNCH_CHECK("sgm_wave_kernel<up>");
+    *done = true;
+    return PB200_OK;
 }
 
 enum { NARROW_ALL = 0, NARROW_H = 1, NARROW_V = 2 };
@@ -846,33 +956,8 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     const bool wta = p.disp != nullptr;
     // wavefront path: the whole stage in two 4-direction passes (single-call runs without tile halos)
     if (phase == NARROW_ALL && p.halo_in == nullptr && p.halo_out == nullptr && !getenv("PB200_SGM_NO_WAVE")) {
-        void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false>;
-        void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
-        const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
-        const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
-        const size_t smem1 = state + (size_t)4 * nwarp * 2 * 32 * (2 * NR) * sizeof(uint32_t);
-        const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
-        int occ1 = 0, occ2 = 0;
-        if (wthreads <= 512 && smem1 <= 220 * 1024) {
-            PB200_CUDA(cudaFuncSetAttribute((const void *)w1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-            PB200_CUDA(cudaFuncSetAttribute((const void *)w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, (const void *)w1, wthreads, smem1));
-            PB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void *)w2, wthreads, smem2));
-        }
-        if ((long)occ1 * nsm >= nstrips && (long)occ2 * nsm >= nstrips) {
-            p.ring = reinterpret_cast<unsigned long long *>(workspace);
-            const size_t wring = (size_t)nstrips * 12 * NR * 32 * sizeof(unsigned long long);
-            PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
-            void *args[] = {(void *)&p};
-            PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-            PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(wthreads), args, smem1, s));
-            PB200_LAUNCH_CHECK("sgm_wave_kernel<down>");
-            PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-            PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(wthreads), args, smem2, s));
-            PB200_LAUNCH_CHECK("sgm_wave_kernel<up>");
-            *done = true;
-            return PB200_OK;
-        }
+        const int rc = launch_wave<NR, CB, false>(p, nstrips, nwarp, workspace, s, done);
+        if (rc != PB200_OK || *done) return rc;
     }
     const int threads = (nwarp + 1) * 32;
     void (*mid)(const NarrowParams) = sgm_narrow_vsweep_kernel<NR, CB, false, false>;
@@ -951,6 +1036,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.halo_out = reinterpret_cast<uint32_t *>(halo_out);
     if ((reinterpret_cast<uintptr_t>(halo_in) & 15) || (reinterpret_cast<uintptr_t>(halo_out) & 15)) return PB200_OK;
     p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
+    p.descL = p.descR = nullptr; p.pitch = 0; p.half = 0;
     int kdiv = getenv("PB200_SGM_KDIV") ? atoi(getenv("PB200_SGM_KDIV")) : 1;
     if (kdiv > 1) { K = (K / kdiv + 1) / 2 * 2; if (K < 4) K = 4; }
     if (phase == 3) {                 // query only: eligible -> the caller gates its float kernels on the flag
@@ -970,6 +1056,50 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     if (rc != PB200_OK) return rc;
     if (done) *gate = p.flag;
     return PB200_OK;
+}
+
+// Fused Census -> SGM: the two wavefront passes with the first one computing the Hamming costs from the census
+// descriptors (no float cost volume is written or read).  Census costs are integers in [0, window^2] by construction,
+// so the data condition of the packed path holds statically: no flag, no float fall-back.  *done = false when the
+// shape / parameters are not eligible (the caller then runs the Census fill and pb200_sgm separately).
+int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch, int window, float *out, int H, int W, int D, float p1,
+                        float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
+                        size_t workspace_bytes, cudaStream_t s, bool *done) {
+    *done = false;
+    if (D != 64 && D != 128 && D != 256) return PB200_OK;
+    if (window != 3 && window != 5) return PB200_OK;                       // one-word descriptors
+    const float invalid_value = (float)(window * window) + p2 + 1.f;       // cmax + P2 + 1 (census.py:116 gives cmax = w^2)
+    if (!is_small_int(p1, 1, NARROW_MAX) || !is_small_int(p2, 1, NARROW_MAX) || p1 > p2 || !is_small_int(invalid_value, 0, NARROW_MAX) ||
+        (int)invalid_value + (int)p2 > NARROW_MAX)
+        return PB200_OK;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return PB200_OK;
+    const int nsm = sm_count();
+    int K = ceil_div(W, nsm);
+    if (K < 4) K = 4;
+    K = (K + 1) / 2 * 2;
+    if (K / 2 > 14) return PB200_OK;
+    const int NR = D / 64;
+    const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
+    if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
+    if (getenv("PB200_SGM_NO_WAVE")) return PB200_OK;
+
+    NarrowParams p;
+    p.cv = nullptr; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
+    p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
+    p.inv = (uint32_t)invalid_value;
+    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && !getenv("PB200_SGM_NO_BYTE_TIER");
+    p.cost_ok_max = 0.f;
+    p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
+    p.dy = 1; p.overcounting = overcounting;
+    p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
+    p.ring = nullptr; p.halo_in = nullptr; p.halo_out = nullptr;
+    p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
+    p.descL = descL; p.descR = descR; p.pitch = pitch; p.half = window / 2;
+    const int nwarp = K / 2;
+    const int nstrips = ceil_div(W, K);
+    if (NR == 4) return bytes ? launch_wave<4, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<4, 2, true>(p, nstrips, nwarp, workspace, s, done);
+    if (NR == 2) return bytes ? launch_wave<2, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<2, 2, true>(p, nstrips, nwarp, workspace, s, done);
+    return launch_wave<1, 2, true>(p, nstrips, nwarp, workspace, s, done);
 }
 
 }  // namespace pb200

@@ -79,6 +79,41 @@ class Engine:
                 self._stream()))
         return (cv, disp, flags) if fuse_wta else cv
 
+    def census_descriptors(self, left: torch.Tensor, right: torch.Tensor, window: int, rows: Optional[Tuple[int, int]] = None) -> None:
+        """Census transform of both images (or of a band of rows) into the engine's descriptor workspace."""
+        H, W = self._hw(left)
+        ws = self._workspace("census", self.lib.pb200_census_workspace_bytes(H, W, window))
+        r0, r1 = (0, H) if rows is None else rows
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_descriptors_rows(_ptr(left), _ptr(right), H, W, window, _ptr(ws), ws.numel(), int(r0), int(r1),
+                                                                 self._stream()))
+
+    def census_sgm(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int, p1: float, p2: float,
+                   overcounting: bool = False, out: Optional[torch.Tensor] = None, fuse_wta: bool = True, invalid_disparity: float = -9999.0,
+                   disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, descriptors_ready: bool = False):
+        """Fused Census -> SGM [-> WTA] (``pb200_census_sgm``): the Hamming costs go from the census descriptors straight
+        into the first SGM pass, the float32 Census volume is never materialised.  Returns ``None`` when the configuration
+        is not eligible (nothing was computed: run ``census`` + ``sgm``), else (SGM volume, disparity, all-NaN flags)."""
+        import ctypes  # noqa: PLC0415
+
+        H, W = self._hw(left)
+        D = dmax - dmin + 1
+        res = self.empty((H, W, D)) if out is None else out
+        if fuse_wta and disp is None:
+            disp = self.empty((H, W))
+            flags = self.empty((H, W), torch.uint8)
+        cws = self._workspace("census", self.lib.pb200_census_workspace_bytes(H, W, window))
+        sws = self._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, W, D))
+        ran = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_sgm(
+                _ptr(left), _ptr(right), H, W, window, dmin, D, float(p1), float(p2), int(bool(overcounting)), _ptr(res), _ptr(cws),
+                cws.numel(), _ptr(sws), sws.numel(), _ptr(disp) if fuse_wta else None, float(invalid_disparity),
+                _ptr(flags) if fuse_wta else None, int(bool(descriptors_ready)), ctypes.addressof(ran), self._stream()))
+        if not ran.value:
+            return None
+        return (res, disp, flags) if fuse_wta else (res, None, None)
+
     def sad_ssd(self, left, right, window: int, dmin: int, dmax: int, squared: bool = False, out=None) -> torch.Tensor:
         H, W = self._hw(left)
         D = dmax - dmin + 1
