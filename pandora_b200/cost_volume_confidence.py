@@ -33,6 +33,12 @@ class AbstractCostVolumeConfidence:
         return decorator
 
     @staticmethod
+    def normalize_with_extremum(confidence: np.ndarray, dataset, nbr_etas: int, subpix: int = 1) -> np.ndarray:
+        """cost_volume_confidence.py:115-138: confidence / ((global_disp_max - global_disp_min) * nbr_etas * subpix)."""
+        global_disp_min, global_disp_max = dataset.attrs["global_disparity"][0], dataset.attrs["global_disparity"][1]
+        return np.copy(confidence) / ((global_disp_max - global_disp_min) * nbr_etas * subpix)
+
+    @staticmethod
     def allocate_confidence_map(name_confidence_measure: str, confidence_map: np.ndarray, disp=None, cv=None):
         """cost_volume_confidence.py:129-250: append one (row, col) indicator to ``confidence_measure`` of both datasets."""
         if "disp_min" not in name_confidence_measure and "disp_max" not in name_confidence_measure:
@@ -134,9 +140,13 @@ class Ambiguity(AbstractCostVolumeConfidence):
         grids, disparity_range, is_max = self._inputs(img_left, cv)
         amb = eng.confidence(device_volume(eng, cv), self._etas, grids, disparity_range, is_max=is_max)["ambiguity"].cpu().numpy()
         if self._normalization:
-            if "global_disparity" in img_left.attrs or (img_right is not None and "global_disparity" in img_right.attrs):
-                raise NotImplementedError("normalize_with_extremum (global_disparity) stays Pandora's")
-            amb = self.normalize_with_percentile(amb)
+            subpix = int(cv.attrs.get("subpixel", 1))
+            if "global_disparity" in img_left.attrs:                                   # ambiguity.py:148-162
+                amb = self.normalize_with_extremum(amb, img_left, self._nbr_etas, subpix)
+            elif img_right is not None and "global_disparity" in img_right.attrs:
+                amb = self.normalize_with_extremum(amb, img_right, self._nbr_etas, subpix)
+            else:
+                amb = self.normalize_with_percentile(amb)
         return self.allocate_confidence_map(self._indicator, 1 - amb, disp, cv)
 
 

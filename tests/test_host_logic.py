@@ -201,3 +201,16 @@ def test_allocate_confidence_map_appends_indicators():
         assert ds["confidence_measure"].data.shape == (2, 3, 2)
         assert list(ds.coords["indicator"].data) == ["confidence_from_ambiguity", "confidence_from_risk_max"]
         np.testing.assert_array_equal(ds["confidence_measure"].data[:, :, 1], second)
+
+
+def test_normalize_with_extremum():                                # tests/test_confidence/test_ambiguity.py:204-231
+    from pandora_b200.cost_volume_confidence import AbstractCostVolumeConfidence
+
+    class _Img:
+        attrs = {"disp_min": 0, "disp_max": 1, "global_disparity": [-2, 2]}
+
+    ambiguity_ = AbstractCostVolumeConfidence(confidence_method="ambiguity", eta_max=0.2, eta_step=0.1)
+    ambiguity = np.ones((4, 4))
+    got = ambiguity_.normalize_with_extremum(ambiguity, _Img(), ambiguity_._nbr_etas)
+    nbr_etas = np.arange(0.0, 0.2, 0.1).shape[0]
+    np.testing.assert_array_equal(got, np.copy(ambiguity) / ((2 - (-2)) * nbr_etas))
