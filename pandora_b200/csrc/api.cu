@@ -24,6 +24,7 @@ void set_error(const char *fmt, ...) {
 int check_cuda(cudaError_t err, const char *what) {
     if (err == cudaSuccess) return PB200_OK;
     set_error("CUDA error in %s: %s", what, cudaGetErrorString(err));
+    cudaGetLastError();                 // a reported error must not resurface in the launch check of an unrelated later call
     return PB200_ERR_CUDA;
 }
 
@@ -166,7 +167,7 @@ extern "C" int pb200_cbca_host(const float *input, int H, int W, const int16_t *
 }
 
 #ifndef PB200_FUSE_CENSUS_SGM_DEFAULT
-#define PB200_FUSE_CENSUS_SGM_DEFAULT 0
+#define PB200_FUSE_CENSUS_SGM_DEFAULT 1
 #endif
 
 // Whole pipeline on host images (the end-to-end path bench.py reports as `e2e`).

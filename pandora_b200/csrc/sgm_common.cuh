@@ -4,12 +4,14 @@
 
 namespace pb200 {
 
-// upper bound of the strip-exchange ring of any SGM sweep (float states, one strip per 4 columns); the narrow-path
-// flag lives 256 bytes behind it (pb200_sgm_workspace_bytes = this + 512)
+// upper bound of the strip-exchange ring of any SGM sweep, at most one strip per 4 columns: the float / packed strip
+// sweeps use 2 x 2 vectors of vs 64-bit words per strip, the wavefront passes (sgm_wave_kernel) 12 mailbox vectors of
+// D/2 <= vs/2 words = 6 vs words -- the larger one.  The narrow-path flag lives 256 bytes behind it
+// (pb200_sgm_workspace_bytes = this + 512).
 static inline size_t sgm_ring_max_bytes(int W, int D) {
     const size_t nstrips = (size_t)(W + 3) / 4;
     const size_t vs = (size_t)((D + 31) / 32) * 32;
-    return nstrips * (2 * 2 * vs * sizeof(unsigned long long));
+    return nstrips * (6 * vs * sizeof(unsigned long long));
 }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {

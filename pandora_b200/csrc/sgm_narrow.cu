@@ -676,24 +676,22 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             if (c != 0 || !valid[0] || r >= H) return;        // one request per row, issued with pixel A (one row ahead)
             const uint32_t sg = cstg_base + (uint32_t)(r & (NSTG - 1)) * cstg_stage;
             const uint32_t *rowR = p.descR + (size_t)r * p.pitch, *rowL = p.descL + (size_t)r * p.pitch;
-            const int col0 = xl[0] + p.dmin;
+            // A column outside the image is clamped to column 0 or column W: both always carry the "window leaves the
+            // image" flag (half >= 1; [W, pitch) is flagged padding), so every lane issues the same copies -- the strips
+            // at the image border cost exactly what the others do (the slowest strip sets the pace of the whole wave).
+            const int col0 = xl[0] + p.dmin + lane * NR;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
-                    const int sidx = h * VS + lane * NR + j;
-                    const int col = col0 + sidx;
-                    if (col >= 0 && col < p.pitch) cp_async_words<1>(sg + (uint32_t)sidx * 4u, rowR + col);
-                    else sts_u32(sg + (uint32_t)sidx * 4u, 0x80000000u);
+                    const int sidx = h * VS + j;
+                    const int col = __vimin_s32_relu(col0 + sidx, W);
+                    cp_async_words<1>(sg + lane_b + (uint32_t)sidx * 4u, rowR + col);
                 }
             }
             if (lane < 3) {
-                const int sidx = 2 * VS + lane;
-                const int col = (lane == 0) ? col0 + 2 * VS : xl[0] + lane - 1;
-                const bool ok = (lane == 0) ? (col >= 0 && col < p.pitch) : (col < W);
-                const uint32_t *src = (lane == 0 ? rowR : rowL) + col;
-                if (ok) cp_async_words<1>(sg + (uint32_t)sidx * 4u, src);
-                else sts_u32(sg + (uint32_t)sidx * 4u, 0x80000000u);
+                const int col = (lane == 0) ? __vimin_s32_relu(xl[0] + p.dmin + 2 * VS, W) : min(xl[0] + lane - 1, W);
+                cp_async_words<1>(sg + (uint32_t)(2 * VS + lane) * 4u, (lane == 0 ? rowR : rowL) + col);
             }
             return;
         }
@@ -712,40 +710,48 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     const float nan_code = (float)(p.inv | Tier<CB>::FLAG1);
     const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
     bool bad = false;
+    uint32_t rawA[2 * NR], rawAn[2 * NR];                  // CENSUS: pixel A's right descriptors of the current / next row
+#pragma unroll
+    for (int j = 0; j < 2 * NR; ++j) rawA[j] = rawAn[j] = 0u;
     // unpack pixel c of row r from its staging slot (pass 1: verify + pack + write the cost code; zeros outside the image)
     auto load_pix = [&](int c, int r, uint32_t (&c16)[NR], uint32_t (&p16)[NR]) {
         const uint32_t sg = stg_base + (uint32_t)(r & (NSTG - 1)) * stg_stage + c * stg_pix;
         if (CENSUS) {
             // Hamming costs straight from the descriptors (census.cpp:97-180): popcount(left ^ right), NaN code when either
-            // window leaves the image.  B's window is A's shifted by one column.
+            // window leaves the image.  Pixel A reads its D right descriptors as two aligned vectors and keeps them: pixel
+            // B of the same row (one iteration later) needs the same window shifted by one column, i.e. A's registers
+            // moved down by one, the last one coming from the next lane (lane 31: the first word of the other half / the
+            // extra word D).
             const uint32_t cg = cstg_base + (uint32_t)(r & (NSTG - 1)) * cstg_stage;
             uint32_t lw[1], ra[NR], rb[NR];
             lds_words<1>(cg + (uint32_t)(2 * VS + 1 + c) * 4u, lw);
             if (c == 0) {
                 lds_words<NR>(cg + lane_b, ra);
                 lds_words<NR>(cg + (uint32_t)VS * 4u + lane_b, rb);
-            } else {
 #pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    uint32_t t[1];
-                    lds_words<1>(cg + lane_b + (uint32_t)(1 + j) * 4u, t);
-                    ra[j] = t[0];
-                    lds_words<1>(cg + (uint32_t)VS * 4u + lane_b + (uint32_t)(1 + j) * 4u, t);
-                    rb[j] = t[0];
-                }
+                for (int j = 0; j < NR; ++j) { rawAn[j] = ra[j]; rawAn[NR + j] = rb[j]; }
+            } else {
+                uint32_t ex[1];
+                lds_words<1>(cg + (uint32_t)(2 * VS) * 4u, ex);
+                const uint32_t t1 = __shfl_sync(0xffffffffu, rawA[0], (lane + 1) & 31);
+                const uint32_t t2 = __shfl_sync(0xffffffffu, rawA[NR], (lane + 1) & 31);
+#pragma unroll
+                for (int j = 0; j + 1 < NR; ++j) { ra[j] = rawA[j + 1]; rb[j] = rawA[NR + j + 1]; }
+                ra[NR - 1] = (lane == 31) ? t2 : t1;
+                rb[NR - 1] = (lane == 31) ? ex[0] : t2;
             }
-            const int xr0 = xl[c] + p.dmin;                    // right column of disparity index 0
-            const bool full = !(lw[0] >> 31) && xr0 >= p.half && xr0 + 2 * VS - 1 < W - p.half;    // warp-uniform
-            if (full) {
+            const uint32_t nan2 = (p.inv | Tier<CB>::FLAG1) * 0x10001u;
+            if (lw[0] >> 31) {                                  // warp-uniform: the left window leaves the image
 #pragma unroll
-                for (int j = 0; j < NR; ++j) c16[j] = __byte_perm(__popc(lw[0] ^ ra[j]), __popc(lw[0] ^ rb[j]), 0x5410);
+                for (int j = 0; j < NR; ++j) c16[j] = nan2;
             } else {
-                const uint32_t nanc = p.inv | Tier<CB>::FLAG1;
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
-                    const uint32_t lo = ((int32_t)(lw[0] | ra[j]) < 0) ? nanc : (uint32_t)__popc(lw[0] ^ ra[j]);
-                    const uint32_t hi = ((int32_t)(lw[0] | rb[j]) < 0) ? nanc : (uint32_t)__popc(lw[0] ^ rb[j]);
-                    c16[j] = lo | (hi << 16);
+                    const uint32_t xlo = lw[0] ^ ra[j], xhi = lw[0] ^ rb[j];          // bit 31 = the right window leaves the image
+                    const uint32_t pk = __byte_perm(__popc(xlo), __popc(xhi), 0x5410);
+                    uint32_t fl;                                                     // sign-replicated top bytes: 0xFFFF per flagged half
+                    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(fl) : "r"(xlo), "r"(xhi));
+                    c16[j] = (pk & ~fl) | (nan2 & fl);
                 }
             }
 #pragma unroll
@@ -786,6 +792,8 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     cp_async_wait<PFD>();                                  // pixel A of row 0
     if (CENSUS) __syncwarp();                              // a lane reads descriptors its neighbours copied
     load_pix(0, 0, c16A, p16A);
+#pragma unroll
+    for (int j = 0; j < 2 * NR; ++j) rawA[j] = rawAn[j];
     {
         uint32_t ccA[NR];
 #pragma unroll
@@ -904,6 +912,10 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         }
 #pragma unroll
         for (int j = 0; j < NR; ++j) { SEA_prev[j] = L_SE_A[j]; SWA_cur[j] = SWA_next[j]; c16A[j] = c16An[j]; p16A[j] = p16An[j]; }
+        if (CENSUS) {
+#pragma unroll
+            for (int j = 0; j < 2 * NR; ++j) rawA[j] = rawAn[j];
+        }
     }
     if (!FINAL && !CENSUS && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
 }
@@ -930,6 +942,7 @@ int launch_wave(NarrowParams p, int nstrips, int nwarp, void *workspace, cudaStr
     if ((long)occ1 * nsm < nstrips || (long)occ2 * nsm < nstrips) return PB200_OK;
     p.ring = reinterpret_cast<unsigned long long *>(workspace);
     const size_t wring = (size_t)nstrips * 12 * NR * 32 * sizeof(unsigned long long);
+    if ((size_t)(reinterpret_cast<char *>(p.flag) - reinterpret_cast<char *>(workspace)) < wring) return PB200_OK;   // ring must end before the flag
     PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
     void *args[] = {(void *)&p};
     PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));

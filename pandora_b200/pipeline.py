@@ -19,7 +19,7 @@ from .disparity import AbstractDisparity
 from .matching_cost import AbstractMatchingCost
 from .optimization import AbstractOptimization
 
-FUSE_CENSUS_SGM_DEFAULT = "0"
+FUSE_CENSUS_SGM_DEFAULT = "1"
 
 HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity", "refinement", "filter", "validation",
                   "cost_volume_confidence")
@@ -159,6 +159,7 @@ class StereoPipeline:
         self.h_disp = torch.empty((H, W), dtype=torch.float32, pin_memory=True)
         self.final_cv = None
         self._copy_stream = None
+        self._slots, self._submitted, self._d2h_stream = None, 0, None
         if method == "census":
             self.cmax = float(window * window)
         elif method == "zncc":
@@ -278,6 +279,64 @@ class StereoPipeline:
         self.h_disp.copy_(disp, non_blocking=True)
         cur.synchronize()
         return self.h_disp.numpy()
+
+    # ---- streaming entry: a sequence of stereo pairs, copies overlapped with the kernels ---------------------------
+    def submit_host(self, left, right) -> int:
+        """Asynchronous end-to-end step for a stream of stereo pairs: enqueue upload -> pipeline -> download of one pair
+        and return a ticket for ``result_host``.  Two buffer sets alternate, so the upload of pair k + 1 (copy stream)
+        and the download of pair k - 1 (a second copy stream) overlap the kernels of pair k; at most two pairs may be in
+        flight (collect ticket k - 1 before submitting pair k + 1).  ``final_cv`` belongs to the pair submitted last."""
+        t = self.torch
+        dev = self.eng.device
+        if self._slots is None:
+            with t.cuda.device(dev):
+                self._slots = [dict(d_left=self.eng.empty((self.H, self.W)), d_right=self.eng.empty((self.H, self.W)),
+                                    d_disp=self.eng.empty((self.H, self.W)),
+                                    h_left=t.empty((self.H, self.W), dtype=t.float32, pin_memory=True),
+                                    h_right=t.empty((self.H, self.W), dtype=t.float32, pin_memory=True),
+                                    h_disp=t.empty((self.H, self.W), dtype=t.float32, pin_memory=True),
+                                    ev_h2d=None, ev_compute=None, ev_d2h=None) for _ in range(2)]
+                self._copy_stream = self._copy_stream or t.cuda.Stream(device=dev)
+                self._d2h_stream = t.cuda.Stream(device=dev)
+        ticket = self._submitted
+        self._submitted += 1
+        s = self._slots[ticket % 2]
+        cur = t.cuda.current_stream(dev)
+        if s["ev_h2d"] is not None:
+            s["ev_h2d"].synchronize()                             # the slot's staging buffers are free again (pageable inputs)
+        hl, hr = self._pinned(left, s["h_left"]), self._pinned(right, s["h_right"])
+        cs = self._copy_stream
+        with t.cuda.stream(cs):
+            if s["ev_compute"] is not None:
+                cs.wait_event(s["ev_compute"])                    # pair k - 2 has read the slot's device images
+            else:
+                cs.wait_stream(cur)
+            s["d_left"].copy_(hl, non_blocking=True)
+            s["d_right"].copy_(hr, non_blocking=True)
+            s["ev_h2d"] = t.cuda.Event()
+            s["ev_h2d"].record(cs)
+        cur.wait_event(s["ev_h2d"])
+        if s["ev_d2h"] is not None:
+            cur.wait_event(s["ev_d2h"])                           # the download of pair k - 2 has read the slot's disparity map
+        disp = self.run_device(s["d_left"], s["d_right"])
+        s["d_disp"].copy_(disp, non_blocking=True)
+        s["ev_compute"] = t.cuda.Event()
+        s["ev_compute"].record(cur)
+        ds = self._d2h_stream
+        with t.cuda.stream(ds):
+            ds.wait_event(s["ev_compute"])
+            s["h_disp"].copy_(s["d_disp"], non_blocking=True)
+            s["ev_d2h"] = t.cuda.Event()
+            s["ev_d2h"].record(ds)
+        return ticket
+
+    def result_host(self, ticket: int) -> np.ndarray:
+        """Disparity map of a submitted pair (host array, valid until two more pairs have been submitted)."""
+        if not (self._submitted - 2 <= ticket < self._submitted):
+            raise ValueError(f"ticket {ticket} is not in flight (submitted so far: {self._submitted})")
+        s = self._slots[ticket % 2]
+        s["ev_d2h"].synchronize()
+        return s["h_disp"].numpy()
 
     def _pinned(self, arr, staging):
         """``arr`` as a pinned float32 host tensor: itself when it already is one, else a copy into ``staging``."""

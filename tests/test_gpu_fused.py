@@ -175,3 +175,32 @@ def test_disparity_host_fused(eng, oracle):
     np.testing.assert_array_equal(disp, exp)
     np.testing.assert_array_equal(vm, oracle.wta_validity_mask(mask, inv))
     assert launched <= 7, launched        # 2 transforms + 2 wavefront passes + 3 validity-mask kernels: no Census fill
+
+
+@pytest.mark.parametrize("cfg", [dict(sgm=(8, 32)), dict(sgm=(8, 32), fuse_census_sgm=False), dict(), dict(cbca=(5, 30.0))])
+def test_stream_of_pairs_equals_single_calls(eng, cfg):
+    """submit_host / result_host: a stream of different pairs, two in flight, pinned and pageable inputs -- every
+    disparity map equals the synchronous device run of the same pair (no buffer of a pair in flight is reused early)."""
+    import torch
+
+    import pandora_b200
+
+    H, W, D = 300, 400, 64
+    pipe = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, **cfg)
+    pairs = [pair(100 + i, H, W) for i in range(5)]
+    refs = [pipe.run_device(eng.to_device(l), eng.to_device(r)).cpu().numpy().copy() for l, r in pairs]
+    inputs = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) if i % 2 == 0 else (l, r) for i, (l, r) in enumerate(pairs)]
+    prev, got = None, {}
+    for i, (l, r) in enumerate(inputs):
+        tk = pipe.submit_host(l, r)
+        assert tk == i
+        if prev is not None:
+            got[prev] = pipe.result_host(prev).copy()
+        prev = tk
+    got[prev] = pipe.result_host(prev).copy()
+    for i in range(5):
+        np.testing.assert_array_equal(got[i], refs[i])
+    with pytest.raises(ValueError):
+        pipe.result_host(1)                                   # no longer in flight
+    # the synchronous entry still works on the same pipeline object
+    np.testing.assert_array_equal(pipe.run_host(*pairs[2]), refs[2])
