@@ -676,22 +676,23 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             if (c != 0 || !valid[0] || r >= H) return;        // one request per row, issued with pixel A (one row ahead)
             const uint32_t sg = cstg_base + (uint32_t)(r & (NSTG - 1)) * cstg_stage;
             const uint32_t *rowR = p.descR + (size_t)r * p.pitch, *rowL = p.descL + (size_t)r * p.pitch;
-            // A column outside the image is clamped to column 0 or column W: both always carry the "window leaves the
-            // image" flag (half >= 1; [W, pitch) is flagged padding), so every lane issues the same copies -- the strips
-            // at the image border cost exactly what the others do (the slowest strip sets the pace of the whole wave).
-            const int col0 = xl[0] + p.dmin + lane * NR;
+            // Positions whose column lies outside the descriptor row are never copied: they are the same for every row and
+            // were filled with the "window leaves the image" flag once, before the loop (census_prefill below).  No lane
+            // ever reads a substitute address: copies of one instruction that alias one global word serialise in the LSU,
+            // and the slowest strip sets the pace of the whole wave.
+            const int colb = xl[0] + p.dmin + lane * NR;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
                     const int sidx = h * VS + j;
-                    const int col = __vimin_s32_relu(col0 + sidx, W);
-                    cp_async_words<1>(sg + lane_b + (uint32_t)sidx * 4u, rowR + col);
+                    const int col = colb + sidx;
+                    if ((unsigned)col < (unsigned)p.pitch) cp_async_words<1>(sg + lane_b + (uint32_t)sidx * 4u, rowR + col);
                 }
             }
             if (lane < 3) {
-                const int col = (lane == 0) ? __vimin_s32_relu(xl[0] + p.dmin + 2 * VS, W) : min(xl[0] + lane - 1, W);
-                cp_async_words<1>(sg + (uint32_t)(2 * VS + lane) * 4u, (lane == 0 ? rowR : rowL) + col);
+                const int col = (lane == 0) ? xl[0] + p.dmin + 2 * VS : xl[0] + lane - 1;
+                if ((unsigned)col < (unsigned)p.pitch) cp_async_words<1>(sg + (uint32_t)(2 * VS + lane) * 4u, (lane == 0 ? rowR : rowL) + col);
             }
             return;
         }
@@ -778,6 +779,25 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             for (int j = 0; j < NR; ++j) c16[j] = p16[j] = 0u;              // outside the image: zero costs, flat states
         }
     };
+    if (CENSUS && valid[0]) {                              // census_prefill: flag words of the positions no copy ever writes
+        const int colb = xl[0] + p.dmin + lane * NR;
+        for (int sl = 0; sl < NSTG; ++sl) {
+            const uint32_t sg = cstg_base + (uint32_t)sl * cstg_stage;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const int sidx = h * VS + j;
+                    if (!((unsigned)(colb + sidx) < (unsigned)p.pitch)) sts_u32(sg + lane_b + (uint32_t)sidx * 4u, 0x80000000u);
+                }
+            }
+            if (lane < 3) {
+                const int col = (lane == 0) ? xl[0] + p.dmin + 2 * VS : xl[0] + lane - 1;
+                if (!((unsigned)col < (unsigned)p.pitch)) sts_u32(sg + (uint32_t)(2 * VS + lane) * 4u, 0x80000000u);
+            }
+        }
+        __syncwarp();
+    }
     stage_pix(0, 0);
     cp_async_commit();
     for (int r = 0; r < PFD; ++r) {
@@ -879,16 +899,17 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
                     for (int j = 0; j < NR; ++j) {
                         uint32_t t = tot[j];
                         if (p.overcounting) t = t - 7u * cc[c][j];   // S >= 8 C in every half: no borrow
-                        // 16-bit integer -> float32: PRMT builds 0x4B00'nnnn, one FADD removes the 2^23
-                        const float vlo = __uint_as_float(__byte_perm(t, 0x4B00u, 0x5410)) - 8388608.0f;
-                        const float vhi = __uint_as_float(__byte_perm(t, 0x4B00u, 0x5432)) - 8388608.0f;
+                        // 16-bit integer -> float32: PRMT builds 0x4B00'nnnn, one FADD removes the 2^23.  A NaN cell gets the
+                        // upper half 0x7F80 / 0x7FFF instead of 0x4B00: exponent all ones over a non-zero mantissa (its sum
+                        // is >= invalid_value > 0), i.e. a NaN that the same FADD passes through -- no select.
                         const uint32_t fl = c16[c][j] & Tier<CB>::FLAGS;
-                        fa[j] = (fl & 0xFFFFu) ? nan_f() : vlo;
-                        fb[j] = (fl >> 16) ? nan_f() : vhi;
+                        const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;     // 0xFF80 / 0xFFFF per NaN half
+                        const uint32_t hx = 0x4B004B00u | (sat & 0x34FF34FFu);
+                        fa[j] = __uint_as_float(__byte_perm(t, hx, 0x5410)) - 8388608.0f;
+                        fb[j] = __uint_as_float(__byte_perm(t, hx, 0x7632)) - 8388608.0f;
                         if (WTA) {
                             // NaN cells saturate their half (no valid sum reaches the sentinel), then one 32-bit key per
                             // half: (sum << 16) | register index; the lane offset of the disparity is added once below
-                            const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;
                             const uint32_t tk = t | sat;
                             bl = min(bl, __byte_perm(tk, (uint32_t)j, 0x1054));      // (low sum << 16) | j
                             bh = min(bh, __byte_perm(tk, (uint32_t)j, 0x3254));      // (high sum << 16) | j

@@ -156,6 +156,7 @@ def test_disparity_host_fused(eng, oracle):
     dmin, dmax = -63, 0
     S, exp, inv = oracle_chain(oracle, left, right, 5, dmin, dmax, 8, 32, False)
     mask = oracle.validity_mask(H, W, dmin, dmax, 2)
+    oracle.cv_masked(oracle.census_cost_volume(left, right, 5, dmin, dmax)[0], mask, 2)     # the all-NaN bits of the cost step
     disp = np.empty((H, W), dtype=np.float32)
     vm = np.empty((H, W), dtype=np.uint16)
     out = np.empty((H, W, 64), dtype=np.float32)
