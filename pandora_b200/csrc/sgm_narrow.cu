@@ -853,34 +853,37 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             if (!nowait) flag_wait(fs_base + (vme + 1u) * 4u, tag - 1);
             lds_words<NR>(sw_base + (uint32_t)((i - 1) & 3) * SLOT + (vme + 1u) * VB, SW_in);
         }
+        // Independent recurrence steps sit in one basic block (no flag, no warp barrier between them) so that the
+        // scheduler can fill the latency bubbles of one chain (min tree -> redux -> per-register ops) with the others:
+        // SW_B, SE_B and S_B only need values at hand; SW_A(i + 1) follows SW_B, S_A is independent.
         nstep<NR>(cc[1], SW_in, L_SW_B, lane, p1p1, p2p2);                   // SW_B(i)
+        nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p1p1, p2p2);                // SE_B(i) from the pair's own SE_A(i - 1)
+        nstep<NR>(cc[1], Sv[1], L0, lane, p1p1, p2p2);                       // S_B(i)
+#pragma unroll
+        for (int j = 0; j < NR; ++j) Sv[1][j] = L0[j];
         nstep<NR>(ccAn, L_SW_B, SWA_next, lane, p1p1, p2p2);                 // SW_A(i + 1), one row ahead
+        nstep<NR>(cc[0], Sv[0], L0, lane, p1p1, p2p2);                       // S_A(i)
+#pragma unroll
+        for (int j = 0; j < NR; ++j) Sv[0][j] = L0[j];
         sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, SWA_next);
+        sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
         __syncwarp();
         if (lane == 0) flag_publish(fs_base + vme * 4u, tag + 1, relaxed);
-        nstep<NR>(cc[1], SEA_prev, L_SE_B, lane, p1p1, p2p2);
-        sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            nstep<NR>(cc[c], Sv[c], L0, lane, p1p1, p2p2);
-#pragma unroll
-            for (int j = 0; j < NR; ++j) Sv[c][j] = L0[j];
-        }
 
-        // ---- phase 2: the E chain -- wait, two steps, publish -------------------------------------------------
+        // ---- phase 2: the E chain -- wait, two steps, publish; SE_A (the left neighbour's SE state of the previous row is
+        // visible since its E flag of this row) fills the bubbles of the E_A -> E_B chain ----------------------------------
         uint32_t E_in[NR], SE_in[NR], L_E_A[NR], L_E_B[NR], L_SE_A[NR];
         if (!nowait) flag_wait(fe_base + (vme - 1u) * 4u, tag);
         lds_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + (vme - 1u) * VB, E_in);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) SE_in[j] = 0u;
+        if (i > 0) lds_words<NR>(se_base + (uint32_t)((i - 1) & 3) * SLOT + (vme - 1u) * VB, SE_in);
         nstep<NR>(cc[0], E_in, L_E_A, lane, p1p1, p2p2);
+        nstep<NR>(cc[0], SE_in, L_SE_A, lane, p1p1, p2p2);
         nstep<NR>(cc[1], L_E_A, L_E_B, lane, p1p1, p2p2);
         sts_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_E_B);
         __syncwarp();
         if (lane == 0) flag_publish(fe_base + vme * 4u, tag, relaxed);
-        // ---- phase 3: the left neighbour's SE state of the previous row (visible since its E flag of this row) ----
-#pragma unroll
-        for (int j = 0; j < NR; ++j) SE_in[j] = 0u;
-        if (i > 0) lds_words<NR>(se_base + (uint32_t)((i - 1) & 3) * SLOT + (vme - 1u) * VB, SE_in);
-        nstep<NR>(cc[0], SE_in, L_SE_A, lane, p1p1, p2p2);
 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
