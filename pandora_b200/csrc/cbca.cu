@@ -20,6 +20,8 @@
 // same order of additions) and an int32 prefix of Nh in a shared-memory ring of 4*MA rows, so
 // E and N are two differences each.  Every cost is read from HBM once (+ halo columns from L2)
 // and written once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -368,6 +370,174 @@ __global__ void __launch_bounds__(32 * CBCA_TX) cbca_aggregate_pipe_kernel(const
     }
 }
 
+// ---- aggregation, register version (MA <= 4: cbca_distance <= 5, the default) -------------------------------
+// Same arithmetic again, organised so that NOTHING is shared between threads: no block barrier, no staging ring, no
+// serial row scan.  Lanes run over 32 disparities (every volume access of a warp is one 128-byte line), a thread owns
+// TX = 4 adjacent columns and marches down the rows.  Per row it loads the 4 + 2*MA costs its horizontal arm sums can
+// meet straight into registers (one row ahead: the loads of row i + 1 are in flight while row i is computed), adds the
+// arm taps with predicates (l, r <= 4: at most eight predicated adds around the centre), keeps the running column
+// prefixes of Eh (float32, the reference's step-3 order of additions) and Nh in registers and their last RING = 12
+// rows in a THREAD-PRIVATE shared-memory ring ([slot][column][lane]: conflict-free, no synchronisation), from which
+// the vertical arm sums of row i - MA are two differences.  The vertical arms and the "centre cost is NaN" bits of the
+// last MA rows travel in two small register histories, so every support entry and every cost is loaded exactly once
+// per thread (halo columns: twice more from L2 by the neighbouring strips).
+// Integer costs: every sum is exact, one correctly rounded division -> bit-identical to the reference; float costs:
+// direct <= 9-term sums instead of row-prefix differences (more accurate; tests/test_gpu_parity.py states the tolerance).
+constexpr int CBR_TX = 4, CBR_MA = 4, CBR_RING = 12;
+
+__device__ __forceinline__ int2 ldg_support(const short4 *p) { return __ldg(reinterpret_cast<const int2 *>(p)); }
+
+__global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float *__restrict__ cv_in, float *__restrict__ cv_out, int H, int W,
+                                                                 int D, int dmin, int off, const short4 *__restrict__ crossL,
+                                                                 const short4 *__restrict__ crossR, int band_rows) {
+    constexpr int TX = CBR_TX, MA = CBR_MA, RING = CBR_RING, CW = TX + 2 * MA;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x, wy = threadIdx.y, nw = blockDim.y;
+    // thread-private rings, addressed by 32-bit shared addresses: PE [RING][TX][32] float, PN [RING][TX][32] uint16
+    const uint32_t pe_base = smem_u32(smem_raw) + (uint32_t)((wy * RING * TX * 32 + lane) * 4);
+    const uint32_t pn_base = smem_u32(smem_raw) + (uint32_t)(nw * RING * TX * 32 * 4) + (uint32_t)((wy * RING * TX * 32 + lane) * 2);
+    auto pe_ld = [&](int slot, int c) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(pe_base + (uint32_t)((slot * TX + c) * 128))); return v; };
+    auto pn_ld = [&](int slot, int c) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(pn_base + (uint32_t)((slot * TX + c) * 64))); return (unsigned)v; };
+    auto pe_st = [&](int slot, int c, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(pe_base + (uint32_t)((slot * TX + c) * 128)), "f"(v) : "memory"); };
+    auto pn_st = [&](int slot, int c, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(pn_base + (uint32_t)((slot * TX + c) * 64)), "h"((unsigned short)v) : "memory"); };
+    const int Hi = H - 2 * off, Wi = W - 2 * off;
+    const int k = (blockIdx.y * nw + wy) * 32 + lane;
+    const int x0 = blockIdx.x * TX;
+    const bool kact = k < D;
+    // Row bands (blockIdx.z): outputs for rows [R0, R1).  The march starts MA + 1 rows above the band with empty prefixes
+    // -- only differences of prefixes are used, and no row above R0 - MA - 1 enters one -- and ends MA rows below it.
+    const int R0 = blockIdx.z * band_rows, R1 = min(Hi, R0 + band_rows);
+    const int i_start = max(0, R0 - MA - 1), i_hend = min(Hi, R1 + MA);
+    const int d = dmin + k;
+    const size_t row_elems = (size_t)W * D;
+
+    // column ranges as a few integers (cheaper to keep than one predicate per column): c is active for c < c_act, its
+    // right-image column exists for v_lo <= c < v_hi; staged column j lies inside the interior view for j_lo <= j < j_hi
+    const int c_act = kact ? min(TX, Wi - x0) : 0;
+    const int v_lo = max(0, -(x0 + d)), v_hi = min(c_act, Wi - (x0 + d));
+    const int j_lo = kact ? max(0, MA - x0) : CW, j_hi = kact ? min(CW, Wi - x0 + MA) : 0;
+#define act(c) ((c) < c_act)
+#define vcol(c) ((c) >= v_lo && (c) < v_hi)
+#define cok(j) ((j) >= j_lo && (j) < j_hi)
+    const float *crow0 = cv_in + ((size_t)off * W + (size_t)(x0 - MA + off)) * D + k;      // column j of row 0: crow0 + j * D (only dereferenced when cok[j])
+    const short4 *xl0 = crossL + x0;
+    const short4 *xr0 = crossR + x0 + d;
+    float *orow = cv_out + ((size_t)off * W + (size_t)(x0 + off)) * D + k;                 // column c of row yo = 0: orow + c * D
+
+
+    float pe[TX];
+    unsigned pn[TX], tbh[TX];
+#pragma unroll
+    for (int c = 0; c < TX; ++c) { pe[c] = 0.f; pn[c] = 0u; tbh[c] = 0u; }
+    unsigned nanh = 0u;                           // centre-is-NaN bits, 4 per row, newest row in the low nibble
+    int rm = 0;                                   // i mod RING: the ring slot row i is written to
+    // Iteration i: (a) issue the loads of row i, (b) vertical stage of row yo = i - MA - 1 from the ring and the
+    // histories -- it needs rows <= yo + MA = i - 1 only, so it runs while the loads are in flight --, (c) horizontal
+    // stage of row i.  The kernel is bound by its instruction count (measured: 24 resident warps per SM at 80
+    // registers beat 12 warps at 122 registers with every load prefetched a row ahead), hence no register prefetch.
+    for (int i = i_start; i < R1 + MA + 1; ++i) {
+        float cc[CW];
+        int2 xl[TX], xr[TX];
+        if (i < i_hend) {
+            const float *src = crow0 + (size_t)i * row_elems;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) cc[j] = cok(j) ? __ldg(src + (size_t)j * D) : 0.f;
+            const short4 *pl = xl0 + (size_t)i * Wi, *pr = xr0 + (size_t)i * Wi;
+#pragma unroll
+            for (int c = 0; c < TX; ++c) {
+                xl[c] = vcol(c) ? ldg_support(pl + c) : make_int2(0, 0);
+                xr[c] = vcol(c) ? ldg_support(pr + c) : make_int2(0, 0);
+            }
+        }
+        // ---- vertical arm sums of row yo = i - MA - 1 -----------------------------------------------------------
+        const int yo = i - MA - 1;
+        if (yo >= R0) {
+            float *o = orow + (size_t)yo * row_elems;
+#pragma unroll
+            for (int c = 0; c < TX; ++c) {
+                // branch-free: a column without a right-image partner has t = b = 0 and empty prefixes pushed for it,
+                // so the same differences give e = 0, n = 1
+                const unsigned tb = tbh[c] >> 24;                           // pushed MA + 1 rows ago, shifted MA times since
+                const int t = (int)(tb >> 3) & 7, b = (int)(tb & 7u);
+                int s1 = rm - (MA + 1 - b);                                 // slot of row yo + b
+                s1 += (s1 < 0) ? RING : 0;
+                int s0 = rm - (MA + 2 + t);                                 // slot of row yo - t - 1
+                s0 += (s0 < 0) ? RING : 0;
+                const bool has0 = (yo - t - 1 >= i_start);                  // rows above the march never entered a prefix
+                const float e1 = pe_ld(s1, c), e0r = pe_ld(s0, c);
+                const unsigned n1 = pn_ld(s1, c), n0r = pn_ld(s0, c);
+                const float e = e1 - (has0 ? e0r : 0.f);
+                const unsigned n = ((n1 - (has0 ? n0r : 0u)) & 0xFFFFu) + (unsigned)(t + b + 1);
+                const bool cnan = ((nanh >> (4 * MA + c)) & 1u) != 0u;
+                if (act(c)) o[(size_t)c * D] = cnan ? nan_f() : e / (float)n;   // (0*c + E) / N
+            }
+        }
+        // ---- horizontal arm sums of row i, pushed into the ring and the histories ---------------------------------
+        unsigned nan_i = 0u;
+        if (i < i_hend) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const bool nn = (cc[j] != cc[j]);
+                if (j >= MA && j < MA + TX) nan_i |= nn ? (1u << (j - MA)) : 0u;
+                cc[j] = nn ? 0.f : cc[j];                                   // step 1 does not propagate NaN
+            }
+#pragma unroll
+            for (int c = 0; c < TX; ++c) {
+                float eh = 0.f;
+                unsigned nh = 0u, tb = 0u;
+                if (vcol(c)) {
+                    // short4 (left, right, up, bottom) as two words of two 16-bit arms: one SIMD minimum each, clamped to MA
+                    const unsigned lr = __vminu2(__vminu2((unsigned)xl[c].x, (unsigned)xr[c].x), (unsigned)MA * 0x10001u);
+                    const unsigned ud = __vminu2(__vminu2((unsigned)xl[c].y, (unsigned)xr[c].y), (unsigned)MA * 0x10001u);
+                    const int l = (int)(lr & 0xFFFFu), r = (int)(lr >> 16);
+                    eh = cc[MA + c];
+#pragma unroll
+                    for (int q = 1; q <= MA; ++q) {
+                        if (q <= l) eh += cc[MA + c - q];
+                        if (q <= r) eh += cc[MA + c + q];
+                    }
+                    nh = (unsigned)(l + r);
+                    tb = ((ud & 0xFFFFu) << 3) | (ud >> 16);
+                }
+                pe[c] = pe[c] + eh;                                         // the reference's step-3 column prefix
+                pn[c] += nh;
+                pe_st(rm, c, pe[c]);
+                pn_st(rm, c, pn[c]);
+                tbh[c] = (tbh[c] << 6) | tb;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < TX; ++c) tbh[c] <<= 6;
+        }
+        nanh = (nanh << 4) | nan_i;
+        rm = (rm + 1 == RING) ? 0 : rm + 1;
+    }
+#undef act
+#undef vcol
+#undef cok
+}
+
+static int launch_cbca_reg(const float *in, float *out, int H, int W, int D, int dmin, int off, const int16_t *cl, const int16_t *cr,
+                           cudaStream_t s) {
+    const int kg = ceil_div(D, 32);
+    const int nw = kg < 8 ? kg : 8;                                          // warps (disparity groups) per CTA
+    const size_t smem = (size_t)nw * CBR_RING * CBR_TX * 32 * (sizeof(float) + sizeof(unsigned short));
+    PB200_CUDA(cudaFuncSetAttribute(cbca_aggregate_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // row bands: enough CTAs for several waves (a CTA marches its whole band), at least 128 rows each so that the
+    // 2 * MA + 1 extra rows of a band stay a few per cent
+    const int Hi = H - 2 * off, strips = ceil_div(W - 2 * off, CBR_TX), kb = ceil_div(kg, nw);
+    int bands = ceil_div(8L * sm_count(), (long)strips * kb);
+    if (bands > Hi / 128) bands = Hi / 128;
+    if (bands < 1) bands = 1;
+    if (getenv("PB200_CBCA_BANDS")) bands = atoi(getenv("PB200_CBCA_BANDS"));
+    if (bands < 1) bands = 1;
+    const int band_rows = ceil_div(Hi, bands);
+    dim3 block(32, nw), grid(strips, kb, ceil_div(Hi, band_rows));
+    cbca_aggregate_reg_kernel<<<grid, block, smem, s>>>(in, out, H, W, D, dmin, off, (const short4 *)cl, (const short4 *)cr, band_rows);
+    PB200_LAUNCH_CHECK("cbca_aggregate_reg_kernel");
+    return PB200_OK;
+}
+
 // copy of the `off`-wide border ring (cells the aggregation leaves untouched, cbca.py:173-177)
 __global__ void __launch_bounds__(256) cbca_border_kernel(const float *__restrict__ cv_in, float *__restrict__ cv_out, int H, int W,
                                                           int D, int off) {
@@ -423,6 +593,8 @@ static int launch_cbca(const float *in, float *out, float *out_n, int H, int W, 
 int cbca_dispatch(const float *in, float *out, float *out_n, int H, int W, int D, int dmin, int off, const int16_t *cl,
                   const int16_t *cr, int len_arms, cudaStream_t s) {
     const int ma = len_arms - 1;
+    // the register kernel takes the common case (cbca_distance <= 5, normalised output); PB200_CBCA_PIPE=1 keeps the staged one
+    if (ma <= CBR_MA && out_n == nullptr && !getenv("PB200_CBCA_PIPE")) return launch_cbca_reg(in, out, H, W, D, dmin, off, cl, cr, s);
 #define PB200_C(MA)                                                                                     \
     return out_n ? launch_cbca<MA, true>(in, out, out_n, H, W, D, dmin, off, cl, cr, s)                 \
                  : launch_cbca<MA, false>(in, out, nullptr, H, W, D, dmin, off, cl, cr, s)

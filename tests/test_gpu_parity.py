@@ -224,6 +224,31 @@ def test_cbca_census_vs_oracle(eng, oracle, cfg):
     np.testing.assert_array_equal(got, ref)          # integer costs: sums and counts exact, one division
 
 
+@pytest.mark.parametrize("cfg", [(97, 131, -40, 23, 5, 5, 30.0), (64, 258, -100, -5, 5, 4, 12.0), (33, 67, 3, 70, 3, 5, 8.0),
+                                 (150, 41, -7, 8, 5, 2, 20.0), (260, 90, -95, 0, 5, 5, 25.0)])
+def test_cbca_register_kernel_vs_oracle_and_staged_kernel(eng, oracle, cfg):
+    """cbca_distance <= 5 runs the register kernel (no barriers, thread-private prefix rings): bit-exact against the
+    oracle on integer costs, for disparity counts that are not multiples of 32, widths that are not multiples of 4,
+    more rows than the ring is deep, ranges that leave the image on either side -- and identical to the staged kernel."""
+    import torch
+
+    H, W, dmin, dmax, w, dist, tau = cfg
+    left, right = rand_pair(H * 3 + W, H, W)
+    left[5:9, 10:20] = left[5, 10]                               # flat patches: long arms
+    right[5:9, 12:22] = left[5, 10]
+    cv, _ = oracle.census_cost_volume(left, right, w, dmin, dmax)
+    ref, _ = oracle.cbca_cost_volume(left, right, cv, w // 2, dmin, dist, tau)
+    dl, dr, dcv = dev(eng, left), dev(eng, right), dev(eng, cv)
+    got = eng.cbca(dl, dr, dcv, w // 2, dmin, dist, tau)
+    np.testing.assert_array_equal(host(got), ref)
+    os.environ["PB200_CBCA_PIPE"] = "1"
+    try:
+        staged = eng.cbca(dl, dr, dcv, w // 2, dmin, dist, tau)
+    finally:
+        del os.environ["PB200_CBCA_PIPE"]
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(staged, nan=-7.0))
+
+
 def test_cbca_float_costs_tolerance(eng, oracle):
     left, right = rand_pair(9, 33, 47, as_float=True)
     cv, _ = oracle.zncc_cost_volume(left, right, 3, -6, 6)
