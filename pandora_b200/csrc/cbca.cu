@@ -21,6 +21,7 @@
 // E and N are two differences each.  Every cost is read from HBM once (+ halo columns from L2)
 // and written once.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -387,10 +388,13 @@ constexpr int CBR_TX = 4, CBR_MA = 4, CBR_RING = 12;
 
 __device__ __forceinline__ int2 ldg_support(const short4 *p) { return __ldg(reinterpret_cast<const int2 *>(p)); }
 
+// DT: the number of disparities when it is one of the usual ones (column strides become immediates), 0 = run time.
+template <int DT>
 __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float *__restrict__ cv_in, float *__restrict__ cv_out, int H, int W,
-                                                                 int D, int dmin, int off, const short4 *__restrict__ crossL,
+                                                                 int D_rt, int dmin, int off, const short4 *__restrict__ crossL,
                                                                  const short4 *__restrict__ crossR, int band_rows) {
     constexpr int TX = CBR_TX, MA = CBR_MA, RING = CBR_RING, CW = TX + 2 * MA;
+    const int D = DT > 0 ? DT : D_rt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x, wy = threadIdx.y, nw = blockDim.y;
     // thread-private rings, addressed by 32-bit shared addresses: PE [RING][TX][32] float, PN [RING][TX][32] uint16
@@ -416,9 +420,13 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
     const int c_act = kact ? min(TX, Wi - x0) : 0;
     const int v_lo = max(0, -(x0 + d)), v_hi = min(c_act, Wi - (x0 + d));
     const int j_lo = kact ? max(0, MA - x0) : CW, j_hi = kact ? min(CW, Wi - x0 + MA) : 0;
-#define act(c) ((c) < c_act)
-#define vcol(c) ((c) >= v_lo && (c) < v_hi)
-#define cok(j) ((j) >= j_lo && (j) < j_hi)
+    // FAST (warp-uniform): every lane has a disparity, every staged column lies inside the view and every column of every
+    // lane has its right-image partner -- true for all strips but those near the left / right image border; the march is
+    // instantiated twice so that this common case carries no per-load predicate at all
+    const bool fast = __all_sync(0xffffffffu, kact && c_act == TX && v_lo == 0 && v_hi == TX && j_lo == 0 && j_hi == CW);
+#define act(c) (FAST || (c) < c_act)
+#define vcol(c) (FAST || ((c) >= v_lo && (c) < v_hi))
+#define cok(j) (FAST || ((j) >= j_lo && (j) < j_hi))
     const float *crow0 = cv_in + ((size_t)off * W + (size_t)(x0 - MA + off)) * D + k;      // column j of row 0: crow0 + j * D (only dereferenced when cok[j])
     const short4 *xl0 = crossL + x0;
     const short4 *xr0 = crossR + x0 + d;
@@ -435,6 +443,8 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
     // histories -- it needs rows <= yo + MA = i - 1 only, so it runs while the loads are in flight --, (c) horizontal
     // stage of row i.  The kernel is bound by its instruction count (measured: 24 resident warps per SM at 80
     // registers beat 12 warps at 122 registers with every load prefetched a row ahead), hence no register prefetch.
+    auto march = [&](auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
     for (int i = i_start; i < R1 + MA + 1; ++i) {
         float cc[CW];
         int2 xl[TX], xr[TX];
@@ -512,6 +522,9 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
         nanh = (nanh << 4) | nan_i;
         rm = (rm + 1 == RING) ? 0 : rm + 1;
     }
+    };
+    if (fast) march(std::true_type{});
+    else march(std::false_type{});
 #undef act
 #undef vcol
 #undef cok
@@ -522,7 +535,10 @@ static int launch_cbca_reg(const float *in, float *out, int H, int W, int D, int
     const int kg = ceil_div(D, 32);
     const int nw = kg < 8 ? kg : 8;                                          // warps (disparity groups) per CTA
     const size_t smem = (size_t)nw * CBR_RING * CBR_TX * 32 * (sizeof(float) + sizeof(unsigned short));
-    PB200_CUDA(cudaFuncSetAttribute(cbca_aggregate_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const float *, float *, int, int, int, int, int, const short4 *, const short4 *, int) =
+        D == 64 ? cbca_aggregate_reg_kernel<64> : D == 128 ? cbca_aggregate_reg_kernel<128> : D == 192 ? cbca_aggregate_reg_kernel<192>
+        : D == 256 ? cbca_aggregate_reg_kernel<256> : cbca_aggregate_reg_kernel<0>;
+    PB200_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // row bands: enough CTAs for several waves (a CTA marches its whole band), at least 128 rows each so that the
     // 2 * MA + 1 extra rows of a band stay a few per cent
     const int Hi = H - 2 * off, strips = ceil_div(W - 2 * off, CBR_TX), kb = ceil_div(kg, nw);
@@ -533,7 +549,7 @@ static int launch_cbca_reg(const float *in, float *out, int H, int W, int D, int
     if (bands < 1) bands = 1;
     const int band_rows = ceil_div(Hi, bands);
     dim3 block(32, nw), grid(strips, kb, ceil_div(Hi, band_rows));
-    cbca_aggregate_reg_kernel<<<grid, block, smem, s>>>(in, out, H, W, D, dmin, off, (const short4 *)cl, (const short4 *)cr, band_rows);
+    kern<<<grid, block, smem, s>>>(in, out, H, W, D, dmin, off, (const short4 *)cl, (const short4 *)cr, band_rows);
     PB200_LAUNCH_CHECK("cbca_aggregate_reg_kernel");
     return PB200_OK;
 }
