@@ -72,6 +72,10 @@ cv2 = eng.empty((H, W, D))
 timeit("C2 census fill 2048x2048x192", lambda: eng.census(l, r, 5, -(D - 1), 0, out=cv), (4 * D + 8) * H * W)
 timeit("C2 cbca supports (2x median3 + 2x cross_support)", lambda: eng.cbca_supports(l, r, 2, 5, 30.0), 2 * (4 + 4 + 4 + 8) * H * W)
 timeit("C2 cbca (supports + aggregate) 2048x2048x192", lambda: eng.cbca(l, r, cv, 2, -(D - 1), 5, 30.0, out=cv2), (8 * D + 24) * H * W)
+cl2, cr2 = eng.cbca_supports(l, r, 2, 5, 30.0)
+timeit("C2 cbca aggregate only (register kernel)", lambda: pandora_b200._native.check(eng.lib.pb200_cbca_aggregate(
+    cv.data_ptr(), cv2.data_ptr(), H, W, D, -(D - 1), 2, cl2.data_ptr(), cr2.data_ptr(), 5, torch.cuda.current_stream().cuda_stream)),
+    (8 * D + 24) * H * W)
 timeit("C2 wta 2048x2048x192", lambda: eng.wta(cv2, -(D - 1)), (4 * D + 6) * H * W)
 p2 = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, cbca=(5, 30.0))
 timeit("C2 pipeline census+cbca+wta", lambda: p2.run_device(l, r), (12 * D + 36) * H * W)
@@ -84,7 +88,9 @@ l, r = pair(H, W, D)
 p3 = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, sgm=(8.0, 32.0))
 timeit("C3 census fill 4096x4096x256", lambda: eng.census(l, r, 5, -(D - 1), 0, out=p3.cv_a), (4 * D + 8) * H * W)
 timeit("C3 sgm 8-path + fused WTA", lambda: eng.sgm(p3.cv_a, 8.0, 32.0, 58.0, out=p3.cv_b, fuse_wta=True, dmin=-(D - 1), disp=p3.disp, flags=p3.flags), 8 * D * H * W)
-timeit("C3 pipeline census+sgm+wta", lambda: p3.run_device(l, r), (12 * D + 12) * H * W)
+timeit("C3 fused census+sgm+wta stage (pb200_census_sgm incl. the two transforms)",
+       lambda: eng.census_sgm(l, r, 5, -(D - 1), 0, 8.0, 32.0, out=p3.cv_b, disp=p3.disp, flags=p3.flags), 8 * D * H * W)
+timeit("C3 pipeline census+sgm+wta (StereoPipeline, fused stage)", lambda: p3.run_device(l, r), (12 * D + 12) * H * W)
 timeit("C3 wta standalone 4096x4096x256", lambda: eng.wta(p3.cv_b, -(D - 1)), (4 * D + 6) * H * W)
 timeit("C3 reverse_cost_volume", lambda: eng.reverse_cost_volume(p3.cv_a, 0), 8 * D * H * W, reps=2)
 # next rows on the C3 SGM result: algorithmic bytes = one read of the volume (+ O(H*W) maps)
