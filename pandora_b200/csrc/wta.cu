@@ -7,6 +7,8 @@
 // WTA is HBM-read bound (4*D bytes per pixel in, 4 out): one warp per pixel, lanes read 16-byte
 // vectors so a warp instruction covers 512 contiguous bytes of the pixel's disparity vector; the
 // (value, index) pair is reduced with warp shuffles, lowest index winning ties like np.argmin.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -108,6 +110,45 @@ __global__ void __launch_bounds__(256) reverse_cv_kernel(const float *__restrict
     }
 }
 
+// Tiled version: right(row, j, d) = left(row, j + d + min_disp, D - 1 - d) is a bijection between cells, and the cells an
+// input pixel x gives to a tile of 32 output pixels [j0, j0 + 32) are ONE run of 32 consecutive disparities
+// e = e_lo(x) + lane, e_lo(x) = D - 1 - (x - min_disp - j0), landing on a diagonal of the tile (pixel `lane`, disparity
+// D - 1 - e).  A CTA owns (row, tile): its warps walk the D + 31 input pixels of the band, every load is one contiguous
+// 128-byte run, the diagonal goes into a shared-memory tile whose pitch is even (lane stride pitch - 1 is odd: no bank
+// conflict), and the finished tile -- 32 pixels x D floats, contiguous in the volume -- is written with 16-byte stores.
+// Every cell is read once and written once.
+__global__ void __launch_bounds__(256) reverse_cv_tiled_kernel(const float *__restrict__ left, int H, int W, int D, int min_disp,
+                                                               float *__restrict__ right, int tiles_x) {
+    extern __shared__ __align__(16) float rtile[];                      // [32][pitch]
+    const int pitch = (D + 1) & ~1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long t = blockIdx.x; t < (long)H * tiles_x; t += gridDim.x) {
+        const long row = t / tiles_x;
+        const int j0 = (int)(t % tiles_x) * 32;
+        const int npix = min(32, W - j0);
+        const float *lrow = left + (size_t)row * W * D;
+        const int xb = j0 + min_disp;                                   // input pixel of (pixel 0, disparity 0)
+        for (int q = warp; q < D + 31; q += 8) {
+            const int x = xb + q;
+            const int e = D - 1 - q + lane;                             // e_lo = D - 1 - (x - min_disp - j0) = D - 1 - q
+            if (e >= 0 && e < D) {
+                const float v = (x >= 0 && x < W) ? __ldg(lrow + (size_t)x * D + e) : nan_f();
+                rtile[lane * pitch + (D - 1 - e)] = v;
+            }
+        }
+        __syncthreads();
+        float *orow = right + ((size_t)row * W + j0) * D;
+        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(right) & 15) == 0) {   // pitch == D: the tile is contiguous
+            const int n4 = npix * D / 4;
+            for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4 *>(orow)[i] = reinterpret_cast<const float4 *>(rtile)[i];
+        } else {
+            for (int j = warp; j < npix; j += 8)
+                for (int d = lane; d < D; d += 32) orow[(size_t)j * D + d] = rtile[j * pitch + d];
+        }
+        __syncthreads();
+    }
+}
+
 // MedianFilter.filter_disparity (filter/median.py:96-132), the two element-wise halves around the 3x3 NaN-median:
 // (a) masked = invalid pixel ? NaN : disparity; (b) disparity = isfinite(masked) ? median(masked) : disparity.
 __global__ void __launch_bounds__(256) filter_mask_kernel(const float *__restrict__ disp, const uint16_t *__restrict__ mask, long n,
@@ -190,6 +231,17 @@ extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, i
     if (!d_left_cv || !d_right_cv || H <= 0 || W <= 0 || D <= 0) {
         set_error("pb200_reverse_cost_volume: bad argument");
         return PB200_ERR_BAD_ARG;
+    }
+    const size_t tile_bytes = (size_t)32 * ((D + 1) & ~1) * sizeof(float);
+    if (D >= 8 && tile_bytes <= 96 * 1024 && !getenv("PB200_REVERSE_GATHER")) {
+        const int tiles_x = ceil_div(W, 32);
+        long grid = (long)H * tiles_x;
+        const long cap = (long)sm_count() * 32;
+        if (grid > cap) grid = cap;
+        PB200_CUDA(cudaFuncSetAttribute(reverse_cv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+        reverse_cv_tiled_kernel<<<(int)grid, 256, tile_bytes, (cudaStream_t)stream>>>(d_left_cv, H, W, D, min_disp, d_right_cv, tiles_x);
+        PB200_LAUNCH_CHECK("reverse_cv_tiled_kernel");
+        return PB200_OK;
     }
     long blocks = ((long)H * W * D + 255) / 256;
     const long cap = (long)sm_count() * 16;

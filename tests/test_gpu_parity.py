@@ -181,6 +181,23 @@ def test_reverse_cost_volume(eng, oracle):
         np.testing.assert_array_equal(host(eng.reverse_cost_volume(dev(eng, cv), md)), oracle.reverse_cost_volume(cv, md))
 
 
+@pytest.mark.parametrize("shape,md", [((5, 70, 64), -63), ((3, 100, 37), -20), ((4, 33, 256), -255), ((2, 500, 128), 6), ((6, 45, 8), -3),
+                                      ((3, 64, 5), 0)])
+def test_reverse_cost_volume_tiled(eng, oracle, shape, md):
+    """The tiled kernel (D >= 8): disparity counts that are odd / not multiples of 4, partial tiles, ranges on either side;
+    bit-identical to the oracle (matching_cost.cpp:26-57) and to the plain gather kernel."""
+    g = np.random.default_rng(shape[1] + shape[2])
+    cv = g.random(shape).astype(np.float32)
+    cv[g.random(shape) < 0.2] = np.nan
+    got = host(eng.reverse_cost_volume(dev(eng, cv), md))
+    np.testing.assert_array_equal(got, oracle.reverse_cost_volume(cv, md))
+    os.environ["PB200_REVERSE_GATHER"] = "1"
+    try:
+        np.testing.assert_array_equal(host(eng.reverse_cost_volume(dev(eng, cv), md)), got)
+    finally:
+        del os.environ["PB200_REVERSE_GATHER"]
+
+
 # ------------------------------------------------------------------------------------------------
 # CBCA
 # ------------------------------------------------------------------------------------------------
