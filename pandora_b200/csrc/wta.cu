@@ -128,12 +128,19 @@ __global__ void __launch_bounds__(256) reverse_cv_tiled_kernel(const float *__re
         const int npix = min(32, W - j0);
         const float *lrow = left + (size_t)row * W * D;
         const int xb = j0 + min_disp;                                   // input pixel of (pixel 0, disparity 0)
-        for (int q = warp; q < D + 31; q += 8) {
-            const int x = xb + q;
-            const int e = D - 1 - q + lane;                             // e_lo = D - 1 - (x - min_disp - j0) = D - 1 - q
-            if (e >= 0 && e < D) {
-                const float v = (x >= 0 && x < W) ? __ldg(lrow + (size_t)x * D + e) : nan_f();
-                rtile[lane * pitch + (D - 1 - e)] = v;
+        // eight independent runs per warp and step: all loads are issued before the first shared-memory store
+        for (int q0 = warp * 8; q0 < D + 31; q0 += 64) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u, x = xb + q;
+                const int e = D - 1 - q + lane;                         // e_lo = D - 1 - (x - min_disp - j0) = D - 1 - q
+                v[u] = (e >= 0 && e < D && x >= 0 && x < W) ? __ldg(lrow + (size_t)x * D + e) : nan_f();
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int d = q0 + u - lane;                            // D - 1 - e
+                if (d >= 0 && d < D) rtile[lane * pitch + d] = v[u];
             }
         }
         __syncthreads();
