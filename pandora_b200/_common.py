@@ -64,3 +64,27 @@ def store_volume(cv, tensor, keep_on_device: bool = True) -> None:
             var.data = LazyVolume(tensor)
     else:
         cv["cost_volume"].data = tensor.detach().cpu().numpy()
+
+
+def deferred_recipe(cv):
+    """The recipe of ``cv["cost_volume"]`` when the matching-cost step deferred it and nothing has read it yet."""
+    var = cv["cost_volume"] if "cost_volume" in cv else None
+    return var.deferred_recipe() if isinstance(var, DataArray) else None
+
+
+def store_deferred_volume(cv, recipe, shape) -> bool:
+    """Leave ``recipe`` in ``cv["cost_volume"]`` instead of a tensor (shim datasets only: a real xarray dataset wants a
+    numpy array at once).  Returns False when the dataset cannot hold it."""
+    var = cv["cost_volume"] if "cost_volume" in cv else None
+    if var is not None and not isinstance(var, DataArray):
+        return False
+    try:
+        if var is None:
+            cv["cost_volume"] = (("row", "col", "disp"), LazyVolume(recipe=recipe, shape=shape))
+            if not isinstance(cv["cost_volume"], DataArray):      # a real xarray.Dataset coerced it
+                return False
+        else:
+            var.data = LazyVolume(recipe=recipe, shape=shape)
+    except Exception:                                             # noqa: BLE001 -- xarray refuses non-array data
+        return False
+    return True

@@ -16,13 +16,29 @@ import numpy as np
 
 
 class LazyVolume:
-    """A float32 (row, col, disp) volume living in HBM; ``materialize()`` performs the D2H copy once."""
+    """A float32 (row, col, disp) volume living in HBM; ``materialize()`` performs the D2H copy once.
 
-    def __init__(self, tensor):
-        self.tensor = tensor
-        self.shape = tuple(int(s) for s in tensor.shape)
+    The volume may also be *deferred*: ``recipe`` is an object with ``compute() -> tensor`` that is only run when
+    somebody asks for ``tensor`` (or ``.data``).  The Census step leaves such a recipe so that a directly following SGM
+    step can run the fused Census -> SGM kernels and never write the Census volume (``matching_cost.CensusRecipe``)."""
+
+    def __init__(self, tensor=None, recipe=None, shape=None):
+        assert tensor is not None or (recipe is not None and shape is not None)
+        self._tensor = tensor
+        self.recipe = recipe
+        self.shape = tuple(int(s) for s in (tensor.shape if tensor is not None else shape))
         self.dtype = np.dtype(np.float32)
         self._host: Optional[np.ndarray] = None
+
+    @property
+    def tensor(self):
+        if self._tensor is None:
+            self._tensor = self.recipe.compute()
+        return self._tensor
+
+    @property
+    def deferred(self) -> bool:
+        return self._tensor is None
 
     def materialize(self) -> np.ndarray:
         if self._host is None:
@@ -55,8 +71,12 @@ class DataArray:
         return self.data
 
     def device_tensor(self):
-        """The HBM copy if the volume has not been handed to the host yet, else None."""
+        """The HBM copy if the volume has not been handed to the host yet, else None (a deferred volume is computed now)."""
         return self._data.tensor if isinstance(self._data, LazyVolume) else None
+
+    def deferred_recipe(self):
+        """The recipe of a volume that has not been computed yet, else None."""
+        return self._data.recipe if isinstance(self._data, LazyVolume) and self._data.deferred else None
 
     @property
     def shape(self):

@@ -8,12 +8,13 @@ The compute happens in ``Engine`` (CUDA); nothing here falls back to a CPU imple
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
 
 from . import constants as cst
-from ._common import ConfigError, device_volume, get_engine, image_array, store_volume
+from ._common import ConfigError, deferred_recipe, device_volume, get_engine, image_array, store_deferred_volume, store_volume
 from .dataset import Dataset
 
 
@@ -138,23 +139,58 @@ class AbstractMatchingCost:
 
         eng = get_engine()
         dmin, dmax = self._disp_bounds(cost_volume)
-        cv_t = device_volume(eng, cost_volume)
-        H, W, _ = (int(s) for s in cv_t.shape)
+        H, W = (int(s) for s in cost_volume["cost_volume"].shape[:2])
         off = int(cost_volume.attrs["offset_row_col"])
         fl, fr = image_mask_flags(eng, img_left, self._window_size), image_mask_flags(eng, img_right, self._window_size)
         gmin_h, gmax_h = np.asarray(disp_min, dtype=np.float32)[:H, :W], np.asarray(disp_max, dtype=np.float32)[:H, :W]
         variable = bool(np.nanmax(gmin_h) != np.nanmin(gmin_h) or np.nanmax(gmax_h) != np.nanmin(gmax_h)
                         or int(np.nanmin(gmin_h)) != dmin or int(np.nanmax(gmax_h)) != dmax)
-        gmin = eng.to_device(gmin_h) if variable else None
-        gmax = eng.to_device(gmax_h) if variable else None
-        flags = eng.cv_masked(cv_t, dmin, fl, fr, gmin, gmax)                # masks the volume, reports all-NaN pixels
-        store_volume(cost_volume, cv_t)
+        recipe = deferred_recipe(cost_volume)
+        if recipe is not None and fl is None and fr is None and not variable:
+            # nothing to mask: the step only needs the all-NaN pixels, which a deferred Census volume knows from its
+            # geometry -- the volume stays deferred (a following SGM step then runs the fused Census -> SGM kernels)
+            flags = recipe.all_nan_flags()
+        else:
+            cv_t = device_volume(eng, cost_volume)
+            gmin = eng.to_device(gmin_h) if variable else None
+            gmax = eng.to_device(gmax_h) if variable else None
+            flags = eng.cv_masked(cv_t, dmin, fl, fr, gmin, gmax)            # masks the volume, reports all-NaN pixels
+            store_volume(cost_volume, cv_t)
         if "validity_mask" in cost_volume:
             mask = eng.to_device(np.ascontiguousarray(cost_volume["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
         else:
             mask = eng.validity_mask_init(H, W, dmin, dmax, off)
         mask = eng.validity_mask(H, W, dmin, dmax, off, flags, mask=mask)
         cost_volume["validity_mask"] = (("row", "col"), mask.cpu().numpy().view(np.uint16))
+
+
+class CensusRecipe:
+    """A Census cost volume that has not been computed yet (``LazyVolume(recipe=...)``): ``compute()`` runs the fill,
+    ``all_nan_flags()`` gives what ``cv_masked`` needs without it, and ``Sgm.optimize_cv`` hands the images to the fused
+    Census -> SGM kernels (``Engine.census_sgm``) so that the float Census volume is never written."""
+
+    kind = "census"
+
+    def __init__(self, eng, left, right, window: int, dmin: int, dmax: int):
+        self.eng, self.left, self.right, self.window, self.dmin, self.dmax = eng, left, right, int(window), int(dmin), int(dmax)
+
+    def compute(self):
+        return self.eng.census(self.left, self.right, self.window, self.dmin, self.dmax)
+
+    def all_nan_flags(self):
+        """uint8 (H, W), 1 where every cell of the pixel is NaN: the window leaves the left image, or no disparity of the
+        range puts it inside the right one (census.cpp:97-180: half <= x + d < W - half)."""
+        import torch  # noqa: PLC0415
+
+        H, W = (int(s) for s in self.left.shape)
+        half = self.window // 2
+        dev = self.left.device
+        ys, xs = torch.arange(H, device=dev), torch.arange(W, device=dev)
+        row_ok = (ys >= half) & (ys < H - half)
+        lo = torch.clamp(half - xs, min=self.dmin)
+        hi = torch.clamp(W - half - 1 - xs, max=self.dmax)
+        col_ok = (xs >= half) & (xs < W - half) & (lo <= hi)
+        return (~(row_ok[:, None] & col_ok[None, :])).to(torch.uint8).contiguous()
 
 
 @AbstractMatchingCost.register_subclass("census")
@@ -169,6 +205,11 @@ class Census(AbstractMatchingCost):
         cost_volume.attrs.update({"type_measure": "min", "cmax": int(self._window_size**2)})     # census.py:116-122
         left = eng.to_device(image_array(img_left, self._band))
         right = eng.to_device(image_array(img_right, self._band))
+        if os.environ.get("PB200_FUSE_CENSUS_SGM", "1") != "0":
+            # deferred: computed when something reads it; a directly following SGM step fuses it away (CensusRecipe)
+            recipe = CensusRecipe(eng, left, right, self._window_size, dmin, dmax)
+            if store_deferred_volume(cost_volume, recipe, (left.shape[0], left.shape[1], dmax - dmin + 1)):
+                return cost_volume
         store_volume(cost_volume, eng.census(left, right, self._window_size, dmin, dmax))
         return cost_volume
 

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 from typing import Dict
 
-from ._common import ConfigError, device_volume, get_engine, store_volume
+from ._common import ConfigError, deferred_recipe, device_volume, get_engine, store_volume
 
 
 class UniformMargins:
@@ -85,9 +85,18 @@ class Sgm(AbstractOptimization):
 
     def optimize_cv(self, cv, img_left, img_right):
         eng = get_engine()
-        cv_t = device_volume(eng, cv)
         cmax = float(cv.attrs["cmax"])
         is_max = cv.attrs.get("type_measure") == "max"
+        recipe = deferred_recipe(cv)
+        if recipe is not None and getattr(recipe, "kind", None) == "census" and not is_max and cmax == float(recipe.window**2):
+            # the Census volume was never computed: fused Census -> SGM (same bits, no float Census volume)
+            fused = eng.census_sgm(recipe.left, recipe.right, recipe.window, recipe.dmin, recipe.dmax, self._p1, self._p2,
+                                   self._overcounting, fuse_wta=False)
+            if fused is not None:
+                store_volume(cv, fused[0])
+                cv.attrs["optimization"] = "sgm"
+                return cv
+        cv_t = device_volume(eng, cv)
         src = -cv_t if is_max else cv_t
         out = eng.sgm(src, self._p1, self._p2, cmax + self._p2 + 1.0, self._overcounting)
         if is_max:

@@ -205,3 +205,43 @@ def test_stream_of_pairs_equals_single_calls(eng, cfg):
         pipe.result_host(1)                                   # no longer in flight
     # the synchronous entry still works on the same pipeline object
     np.testing.assert_array_equal(pipe.run_host(*pairs[2]), refs[2])
+
+
+def test_plugin_steps_fuse_census_into_sgm(eng, oracle):
+    """Through the step classes (pandora_b200.run): the Census step leaves a deferred volume, cv_masked gets its all-NaN
+    pixels from the geometry, and a directly following SGM step runs the fused kernels -- same datasets as with the
+    separate steps and as the oracle chain, without a Census fill launch; anything that reads the volume in between
+    (here: CBCA) computes it."""
+    import pandora_b200 as pb
+
+    left, right = pair(21, 90, 200)
+    dl = pb.create_image_dataset(left, disparity=[-63, 0])
+    dr = pb.create_image_dataset(right)
+    cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": 5},
+                        "optimization": {"optimization_method": "sgm", "penalty": {"P1": 8, "P2": 32}},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": -9999}}}
+    before = pb.kernel_launches()
+    disp, cv = pb.run(dl, dr, cfg)
+    fused_launches = pb.kernel_launches() - before
+    S, exp, inv = oracle_chain(oracle, left, right, 5, -63, 0, 8, 32, False)
+    np.testing.assert_array_equal(disp["disparity_map"].data, exp)
+    np.testing.assert_array_equal(cv["cost_volume"].data, S)
+    os.environ["PB200_FUSE_CENSUS_SGM"] = "0"
+    try:
+        before = pb.kernel_launches()
+        disp2, cv2 = pb.run(dl, dr, cfg)
+        plain_launches = pb.kernel_launches() - before
+    finally:
+        del os.environ["PB200_FUSE_CENSUS_SGM"]
+    np.testing.assert_array_equal(disp2["disparity_map"].data, disp["disparity_map"].data)
+    np.testing.assert_array_equal(np.asarray(disp2["validity_mask"].data), np.asarray(disp["validity_mask"].data))
+    np.testing.assert_array_equal(cv2["cost_volume"].data, cv["cost_volume"].data)
+    assert fused_launches < plain_launches, (fused_launches, plain_launches)
+    # a reader between the two steps (CBCA) gets the real Census volume
+    cfg2 = {"pipeline": {"matching_cost": cfg["pipeline"]["matching_cost"], "aggregation": {"aggregation_method": "cbca"},
+                         "optimization": cfg["pipeline"]["optimization"], "disparity": cfg["pipeline"]["disparity"]}}
+    disp3, _ = pb.run(dl, dr, cfg2)
+    ref, attrs = oracle.census_cost_volume(left, right, 5, -63, 0)
+    ref, cmax = oracle.cbca_cost_volume(left, right, ref, 2, -63, 5, 30.0, attrs["cmax"])
+    ref = oracle.sgm_cost_volume(ref, 8, 32, cmax=cmax)
+    np.testing.assert_array_equal(disp3["disparity_map"].data, oracle.wta(ref, np.arange(-63, 1))[0])
