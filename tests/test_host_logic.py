@@ -214,3 +214,21 @@ def test_normalize_with_extremum():                                # tests/test_
     got = ambiguity_.normalize_with_extremum(ambiguity, _Img(), ambiguity_._nbr_etas)
     nbr_etas = np.arange(0.0, 0.2, 0.1).shape[0]
     np.testing.assert_array_equal(got, np.copy(ambiguity) / ((2 - (-2)) * nbr_etas))
+
+
+@pytest.mark.parametrize("H,W,w,dmin,dmax", [(9, 30, 5, -7, 3), (7, 12, 3, -20, -4), (6, 15, 5, 4, 11), (5, 9, 7, -2, 2), (8, 40, 3, -63, 0),
+                                             (4, 4, 5, -1, 1), (10, 11, 13, 0, 0)])
+def test_census_recipe_all_nan_geometry(H, W, w, dmin, dmax):
+    """CensusRecipe.all_nan_flags (what cv_masked uses instead of reading a deferred volume) against the all-NaN pixels
+    of the oracle's Census volume: pure index arithmetic, checked on CPU tensors."""
+    import torch
+
+    from oracle import oracle as orc
+    from pandora_b200.matching_cost import CensusRecipe
+
+    g = np.random.default_rng(H * W + w)
+    left = g.integers(0, 50, (H, W)).astype(np.float32)
+    right = g.integers(0, 50, (H, W)).astype(np.float32)
+    cv, _ = orc.census_cost_volume(left, right, w, dmin, dmax)
+    rec = CensusRecipe(None, torch.from_numpy(left), torch.from_numpy(right), w, dmin, dmax)
+    np.testing.assert_array_equal(rec.all_nan_flags().numpy().astype(bool), np.isnan(cv).all(axis=2))
