@@ -232,3 +232,39 @@ def test_census_recipe_all_nan_geometry(H, W, w, dmin, dmax):
     cv, _ = orc.census_cost_volume(left, right, w, dmin, dmax)
     rec = CensusRecipe(None, torch.from_numpy(left), torch.from_numpy(right), w, dmin, dmax)
     np.testing.assert_array_equal(rec.all_nan_flags().numpy().astype(bool), np.isnan(cv).all(axis=2))
+
+
+def test_deferred_volume_protocol():
+    """LazyVolume(recipe=...): nothing is computed until somebody asks for the tensor or ``.data``; afterwards the
+    recipe is gone; a dataset variable that is not the shim's DataArray refuses the deferral."""
+    import torch
+
+    from pandora_b200._common import deferred_recipe, device_volume, store_deferred_volume
+    from pandora_b200.dataset import Dataset
+
+    calls = []
+
+    class _Recipe:
+        kind = "census"
+
+        def compute(self):
+            calls.append(1)
+            return torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+
+    cv = Dataset(coords={"row": np.arange(2), "col": np.arange(3), "disp": np.arange(4)})
+    rec = _Recipe()
+    assert store_deferred_volume(cv, rec, (2, 3, 4))
+    assert cv["cost_volume"].shape == (2, 3, 4) and not calls
+    assert deferred_recipe(cv) is rec and not calls                 # asking for the recipe computes nothing
+    t = device_volume(None, cv)                                     # the first reader computes it, once
+    assert calls == [1] and tuple(t.shape) == (2, 3, 4)
+    assert deferred_recipe(cv) is None
+    np.testing.assert_array_equal(cv["cost_volume"].data, np.arange(24, dtype=np.float32).reshape(2, 3, 4))
+    assert calls == [1]
+
+    class _Foreign(dict):                                           # e.g. a real xarray.Dataset: holds arrays only
+        pass
+
+    foreign = _Foreign()
+    foreign["cost_volume"] = np.zeros((2, 3, 4), dtype=np.float32)
+    assert not store_deferred_volume(foreign, rec, (2, 3, 4))
