@@ -126,6 +126,59 @@ def census_cost_volume(left, right, window: int, dmin: int, dmax: int):
     return cv, {"type_measure": "min", "cmax": int(window**2)}
 
 
+def shift_right_img(right, subpix: int, order: int = 1):
+    """img_tools.shift_right_img (img_tools.py:713-752): the right image and its subpix - 1 resampled copies at column
+    offsets k / subpix (scipy.ndimage.zoom along the columns, one column shorter than the image)."""
+    from scipy.ndimage import zoom  # noqa: PLC0415
+
+    right = np.asarray(right)
+    nx = right.shape[1]
+    out = [right]
+    for ind in range(1, subpix):
+        out.append(zoom(right, (1, (nx * subpix - (subpix - 1)) / float(nx)), order=order)[:, ind::subpix])
+    return out
+
+
+def _census_bits(img: np.ndarray, w: int) -> np.ndarray:
+    """census_transform (census.cpp:45-95) as an (H, W, w*w) boolean array; False outside the valid interior."""
+    H, W = img.shape
+    half = w // 2
+    bits = np.zeros((H, W, w * w), dtype=bool)
+    if H > 2 * half and W > 2 * half:
+        c = img[half:H - half, half:W - half]
+        for wy in range(w):
+            for wx in range(w):
+                bits[half:H - half, half:W - half, wy * w + wx] = img[wy:wy + H - 2 * half, wx:wx + W - 2 * half] > c
+    return bits
+
+
+def census_cost_volume_subpix(left, right, window: int, dmin: int, dmax: int, subpix: int, order: int = 1):
+    """Census volume with sub-pixel disparities (census.py:109-153 + census.cpp:97-180, every branch): disparity index
+    k = subpix * (d - dmin) + id_right uses the id_right-th shifted right image; a shifted image is one column shorter,
+    its last usable centre is therefore one column earlier (census.cpp:144-150).  Small sizes only (pure numpy)."""
+    left = _f32(left)
+    rights = [_f32(r) for r in shift_right_img(_f32(right), subpix, order)]
+    H, W = left.shape
+    half = window // 2
+    n_disp = (dmax - dmin) * subpix + 1
+    cv = np.full((H, W, n_disp), np.nan, dtype=np.float32)
+    bl = _census_bits(left, window)
+    brs = [_census_bits(r, window) for r in rights]
+    for row in range(half, H - half):
+        for col in range(half, W - half):
+            for disp in range(0, n_disp, subpix):
+                rx = col + disp // subpix + dmin
+                if rx < half or rx >= W - half:
+                    continue
+                for idr in range(subpix):
+                    if disp + idr >= n_disp:
+                        break
+                    if idr != 0 and rx >= W - half - 1:
+                        break
+                    cv[row, col, disp + idr] = np.count_nonzero(bl[row, col] != brs[idr][row, rx])
+    return cv, {"type_measure": "min", "cmax": int(window**2)}
+
+
 # --------------------------------------------------------------------------------------------
 # SAD / SSD: matching_cost/sad_ssd.py:110-207, 209-224, 340-368 ; point_interval matching_cost.py:429-482
 # --------------------------------------------------------------------------------------------

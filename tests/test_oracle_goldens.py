@@ -300,3 +300,18 @@ def test_sgm_nan_and_invalid_value(oracle):
     out = oracle.sgm_cost_volume(C, 8, 32, cmax=25)
     assert np.array_equal(np.isnan(out), np.isnan(C))
     assert oracle.sgm_invalid_value(25, 32) == 58.0
+
+
+def test_census_subpix_golden(oracle, goldens):
+    """tests/test_matching_cost/test_matching_cost_census.py:637-683 ("Census window=3, subpix=2, full cost volume test"),
+    and subpix = 1 of the same restatement equals the C port."""
+    k = "test_matching_cost/test_matching_cost_census.py::test_census[7]::"
+    assert int(goldens[k + "subpix"]) == 2 and int(goldens[k + "window_size"]) == 3
+    dmin, dmax = (int(v) for v in goldens[k + "disp_interval"])
+    cv, _ = oracle.census_cost_volume_subpix(goldens[k + "left_data"], goldens[k + "right_data"], 3, dmin, dmax, 2)
+    np.testing.assert_array_equal(cv, goldens[k + "ref_out"])
+    np.testing.assert_array_equal(oracle.shift_right_img(goldens[k + "right_data"], 2)[1],
+                                  np.array([[0, 0, 0, 2], [2.5, 1.5, 2.5, 1.5], [2, 4, 2, 2]], dtype=np.float64))   # the test's own comment
+    g = np.random.default_rng(1)
+    left, right = g.integers(0, 9, (10, 18)).astype(np.float32), g.integers(0, 9, (10, 18)).astype(np.float32)
+    np.testing.assert_array_equal(oracle.census_cost_volume_subpix(left, right, 5, -5, 4, 1)[0], oracle.census_cost_volume(left, right, 5, -5, 4)[0])

@@ -30,6 +30,23 @@ def test_census_vs_reference_float_images(oracle, ref_modules):
     np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("cfg", [(9, 17, 3, -4, 3, 2), (11, 20, 5, -6, 2, 4), (8, 15, 5, 1, 5, 2), (9, 14, 3, -3, 0, 4), (7, 30, 7, -9, 9, 2)])
+def test_census_subpix_vs_reference(oracle, ref_modules, cfg):
+    """Sub-pixel Census (subpix 2 and 4): the oracle's restatement of census.py:109-153 + census.cpp:97-180 with the
+    shifted right images of img_tools.shift_right_img against the compiled reference on the same images."""
+    mc, _ = ref_modules
+    H, W, w, dmin, dmax, subpix = cfg
+    gen = np.random.default_rng(H * W + subpix)
+    left = gen.integers(0, 9, (H, W)).astype(np.float32)
+    right = gen.integers(0, 9, (H, W)).astype(np.float32)
+    got, attrs = oracle.census_cost_volume_subpix(left, right, w, dmin, dmax, subpix)
+    disps = np.arange(dmin, dmax + 1e-9, 1.0 / subpix).astype(np.float32)
+    assert got.shape == (H, W, len(disps)) and attrs["cmax"] == w * w
+    shifted = [x.astype(np.float32) for x in oracle.shift_right_img(right, subpix)]
+    ref = mc.compute_matching_costs(left, shifted, np.full(got.shape, np.nan, np.float32), disps, w, w)
+    np.testing.assert_array_equal(got, ref)
+
+
 @pytest.mark.parametrize("arms,tau", [(3, 5.0), (5, 30.0), (9, 2.5), (1, 4.0)])
 def test_cross_support_vs_reference(oracle, ref_modules, arms, tau):
     _, agg = ref_modules
