@@ -62,6 +62,22 @@ PB200_API const char *pb200_last_error(void);      /* thread-local, never NULL  
 PB200_API int pb200_device_count(void);            /* number of visible CUDA devices (0 when none / no driver)   */
 PB200_API uint64_t pb200_kernel_launches(void);    /* kernels launched by this library since load (this process) */
 
+/* Kernel-selection options (process-wide; -1 = the library's own choice, the default).  Several stages have more than one
+ * kernel computing the same bits; the parity tests pin one or the other through these names:
+ *   "sgm.no_wave" 1 = four-launch packed schedule;  "sgm.no_byte_tier" 1 = 16-bit cost storage;
+ *   "sgm.wave_kernel" 1 = one column per warp, 2 = two columns per warp;  "census.direct" 0 / 1;  "census.tile" floats;
+ *   "cbca.pipe" 1 = staged kernel;  "cbca.bands" n;  "reverse.gather" 1;  "fuse_census_sgm" 0 = pb200_disparity_host
+ *   keeps the Census and SGM steps apart.
+ * No option changes a result; none is read from the environment. */
+PB200_API int pb200_set_option(const char *name, int value);
+PB200_API int pb200_get_option(const char *name);
+/* Which kernel family served the LAST call of a stage on this thread: stage in {"sgm", "cbca", "census", "reverse", "sad"}.
+ * sgm: 1 float kernels, 2 packed four-launch schedule, 3 / 4 two-column wavefront (4 = Census costs computed inside),
+ * 5 / 6 one-column wavefront (6 = Census inside); cbca: 10 register kernel (*detail = compile-time D or 0), 11 pipelined,
+ * 12 staged; census: 20 TMA-tiled, 21 direct, 22 sub-pixel; reverse: 30 tiled, 31 gather; sad: 40 tap-ordered, 41 running sums.
+ * The parity tests assert it so that a silent fall-back to a slower kernel family cannot pass unnoticed. */
+PB200_API int pb200_last_path(const char *stage, int *detail);
+
 /* ---- matching cost ---------------------------------------------------------------------------- */
 /* bytes of device scratch pb200_census_cost_volume needs (two planar census-descriptor images). */
 PB200_API size_t pb200_census_workspace_bytes(int H, int W, int window);

@@ -7,8 +7,8 @@ C-ABI shared library (``include/pandora_b200.h``).  Importing this package does 
 compute call does -- there is no CPU fallback.
 """
 from . import constants  # noqa: F401
-from ._common import ConfigError, get_engine  # noqa: F401
-from ._native import LIB_PATH, Pb200Error, build, kernel_launches, load  # noqa: F401
+from ._common import ConfigError, MachineError, get_engine  # noqa: F401
+from ._native import LIB_PATH, Pb200Error, build, get_option, kernel_launches, last_path, load, option, set_option  # noqa: F401
 from .aggregation import AbstractAggregation, CrossBasedCostAggregation  # noqa: F401
 from .dataset import DataArray, Dataset, LazyVolume, add_disparity, create_image_dataset  # noqa: F401
 from .disparity import AbstractDisparity, WinnerTakesAll  # noqa: F401

@@ -13,6 +13,11 @@ class ConfigError(ValueError):
     names the offending key the same way, e.g. tests/test_matching_cost/test_matching_cost_census.py:48-52)."""
 
 
+class MachineError(Exception):
+    """A step triggered in a state that has no transition for it (``transitions.MachineError`` in the reference:
+    state_machine.py:75-140 lists the legal ones, ``PandoraMachine.run`` re-raises it, state_machine.py:718-720)."""
+
+
 _ENGINES: Dict[str, object] = {}
 
 

@@ -45,6 +45,9 @@ PROTOTYPES = {
     "pb200_last_error": (ctypes.c_char_p, []),
     "pb200_device_count": (_ci, []),
     "pb200_kernel_launches": (ctypes.c_uint64, []),
+    "pb200_set_option": (_ci, [ctypes.c_char_p, _ci]),
+    "pb200_get_option": (_ci, [ctypes.c_char_p]),
+    "pb200_last_path": (_ci, [ctypes.c_char_p, _vp]),
     "pb200_census_workspace_bytes": (_sz, [_ci, _ci, _ci]),
     "pb200_census_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _vp]),
     "pb200_census_cost_volume_rows": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _ci, _ci, _vp]),
@@ -105,3 +108,40 @@ def check(rc: int) -> None:
 
 def kernel_launches() -> int:
     return int(load().pb200_kernel_launches())
+
+
+def set_option(name: str, value: int) -> None:
+    """Kernel-selection option of the library (include/pandora_b200.h: pb200_set_option); -1 restores the default."""
+    check(load().pb200_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    return int(load().pb200_get_option(name.encode()))
+
+
+class option:
+    """``with option("cbca.pipe", 1): ...`` -- run a block with one kernel-selection option pinned."""
+
+    def __init__(self, name: str, value: int):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = int(load().pb200_get_option(self.name.encode()))
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False
+
+
+PATHS = {0: "none", 1: "sgm_float", 2: "sgm_packed4", 3: "sgm_wave2", 4: "sgm_wave2_census", 5: "sgm_wave1", 6: "sgm_wave1_census",
+         10: "cbca_reg", 11: "cbca_pipe", 12: "cbca_staged", 20: "census_tma", 21: "census_direct", 22: "census_subpix",
+         30: "reverse_tiled", 31: "reverse_gather", 40: "sad_taps", 41: "sad_running"}
+
+
+def last_path(stage: str):
+    """(name, detail) of the kernel family that served the last call of ``stage`` on this thread."""
+    detail = ctypes.c_int(0)
+    code = int(load().pb200_last_path(stage.encode(), ctypes.byref(detail)))
+    return PATHS.get(code, str(code)), int(detail.value)

@@ -30,6 +30,19 @@ int check_cuda(cudaError_t err, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_options[OPT_COUNT];
+static const char *const g_option_names[OPT_COUNT] = {"sgm.no_wave", "sgm.no_byte_tier", "sgm.wave_kernel", "census.direct", "census.tile",
+                                                      "cbca.pipe", "cbca.bands", "reverse.gather", "fuse_census_sgm"};
+static bool g_options_init = [] {
+    for (auto &o : g_options) o.store(-1);
+    return true;
+}();
+int option(Option o) { return g_options[o].load(std::memory_order_relaxed); }
+
+static thread_local int g_path[STAGE_COUNT], g_path_detail[STAGE_COUNT];
+static const char *const g_stage_names[STAGE_COUNT] = {"sgm", "cbca", "census", "reverse", "sad"};
+void note_path(Stage st, int path, int detail) { g_path[st] = path; g_path_detail[st] = detail; }
+
 int sm_count() {
     static int cached = 0;
     if (cached == 0) {
@@ -57,6 +70,29 @@ using namespace pb200;
 extern "C" int pb200_version(void) { return 100; }
 extern "C" const char *pb200_last_error(void) { return g_err; }
 extern "C" uint64_t pb200_kernel_launches(void) { return g_launches.load(); }
+extern "C" int pb200_set_option(const char *name, int value) {
+    (void)g_options_init;
+    for (int i = 0; name && i < OPT_COUNT; ++i)
+        if (strcmp(name, g_option_names[i]) == 0) {
+            g_options[i].store(value);
+            return PB200_OK;
+        }
+    set_error("pb200_set_option: unknown option %s", name ? name : "(null)");
+    return PB200_ERR_BAD_ARG;
+}
+extern "C" int pb200_get_option(const char *name) {
+    for (int i = 0; name && i < OPT_COUNT; ++i)
+        if (strcmp(name, g_option_names[i]) == 0) return g_options[i].load();
+    return -1;
+}
+extern "C" int pb200_last_path(const char *stage, int *detail) {
+    for (int i = 0; stage && i < STAGE_COUNT; ++i)
+        if (strcmp(stage, g_stage_names[i]) == 0) {
+            if (detail) *detail = g_path_detail[i];
+            return g_path[i];
+        }
+    return PB200_ERR_BAD_ARG;
+}
 extern "C" int pb200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -200,8 +236,8 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
         const size_t wsb = pb200_census_workspace_bytes(H, W, window);
         PB200_RC(ws.alloc(wsb));
         // Census directly followed by SGM: one fused stage when eligible (the Census volume is never written)
-        const char *fenv = getenv("PB200_FUSE_CENSUS_SGM");
-        if (do_sgm && !do_cbca && (fenv ? atoi(fenv) != 0 : PB200_FUSE_CENSUS_SGM_DEFAULT)) {
+        const int fopt = option(OPT_FUSE_CENSUS_SGM);
+        if (do_sgm && !do_cbca && (fopt >= 0 ? fopt != 0 : PB200_FUSE_CENSUS_SGM_DEFAULT)) {
             const size_t swsb = pb200_sgm_workspace_bytes(H, W, D);
             PB200_RC(sws.alloc(swsb));
             int ran = 0;

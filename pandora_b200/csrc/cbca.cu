@@ -545,12 +545,13 @@ static int launch_cbca_reg(const float *in, float *out, int H, int W, int D, int
     int bands = ceil_div(8L * sm_count(), (long)strips * kb);
     if (bands > Hi / 128) bands = Hi / 128;
     if (bands < 1) bands = 1;
-    if (getenv("PB200_CBCA_BANDS")) bands = atoi(getenv("PB200_CBCA_BANDS"));
+    if (option(OPT_CBCA_BANDS) > 0) bands = option(OPT_CBCA_BANDS);
     if (bands < 1) bands = 1;
     const int band_rows = ceil_div(Hi, bands);
     dim3 block(32, nw), grid(strips, kb, ceil_div(Hi, band_rows));
     kern<<<grid, block, smem, s>>>(in, out, H, W, D, dmin, off, (const short4 *)cl, (const short4 *)cr, band_rows);
     PB200_LAUNCH_CHECK("cbca_aggregate_reg_kernel");
+    note_path(STAGE_CBCA, PATH_CBCA_REG, (D == 64 || D == 128 || D == 192 || D == 256) ? D : 0);
     return PB200_OK;
 }
 
@@ -588,6 +589,7 @@ static int launch_cbca_pipe(const float *in, float *out, float *out_n, int H, in
     cbca_aggregate_pipe_kernel<MA, RAW><<<grid, block, smem, s>>>(in, out, out_n, H, W, D, dmin, off, (const short4 *)cl,
                                                                    (const short4 *)cr);
     PB200_LAUNCH_CHECK("cbca_aggregate_pipe_kernel");
+    note_path(STAGE_CBCA, PATH_CBCA_PIPE, MA);
     return PB200_OK;
 }
 
@@ -602,6 +604,7 @@ static int launch_cbca(const float *in, float *out, float *out_n, int H, int W, 
     cbca_aggregate_kernel<MA, RAW><<<grid, block, smem, s>>>(in, out, out_n, H, W, D, dmin, off, (const short4 *)cl,
                                                               (const short4 *)cr);
     PB200_LAUNCH_CHECK("cbca_aggregate_kernel");
+    note_path(STAGE_CBCA, PATH_CBCA_STAGED, MA);
     return PB200_OK;
 }
 
@@ -610,7 +613,7 @@ int cbca_dispatch(const float *in, float *out, float *out_n, int H, int W, int D
                   const int16_t *cr, int len_arms, cudaStream_t s) {
     const int ma = len_arms - 1;
     // the register kernel takes the common case (cbca_distance <= 5, normalised output); PB200_CBCA_PIPE=1 keeps the staged one
-    if (ma <= CBR_MA && out_n == nullptr && !getenv("PB200_CBCA_PIPE")) return launch_cbca_reg(in, out, H, W, D, dmin, off, cl, cr, s);
+    if (ma <= CBR_MA && out_n == nullptr && option(OPT_CBCA_PIPE) <= 0) return launch_cbca_reg(in, out, H, W, D, dmin, off, cl, cr, s);
 #define PB200_C(MA)                                                                                     \
     return out_n ? launch_cbca<MA, true>(in, out, out_n, H, W, D, dmin, off, cl, cr, s)                 \
                  : launch_cbca<MA, false>(in, out, nullptr, H, W, D, dmin, off, cl, cr, s)

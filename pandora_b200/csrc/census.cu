@@ -510,11 +510,12 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
     // direct one.  Measured (profiles/r1_stage_bench_final2.json): equal at 4096x4096x256 (3.1 ms), the direct one
     // ahead for smaller volumes and whenever the WTA is fused (C1 pipeline 0.25 -> 0.19 ms).
     const bool direct_ok = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(d_cv) & 15) == 0;
-    const bool want_direct = getenv("PB200_CENSUS_DIRECT") ? atoi(getenv("PB200_CENSUS_DIRECT")) != 0 : (d_disp != nullptr || D < 256);
+    const bool want_direct = option(OPT_CENSUS_DIRECT) >= 0 ? option(OPT_CENSUS_DIRECT) != 0 : (d_disp != nullptr || D < 256);
     if (direct_ok && want_direct) {
         p.TX = 4; p.CH = 4; p.tiles_x = 0; p.n_tiles = 0; p.r_len = 0;
         p.row0 = row_begin;
         p.invalid_disparity = invalid_disparity;
+        note_path(STAGE_CENSUS, PATH_CENSUS_DIRECT, nw);
         switch (nw) {
             case 1: return launch_fill_direct<1>(p, row_end - row_begin, s);
             case 2: return launch_fill_direct<2>(p, row_end - row_begin, s);
@@ -525,7 +526,7 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
         }
     }
     int TX = (8192 / D) & ~3;                       // <= 32 KB of float per tile
-    if (getenv("PB200_CENSUS_TILE")) TX = (atoi(getenv("PB200_CENSUS_TILE")) / D) & ~3;
+    if (option(OPT_CENSUS_TILE) > 0) TX = (option(OPT_CENSUS_TILE) / D) & ~3;
     if (TX < 4) TX = 4;
     if (TX > 128) TX = 128;
     while (TX > 4 && TX >= 2 * (((W + 3) & ~3))) TX >>= 1;   // do not make tiles much wider than the image
@@ -561,6 +562,7 @@ extern "C" int pb200_census_cost_volume_rows(const float *d_left, const float *d
     if (per_sm > 3) per_sm = 3;
     long grid = (long)sm_count() * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
+    note_path(STAGE_CENSUS, PATH_CENSUS_TMA, nw);
     switch (nw) {
         case 1: return launch_fill<1>(p, smem, (int)grid, s);
         case 2: return launch_fill<2>(p, smem, (int)grid, s);

@@ -29,6 +29,34 @@ void count_launch(int n = 1);
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 int sm_count();
 
+// ---- kernel-selection options and the record of which path ran (api.cu owns the storage) -----------
+// Options are set through the C-ABI (pb200_set_option), never through the environment: the parity tests use them to
+// run the alternative kernels of a stage on the same inputs.  -1 = unset (the library's own choice).
+enum Option {
+    OPT_SGM_NO_WAVE = 0,      // 1: keep the four-launch packed schedule instead of the wavefront passes
+    OPT_SGM_NO_BYTE_TIER,     // 1: 16-bit cost storage even when cost + P2 fits a byte
+    OPT_SGM_WAVE_KERNEL,      // 1: one column per warp (sgm_wave1_kernel), 2: two columns per warp (sgm_wave_kernel)
+    OPT_CENSUS_DIRECT,        // 0 / 1: TMA-tiled / direct fill kernel
+    OPT_CENSUS_TILE,          // tile size (floats) of the TMA-tiled fill
+    OPT_CBCA_PIPE,            // 1: staged CBCA kernel instead of the register kernel
+    OPT_CBCA_BANDS,           // row bands of the register kernel
+    OPT_REVERSE_GATHER,       // 1: plain gather kernel for reverse_cost_volume
+    OPT_FUSE_CENSUS_SGM,      // 0: pb200_disparity_host keeps Census and SGM apart
+    OPT_COUNT
+};
+int option(Option o);
+// which kernel family served the last call of a stage (thread-local; read back with pb200_last_path)
+enum Stage { STAGE_SGM = 0, STAGE_CBCA, STAGE_CENSUS, STAGE_REVERSE, STAGE_SAD, STAGE_COUNT };
+enum Path {
+    PATH_NONE = 0,
+    PATH_SGM_FLOAT = 1, PATH_SGM_PACKED4 = 2, PATH_SGM_WAVE2 = 3, PATH_SGM_WAVE2_CENSUS = 4, PATH_SGM_WAVE1 = 5, PATH_SGM_WAVE1_CENSUS = 6,
+    PATH_CBCA_REG = 10, PATH_CBCA_PIPE = 11, PATH_CBCA_STAGED = 12,
+    PATH_CENSUS_TMA = 20, PATH_CENSUS_DIRECT = 21, PATH_CENSUS_SUBPIX = 22,
+    PATH_REVERSE_TILED = 30, PATH_REVERSE_GATHER = 31,
+    PATH_SAD_TAPS = 40, PATH_SAD_RUNNING = 41
+};
+void note_path(Stage st, int path, int detail = 0);
+
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fc00000); }
 

@@ -71,8 +71,12 @@ __global__ void __launch_bounds__(256) validity_masks_kernel(uint16_t *__restric
             if (no_data_right == nd) m = (uint16_t)(m + 2);
         }
         if (gmin != nullptr && gmax != nullptr) {         // partially_missing_variable_ranges (needs gmin <= gmax)
-            const int lo = (int)gmin[i] + c, hi = (int)gmax[i] + c;
-            bool inside = lo >= 0 && hi < W;
+            // a NaN cell of either grid = no range for this pixel (criteria.cpp:66-72 never sees one: the Python side
+            // passes nanmin / nanmax bounds): flagged like a range that leaves the image, and never converted to int
+            const float gl = gmin[i], gh = gmax[i];
+            const bool finite = (gl == gl) && (gh == gh) && fabsf(gl) < 1e9f && fabsf(gh) < 1e9f;
+            const int lo = finite ? (int)gl + c : -1, hi = finite ? (int)gh + c : -1;
+            bool inside = finite && lo >= 0 && hi < W && lo <= hi;
             for (int x = lo; inside && x <= hi; ++x) inside = (r[x] & FLAG_NOT_VALID) == 0;
             if (!inside) m |= 4096;
         }

@@ -535,6 +535,7 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
         return PB200_ERR_UNSUPPORTED;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    note_path(STAGE_SGM, PATH_SGM_FLOAT);                      // overwritten below when a packed path is launched
     // Exact packed-integer fast path (sgm_narrow.cu) for a whole 8-direction call on integer-valued costs: it
     // verifies the data while it runs and raises a device flag when a cost is not a small integer; the float
     // kernels below are then enqueued gated on that flag (they return at once when the fast path succeeded).

@@ -32,6 +32,17 @@ namespace pb200 {
 
 namespace {
 
+// Timing experiments that produce WRONG results (no strip exchange, no mailbox waits) exist only in builds made with
+// -DPB200_DEBUG_SWITCHES (tools/prof_fused.py); the shipped library has no such switch.
+static inline int debug_switches() {
+#ifdef PB200_DEBUG_SWITCHES
+    const char *e = getenv("PB200_SGM_DEBUG");
+    return e ? atoi(e) : 0;
+#else
+    return 0;
+#endif
+}
+
 constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger than any state, INF + P cannot wrap
 constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
 
@@ -975,6 +986,7 @@ int launch_wave(NarrowParams p, int nstrips, int nwarp, void *workspace, cudaStr
     PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
     PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(wthreads), args, smem2, s));
     PB200_LAUNCH_CHECK("sgm_wave_kernel<up>");
+    note_path(STAGE_SGM, CENSUS ? PATH_SGM_WAVE2_CENSUS : PATH_SGM_WAVE2, NR * 10 + CB);
     *done = true;
     return PB200_OK;
 }
@@ -992,7 +1004,7 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
     if (smem > 220 * 1024) return PB200_OK;
     const bool wta = p.disp != nullptr;
     // wavefront path: the whole stage in two 4-direction passes (single-call runs without tile halos)
-    if (phase == NARROW_ALL && p.halo_in == nullptr && p.halo_out == nullptr && !getenv("PB200_SGM_NO_WAVE")) {
+    if (phase == NARROW_ALL && p.halo_in == nullptr && p.halo_out == nullptr && option(OPT_SGM_NO_WAVE) <= 0) {
         const int rc = launch_wave<NR, CB, false>(p, nstrips, nwarp, workspace, s, done);
         if (rc != PB200_OK || *done) return rc;
     }
@@ -1027,6 +1039,7 @@ int launch_narrow(NarrowParams p, int phase, int final, int nstrips, int nwarp, 
             PB200_LAUNCH_CHECK("sgm_narrow_vsweep_kernel");
         }
     }
+    note_path(STAGE_SGM, PATH_SGM_PACKED4, NR * 10 + CB);
     *done = true;
     return PB200_OK;
 }
@@ -1063,7 +1076,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
     // byte tier (C8, and P8 between E and W) when cost + P2 fits 7 bits; else 16-bit storage
-    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && !getenv("PB200_SGM_NO_BYTE_TIER");
+    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
     p.cost_ok_max = (float)((bytes ? 127 : NARROW_MAX) - (int)p2);
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
     p.dy = dy; p.overcounting = overcounting;
@@ -1072,10 +1085,8 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.halo_in = reinterpret_cast<const uint32_t *>(halo_in);
     p.halo_out = reinterpret_cast<uint32_t *>(halo_out);
     if ((reinterpret_cast<uintptr_t>(halo_in) & 15) || (reinterpret_cast<uintptr_t>(halo_out) & 15)) return PB200_OK;
-    p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
+    p.debug = debug_switches();
     p.descL = p.descR = nullptr; p.pitch = 0; p.half = 0;
-    int kdiv = getenv("PB200_SGM_KDIV") ? atoi(getenv("PB200_SGM_KDIV")) : 1;
-    if (kdiv > 1) { K = (K / kdiv + 1) / 2 * 2; if (K < 4) K = 4; }
     if (phase == 3) {                 // query only: eligible -> the caller gates its float kernels on the flag
         *gate = p.flag;
         return PB200_OK;
@@ -1118,19 +1129,19 @@ int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch,
     const int NR = D / 64;
     const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
     if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
-    if (getenv("PB200_SGM_NO_WAVE")) return PB200_OK;
+    if (option(OPT_SGM_NO_WAVE) > 0) return PB200_OK;
 
     NarrowParams p;
     p.cv = nullptr; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
-    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && !getenv("PB200_SGM_NO_BYTE_TIER");
+    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
     p.cost_ok_max = 0.f;
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
     p.dy = 1; p.overcounting = overcounting;
     p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
     p.ring = nullptr; p.halo_in = nullptr; p.halo_out = nullptr;
-    p.debug = getenv("PB200_SGM_DEBUG") ? atoi(getenv("PB200_SGM_DEBUG")) : 0;
+    p.debug = debug_switches();
     p.descL = descL; p.descR = descR; p.pitch = pitch; p.half = window / 2;
     const int nwarp = K / 2;
     const int nstrips = ceil_div(W, K);

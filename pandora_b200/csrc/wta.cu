@@ -240,7 +240,7 @@ extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, i
         return PB200_ERR_BAD_ARG;
     }
     const size_t tile_bytes = (size_t)32 * ((D + 1) & ~1) * sizeof(float);
-    if (D >= 8 && tile_bytes <= 96 * 1024 && !getenv("PB200_REVERSE_GATHER")) {
+    if (D >= 8 && tile_bytes <= 96 * 1024 && option(OPT_REVERSE_GATHER) <= 0) {
         const int tiles_x = ceil_div(W, 32);
         long grid = (long)H * tiles_x;
         const long cap = (long)sm_count() * 32;
@@ -248,6 +248,7 @@ extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, i
         PB200_CUDA(cudaFuncSetAttribute(reverse_cv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
         reverse_cv_tiled_kernel<<<(int)grid, 256, tile_bytes, (cudaStream_t)stream>>>(d_left_cv, H, W, D, min_disp, d_right_cv, tiles_x);
         PB200_LAUNCH_CHECK("reverse_cv_tiled_kernel");
+        note_path(STAGE_REVERSE, PATH_REVERSE_TILED);
         return PB200_OK;
     }
     long blocks = ((long)H * W * D + 255) / 256;
@@ -255,5 +256,6 @@ extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, i
     if (blocks > cap) blocks = cap;
     reverse_cv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_left_cv, H, W, D, min_disp, d_right_cv);
     PB200_LAUNCH_CHECK("reverse_cv_kernel");
+    note_path(STAGE_REVERSE, PATH_REVERSE_GATHER);
     return PB200_OK;
 }

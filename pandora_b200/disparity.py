@@ -75,5 +75,9 @@ class WinnerTakesAll(AbstractDisparity):
             mask_t = eng.validity_mask(H, W, dmin, dmax, 0, flags, wta_invalidate=True, mask=mask_t)
             out["validity_mask"] = (("row", "col"), mask_t.cpu().numpy().view(np.uint16))
         if "confidence_measure" in cv:
+            # disparity.py:462-466: the confidence layers computed on the cost volume travel with their `indicator`
+            # coordinate (cost_volume_confidence runs BEFORE disparity in every legal pipeline, state_machine.py:134-139)
             out["confidence_measure"] = cv["confidence_measure"]
+            if "indicator" in cv.coords:
+                out.coords["indicator"] = cv.coords["indicator"]
         return out

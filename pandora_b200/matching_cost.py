@@ -8,12 +8,12 @@ The compute happens in ``Engine`` (CUDA); nothing here falls back to a CPU imple
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
 
 from . import constants as cst
+from . import _native
 from ._common import ConfigError, deferred_recipe, device_volume, get_engine, image_array, store_deferred_volume, store_volume
 from .dataset import Dataset
 
@@ -205,7 +205,7 @@ class Census(AbstractMatchingCost):
         cost_volume.attrs.update({"type_measure": "min", "cmax": int(self._window_size**2)})     # census.py:116-122
         left = eng.to_device(image_array(img_left, self._band))
         right = eng.to_device(image_array(img_right, self._band))
-        if os.environ.get("PB200_FUSE_CENSUS_SGM", "1") != "0":
+        if _native.get_option("fuse_census_sgm") != 0:
             # deferred: computed when something reads it; a directly following SGM step fuses it away (CensusRecipe)
             recipe = CensusRecipe(eng, left, right, self._window_size, dmin, dmax)
             if store_deferred_volume(cost_volume, recipe, (left.shape[0], left.shape[1], dmax - dmin + 1)):

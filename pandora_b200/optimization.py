@@ -6,7 +6,10 @@ from __future__ import annotations
 
 from typing import Dict
 
+import numpy as np
+
 from ._common import ConfigError, deferred_recipe, device_volume, get_engine, store_volume
+from ._native import SGM_MAX_DISP
 
 
 class UniformMargins:
@@ -84,6 +87,9 @@ class Sgm(AbstractOptimization):
         print("Semi-global matching optimization (B200)")
 
     def optimize_cv(self, cv, img_left, img_right):
+        n_disp = len(np.asarray(cv.coords["disp"].data))
+        if n_disp > SGM_MAX_DISP:                      # before any kernel runs (PB200_SGM_MAX_DISP, include/pandora_b200.h)
+            raise ConfigError(f"sgm: {n_disp} disparities exceed the kernels' maximum of {SGM_MAX_DISP}")
         eng = get_engine()
         cmax = float(cv.attrs["cmax"])
         is_max = cv.attrs.get("type_measure") == "max"

@@ -8,18 +8,22 @@ between.  ``StereoPipeline`` is the fused, allocation-free fast path for a fixed
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple
 
 import numpy as np
 
-from ._common import get_engine
+from . import _native
+from ._common import MachineError, get_engine
 from .aggregation import AbstractAggregation
 from .disparity import AbstractDisparity
 from .matching_cost import AbstractMatchingCost
 from .optimization import AbstractOptimization
 
-FUSE_CENSUS_SGM_DEFAULT = "1"
+# PandoraMachine._transitions_run (state_machine.py:75-140): trigger -> (source state, destination state)
+TRANSITIONS = {"matching_cost": ("begin", "cost_volume"), "aggregation": ("cost_volume", "cost_volume"),
+               "optimization": ("cost_volume", "cost_volume"), "cost_volume_confidence": ("cost_volume", "cost_volume"),
+               "disparity": ("cost_volume", "disp_map"), "filter": ("disp_map", "disp_map"), "refinement": ("disp_map", "disp_map"),
+               "validation": ("disp_map", "disp_map")}
 
 HOT_PATH_STEPS = ("matching_cost", "aggregation", "optimization", "disparity", "refinement", "filter", "validation",
                   "cost_volume_confidence")
@@ -58,10 +62,15 @@ def run(img_left, img_right, cfg: dict, return_right: bool = False):
         right_grids = (img_right["disparity"].data[0], img_right["disparity"].data[1])
     cv = right_cv = None
     disp = right_disp = None
+    state = "begin"
     for step, step_cfg in pipeline.items():
         name = step.split(".")[0]
         if name not in HOT_PATH_STEPS:
             raise NotImplementedError(f"step {step!r} is outside the B200 hot path (use Pandora's own implementation)")
+        source, dest = TRANSITIONS[name]
+        if state != source:                                       # the order PandoraMachine would refuse
+            raise MachineError(f"Can't trigger event {name} from state {state}!")
+        state = dest
         if name == "matching_cost":                               # state_machine.py:292-364
             mc = AbstractMatchingCost(**step_cfg)
             cv = mc.allocate_cost_volume(img_left, disp_grids, cfg)
@@ -133,9 +142,9 @@ class StereoPipeline:
         import torch  # noqa: PLC0415
 
         # Census directly followed by SGM: one fused stage (the Census volume is never written), when the shape is
-        # eligible -- see Engine.census_sgm.  PB200_FUSE_CENSUS_SGM=0 / fuse_census_sgm=False keeps the two steps apart.
+        # eligible -- see Engine.census_sgm.  the library option "fuse_census_sgm" = 0 / fuse_census_sgm=False keeps the two steps apart.
         if fuse_census_sgm is None:
-            fuse_census_sgm = os.environ.get("PB200_FUSE_CENSUS_SGM", FUSE_CENSUS_SGM_DEFAULT) != "0"
+            fuse_census_sgm = _native.get_option("fuse_census_sgm") != 0
         self.fuse_census_sgm = bool(fuse_census_sgm) and method == "census" and sgm is not None and not cbca
         self.fused_ran = False
 
@@ -143,6 +152,8 @@ class StereoPipeline:
         self.eng = get_engine(device)
         self.H, self.W, self.dmin, self.dmax = H, W, dmin, dmax
         self.D = dmax - dmin + 1
+        if sgm is not None and self.D > _native.SGM_MAX_DISP:   # refuse before allocating the volumes
+            raise ValueError(f"sgm: {self.D} disparities exceed the kernels' maximum of {_native.SGM_MAX_DISP}")
         self.method, self.window, self.cbca, self.sgm = method, window, cbca, sgm
         self.invalid_disparity = float(invalid_disparity)
         self.offset = (window - 1) // 2

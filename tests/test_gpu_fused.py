@@ -160,18 +160,11 @@ def test_disparity_host_fused(eng, oracle):
     disp = np.empty((H, W), dtype=np.float32)
     vm = np.empty((H, W), dtype=np.uint16)
     out = np.empty((H, W, 64), dtype=np.float32)
-    old = os.environ.get("PB200_FUSE_CENSUS_SGM")
-    os.environ["PB200_FUSE_CENSUS_SGM"] = "1"
-    try:
+    with _native.option("fuse_census_sgm", 1):
         before = _native.kernel_launches()
         _native.check(lib.pb200_disparity_host(left.ctypes.data, right.ctypes.data, H, W, 0, 5, dmin, dmax, 0, 30.0, 8.0, 32.0, 0, -9999.0,
                                                disp.ctypes.data, vm.ctypes.data, out.ctypes.data))
         launched = _native.kernel_launches() - before
-    finally:
-        if old is None:
-            del os.environ["PB200_FUSE_CENSUS_SGM"]
-        else:
-            os.environ["PB200_FUSE_CENSUS_SGM"] = old
     np.testing.assert_array_equal(out, S)
     np.testing.assert_array_equal(disp, exp)
     np.testing.assert_array_equal(vm, oracle.wta_validity_mask(mask, inv))
@@ -226,13 +219,10 @@ def test_plugin_steps_fuse_census_into_sgm(eng, oracle):
     S, exp, inv = oracle_chain(oracle, left, right, 5, -63, 0, 8, 32, False)
     np.testing.assert_array_equal(disp["disparity_map"].data, exp)
     np.testing.assert_array_equal(cv["cost_volume"].data, S)
-    os.environ["PB200_FUSE_CENSUS_SGM"] = "0"
-    try:
+    with pb.option("fuse_census_sgm", 0):
         before = pb.kernel_launches()
         disp2, cv2 = pb.run(dl, dr, cfg)
         plain_launches = pb.kernel_launches() - before
-    finally:
-        del os.environ["PB200_FUSE_CENSUS_SGM"]
     np.testing.assert_array_equal(disp2["disparity_map"].data, disp["disparity_map"].data)
     np.testing.assert_array_equal(np.asarray(disp2["validity_mask"].data), np.asarray(disp["validity_mask"].data))
     np.testing.assert_array_equal(cv2["cost_volume"].data, cv["cost_volume"].data)

@@ -292,8 +292,8 @@ def test_run_with_next_rows(eng, oracle):
     right = pb.create_image_dataset(right_np)
     cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": 5},
                         "optimization": {"optimization_method": "sgm"},
-                        "disparity": {"disparity_method": "wta"},
                         "cost_volume_confidence": {"confidence_method": "ambiguity", "normalization": False},
+                        "disparity": {"disparity_method": "wta"},
                         "refinement": {"refinement_method": "vfit"},
                         "validation": {"validation_method": "cross_checking_fast", "cross_checking_threshold": 1.0}}}
     disp, cv = pb.run(left, right, cfg)

@@ -191,11 +191,12 @@ def test_reverse_cost_volume_tiled(eng, oracle, shape, md):
     cv[g.random(shape) < 0.2] = np.nan
     got = host(eng.reverse_cost_volume(dev(eng, cv), md))
     np.testing.assert_array_equal(got, oracle.reverse_cost_volume(cv, md))
-    os.environ["PB200_REVERSE_GATHER"] = "1"
-    try:
+    import pandora_b200 as pb
+
+    assert pb.last_path("reverse")[0] == "reverse_tiled"
+    with pb.option("reverse.gather", 1):
         np.testing.assert_array_equal(host(eng.reverse_cost_volume(dev(eng, cv), md)), got)
-    finally:
-        del os.environ["PB200_REVERSE_GATHER"]
+        assert pb.last_path("reverse")[0] == "reverse_gather"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -258,11 +259,12 @@ def test_cbca_register_kernel_vs_oracle_and_staged_kernel(eng, oracle, cfg):
     dl, dr, dcv = dev(eng, left), dev(eng, right), dev(eng, cv)
     got = eng.cbca(dl, dr, dcv, w // 2, dmin, dist, tau)
     np.testing.assert_array_equal(host(got), ref)
-    os.environ["PB200_CBCA_PIPE"] = "1"
-    try:
+    import pandora_b200 as pb
+
+    assert pb.last_path("cbca")[0] == "cbca_reg"
+    with pb.option("cbca.pipe", 1):
         staged = eng.cbca(dl, dr, dcv, w // 2, dmin, dist, tau)
-    finally:
-        del os.environ["PB200_CBCA_PIPE"]
+        assert pb.last_path("cbca")[0] == "cbca_pipe"
     assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(staged, nan=-7.0))
 
 

@@ -268,3 +268,63 @@ def test_deferred_volume_protocol():
     foreign = _Foreign()
     foreign["cost_volume"] = np.zeros((2, 3, 4), dtype=np.float32)
     assert not store_deferred_volume(foreign, rec, (2, 3, 4))
+
+
+def test_run_refuses_step_orders_the_state_machine_refuses():
+    """PandoraMachine._transitions_run (state_machine.py:75-140): volume steps only before `disparity`, map steps only
+    after it.  The check happens before any kernel is needed, so it runs without a GPU."""
+    img = pb.create_image_dataset(np.zeros((6, 9), np.float32), disparity=[-1, 1])
+    with pytest.raises(pb.MachineError, match="cost_volume_confidence from state begin"):
+        pb.run(img, img, {"pipeline": {"cost_volume_confidence": {"confidence_method": "ambiguity"}}})
+    with pytest.raises(pb.MachineError, match="refinement from state begin"):
+        pb.run(img, img, {"pipeline": {"refinement": {"refinement_method": "vfit"}}})
+    with pytest.raises(pb.MachineError, match="disparity from state begin"):
+        pb.run(img, img, {"pipeline": {"disparity": {"disparity_method": "wta"}}})
+
+
+def test_library_options_and_path_record():
+    """pb200_set_option / pb200_get_option / pb200_last_path: unknown names are refused, values round-trip, the context
+    manager restores the previous value; nothing is read from the environment."""
+    from pandora_b200 import _native
+
+    lib = _native.load()
+    assert _native.get_option("cbca.pipe") == -1
+    with _native.option("cbca.pipe", 1):
+        assert _native.get_option("cbca.pipe") == 1
+    assert _native.get_option("cbca.pipe") == -1
+    assert lib.pb200_set_option(b"no.such.option", 1) == _native.ERR_BAD_ARG
+    assert b"no.such.option" in lib.pb200_last_error()
+    assert _native.last_path("sgm") == ("none", 0)
+    assert lib.pb200_last_path(b"nothing", None) == _native.ERR_BAD_ARG
+    src = open(os.path.join(ROOT, "pandora_b200", "csrc", "sgm_narrow.cu")).read()
+    for name in os.listdir(os.path.join(ROOT, "pandora_b200", "csrc")):
+        if name.endswith((".cu", ".cuh")):
+            text = open(os.path.join(ROOT, "pandora_b200", "csrc", name)).read()
+            outside = text.split("#ifdef PB200_DEBUG_SWITCHES")[0] + "".join(t.split("#endif", 1)[-1] for t in text.split("#ifdef PB200_DEBUG_SWITCHES")[1:])
+            assert "getenv" not in outside, f"{name} reads the environment in a release build"
+    assert "PB200_DEBUG_SWITCHES" in src
+
+
+def test_wta_keeps_the_indicator_coordinate_of_the_confidence_layers():
+    """disparity.py:462-466 -- every legal pipeline computes cost_volume_confidence BEFORE disparity, so to_disp must hand
+    both `confidence_measure` and its `indicator` coordinate to the disparity dataset (a later validation step appends to it)."""
+    import inspect
+
+    from pandora_b200 import disparity
+
+    body = inspect.getsource(disparity.WinnerTakesAll.to_disp)
+    assert 'out.coords["indicator"] = cv.coords["indicator"]' in body
+    # the append that used to fail with KeyError('indicator') on a dataset built like to_disp builds it
+    cv = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3)})
+    _, cv = pb.AbstractCostVolumeConfidence.allocate_confidence_map("ambiguity", np.ones((2, 3), np.float32), None, cv)
+    out = pb.Dataset({"disparity_map": (("row", "col"), np.zeros((2, 3), np.float32))}, coords={"row": np.arange(2), "col": np.arange(3)})
+    out["confidence_measure"] = cv["confidence_measure"]
+    out.coords["indicator"] = cv.coords["indicator"]
+    out, _ = pb.AbstractCostVolumeConfidence.allocate_confidence_map("left_right_consistency", np.zeros((2, 3), np.float32), out, None)
+    assert list(out.coords["indicator"].data) == ["confidence_from_ambiguity", "confidence_from_left_right_consistency"]
+
+
+def test_sgm_rejects_too_many_disparities_before_any_work():
+    cv = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3), "disp": np.arange(600)}, attrs={"cmax": 25, "type_measure": "min"})
+    with pytest.raises(pb.ConfigError, match="exceed"):
+        pb.AbstractOptimization(None, optimization_method="sgm").optimize_cv(cv, None, None)
