@@ -24,179 +24,11 @@
 // The data condition (integer costs in [0, 8191 - P2]) is verified by pass E on every cell; a violation raises a
 // device flag, the remaining narrow kernels return at once and the float kernels, enqueued behind them and gated
 // on the same flag, redo the whole stage.  No host synchronisation is involved.
-#include <cstdlib>
-
-#include "sgm_common.cuh"
+#include "sgm_packed.cuh"
 
 namespace pb200 {
 
 namespace {
-
-// Timing experiments that produce WRONG results (no strip exchange, no mailbox waits) exist only in builds made with
-// -DPB200_DEBUG_SWITCHES (tools/prof_fused.py); the shipped library has no such switch.
-static inline int debug_switches() {
-#ifdef PB200_DEBUG_SWITCHES
-    const char *e = getenv("PB200_SGM_DEBUG");
-    return e ? atoi(e) : 0;
-#else
-    return 0;
-#endif
-}
-
-constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger than any state, INF + P cannot wrap
-constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
-
-struct NarrowParams {
-    const float *cv;          // float32 (H, W, D) input costs (pass E only)
-    uint32_t *buf;            // the output buffer as packed words: per pixel [D/2 words C16][D/2 words P16]
-    int H, W, D;
-    uint32_t p1p1, p2p2;      // penalties replicated in both halves
-    uint32_t inv;             // invalid_value
-    float cost_ok_max;        // largest admissible cost
-    int *flag;                // raised (1) when the volume does not qualify
-    int dy, overcounting;     // sweeps
-    float *disp;
-    uint8_t *all_nan;
-    int dmin;
-    float invalid_disparity;
-    unsigned long long *ring;
-    const uint32_t *halo_in;  // packed (3, W, D/2 words) states of the row just outside the tile (order dx = 0, +1, -1) or NULL
-    uint32_t *halo_out;       // packed states of this tile's last row in travel direction or NULL
-    int debug;                // PB200_SGM_DEBUG bit 0: no strip exchange (timing experiments only, wrong results)
-    // fused Census source of the first wavefront pass (CENSUS = true): planar one-word descriptors (census.cu)
-    const uint32_t *descL, *descR;
-    int pitch, half;
-};
-
-template <int NR> struct Words;
-template <> struct Words<4> { using T = uint4; };
-template <> struct Words<2> { using T = uint2; };
-template <> struct Words<1> { using T = uint32_t; };
-
-template <int NR>
-__device__ __forceinline__ void ld_words(const uint32_t *p, uint32_t (&v)[NR]) {
-    const typename Words<NR>::T t = *reinterpret_cast<const typename Words<NR>::T *>(p);
-    if constexpr (NR == 4) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else if constexpr (NR == 2) { v[0] = t.x; v[1] = t.y; }
-    else v[0] = t;
-}
-template <int NR>
-__device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[NR]) {
-    if constexpr (NR == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]);
-    else if constexpr (NR == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
-    else *p = v[0];
-}
-template <int NR>
-__device__ __forceinline__ void ld_floats(const float *p, float (&v)[NR]) {
-    if constexpr (NR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else if constexpr (NR == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
-    else v[0] = *p;
-}
-template <int NR>
-__device__ __forceinline__ void st_floats(float *p, const float (&v)[NR]) {
-    if constexpr (NR == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    else if constexpr (NR == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
-    else *p = v[0];
-}
-
-// ---- storage tiers ------------------------------------------------------------------------------------------
-// CB = bytes per stored cost.  CB == 2: C16 words [0, D/2), P16 words [D/2, D) of a pixel's D-word region.
-// CB == 1 (cost + P2 <= 127): C8 words [0, D/4), P16 words [D/4, 3D/4), and the E -> W hand-over P8 (L_E <= 255)
-// in words [3D/4, D).  In registers a cost is always one 16-bit half; the NaN flag sits in bit 15 (CB 2) or 7 (CB 1).
-template <int CB> struct Tier;
-template <> struct Tier<2> { static constexpr uint32_t FLAGS = 0x80008000u, VALUES = 0x7FFF7FFFu, FLAG1 = 0x8000u; };
-template <> struct Tier<1> { static constexpr uint32_t FLAGS = 0x00800080u, VALUES = 0x007F007Fu, FLAG1 = 0x80u; };
-
-// raw words of a lane's costs (NR * CB / 2 words) and their expansion to one 16-bit half per cost; kept apart so a
-// prefetch can leave the raw words in flight and unpack them only when the row is consumed
-template <int NR, int CB>
-__device__ __forceinline__ void ld_cost_raw(const uint32_t *pix, int lane, uint32_t (&w)[NR * CB / 2]) {
-    ld_words<NR * CB / 2>(pix + lane * (NR * CB / 2), w);
-}
-template <int NR, int CB>
-__device__ __forceinline__ void unpack_cost(const uint32_t (&w)[NR * CB / 2], uint32_t (&c)[NR]) {
-    if constexpr (CB == 2) {
-#pragma unroll
-        for (int j = 0; j < NR; ++j) c[j] = w[j];
-    } else {
-#pragma unroll
-        for (int q = 0; q < NR / 2; ++q) {
-            c[2 * q] = __byte_perm(w[q], 0u, 0x4140);            // bytes (b0, 0, b1, 0)
-            c[2 * q + 1] = __byte_perm(w[q], 0u, 0x4342);        // bytes (b2, 0, b3, 0)
-        }
-    }
-}
-template <int NR, int CB>
-__device__ __forceinline__ void st_cost(uint32_t *pix, int lane, const uint32_t (&c)[NR]) {
-    if constexpr (CB == 2) {
-        st_words<NR>(pix + lane * NR, c);
-    } else {
-        uint32_t w[NR / 2];
-#pragma unroll
-        for (int q = 0; q < NR / 2; ++q) w[q] = __byte_perm(c[2 * q], c[2 * q + 1], 0x6420);
-        st_words<NR / 2>(pix + lane * (NR / 2), w);
-    }
-}
-// word offsets of the partial sums inside a pixel region
-template <int CB> __device__ __forceinline__ int p16_off(int D) { return CB == 2 ? D / 2 : D / 4; }
-__device__ __forceinline__ int p8_off(int D) { return 3 * (D / 4); }
-
-// One recurrence step on packed states: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m).
-// Register j of a lane holds disparity NR*lane + j (low half) and D/2 + NR*lane + j (high half).
-template <int NR>
-__device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (&Lp)[NR], uint32_t (&L)[NR], int lane, uint32_t p1p1,
-                                      uint32_t p2p2) {
-    uint32_t mn = Lp[0];
-    if constexpr (NR >= 3) {
-        mn = __vimin3_u16x2(Lp[0], Lp[1], Lp[2]);
-#pragma unroll
-        for (int j = 3; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
-    } else {
-#pragma unroll
-        for (int j = 1; j < NR; ++j) mn = __vminu2(mn, Lp[j]);
-    }
-    // both halves := min(low, high); a 32-bit minimum over words of the form (v << 16) | v is the minimum of the v's
-    // replicated in both halves, i.e. the word the step needs -- no mask, no multiply
-    mn = __vminu2(mn, __byte_perm(mn, 0u, 0x1032));
-    const uint32_t mm = __reduce_min_sync(0xffffffffu, mn);
-    const uint32_t mp2 = mm + p2p2;
-    const uint32_t up = __shfl_sync(0xffffffffu, Lp[NR - 1], (lane + 31) & 31);
-    const uint32_t dn = __shfl_sync(0xffffffffu, Lp[0], (lane + 1) & 31);
-    // lane 0: d-1 of its low half does not exist, d-1 of its high half (D/2 - 1) is lane 31's last LOW half:
-    // (up << 16) | INF16.  lane 31: d+1 of its low half (D/2) is lane 0's first HIGH half, d+1 of its high half does
-    // not exist: (dn >> 16) | (INF16 << 16).  One PRMT each, with a per-lane (loop-invariant) selector.
-    const uint32_t lo0 = __byte_perm(up, INF16 * 0x10001u, lane == 0 ? 0x1054u : 0x3210u);
-    const uint32_t hiN = __byte_perm(dn, INF16 * 0x10001u, lane == 31 ? 0x5432u : 0x3210u);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-        const uint32_t lo = (j == 0) ? lo0 : Lp[j - 1];
-        const uint32_t hi = (j == NR - 1) ? hiN : Lp[j + 1];
-        const uint32_t t = __vimin3_u16x2(Lp[j], __vminu2(lo, hi) + p1p1, mp2);    // INF16 + P1 stays inside its half
-        L[j] = cc[j] + (t - mm);          // t >= m in both halves: no borrow, and cc + P2 < 2^16: no carry
-    }
-}
-
-// float32 cost -> 16-bit code (value, or invalid_value | 0x8000 for NaN); `bad` is raised for anything else
-template <int CB>
-__device__ __forceinline__ uint32_t encode_cost(float v, uint32_t inv, float ok_max, bool &bad) {
-    const float t = v + 8388608.0f;                       // exact integer extraction for 0 <= v < 2^23
-    const bool isn = (v != v);
-    const bool ok = (t - 8388608.0f == v) && (v >= 0.f) && (v <= ok_max);
-    bad = bad || !(ok || isn);
-    return isn ? (inv | Tier<CB>::FLAG1) : (__float_as_uint(t) & 0xFFFFu);
-}
-
-// Two float32 costs -> one packed word of 16-bit codes (6.5 instructions per cost): NaN is first replaced by the float
-// whose integer code is invalid_value | flag, t = v + 2^23 carries the integer in its low mantissa bits (one PRMT packs
-// both), and the data condition "v is an integer in [0, ok_max]" is the single ordered comparison
-// min(|t - 2^23|, ok_max) <> v  (false for NaN, true for fractions, negatives, too large values and infinities).
-__device__ __forceinline__ uint32_t encode_pair(float vlo, float vhi, float nan_code, float ok_max, bool &bad) {
-    const float alo = (vlo != vlo) ? nan_code : vlo, ahi = (vhi != vhi) ? nan_code : vhi;
-    const float tlo = alo + 8388608.0f, thi = ahi + 8388608.0f;
-    const float clo = fminf(fabsf(tlo - 8388608.0f), ok_max), chi = fminf(fabsf(thi - 8388608.0f), ok_max);
-    bad = bad || (clo < vlo) || (clo > vlo) || (chi < vhi) || (chi > vhi);      // ordered <>: false for NaN
-    return __byte_perm(__float_as_uint(tlo), __float_as_uint(thi), 0x5410);
-}
 
 // ------------------------------------------------------------------------------------------------
 // horizontal passes: one warp per row
@@ -268,53 +100,6 @@ __global__ void __launch_bounds__(128) sgm_narrow_h_kernel(const NarrowParams p)
 // ------------------------------------------------------------------------------------------------
 // vertical sweeps: same strip / exchange-warp scheme as sgm_vsweep_kernel (sgm.cu), packed states
 // ------------------------------------------------------------------------------------------------
-template <int NR>
-__device__ __forceinline__ void ll_send_u32(unsigned long long *slot, int lane, uint32_t tag, const uint32_t (&v)[NR]) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-        const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)v[j];
-        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot + j * 32 + lane), "l"(w) : "memory");
-    }
-}
-template <int NR>
-__device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int lane, uint32_t tag, uint32_t (&v)[NR]) {
-    unsigned long long w[NR];
-    bool ok;
-    do {
-        ok = true;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
-#pragma unroll
-        for (int j = 0; j < NR; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
-    } while (!__all_sync(0xffffffffu, ok));
-#pragma unroll
-    for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
-}
-
-template <int NWORDS>
-__device__ __forceinline__ void cp_async_words(uint32_t smem_addr, const uint32_t *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(gsrc), "n"(NWORDS * 4) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// shared-memory access by 32-bit shared address (no generic-pointer conversion in the row loop)
-template <int NR>
-__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&v)[NR]) {
-    if constexpr (NR == 4) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
-    else if constexpr (NR == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr));
-    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr));
-}
-template <int NR>
-__device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&v)[NR]) {
-    if constexpr (NR == 4) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-    else if constexpr (NR == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
-    else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
-}
-
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-
 // A path start (L = C) is the same as a step from a FLAT previous state (all disparities equal: m = Lp[d], so
 // t - m = 0).  The state buffers therefore start as zeros and image-border halo columns simply stay zero: the row
 // loop has no "first row" / "no predecessor" cases.  Columns right of the image (last strip) run on zero costs,
@@ -561,16 +346,6 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
 // i+3 / i+4 -- proof that its reader finished row i+1, the last row that looks at the slot.  Column 0 / nc+1 of every
 // mailbox belong to the relay warps (the neighbouring strips); at an image border their counters start at "infinity"
 // and the slots stay zero: a flat state, i.e. a path start.
-__device__ __forceinline__ void flag_publish(uint32_t addr, uint32_t v, bool relaxed) {
-    if (relaxed) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-    else asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t target) {
-    uint32_t v;
-    do {
-        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    } while (v < target);
-}
 template <int NR, int CB, bool FINAL, bool WTA, bool CENSUS = false>
 __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) {
     static_assert(!(CENSUS && FINAL), "the Census source only exists for the first pass");
@@ -1071,7 +846,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
     if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
 
-    NarrowParams p;
+    NarrowParams p{};
     p.cv = cv; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
@@ -1106,6 +881,8 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     return PB200_OK;
 }
 
+int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace, cudaStream_t s, bool *done);   // sgm_wave1.cu
+
 // Fused Census -> SGM: the two wavefront passes with the first one computing the Hamming costs from the census
 // descriptors (no float cost volume is written or read).  Census costs are integers in [0, window^2] by construction,
 // so the data condition of the packed path holds statically: no flag, no float fall-back.  *done = false when the
@@ -1131,7 +908,7 @@ int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch,
     if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
     if (option(OPT_SGM_NO_WAVE) > 0) return PB200_OK;
 
-    NarrowParams p;
+    NarrowParams p{};
     p.cv = nullptr; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
@@ -1143,6 +920,10 @@ int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch,
     p.ring = nullptr; p.halo_in = nullptr; p.halo_out = nullptr;
     p.debug = debug_switches();
     p.descL = descL; p.descR = descR; p.pitch = pitch; p.half = window / 2;
+    if (option(OPT_SGM_WAVE_KERNEL) != 2) {                 // one column per warp (sgm_wave1.cu) unless the two-column kernels are pinned
+        const int rc = sgm_census_wave1_launch(p, NR, bytes, workspace, s, done);
+        if (rc != PB200_OK || *done || option(OPT_SGM_WAVE_KERNEL) == 1) return rc;
+    }
     const int nwarp = K / 2;
     const int nstrips = ceil_div(W, K);
     if (NR == 4) return bytes ? launch_wave<4, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<4, 2, true>(p, nstrips, nwarp, workspace, s, done);

@@ -193,7 +193,7 @@ def test_reverse_cost_volume_tiled(eng, oracle, shape, md):
     np.testing.assert_array_equal(got, oracle.reverse_cost_volume(cv, md))
     import pandora_b200 as pb
 
-    assert pb.last_path("reverse")[0] == "reverse_tiled"
+    assert pb.last_path("reverse")[0] == ("reverse_tiled" if shape[2] >= 8 else "reverse_gather")
     with pb.option("reverse.gather", 1):
         np.testing.assert_array_equal(host(eng.reverse_cost_volume(dev(eng, cv), md)), got)
         assert pb.last_path("reverse")[0] == "reverse_gather"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Time (CUDA events) the fused Census -> SGM -> WTA stage alone: python tools/prof_fused.py H W D [reps] [debug,debug,...].
-`debug` = PB200_SGM_DEBUG values (timing experiments, wrong results except 0: bit 0 no strip exchange, bit 1 relaxed
-flag stores, bit 2 no mailbox waits), read by the library at every launch."""
+"""Time (CUDA events) the fused Census -> SGM -> WTA stage alone: python tools/prof_fused.py H W D [reps] [kernels].
+`kernels` = comma list of "sgm.wave_kernel" values (1 = one column per warp, 2 = two columns per warp); with both, the
+outputs are also compared bit for bit."""
 import os
 import sys
 
@@ -13,25 +13,31 @@ from pandora_b200.synthetic import synthetic_pair  # noqa: E402
 
 H, W, D = (int(a) for a in sys.argv[1:4])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-debugs = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
+kernels = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1, 2]
 eng = pandora_b200.get_engine("cuda:0")
 left, right, _ = synthetic_pair(H, W, D)
 dl, dr = eng.to_device(left), eng.to_device(right)
-out = eng.empty((H, W, D))
 disp = eng.empty((H, W))
 flags = eng.empty((H, W), torch.uint8)
 eng.census_descriptors(dl, dr, 5)
-for dbg in debugs:
-    os.environ["PB200_SGM_DEBUG"] = str(dbg)
-    for _ in range(2 if reps > 1 else 0):
-        eng.census_sgm(dl, dr, 5, -(D - 1), 0, 8, 32, out=out, disp=disp, flags=flags, descriptors_ready=True)
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
-        assert eng.census_sgm(dl, dr, 5, -(D - 1), 0, 8, 32, out=out, disp=disp, flags=flags, descriptors_ready=True) is not None
-        ev[i + 1].record()
-    torch.cuda.synchronize()
+outs = {}
+for k in kernels:
+    out = eng.empty((H, W, D))
+    with pandora_b200.option("sgm.wave_kernel", k):
+        for _ in range(2 if reps > 1 else 0):
+            eng.census_sgm(dl, dr, 5, -(D - 1), 0, 8, 32, out=out, disp=disp, flags=flags, descriptors_ready=True)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            assert eng.census_sgm(dl, dr, 5, -(D - 1), 0, 8, 32, out=out, disp=disp, flags=flags, descriptors_ready=True) is not None
+            ev[i + 1].record()
+        torch.cuda.synchronize()
     ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
-    print(f"fused census+sgm+wta {H}x{W}x{D} debug={dbg}: {min(ts):.3f} ms (min of {reps}), {sum(ts) / len(ts):.3f} ms mean; "
-          f"{H * W / min(ts) / 1e3:.1f} Mpix/s; us/row (both passes) = {min(ts) * 1e3 / H:.3f}", flush=True)
+    print(f"fused census+sgm+wta {H}x{W}x{D} kernel={k} path={pandora_b200.last_path('sgm')}: {min(ts):.3f} ms (min of {reps}), "
+          f"{sum(ts) / len(ts):.3f} ms mean; {H * W / min(ts) / 1e3:.1f} Mpix/s; us/row (both passes) = {min(ts) * 1e3 / H:.3f}", flush=True)
+    outs[k] = (out, disp.clone())
+if len(outs) == 2:
+    (a, da), (b, db) = outs.values()
+    same = torch.equal(da, db) and torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+    print("outputs identical:", same, flush=True)
