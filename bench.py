@@ -279,7 +279,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             for i in range(args.steps):
                 fev[i][0].record()
-                e.census_descriptors(d_left, d_right, WINDOW)
+                e.census_sgm_descriptors(d_left, d_right, WINDOW, dmin, dmax, P1, P2)
                 fev[i][1].record()
                 e.census_sgm(d_left, d_right, WINDOW, dmin, dmax, P1, P2, False, out=pipe.cv_b, fuse_wta=True, invalid_disparity=-9999.0,
                              disp=pipe.disp, flags=pipe.flags, descriptors_ready=True)

@@ -111,10 +111,47 @@ PB200_API int pb200_census_descriptors_rows(const float *d_left, const float *d_
  * eligible (window not in {3, 5}, D not in {64, 128, 256}, non-integer or large penalties, image wider than one
  * co-resident wave): nothing has been computed then and the caller runs the two steps separately.
  * Workspaces: pb200_census_workspace_bytes / pb200_sgm_workspace_bytes. */
+/* Workspace and descriptor pre-pass of pb200_census_sgm.  The fused kernels read the census descriptors in a layout of
+ * their own (the skewed wavefront takes the right image's descriptors as four word-shifted, padded copies so that every
+ * pixel's D-wide window is a pair of aligned 16-byte copies): pb200_census_sgm_workspace_bytes sizes d_census_workspace for
+ * it (>= pb200_census_workspace_bytes), pb200_census_sgm_descriptors runs only the transforms (*eligible = 0 and nothing
+ * launched when the configuration is not eligible) so that pb200_census_sgm(..., descriptors_ready = 1) with the same
+ * arguments can follow -- used to time the transforms apart from the SGM passes. */
+PB200_API size_t pb200_census_sgm_workspace_bytes(int H, int W, int window, int dmin, int D);
+PB200_API int pb200_census_sgm_descriptors(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1,
+                                 float p2, void *d_census_workspace, size_t census_workspace_bytes, int *eligible, void *stream);
 PB200_API int pb200_census_sgm(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1, float p2,
                      int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
                      void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
                      uint8_t *d_all_nan, int descriptors_ready, int *ran, void *stream);
+
+/* ---- the fused stage column-tiled over several GPUs (one process per GPU) ---------------------------------------------------
+ * The skewed wavefront (pandora_b200/csrc/sgm_wave1.cu) walks SHEARED columns c = (image column + row) mod Wg, in which every
+ * SGM dependency points to the right; GPU `tile` of `ntiles` owns the sheared columns [tile * Wt, (tile + 1) * Wt), Wt = Wg /
+ * ntiles, and hands the path states of its last column to the next GPU through a LINK buffer in that GPU's memory (NVLink peer
+ * stores issued by the kernel itself; credits flow back the same way).  There is no host-side step and no collective between
+ * the tiles: all GPUs run one wave.  The result is bit-identical to pb200_census_sgm on one GPU.
+ *   - d_left / d_right: the WHOLE images (H, Wg) on every GPU (a tile's pixels drift Wt + H - 1 image columns to the left; only
+ *     the descriptors of those columns are computed).
+ *   - d_cv_tile (H, Wt, D), d_disp_tile / d_all_nan_tile (H, Wt): the tile in SHEARED layout: element (y, c) belongs to image
+ *     column (tile * Wt + c - y) mod Wg.
+ *   - link_local: this GPU's link buffer (pb200_tile_link_bytes, zero-initialised once, e.g. by pb200_ipc_alloc); link_left /
+ *     link_right: the link buffers of tiles (tile - 1) and (tile + 1) mod ntiles mapped into this process (pb200_ipc_open);
+ *     with ntiles == 1 all three are the same buffer.
+ *   - epoch: a counter that is the same on all GPUs for one image and differs between consecutive images (the links are never
+ *     cleared; every word carries the epoch).
+ * pb200_ipc_*: device memory that other processes of the node can map (cudaIpc; the 64-byte handle travels through any host
+ * channel, e.g. torch.distributed). */
+PB200_API size_t pb200_tile_link_bytes(int D);
+PB200_API int pb200_census_sgm_tile(const float *d_left, const float *d_right, int H, int Wg, int window, int dmin, int D, float p1,
+                          float p2, int overcounting, int tile, int ntiles, float *d_cv_tile, void *d_census_workspace,
+                          size_t census_workspace_bytes, void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp_tile,
+                          float invalid_disparity, uint8_t *d_all_nan_tile, void *link_local, void *link_left, void *link_right,
+                          unsigned epoch, void *stream);
+PB200_API int pb200_ipc_alloc(size_t bytes, void **d_ptr, void *handle64);
+PB200_API int pb200_ipc_open(const void *handle64, void **d_ptr);
+PB200_API int pb200_ipc_close(void *d_ptr);
+PB200_API int pb200_ipc_free(void *d_ptr);
 
 /* SAD (squared == 0) / SSD (squared != 0) cost volume, window odd >= 1 (sad_ssd.py:180-206). */
 PB200_API int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,

@@ -93,6 +93,38 @@ extern "C" int pb200_last_path(const char *stage, int *detail) {
         }
     return PB200_ERR_BAD_ARG;
 }
+// ---- peer-visible device memory for the tile links of a multi-GPU run (one process per GPU: CUDA IPC) ------------------------
+extern "C" int pb200_ipc_alloc(size_t bytes, void **d_ptr, void *handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) {
+        set_error("pb200_ipc_alloc: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C-ABI passes IPC handles as 64 bytes");
+    PB200_CUDA(cudaMalloc(d_ptr, bytes));
+    PB200_CUDA(cudaMemset(*d_ptr, 0, bytes));
+    PB200_CUDA(cudaDeviceSynchronize());
+    PB200_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), *d_ptr));
+    return PB200_OK;
+}
+extern "C" int pb200_ipc_open(const void *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) {
+        set_error("pb200_ipc_open: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    PB200_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PB200_OK;
+}
+extern "C" int pb200_ipc_close(void *d_ptr) {
+    if (d_ptr) PB200_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return PB200_OK;
+}
+extern "C" int pb200_ipc_free(void *d_ptr) {
+    if (d_ptr) PB200_CUDA(cudaFree(d_ptr));
+    return PB200_OK;
+}
+
 extern "C" int pb200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -233,7 +265,7 @@ extern "C" int pb200_disparity_host(const float *left, const float *right, int H
     bool sgm_done = false;
     DevBuf sws;
     if (method == 0) {
-        const size_t wsb = pb200_census_workspace_bytes(H, W, window);
+        const size_t wsb = pb200_census_sgm_workspace_bytes(H, W, window, dmin, D);     // >= pb200_census_workspace_bytes
         PB200_RC(ws.alloc(wsb));
         // Census directly followed by SGM: one fused stage when eligible (the Census volume is never written)
         const int fopt = option(OPT_FUSE_CENSUS_SGM);

@@ -38,12 +38,12 @@ static inline int census_pitch(int W) { return ((W + 3) & ~3) + 4; }
 // ------------------------------------------------------------------------------------------------
 template <int WIN>
 __global__ void __launch_bounds__(256) census_transform_kernel(const float *__restrict__ img, int H, int W, int pitch,
-                                                               uint32_t *__restrict__ desc, int row0, int row1) {
+                                                               uint32_t *__restrict__ desc, int row0, int row1, int col0, int col1) {
     constexpr int HALF = WIN / 2;
     constexpr int NW = (WIN * WIN + 31) / 32;
     constexpr int TW = 32, TH = 8;
     __shared__ float tile[TH + 2 * HALF][TW + 2 * HALF + 1];
-    const int x0 = blockIdx.x * TW, y0 = row0 + blockIdx.y * TH;
+    const int x0 = col0 + blockIdx.x * TW, y0 = row0 + blockIdx.y * TH;
     for (int i = threadIdx.y * TW + threadIdx.x; i < (TH + 2 * HALF) * (TW + 2 * HALF); i += TW * TH) {
         const int ty = i / (TW + 2 * HALF), tx = i % (TW + 2 * HALF);
         const int gy = y0 + ty - HALF, gx = x0 + tx - HALF;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) census_transform_kernel(const float *__re
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= pitch || y >= row1) return;
+    if (x >= col1 || y >= row1) return;
     uint32_t words[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) words[i] = 0u;
@@ -367,9 +367,12 @@ static int launch_fill_direct(FillParams p, int rows, cudaStream_t s) {
 }
 
 template <int WIN>
-static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, int row0, int row1, cudaStream_t s) {
-    dim3 block(32, 8), grid(ceil_div(pitch, 32), ceil_div(row1 - row0, 8));
-    census_transform_kernel<WIN><<<grid, block, 0, s>>>(img, H, W, pitch, desc, row0, row1);
+static int launch_transform(const float *img, int H, int W, int pitch, uint32_t *desc, int row0, int row1, cudaStream_t s, int col0 = 0,
+                            int col1 = -1) {
+    if (col1 < 0) col1 = pitch;                      // default: every column of the pitch (the padding gets the flag)
+    if (col1 <= col0) return PB200_OK;
+    dim3 block(32, 8), grid(ceil_div(col1 - col0, 32), ceil_div(row1 - row0, 8));
+    census_transform_kernel<WIN><<<grid, block, 0, s>>>(img, H, W, pitch, desc, row0, row1, col0, col1);
     PB200_LAUNCH_CHECK("census_transform_kernel");
     return PB200_OK;
 }
@@ -387,9 +390,41 @@ static int launch_fill(const FillParams &p, size_t smem, int grid, cudaStream_t 
     return PB200_OK;
 }
 
-int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch, int window, float *out, int H, int W, int D, float p1,
+int sgm_census_plan(int window, int W, int D, float p1, float p2);   // sgm_narrow.cu: 0 = not eligible, 1 = skewed wavefront, 2 = two-column wavefront
+int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, int W, int D, float p1,
                         float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
-                        size_t workspace_bytes, cudaStream_t s, bool *done);   // sgm_narrow.cu
+                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers = nullptr);   // sgm_narrow.cu
+size_t sgm_wave1_edge_bytes(int D);                                            // sgm_wave1.cu
+
+// Right descriptors in the layout of the skewed wavefront (sgm_wave1.cu): copy s, index i = descriptor of image column
+// i + s - padl, or the "window leaves the image" flag.  One thread per (row, column of the padded range) computes the
+// descriptor once and stores it into the four copies.
+template <int WIN>
+__global__ void __launch_bounds__(256) census_transform_shifted_kernel(const float *__restrict__ img, int H, int W, int pitch4, int padl,
+                                                                       uint32_t *__restrict__ desc4, int i0, int i1) {
+    constexpr int HALF = WIN / 2;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= i1) return;
+    const int x = i - padl;
+    uint32_t word = 0x80000000u;
+    if (x >= HALF && x < W - HALF && y >= HALF && y < H - HALF) {
+        const float c = __ldg(img + (size_t)y * W + x);
+        word = 0u;
+#pragma unroll
+        for (int wy = 0; wy < WIN; ++wy)
+#pragma unroll
+            for (int wx = 0; wx < WIN; ++wx)
+                if (__ldg(img + (size_t)(y + wy - HALF) * W + (x + wx - HALF)) > c) word |= 1u << (wy * WIN + wx);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (i - s >= 0 && i - s < pitch4) desc4[((size_t)s * H + y) * pitch4 + (i - s)] = word;
+}
+static inline int census_padl(int dmin) { return (((dmin < 0 ? -dmin : 0) + 3) & ~3) + 4; }
+static inline int census_pitch4(int W, int dmin, int D) {
+    const int dmax = dmin + D - 1;
+    return (census_padl(dmin) + W + (dmax > 0 ? dmax : 0) + 8 + 3) & ~3;
+}
 
 static int census_transform_pair(const float *d_left, const float *d_right, int H, int W, int window, uint32_t *descL, uint32_t *descR,
                                  int row_begin, int row_end, cudaStream_t s) {
@@ -431,6 +466,60 @@ extern "C" int pb200_census_descriptors_rows(const float *d_left, const float *d
     return census_transform_pair(d_left, d_right, H, W, window, descL, descR, row_begin, row_end, (cudaStream_t)stream);
 }
 
+// descriptors of the fused stage in the layout its kernels read (plan 1: left + four shifted right copies; plan 2: the
+// standard pair); workspace: [standard left | standard right] then, for plan 1, the shifted right copies
+// `col0 .. col1` (plan 1 only): the image columns whose PIXELS this call will process (a column tile of a multi-GPU run
+// touches Wt + H - 1 of them); the left descriptors of those columns and the right descriptors their windows can meet
+static int census_sgm_descriptors(int plan, const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
+                                  void *ws, cudaStream_t s, int col0 = 0, int col1 = -1) {
+    const int pitch = census_pitch(W);
+    uint32_t *descL = (uint32_t *)ws, *descR = descL + (size_t)H * pitch;
+    if (plan != 1) return census_transform_pair(d_left, d_right, H, W, window, descL, descR, 0, H, s);
+    const bool all = col1 < 0;
+    int rc = window == 3 ? launch_transform<3>(d_left, H, W, pitch, descL, 0, H, s, all ? 0 : col0, all ? -1 : col1)
+                         : launch_transform<5>(d_left, H, W, pitch, descL, 0, H, s, all ? 0 : col0, all ? -1 : col1);
+    if (rc != PB200_OK) return rc;
+    const int pitch4 = census_pitch4(W, dmin, D), padl = census_padl(dmin);
+    uint32_t *desc4 = descR + (size_t)H * pitch;
+    // copy index i holds image column i + s - padl: the windows of columns [col0, col1) meet [col0 + dmin, col1 + dmin + D)
+    int i0 = 0, i1 = pitch4 + 3;
+    if (!all) {
+        i0 = col0 + dmin + padl - 4;
+        i1 = col1 + dmin + D + padl + 4;
+        if (i0 < 0) i0 = 0;
+        if (i1 > pitch4 + 3) i1 = pitch4 + 3;
+    }
+    if (i1 <= i0) return PB200_OK;
+    dim3 grid(ceil_div(i1 - i0, 256), H);
+    if (window == 3) census_transform_shifted_kernel<3><<<grid, 256, 0, s>>>(d_right, H, W, pitch4, padl, desc4, i0, i1);
+    else census_transform_shifted_kernel<5><<<grid, 256, 0, s>>>(d_right, H, W, pitch4, padl, desc4, i0, i1);
+    PB200_LAUNCH_CHECK("census_transform_shifted_kernel");
+    return PB200_OK;
+}
+
+extern "C" size_t pb200_census_sgm_workspace_bytes(int H, int W, int window, int dmin, int D) {
+    if (H <= 0 || W <= 0 || D <= 0) return 0;
+    size_t bytes = pb200_census_workspace_bytes(H, W, window);
+    if (window == 3 || window == 5) bytes += 4 * (size_t)H * census_pitch4(W, dmin, D) * sizeof(uint32_t);
+    return bytes;
+}
+
+extern "C" int pb200_census_sgm_descriptors(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1,
+                                            float p2, void *d_census_workspace, size_t census_workspace_bytes, int *eligible, void *stream) {
+    if (!d_left || !d_right || !d_census_workspace || !eligible || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_census_sgm_descriptors: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    const int plan = sgm_census_plan(window, W, D, p1, p2);
+    *eligible = plan != 0;
+    if (plan == 0) return PB200_OK;
+    if (census_workspace_bytes < pb200_census_sgm_workspace_bytes(H, W, window, dmin, D)) {
+        set_error("pb200_census_sgm_descriptors: census workspace too small (pb200_census_sgm_workspace_bytes)");
+        return PB200_ERR_WORKSPACE;
+    }
+    return census_sgm_descriptors(plan, d_left, d_right, H, W, window, dmin, D, d_census_workspace, (cudaStream_t)stream);
+}
+
 extern "C" int pb200_census_sgm(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, float p1, float p2,
                                 int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
                                 void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
@@ -444,24 +533,104 @@ extern "C" int pb200_census_sgm(const float *d_left, const float *d_right, int H
         set_error("pb200_census_sgm: bad argument");
         return PB200_ERR_BAD_ARG;
     }
-    if (window != 3 && window != 5) return PB200_OK;                 // not eligible: the caller runs the two steps separately
-    if (census_workspace_bytes < pb200_census_workspace_bytes(H, W, window)) {
-        set_error("pb200_census_sgm: census workspace too small");
+    // eligibility first: nothing is launched for a configuration the fused kernels do not take (the caller runs the two steps)
+    int plan = sgm_census_plan(window, W, D, p1, p2);
+    if (plan == 0) return PB200_OK;
+    if (census_workspace_bytes < pb200_census_sgm_workspace_bytes(H, W, window, dmin, D)) {
+        set_error("pb200_census_sgm: census workspace too small (pb200_census_sgm_workspace_bytes)");
         return PB200_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int pitch = census_pitch(W);
     uint32_t *descL = (uint32_t *)d_census_workspace;
     uint32_t *descR = descL + (size_t)H * pitch;
-    if (!descriptors_ready) {
-        const int rc = census_transform_pair(d_left, d_right, H, W, window, descL, descR, 0, H, s);
+    if (!descriptors_ready) {                        // else: pb200_census_sgm_descriptors ran with the same arguments
+        const int rc = census_sgm_descriptors(plan, d_left, d_right, H, W, window, dmin, D, d_census_workspace, s);
         if (rc != PB200_OK) return rc;
     }
+    CensusDesc desc;
+    desc.L = descL; desc.R = descR; desc.pitch = pitch;
+    desc.R4 = plan == 1 ? descR + (size_t)H * pitch : nullptr;
+    desc.pitch4 = census_pitch4(W, dmin, D); desc.padl = census_padl(dmin);
     bool done = false;
-    const int rc = sgm_census_wave_try(descL, descR, pitch, window, d_cv_out, H, W, D, p1, p2, overcounting, d_disp, dmin, invalid_disparity,
+    const int rc = sgm_census_wave_try(desc, window, d_cv_out, H, W, D, p1, p2, overcounting, d_disp, dmin, invalid_disparity,
                                        d_all_nan, d_sgm_workspace, sgm_workspace_bytes, s, &done);
     if (rc != PB200_OK) return rc;
     *ran = done ? 1 : 0;
+    return PB200_OK;
+}
+
+// ---- column-tiled multi-GPU runs of the fused stage -----------------------------------------------------------------------
+extern "C" size_t pb200_tile_link_bytes(int D) {
+    if (D <= 0) return 0;
+    // [pass-1 boundary block | pass-2 boundary block | pass-1 credit line | pass-2 credit line], each block 256-byte aligned
+    const size_t blk = (sgm_wave1_edge_bytes(D) + 255) & ~(size_t)255;
+    return 2 * blk + 512;
+}
+
+extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, int H, int Wg, int window, int dmin, int D, float p1,
+                                     float p2, int overcounting, int tile, int ntiles, float *d_cv_tile, void *d_census_workspace,
+                                     size_t census_workspace_bytes, void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp_tile,
+                                     float invalid_disparity, uint8_t *d_all_nan_tile, void *link_local, void *link_left, void *link_right,
+                                     unsigned epoch, void *stream) {
+    if (!d_left || !d_right || !d_cv_tile || !d_census_workspace || !d_sgm_workspace || !link_local || !link_left || !link_right || H <= 0 ||
+        Wg <= 0 || D <= 0 || ntiles < 1 || tile < 0 || tile >= ntiles || Wg % ntiles != 0) {
+        set_error("pb200_census_sgm_tile: bad argument (the image width must be a multiple of the number of tiles)");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (H >= 65535) {
+        set_error("pb200_census_sgm_tile: at most 65534 rows (row tags share a word with the epoch)");
+        return PB200_ERR_UNSUPPORTED;
+    }
+    const int Wt = Wg / ntiles;
+    if (sgm_census_plan(window, Wt, D, p1, p2) != 1) {
+        set_error("pb200_census_sgm_tile: the skewed wavefront does not take this configuration (window 3 / 5, D in {64, 128, 256}, "
+                  "small integer penalties, tile width <= 28 columns per SM)");
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (census_workspace_bytes < pb200_census_sgm_workspace_bytes(H, Wg, window, dmin, D)) {
+        set_error("pb200_census_sgm_tile: census workspace too small (pb200_census_sgm_workspace_bytes of the WHOLE image)");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // descriptors, indexed by global image column; only the columns this tile's pixels visit are computed: the sheared tile
+    // [tile * Wt, (tile + 1) * Wt) drifts one image column to the left per row, Wt + H - 1 columns in all (cyclically)
+    const int span = Wt + H - 1 < Wg ? Wt + H - 1 : Wg;
+    const int lo = ((tile * Wt - (H - 1)) % Wg + Wg) % Wg;
+    int rc;
+    if (span == Wg) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s);
+    else if (lo + span <= Wg) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, lo, lo + span);
+    else {
+        rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, lo, Wg);
+        if (rc == PB200_OK) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, 0, lo + span - Wg);
+    }
+    if (rc != PB200_OK) return rc;
+    const int pitch = census_pitch(Wg);
+    CensusDesc desc;
+    desc.L = (uint32_t *)d_census_workspace; desc.R = desc.L + (size_t)H * pitch; desc.pitch = pitch;
+    desc.R4 = desc.R + (size_t)H * pitch;
+    desc.pitch4 = census_pitch4(Wg, dmin, D); desc.padl = census_padl(dmin);
+    // link buffers: [in pass 1 | in pass 2 | credit pass 1 | credit pass 2].  Pass 1 travels left -> right (data comes from the
+    // left tile, credits come from the right one), pass 2 right -> left.
+    const size_t blk = (sgm_wave1_edge_bytes(D) + 255) & ~(size_t)255;
+    auto at = [](void *base, size_t off) { return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + off); };
+    Wave1Peers peers;
+    peers.in[0] = at(link_local, 0);            peers.in[1] = at(link_local, blk);
+    peers.ack_in[0] = at(link_local, 2 * blk);  peers.ack_in[1] = at(link_local, 2 * blk + 256);
+    peers.out[0] = at(link_right, 0);           peers.ack_out[0] = at(link_left, 2 * blk);
+    peers.out[1] = at(link_left, blk);          peers.ack_out[1] = at(link_right, 2 * blk + 256);
+    peers.Wg = Wg;
+    peers.c_off[0] = tile * Wt;
+    peers.c_off[1] = (((H - 1 - (tile + 1) * Wt) % Wg) + Wg) % Wg;
+    peers.epoch = epoch & 0xFFFFu;
+    bool done = false;
+    rc = sgm_census_wave_try(desc, window, d_cv_tile, H, Wt, D, p1, p2, overcounting, d_disp_tile, dmin, invalid_disparity, d_all_nan_tile,
+                             d_sgm_workspace, sgm_workspace_bytes, s, &done, &peers);
+    if (rc != PB200_OK) return rc;
+    if (!done) {
+        set_error("pb200_census_sgm_tile: the wavefront kernels could not be made co-resident (workspace or shared memory)");
+        return PB200_ERR_UNSUPPORTED;
+    }
     return PB200_OK;
 }
 

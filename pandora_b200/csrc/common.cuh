@@ -57,6 +57,24 @@ enum Path {
 };
 void note_path(Stage st, int path, int detail = 0);
 
+struct CensusDesc {                                   // what the fused Census -> SGM kernels read (census.cu -> sgm_narrow.cu)
+    const uint32_t *L, *R;                            // planar one-word descriptors, row pitch `pitch`
+    int pitch;
+    const uint32_t *R4;                               // four shifted, padded copies of the right descriptors (skewed wavefront) or NULL
+    int pitch4, padl;
+};
+
+// Edge buffers of a column-tiled multi-GPU run of the skewed wavefront, per pass (0 = top-down, 1 = bottom-up): `in` =
+// local boundary block the travel-frame LEFT neighbour stores into, `ack_out` = that neighbour's credit word (peer
+// pointer), `out` = the travel-frame RIGHT neighbour's boundary block (peer pointer), `ack_in` = local credit word it
+// stores into; `c_off` = global sheared column of this tile's column 0 in that pass's frame.
+struct Wave1Peers {
+    unsigned long long *in[2], *ack_out[2], *out[2], *ack_in[2];
+    int c_off[2];
+    int Wg;
+    uint32_t epoch;
+};
+
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fc00000); }
 

@@ -9,9 +9,12 @@ namespace pb200 {
 // D/2 <= vs/2 words = 6 vs words -- the larger one.  The narrow-path flag lives 256 bytes behind it
 // (pb200_sgm_workspace_bytes = this + 512).
 static inline size_t sgm_ring_max_bytes(int W, int D) {
-    const size_t nstrips = (size_t)(W + 3) / 4;
+    const size_t nstrips = (size_t)(W + 3) / 4 + 1;
     const size_t vs = (size_t)((D + 31) / 32) * 32;
-    return nstrips * (6 * vs * sizeof(unsigned long long));
+    const size_t old_block = 6 * vs * sizeof(unsigned long long);
+    // skewed wavefront (sgm_wave1.cu): 8 rows x 4 vectors of D / 2 tagged words + a credit line per strip boundary
+    const size_t skew_block = ((size_t)8 * 4 * ((D + 63) / 64) * 32 + 16) * sizeof(unsigned long long);
+    return nstrips * (old_block > skew_block ? old_block : skew_block);
 }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {

@@ -881,32 +881,46 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     return PB200_OK;
 }
 
-int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace, cudaStream_t s, bool *done);   // sgm_wave1.cu
+int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace, size_t ring_room, const Wave1Peers *peers, cudaStream_t s,
+                            bool *done);   // sgm_wave1.cu
+
+// Which fused Census -> SGM kernels take a configuration: 0 = none (the caller runs the Census fill and pb200_sgm), 1 = the
+// skewed one-column wavefront (sgm_wave1.cu; reads the shifted descriptor layout), 2 = the two-column wavefront.
+static bool census_wave_common(int window, int D, float p1, float p2) {
+    if (D != 64 && D != 128 && D != 256) return false;
+    if (window != 3 && window != 5) return false;                          // one-word descriptors
+    const float invalid_value = (float)(window * window) + p2 + 1.f;       // cmax + P2 + 1 (census.py:116 gives cmax = w^2)
+    return is_small_int(p1, 1, NARROW_MAX) && is_small_int(p2, 1, NARROW_MAX) && p1 <= p2 && is_small_int(invalid_value, 0, NARROW_MAX) &&
+           (int)invalid_value + (int)p2 <= NARROW_MAX;
+}
+int sgm_wave1_strip_width(int W);                                           // sgm_wave1.cu: 0 when the image is too wide for one wave
+int sgm_census_plan(int window, int W, int D, float p1, float p2) {
+    if (!census_wave_common(window, D, p1, p2) || option(OPT_SGM_NO_WAVE) > 0) return 0;
+    const int pin = option(OPT_SGM_WAVE_KERNEL);
+    if (pin != 2 && sgm_wave1_strip_width(W) > 0) return 1;
+    int K = ceil_div(W, sm_count());
+    if (K < 4) K = 4;
+    K = (K + 1) / 2 * 2;
+    if (pin != 1 && K / 2 <= 14) return 2;
+    return 0;
+}
 
 // Fused Census -> SGM: the two wavefront passes with the first one computing the Hamming costs from the census
 // descriptors (no float cost volume is written or read).  Census costs are integers in [0, window^2] by construction,
 // so the data condition of the packed path holds statically: no flag, no float fall-back.  *done = false when the
 // shape / parameters are not eligible (the caller then runs the Census fill and pb200_sgm separately).
-int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch, int window, float *out, int H, int W, int D, float p1,
+int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, int W, int D, float p1,
                         float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
-                        size_t workspace_bytes, cudaStream_t s, bool *done) {
+                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers) {
+    // `peers` != NULL: W is the width of this GPU's column tile of a peers->Wg wide image (skewed wavefront only)
     *done = false;
-    if (D != 64 && D != 128 && D != 256) return PB200_OK;
-    if (window != 3 && window != 5) return PB200_OK;                       // one-word descriptors
-    const float invalid_value = (float)(window * window) + p2 + 1.f;       // cmax + P2 + 1 (census.py:116 gives cmax = w^2)
-    if (!is_small_int(p1, 1, NARROW_MAX) || !is_small_int(p2, 1, NARROW_MAX) || p1 > p2 || !is_small_int(invalid_value, 0, NARROW_MAX) ||
-        (int)invalid_value + (int)p2 > NARROW_MAX)
-        return PB200_OK;
+    const int plan = sgm_census_plan(window, W, D, p1, p2);
+    if (plan == 0 || (plan == 1 && desc.R4 == nullptr) || (peers != nullptr && plan != 1)) return PB200_OK;
     if (reinterpret_cast<uintptr_t>(out) & 15) return PB200_OK;
-    const int nsm = sm_count();
-    int K = ceil_div(W, nsm);
-    if (K < 4) K = 4;
-    K = (K + 1) / 2 * 2;
-    if (K / 2 > 14) return PB200_OK;
+    const float invalid_value = (float)(window * window) + p2 + 1.f;
     const int NR = D / 64;
     const size_t flag_off = sgm_ring_max_bytes(W, D) + 256;
     if (workspace == nullptr || workspace_bytes < flag_off + sizeof(int) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PB200_OK;
-    if (option(OPT_SGM_NO_WAVE) > 0) return PB200_OK;
 
     NarrowParams p{};
     p.cv = nullptr; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
@@ -919,11 +933,12 @@ int sgm_census_wave_try(const uint32_t *descL, const uint32_t *descR, int pitch,
     p.disp = disp; p.all_nan = all_nan; p.dmin = dmin; p.invalid_disparity = invalid_disparity;
     p.ring = nullptr; p.halo_in = nullptr; p.halo_out = nullptr;
     p.debug = debug_switches();
-    p.descL = descL; p.descR = descR; p.pitch = pitch; p.half = window / 2;
-    if (option(OPT_SGM_WAVE_KERNEL) != 2) {                 // one column per warp (sgm_wave1.cu) unless the two-column kernels are pinned
-        const int rc = sgm_census_wave1_launch(p, NR, bytes, workspace, s, done);
-        if (rc != PB200_OK || *done || option(OPT_SGM_WAVE_KERNEL) == 1) return rc;
-    }
+    p.descL = desc.L; p.descR = desc.R; p.pitch = desc.pitch; p.half = window / 2;
+    p.descR4 = desc.R4; p.pitch4 = desc.pitch4; p.padl = desc.padl;
+    if (plan == 1) return sgm_census_wave1_launch(p, NR, bytes, workspace, flag_off - 256, peers, s, done);
+    int K = ceil_div(W, sm_count());
+    if (K < 4) K = 4;
+    K = (K + 1) / 2 * 2;
     const int nwarp = K / 2;
     const int nstrips = ceil_div(W, K);
     if (NR == 4) return bytes ? launch_wave<4, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<4, 2, true>(p, nstrips, nwarp, workspace, s, done);

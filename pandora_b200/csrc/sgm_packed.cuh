@@ -28,6 +28,11 @@ struct NarrowParams {
     // fused Census source of the first wavefront pass (CENSUS = true): planar one-word descriptors (census.cu)
     const uint32_t *descL, *descR;
     int pitch, half;
+    // skewed wavefront: the right descriptors as FOUR word-shifted, padded copies [s][H][pitch4]: copy s, index i holds the
+    // descriptor of image column i + s - padl (flagged outside the image), so that the D-wide window of ANY pixel starts
+    // on a 16-byte boundary in the copy s = (column + dmin) & 3 and needs no bounds check
+    const uint32_t *descR4;
+    int pitch4, padl;
     // one-column wavefront (sgm_wave1.cu): columns per strip, and the mailbox rings of a COLUMN-tiled multi-GPU run:
     // the strip at either edge of this GPU's tile exchanges its border states with the neighbouring GPU through
     // peer-mapped memory (NVLink) instead of the local L2 ring.  `l` / `r` are the logical sides of this pass's travel
@@ -35,7 +40,10 @@ struct NarrowParams {
     int K;
     unsigned long long *peer_in_l, *peer_out_l, *peer_in_r, *peer_out_r;
     uint32_t tag_base;        // added to every ring tag: (epoch << 16) for peer rings that are never cleared
+    int Wg, c_off;            // skewed wavefront: width of the (global) sheared ring, sheared column of this tile's column 0
+    int sheared_store;        // 1: the volume / disparity tile is stored by sheared column (multi-GPU tiles), 0: by image column
 };
+
 
 namespace {
 

@@ -1,48 +1,58 @@
-// sgm_wave1.cu -- the wavefront SGM passes with ONE COLUMN PER WARP.
+// sgm_wave1.cu -- the SKEWED wavefront: the two 4-direction SGM passes with one column per warp and no counter-flow.
 //
 // Same arithmetic, same two passes and the same intermediate format as sgm_wave_kernel (sgm_narrow.cu): pass 1 walks the
 // image top-down and runs E, SE, S, SW; pass 2 walks it bottom-up on the frame flipped in both axes (W, NW, N, NE), adds
 // its four directions to the 16-bit partial sums of pass 1 and emits float32 S (+ NaN restore, overcounting, WTA) in
-// place.  What changes is the shape of the machine:
+// place.  What changes is the geometry of the wave.
 //
-//   * a strip is K <= 28 columns and a CTA has one compute warp per column (28 instead of 14 recurrence chains per SM:
-//     the two-column kernel ran at 3.5 warps per scheduler and was bound by the dependent-issue latency of its chains,
-//     profiles/r1_ncu_fused_pass1.txt), at <= 64 registers per thread: a warp keeps only its vertical state S, the
-//     pixel's cost and the running total; E / SE come from the left neighbour's mailbox, SW from the right one's;
-//   * mailboxes are two-deep for E and SW and four-deep for SE (slot discipline below), progress counters per column;
-//   * the first pass takes its Census costs from descriptor rows staged ONCE per CTA row by a loader warp (cp.async,
-//     four word-shifted copies so that every column reads its D-wide window as aligned vectors) instead of once per warp;
-//   * the relay warps poll both directions independently (a small two-counter state machine), so a late E of this strip
-//     never delays the SW coming in from the next one;
-//   * the strips at the two ends of the image may hand their border states to ANOTHER GPU: the relay then stores into
-//     peer-mapped memory (NVLink) and polls a local buffer the neighbour stores into -- a column-tiled multi-GPU run is
-//     one wave across all GPUs, with no host-side step in between (pandora_b200/tiling.py).
+// In the straight frame a pixel (y, k) takes E from (y, k-1), SE from (y-1, k-1), S from (y-1, k) -- all from the left
+// or from itself -- but SW from (y-1, k+1): against the direction the wave travels.  That one counter-flow edge closes a
+// cycle between every pair of neighbouring columns (E to the right, SW back to the left) which pins them within one row
+// of each other, so the hand-over latency of the SLOWEST link -- a strip boundary through L2, or a GPU boundary through
+// NVLink -- bounds the row rate of the whole image (measured: 3.85 us per row with 1.3 k-cycle strip boundaries against
+// 2.3 us of issue time).  Here a warp owns a SHEARED column c = (k + y) mod W instead: it steps one image column to the
+// left with every row.  In that frame
+//      E  (y, k-1)   -> column c-1, this row          S  (y-1, k)   -> column c-1, previous row
+//      SE (y-1, k-1) -> column c-2, previous row      SW (y-1, k+1) -> column c itself (registers)
+// every edge points to the right.  The pipeline is one-directional and cyclic (column 0 follows column W-1, the row-y
+// chain starts at column y mod W, where k = 0 and the left inputs are path starts): neighbours are coupled only by the
+// depth of their mailboxes, a slow link costs latency once (fill) instead of bandwidth, and the same kernel runs
+// COLUMN-TILED over several GPUs -- the relay warp of a tile's last strip stores straight into the next GPU's memory
+// (NVLink peer stores, {tag, value} words) and the first strip's relay polls local memory: one wave across all GPUs,
+// no host-side step, no collective.
 //
-// Row program of column x (mailbox column v = x - strip start + 1), row i in travel order:
-//   1  cost c(i)                                         (descriptor ring / cp.async staging)
-//   2  wait fs[v+1] >= i;      SW(i) = step(c, sw[(i-1)&1][v+1]);  -> sw[i&1][v],  fs[v] = i+1
-//   3  S(i) = step(c, S(i-1))                            (registers)
-//   4  wait fe[v-1] >= i+1;    E(i)  = step(c, e[i&1][v-1]);       -> e[i&1][v],   fe[v] = i+1
-//   5  SE(i) = step(c, se[(i-1)&3][v-1]);                          -> se[i&3][v]   (visible with fe[v] = i+2)
-//   6  total = [P16 +] SW + S + E + SE -> global
-// Slot discipline: x overwrites sw[i&1] at row i+2, which it reaches only after E(i+1, x-1), published after x-1 read
-// SW(i, x) in its row i+1; x overwrites e[i&1] at row i+2 step 4, i.e. after SW(i+1, x+1), published after x+1 read
-// E(i, x) in its row i; se[i&3] is overwritten at row i+4, three SW hand-overs later.  Row 0 needs no special case: the
-// counters start at 0, the slots it reads ((i-1)&1 = 1, (i-1)&3 = 3) are still zero = a flat state = a path start, and
-// an image border is a mailbox column whose counter is "infinity" and whose slots stay zero.
+// CTA = one strip of K <= 28 sheared columns: K compute warps (<= 64 registers: the SW state, the pixel's cost, the
+// running total), an in-relay (ring -> mailbox columns 0 / 1) and an out-relay (last two columns -> ring).  Every warp
+// stages its own inputs three rows ahead with cp.async into a private ring: in the first pass the D right census
+// descriptors of its pixel as two aligned 16-byte copies per lane (the descriptors come in four word-shifted, padded
+// copies, census.cu), in the second pass the packed costs and partial sums.  A strip-wide descriptor ring does not work
+// here: behind the image seam the columns of a strip legitimately sit up to K rows apart.
+// Hand-over events are mbarrier phases (a waiting warp sleeps in hardware instead of spinning through issue slots).
+//
+// Row program of sheared column v (mailbox column; 0 / 1 = the previous strip's last two columns), row y, pixel k:
+//   1  cost c(y);  SW(y) = step(c, SW(y-1))  [registers; flat when k = W-1]
+//   2  wait E-event(v-1, y);  load E_in = e[y&1][v-1], S_in = s[(y-1)&1][v-1], SE_in = se[(y-1)&1][v-2]
+//   3  E(y) = step(c, E_in) -> e[y&1][v], E-event(v, y), prog[v] = y+1     (slot free once prog[v+2] >= y)
+//   4  S(y), SE(y) -> s[y&1][v], se[y&1][v]   (visible to the right with the next E-event)
+//   5  total = [P16 +] SW + S + E + SE -> global
+// k = 0 (chain start, once per W rows): no wait, E_in = SE_in = flat, and steps 3 / 4 swap so that S and SE are stored
+// before the E-event: the right neighbour starts the NEXT row's chain and has no later event of ours to acquire.
 #include "sgm_packed.cuh"
 
 namespace pb200 {
 
 namespace {
 
-constexpr int W1_MAXK = 28;                 // columns (compute warps) per strip
-constexpr int W1_THREADS = (W1_MAXK + 3) * 32;   // + left relay, right relay, loader
-constexpr int W1_RING = 16;                 // descriptor rows in the loader's ring
-constexpr int W1_PF = 4;                    // descriptor rows in flight
-constexpr int W1_FLAG_WORDS = 272;          // 128 mbarriers (FE[32][2] | FS[32][2]) + the loader's two counters
+constexpr int W1_MAXK = 28;                        // sheared columns (compute warps) per strip
+constexpr int W1_THREADS = (W1_MAXK + 2) * 32;     // + in-relay, out-relay
+constexpr int W1_NRG = 8;                          // rows in flight across a strip / GPU boundary
+constexpr int W1_FLAG_WORDS = 256;                 // events E[32][2] (512 B) | RD[2][2] | prog[36] | rdc
 
-template <int NR> struct W1Cpw { static constexpr int value = W1_MAXK + 2 * NR * 32 + 4; };   // words per shifted copy of a descriptor row
+template <int NR> struct W1Geo {
+    static constexpr int VS = NR * 32;
+    static constexpr int CIN = 2 * VS + 4;                     // first pass, staged words per pixel: D right descriptors + the left one
+    static constexpr size_t BLK = (size_t)W1_NRG * 4 * VS + 16;   // 64-bit words per boundary block: data | ack
+};
 
 template <int NR>
 __device__ __forceinline__ bool ll_try_recv_u32(const unsigned long long *slot, int lane, uint32_t tag, uint32_t (&v)[NR]) {
@@ -61,45 +71,32 @@ __device__ __forceinline__ uint32_t flag_peek(uint32_t addr) {
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-// every lane stores the same counter (one shared-memory transaction, no divergent branch); the warp barrier in front
-// orders the other lanes' data stores before it
-__device__ __forceinline__ void flag_set(uint32_t addr, uint32_t v) {
+__device__ __forceinline__ void flag_set(uint32_t addr, uint32_t v) {      // release: the warp barrier orders the other lanes' stores
     __syncwarp();
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// a counter that is only read now and then (loader ring): wait without occupying the issue slots of the working warps
+// counters that are read now and then (ring rows, slot credits): wait without occupying the working warps' issue slots
 __device__ __forceinline__ void flag_wait_sleep(uint32_t addr, uint32_t target) {
-    while (flag_peek(addr) < target) __nanosleep(100);
+    while ((int)(flag_peek(addr) - target) < 0) __nanosleep(64);
 }
 
-// Hand-over events between warps are mbarrier PHASES, not spin flags: a consumer that is early is suspended by the
-// hardware (mbarrier.try_wait) instead of burning issue slots in an LDS / compare / branch loop -- in the two-column
-// kernel those loops were 44 % of all issued instructions (profiles/r1_ncu_fused_pass1.txt).  Every event stream (the E
-// hand-over of a column, its SW hand-over) owns TWO barriers used by even and odd rows in turn; row i completes phase
-// i >> 1 of barrier i & 1.  The protocol never lets a producer run two rows ahead of its consumer's wait, so a barrier
-// is at most one completed phase ahead of the phase a waiter asks for, which is what parity waits can distinguish.
+// Hand-over events are mbarrier PHASES: a consumer that is early is suspended by the hardware (mbarrier.try_wait) instead
+// of burning issue slots in an LDS / compare / branch loop (44 % of all issued instructions in the two-column kernel,
+// profiles/r1_ncu_fused_pass1.txt).  Every event stream owns TWO barriers used by even and odd rows in turn; row i
+// completes phase i >> 1 of barrier i & 1.  The slot credits (prog) never let a producer run two rows ahead of its
+// consumer's wait, so a barrier is at most one completed phase ahead of the phase a waiter asks for, which is what a
+// parity wait can tell apart.
 __device__ __forceinline__ void ev_wait(uint32_t bar, int i) {
     const uint32_t addr = bar + (uint32_t)(i & 1) * 8u, parity = (uint32_t)(i >> 1) & 1u;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "W1_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // suspend-time hint: sleep, do not poll
         "@p bra W1_DONE;\n"
         "bra W1_WAIT;\n"
         "W1_DONE:\n"
-        "}\n" ::"r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool ev_test(uint32_t bar, int i) {
-    const uint32_t addr = bar + (uint32_t)(i & 1) * 8u, parity = (uint32_t)(i >> 1) & 1u;
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
+        "}\n" ::"r"(addr), "r"(parity), "r"(1000000u) : "memory");
 }
 // one arrival (lane 0, predicated: no divergent branch) with release semantics; the warp barrier in front orders the
 // other lanes' data stores before it
@@ -119,176 +116,172 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     static_assert(!(CENSUS && FINAL), "the Census source only exists for the first pass");
     static_assert(FINAL || CENSUS, "the float-input first pass stays with sgm_wave_kernel");
     extern __shared__ __align__(16) uint32_t w1_smem[];
-    constexpr int VS = NR * 32;                          // words per packed state vector
+    using G = W1Geo<NR>;
+    constexpr int VS = G::VS;
     constexpr int RW = NR * CB / 2;                      // raw cost words per lane
-    constexpr int CPW = W1Cpw<NR>::value;
-    constexpr int CSLOT = 4 * CPW + 32;                  // words per descriptor-ring row: four shifted copies + the left descriptors
-    constexpr int NSTG = 4, PFD = 3;                     // pass 2 input staging (per warp, cp.async)
-    constexpr int SIN = RW + NR;
+    constexpr int NSTG = 4, PFD = 3;                     // input staging (per warp, cp.async): rows in the ring / in flight
+    constexpr int SIN = CENSUS ? G::CIN : 32 * (RW + NR);   // staged words per pixel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int K = p.K, NV = K + 2;
+    const int K = p.K, NVM = K + 2;                      // mailbox columns: 0 / 1 = previous strip's last two columns, 2 .. K+1 = ours
     const int strip = blockIdx.x, nstrips = gridDim.x;
-    const int H = p.H, W = p.W, D = p.D;
+    const int H = p.H, D = p.D;
+    const int Wt = p.W, Wg = p.Wg;                       // local (tile) width = storage pitch, global width of the sheared ring
     const int x0 = strip * K;
-    const int nce = min(K, W - x0);                      // columns of this strip inside the image
-    // shared: e[2][NV][VS] | se[4][NV][VS] | sw[2][NV][VS] | events FE[32][2] FS[32][2] (mbarriers) | ld, done | staging
-    const int mbox_words = 8 * NV * VS, flag_words = W1_FLAG_WORDS;
-    const int stage_words = CENSUS ? W1_RING * CSLOT : NSTG * K * 32 * SIN;
-    for (int i = threadIdx.x; i < mbox_words + flag_words + stage_words; i += blockDim.x) w1_smem[i] = 0u;
+    const int nce = min(K, Wt - x0);                     // sheared columns of this strip
+    // shared: e[2][NVM][VS] | s[2][NVM][VS] | se[2][NVM][VS] | events, counters | staging
+    const int mbox_words = 6 * NVM * VS;
+    const int stage_words = NSTG * K * SIN;
+    for (int i = threadIdx.x; i < mbox_words + W1_FLAG_WORDS + stage_words; i += blockDim.x) w1_smem[i] = 0u;
     __syncthreads();
-    const bool has_left = strip > 0 || p.peer_in_l != nullptr;
-    const bool has_right = strip + 1 < nstrips || p.peer_in_r != nullptr;
-    if (threadIdx.x < 128)                                                       // FE[32][2] | FS[32][2], one arrival per phase
+    if (threadIdx.x < 68)                                                        // E[32][2] | RD[2][2], one arrival per phase
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(w1_smem + mbox_words) + threadIdx.x * 8u) : "memory");
     __syncthreads();
     const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
-    const uint32_t VB = (uint32_t)VS * 4u, SLOTB = (uint32_t)(NV * VS) * 4u;      // bytes per vector / per mailbox slot
+    const uint32_t VB = (uint32_t)VS * 4u, SLOTB = (uint32_t)(NVM * VS) * 4u;     // bytes per vector / per mailbox slot
     const uint32_t e_base = smem_u32(w1_smem) + lane_b;
-    const uint32_t se_base = e_base + 2u * SLOTB;
-    const uint32_t sw_base = se_base + 4u * SLOTB;
-    const uint32_t fe_base = smem_u32(w1_smem) + (uint32_t)mbox_words * 4u, fs_base = fe_base + 512u;   // event v: base + 16 v
-    const uint32_t ld_flag = fe_base + 1024u, done_flag = fe_base + 1028u;
-    const uint32_t stg_base0 = fe_base + (uint32_t)flag_words * 4u;
+    const uint32_t s_base = e_base + 2u * SLOTB;
+    const uint32_t se_base = s_base + 2u * SLOTB;
+    const uint32_t ev_base = smem_u32(w1_smem) + (uint32_t)mbox_words * 4u;       // E-event of mailbox column v: ev_base + 16 v
+    const uint32_t rd_base = ev_base + 512u;                                      // RD-event of the last (0) / second-to-last (1) column
+    const uint32_t prog_base = ev_base + 544u;                                    // prog[v], v = 0 .. K+3 (K+2 / K+3 = the out-relay)
+    const uint32_t rdc_flag = ev_base + 704u;
+    const uint32_t stg_base0 = ev_base + (uint32_t)W1_FLAG_WORDS * 4u;
     const uint32_t tag0 = p.tag_base;
+    const uint32_t v_last = (uint32_t)(nce + 1), v_prev = (uint32_t)nce;          // mailbox columns of this strip's last two sheared columns
 
-    // ---- relay warps: mailbox <-> ring (the local L2 ring between strips, or a neighbouring GPU's memory at a tile edge).
-    // Ring block of a boundary: 12 vectors of VS 64-bit {tag, value} words: e[4] | se[4] | sw[4].
-    if (warp == K) {                                      // left relay: E / SE in, SW out
-        if (!has_left) return;
-        const unsigned long long *rin = strip > 0 ? p.ring + (size_t)(strip - 1) * 12 * VS : p.peer_in_l;
-        unsigned long long *rout = strip > 0 ? p.ring + (size_t)(strip - 1) * 12 * VS : p.peer_out_l;
-        int oi = 0, ii = 0;
-        while (oi < H || ii < H) {
+    // ---- in-relay: the left boundary's ring block -> mailbox columns 1 (E, S, SE of the previous column) and 0 (its left
+    // neighbour's SE).  Block: W1_NRG rows x {E, S, SE, SE2} vectors of VS 64-bit {tag, value} words, then the ack word.
+    if (warp == K) {
+        const bool peer = strip == 0 && p.peer_in_l != nullptr;
+        const size_t bl = (size_t)(strip == 0 ? nstrips - 1 : strip - 1) * G::BLK;
+        const unsigned long long *rin = peer ? p.peer_in_l : p.ring + bl;
+        unsigned long long *ack = peer ? p.peer_out_l : p.ring + bl + (size_t)W1_NRG * 4 * VS;
+        for (int y = 0; y < H; ++y) {
             uint32_t v[NR];
-            if (oi < H && ev_test(fs_base + 16u, oi)) {                          // SW(oi) of the first column
-                lds_words<NR>(sw_base + (uint32_t)(oi & 1) * SLOTB + VB, v);
-                ll_send_u32<NR>(rout + (size_t)(8 + (oi & 3)) * VS, lane, tag0 + (uint32_t)(oi + 1), v);
-                ++oi;
+            if (y >= 1) flag_wait_sleep(prog_base + 3u * 4u, (uint32_t)(y - 1));     // columns 2 / 3 have loaded their inputs of row y - 2
+            if (y > 0) {                                  // B(y-1): S, SE of the previous column and SE of the one before, row y - 1
+                const unsigned long long *src = rin + (size_t)((y - 1) & (W1_NRG - 1)) * 4 * VS;
+                const uint32_t pb = (uint32_t)((y - 1) & 1) * SLOTB;
+                while (!ll_try_recv_u32<NR>(src + 1 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                sts_words<NR>(s_base + pb + VB, v);
+                while (!ll_try_recv_u32<NR>(src + 2 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                sts_words<NR>(se_base + pb + VB, v);
+                flag_set(rdc_flag, (uint32_t)y);          // the chain start of row y (column 2 when its k = 0) waits for this
+                // SE of the column before the previous one: when that column closed the chain of row y - 1 it arrives a whole
+                // traversal later -- nobody needs it before E(y), which it always precedes
+                while (!ll_try_recv_u32<NR>(src + 3 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                sts_words<NR>(se_base + pb, v);
             }
-            if (ii < H && ll_try_recv_u32<NR>(rin + (size_t)(ii & 3) * VS, lane, tag0 + (uint32_t)(ii + 1), v)) {   // E(ii)
-                uint32_t u[NR];
-                if (ii > 0) {                             // SE(ii - 1) was sent before E(ii): one more poll at most
-                    while (!ll_try_recv_u32<NR>(rin + (size_t)(4 + ((ii - 1) & 3)) * VS, lane, tag0 + (uint32_t)ii, u)) {}
-                    sts_words<NR>(se_base + (uint32_t)((ii - 1) & 3) * SLOTB, u);
-                }
-                sts_words<NR>(e_base + (uint32_t)(ii & 1) * SLOTB, v);
-                ev_signal(fe_base, ii, lane);
-                ++ii;
-            }
+            const unsigned long long *src = rin + (size_t)(y & (W1_NRG - 1)) * 4 * VS;
+            while (!ll_try_recv_u32<NR>(src, lane, tag0 + (uint32_t)(y + 1), v)) {}      // A(y): E of the previous column
+            sts_words<NR>(e_base + (uint32_t)(y & 1) * SLOTB + VB, v);
+            ev_signal(ev_base + 16u, y, lane);
+            if (lane == 0) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(ack), "l"((unsigned long long)(tag0 + (uint32_t)(y + 1))) : "memory");
         }
         return;
     }
-    if (warp == K + 1) {                                  // right relay: E / SE out, SW in
-        if (!has_right) return;
-        unsigned long long *rout = strip + 1 < nstrips ? p.ring + (size_t)strip * 12 * VS : p.peer_out_r;
-        const unsigned long long *rin = strip + 1 < nstrips ? p.ring + (size_t)strip * 12 * VS : p.peer_in_r;
-        const uint32_t vc = (uint32_t)nce;                // mailbox column of the last image column of this strip
-        int oi = 0, ii = 0;
-        while (oi < H || ii < H) {
+    // ---- out-relay: this strip's last two columns -> the right boundary's ring block (the next strip's, or the next GPU's)
+    if (warp == K + 1) {
+        const bool peer = strip + 1 == nstrips && p.peer_out_r != nullptr;
+        const size_t br = (size_t)strip * G::BLK;
+        unsigned long long *rout = peer ? p.peer_out_r : p.ring + br;
+        const unsigned long long *ack = peer ? p.peer_in_r : p.ring + br + (size_t)W1_NRG * 4 * VS;
+        uint32_t acked = tag0;                            // rows the receiver has consumed (tag space)
+        for (int y = 0; y < H; ++y) {
             uint32_t v[NR];
-            if (oi < H && ev_test(fe_base + vc * 16u, oi)) {                     // E(oi) is out, and with it SE(oi - 1)
-                if (oi > 0) {
-                    lds_words<NR>(se_base + (uint32_t)((oi - 1) & 3) * SLOTB + vc * VB, v);
-                    ll_send_u32<NR>(rout + (size_t)(4 + ((oi - 1) & 3)) * VS, lane, tag0 + (uint32_t)oi, v);
+            if (y >= W1_NRG) {                            // ring credit: row y - NRG has left the block
+                const uint32_t need = tag0 + (uint32_t)(y - W1_NRG + 1);
+                while ((int)(acked - need) < 0) {
+                    const uint32_t a = (uint32_t)ll_load(ack);
+                    if ((int)(a - tag0) >= 0 && (int)(a - tag0) <= H) acked = a;     // words of an older epoch are not credits
+                    if ((int)(acked - need) < 0) __nanosleep(200);
                 }
-                lds_words<NR>(e_base + (uint32_t)(oi & 1) * SLOTB + vc * VB, v);
-                ll_send_u32<NR>(rout + (size_t)(oi & 3) * VS, lane, tag0 + (uint32_t)(oi + 1), v);
-                ++oi;
             }
-            if (ii < H && ll_try_recv_u32<NR>(rin + (size_t)(8 + (ii & 3)) * VS, lane, tag0 + (uint32_t)(ii + 1), v)) {   // SW(ii)
-                sts_words<NR>(sw_base + (uint32_t)(ii & 1) * SLOTB + (vc + 1u) * VB, v);
-                ev_signal(fs_base + (vc + 1u) * 16u, ii, lane);
-                ++ii;
+            if (y > 0) {
+                // S, SE of the last column as soon as IT has finished row y - 1: the next strip's first column may be the
+                // start of chain y and then needs nothing else.  The SE of the column before it follows when that column has
+                // finished -- a whole traversal later when it closed chain y - 1 -- and always before E(y).
+                unsigned long long *dst = rout + (size_t)((y - 1) & (W1_NRG - 1)) * 4 * VS;
+                const uint32_t pb = (uint32_t)((y - 1) & 1) * SLOTB;
+                ev_wait(rd_base, y - 1);
+                lds_words<NR>(s_base + pb + v_last * VB, v);
+                ll_send_u32<NR>(dst + 1 * VS, lane, tag0 + (uint32_t)y, v);
+                lds_words<NR>(se_base + pb + v_last * VB, v);
+                ll_send_u32<NR>(dst + 2 * VS, lane, tag0 + (uint32_t)y, v);
+                if (nce >= 2) ev_wait(rd_base + 16u, y - 1);
+                lds_words<NR>(se_base + pb + v_prev * VB, v);
+                ll_send_u32<NR>(dst + 3 * VS, lane, tag0 + (uint32_t)y, v);
             }
+            ev_wait(ev_base + v_last * 16u, y);           // A(y)
+            lds_words<NR>(e_base + (uint32_t)(y & 1) * SLOTB + v_last * VB, v);
+            ll_send_u32<NR>(rout + (size_t)(y & (W1_NRG - 1)) * 4 * VS, lane, tag0 + (uint32_t)(y + 1), v);
+            __syncwarp();
+            if (lane < 2) sts_u32(prog_base + (v_last + 1u + (uint32_t)lane) * 4u, (uint32_t)(y + 1));   // slot credits of the last two columns
         }
         return;
     }
-    // ---- loader warp (first pass): descriptor rows of the strip, once per CTA row ----------------------------------------
-    // Row r of the ring holds, for s = 0..3, copy_s[m] = right descriptor of column c0 + s + m (c0 = strip start + dmin
-    // rounded down to a multiple of 4), and the K left descriptors.  Column x reads its window from the copy whose shift
-    // makes x + dmin - c0 - s a multiple of 4: aligned vectors for every column.  Positions outside the descriptor row are
-    // the same for every row: filled once with the "window leaves the image" flag, never copied.
-    if (warp == K + 2) {
-        if (!CENSUS) return;
-        const int c0 = (x0 + p.dmin) & ~3;
-        for (int sl = 0; sl < W1_RING; ++sl)
-            for (int idx = lane; idx < CSLOT; idx += 32) {
-                const int col = idx < 4 * CPW ? c0 + idx / CPW + idx % CPW : x0 + (idx - 4 * CPW);
-                if (!((unsigned)col < (unsigned)p.pitch)) sts_u32(stg_base0 + (uint32_t)(sl * CSLOT + idx) * 4u, 0x80000000u);
-            }
-        __syncwarp();
-        for (int r = 0; r < H; ++r) {
-            if (r >= W1_RING) flag_wait_sleep(done_flag, (uint32_t)(r - W1_RING + 1));   // every column is past row r - RING
-            const uint32_t dst = stg_base0 + (uint32_t)((r & (W1_RING - 1)) * CSLOT) * 4u;
-            const uint32_t *rowR = p.descR + (size_t)r * p.pitch, *rowL = p.descL + (size_t)r * p.pitch;
-#pragma unroll 4
-            for (int idx = lane; idx < 4 * CPW; idx += 32) {
-                const int col = c0 + idx / CPW + idx % CPW;
-                if ((unsigned)col < (unsigned)p.pitch) cp_async_words<1>(dst + (uint32_t)idx * 4u, rowR + col);
-            }
-            if (lane < K && (unsigned)(x0 + lane) < (unsigned)p.pitch) cp_async_words<1>(dst + (uint32_t)(4 * CPW + lane) * 4u, rowL + x0 + lane);
-            cp_async_commit();
-            if (r >= W1_PF) {
-                cp_async_wait<W1_PF>();
-                flag_set(ld_flag, (uint32_t)(r - W1_PF + 1));
-            }
-        }
-        cp_async_wait<0>();
-        flag_set(ld_flag, (uint32_t)H);
-        return;
-    }
-
-    // ---- compute warps: one column each ---------------------------------------------------------------------------------
+    // ---- compute warps: one sheared column each -----------------------------------------------------------------------------
     if (warp >= nce) return;
-    const uint32_t vme = (uint32_t)(warp + 1);            // this column's mailbox column
-    const int xl = x0 + warp;                             // logical column (pass 2: the frame is flipped in both axes)
-    const int y0 = FINAL ? H - 1 : 0;
-    const long row_stride = (FINAL ? -1L : 1L) * W * D;   // words (== floats)
-    uint32_t *gpix = p.buf + ((size_t)y0 * W + (FINAL ? W - 1 - xl : xl)) * D;
+    const uint32_t vme = (uint32_t)(warp + 2);            // this column's mailbox column
+    int k = (p.c_off + x0 + warp) % Wg;                   // image column (travel frame) of this sheared column in row 0
     const int poff = p16_off<CB>(D) + lane * NR;
-    size_t pixi = (size_t)y0 * W + (FINAL ? W - 1 - xl : xl);
     const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
-    // first pass: where this column's window starts inside the descriptor ring rows
-    const int cen_off = (xl + p.dmin) - ((x0 + p.dmin) & ~3);
-    const uint32_t cen_win = stg_base0 + (uint32_t)((cen_off & 3) * CPW + (cen_off & ~3)) * 4u + lane_b;
-    const uint32_t cen_left = stg_base0 + (uint32_t)(4 * CPW + warp) * 4u;
-    // second pass: private staging ring [NSTG][K][32 * SIN], a pixel's block = [32][RW] cost words | [32][NR] partial sums
-    const uint32_t stg_pix = (uint32_t)(32 * SIN) * 4u, stg_stage = (uint32_t)K * stg_pix;
+    const bool is_last = warp + 1 == nce, is_prev = warp + 2 == nce;
+    // storage: by image coordinates (one GPU: the (H, W, D) volume of the C-ABI) or by sheared column (a tile of a multi-GPU run)
+    auto pixel = [&](int y, int kk) -> size_t {
+        const int yi = FINAL ? H - 1 - y : y;
+        const int col = p.sheared_store ? (FINAL ? Wt - 1 - (x0 + warp) : x0 + warp) : (FINAL ? Wg - 1 - kk : kk);
+        return (size_t)yi * Wt + col;
+    };
+    // private staging ring [NSTG][K][SIN].  First pass: a pixel's block = its D right descriptors (lane-major) | the left one;
+    // second pass: [32][RW] cost words | [32][NR] partial sums.
+    const uint32_t stg_pix = (uint32_t)SIN * 4u, stg_stage = (uint32_t)K * stg_pix;
     const uint32_t stg_me = stg_base0 + (uint32_t)warp * stg_pix;
     const uint32_t off0 = (uint32_t)(lane * RW) * 4u, off1 = (uint32_t)(32 * RW + lane * NR) * 4u;
+    int kpf = k;                                          // image column of the row being prefetched
     auto stage_row = [&](int r) {
-        if (!FINAL || r >= H) return;
-        const uint32_t sg = stg_me + (uint32_t)(r & (NSTG - 1)) * stg_stage;
-        const uint32_t *src = gpix + (long)r * row_stride;
-        cp_async_words<RW>(sg + off0, src + lane * RW);
-        cp_async_words<NR>(sg + off1, src + poff);
-    };
-    if (FINAL) {
-        for (int r = 0; r < PFD; ++r) {
-            stage_row(r);
-            cp_async_commit();
+        if (r < H) {
+            const uint32_t sg = stg_me + (uint32_t)(r & (NSTG - 1)) * stg_stage;
+            if (CENSUS) {
+                // the window [kpf + dmin, kpf + dmin + D) starts 16-byte aligned in the copy whose shift is (kpf + dmin) & 3
+                const int ws = kpf + p.dmin, sh = ws & 3;
+                const uint32_t *src = p.descR4 + ((size_t)sh * H + r) * p.pitch4 + (ws - sh + p.padl) + lane * NR;
+                cp_async_words<NR>(sg + lane_b, src);
+                cp_async_words<NR>(sg + VB + lane_b, src + VS);
+                if (lane == 0) cp_async_words<1>(sg + 2u * VB, p.descL + (size_t)r * p.pitch + kpf);
+            } else {
+                const uint32_t *src = p.buf + pixel(r, kpf) * D;
+                cp_async_words<RW>(sg + off0, src + lane * RW);
+                cp_async_words<NR>(sg + off1, src + poff);
+            }
         }
+        kpf = kpf == 0 ? Wg - 1 : kpf - 1;
+    };
+    for (int r = 0; r < PFD; ++r) {
+        stage_row(r);
+        cp_async_commit();
     }
-    uint32_t Sv[NR];
+    uint32_t SW[NR];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) Sv[j] = 0u;
+    for (int j = 0; j < NR; ++j) SW[j] = 0u;
     const uint32_t nan2 = (p.inv | Tier<CB>::FLAG1) * 0x10001u;
-    // an image border is a neighbour that never has to be waited for (its mailbox slots stay zero: flat states = path starts)
-    const bool wait_l = has_left || warp > 0, wait_r = has_right || warp + 1 < nce, last_col = warp + 1 == nce;
 
 #pragma unroll 1
-    for (int i = 0; i < H; ++i) {
-        const uint32_t par = (uint32_t)(i & 1) * SLOTB, q = (uint32_t)(i & 3) * SLOTB, qm = (uint32_t)((i - 1) & 3) * SLOTB;
-        uint32_t *grow = gpix + (long)i * row_stride;
-        // ---- 1: the pixel's cost codes (16 bits each, NaN flag in bit 15 / 7) and the partial sums so far ----------------
+    for (int y = 0; y < H; ++y) {
+        const uint32_t par = (uint32_t)(y & 1) * SLOTB, prv = SLOTB - par;
+        uint32_t *grow = p.buf + pixel(y, k) * D;
+        // ---- the pixel's cost codes (16 bits each, NaN flag in bit 15 / 7) and the partial sums so far -------------------------
         uint32_t c16[NR], cc[NR], tot[NR];
+        stage_row(y + PFD);
+        cp_async_commit();
+        cp_async_wait<PFD>();                              // this lane's copies of row y have landed
+        const uint32_t sg = stg_me + (uint32_t)(y & (NSTG - 1)) * stg_stage;
         if (CENSUS) {
-            flag_wait_sleep(ld_flag, (uint32_t)(i + 1));
-            const uint32_t cg = (uint32_t)((i & (W1_RING - 1)) * CSLOT) * 4u;
+            __syncwarp();                                  // the left descriptor was copied by lane 0
             uint32_t lw[1], ra[NR], rb[NR];
-            lds_words<1>(cen_left + cg, lw);
-            lds_words<NR>(cen_win + cg, ra);
-            lds_words<NR>(cen_win + cg + VB, rb);
+            lds_words<1>(sg + 2u * VB, lw);
+            lds_words<NR>(sg + lane_b, ra);
+            lds_words<NR>(sg + VB + lane_b, rb);
             if (lw[0] >> 31) {                            // warp-uniform: the left window leaves the image
 #pragma unroll
                 for (int j = 0; j < NR; ++j) c16[j] = nan2;
@@ -306,10 +299,6 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] = 0u;
         } else {
-            stage_row(i + PFD);
-            cp_async_commit();
-            cp_async_wait<PFD>();                          // this lane's copies of row i have landed
-            const uint32_t sg = stg_me + (uint32_t)(i & (NSTG - 1)) * stg_stage;
             uint32_t craw[RW];
             lds_words<RW>(sg + off0, craw);
             lds_words<NR>(sg + off1, tot);
@@ -318,35 +307,63 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 #pragma unroll
         for (int j = 0; j < NR; ++j) cc[j] = c16[j] & Tier<CB>::VALUES;
 
-        uint32_t Lp[NR], L[NR];
-        // ---- 2: SW, from the right neighbour's state of the previous row; published first (it travels against the wave) ----
-        if (i > 0 && wait_r) ev_wait(fs_base + (vme + 1u) * 16u, i - 1);
-        lds_words<NR>(sw_base + (SLOTB - par) + (vme + 1u) * VB, Lp);
-        nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
-        sts_words<NR>(sw_base + par + vme * VB, L);
-        ev_signal(fs_base + vme * 16u, i, lane);
+        uint32_t Lp[NR], Lq[NR], L[NR];
+        // ---- SW: this column's own state of the previous row (the pixel up-right); a path start at the right image border --------
+        if (k == Wg - 1) {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) tot[j] += L[j];
-        // ---- 3: S, registers only -------------------------------------------------------------------------------------------
-        nstep<NR>(cc, Sv, L, lane, p1p1, p2p2);
+            for (int j = 0; j < NR; ++j) SW[j] = 0u;
+        }
+        nstep<NR>(cc, SW, L, lane, p1p1, p2p2);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { Sv[j] = L[j]; tot[j] += L[j]; }
-        // ---- 4: the E chain: wait, one step, publish -----------------------------------------------------------------------
-        if (wait_l) ev_wait(fe_base + (vme - 1u) * 16u, i);
-        lds_words<NR>(e_base + par + (vme - 1u) * VB, Lp);
-        nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
-        sts_words<NR>(e_base + par + vme * VB, L);
-        ev_signal(fe_base + vme * 16u, i, lane);
-        if (CENSUS && last_col) sts_u32(done_flag, (uint32_t)(i + 1));            // the loader may reuse the ring row of i + 1 - RING
+        for (int j = 0; j < NR; ++j) { SW[j] = L[j]; tot[j] += L[j]; }
+        // slot credit: e / s / se[y & 1] of this column still hold row y - 2 until column v + 2 has loaded its inputs of row y - 1
+        flag_wait_sleep(prog_base + (vme + 2u) * 4u, (uint32_t)y);
+        if (k != 0) {
+            // ---- the E chain: wait for the left neighbour, one step, publish; S and SE behind it -----------------------------------
+            ev_wait(ev_base + (vme - 1u) * 16u, y);
+            lds_words<NR>(e_base + par + (vme - 1u) * VB, Lp);
+            lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
+            nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
+            sts_words<NR>(e_base + par + vme * VB, L);
+            ev_signal(ev_base + vme * 16u, y, lane);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) tot[j] += L[j];
-        // ---- 5: SE (the left neighbour's SE of the previous row became visible with its E flag of this row) ----------------
-        lds_words<NR>(se_base + qm + (vme - 1u) * VB, Lp);
-        nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
-        sts_words<NR>(se_base + q + vme * VB, L);
+            for (int j = 0; j < NR; ++j) tot[j] += L[j];
+            lds_words<NR>(se_base + prv + (vme - 2u) * VB, Lp);
+            nstep<NR>(cc, Lq, L, lane, p1p1, p2p2);                       // S
+            sts_words<NR>(s_base + par + vme * VB, L);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) tot[j] += L[j];
-        // ---- 6: out --------------------------------------------------------------------------------------------------------
+            for (int j = 0; j < NR; ++j) tot[j] += L[j];
+            nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);                       // SE
+            sts_words<NR>(se_base + par + vme * VB, L);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tot[j] += L[j];
+        } else {
+            // ---- chain start (left image border): E and SE are path starts, S comes from the left neighbour's previous row, which
+            // that neighbour finished as a chain start itself; everything is stored BEFORE the E-event (see the file header) ---------
+            if (y > 0) {
+                if (vme == 2u) flag_wait_sleep(rdc_flag, (uint32_t)y);    // across the strip boundary: the in-relay has delivered row y - 1
+                lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Lq[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) Lp[j] = 0u;
+            nstep<NR>(cc, Lq, L, lane, p1p1, p2p2);                       // S
+            sts_words<NR>(s_base + par + vme * VB, L);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tot[j] += L[j];
+            nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);                       // E = SE = a path start: c itself
+            sts_words<NR>(se_base + par + vme * VB, L);
+            sts_words<NR>(e_base + par + vme * VB, L);
+            ev_signal(ev_base + vme * 16u, y, lane);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tot[j] += 2u * L[j];
+        }
+        sts_u32(prog_base + vme * 4u, (uint32_t)(y + 1));                 // inputs of row y are in registers: credit for column v - 2
+        if (is_last) ev_signal(rd_base, y, lane);                          // the out-relay forwards S / SE of row y
+        if (is_prev) ev_signal(rd_base + 16u, y, lane);
+        // ---- out ------------------------------------------------------------------------------------------------------------------
         if (!FINAL) {
             st_words<NR>(grow + poff, tot);
         } else {
@@ -377,27 +394,31 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
                 uint32_t best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
                 best = __reduce_min_sync(0xffffffffu, best);
                 if (lane == 0) {
-                    const size_t pix = pixi - (size_t)i * W;
+                    const size_t pix = pixel(y, k);
                     const bool none = (best >> 16) >= ((CB == 1) ? 0xFF80u : 0xFFFFu);
                     p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
                     if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
                 }
             }
         }
+        k = k == 0 ? Wg - 1 : k - 1;
     }
 }
 
 template <int NR, int CB>
-int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, cudaStream_t s, bool *done) {
+int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, size_t ring_room, const Wave1Peers *peers, cudaStream_t s, bool *done) {
     *done = false;
+    using G = W1Geo<NR>;
     const bool wta = p.disp != nullptr;
     void (*w1)(const NarrowParams) = sgm_wave1_kernel<NR, CB, false, false, true>;
     void (*w2)(const NarrowParams) = wta ? sgm_wave1_kernel<NR, CB, true, true, false> : sgm_wave1_kernel<NR, CB, true, false, false>;
-    const int threads = (K + 3) * 32;
-    const size_t fixed = ((size_t)8 * (K + 2) * NR * 32 + W1_FLAG_WORDS) * sizeof(uint32_t);
-    const size_t smem1 = fixed + (size_t)W1_RING * (4 * W1Cpw<NR>::value + 32) * sizeof(uint32_t);
+    const int threads = (K + 2) * 32;
+    const size_t fixed = ((size_t)6 * (K + 2) * NR * 32 + W1_FLAG_WORDS) * sizeof(uint32_t);
+    const size_t smem1 = fixed + (size_t)4 * K * G::CIN * sizeof(uint32_t);
     const size_t smem2 = fixed + (size_t)4 * K * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
     if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return PB200_OK;
+    const size_t wring = (size_t)nstrips * G::BLK * sizeof(unsigned long long);
+    if (wring > ring_room) return PB200_OK;                                      // the boundary blocks must end before the flag
     int occ1 = 0, occ2 = 0;
     PB200_CUDA(cudaFuncSetAttribute((const void *)w1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     PB200_CUDA(cudaFuncSetAttribute((const void *)w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -407,22 +428,22 @@ int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, cudaStream
     if ((long)occ1 * nsm < nstrips || (long)occ2 * nsm < nstrips) return PB200_OK;       // every strip must be resident
     p.K = K;
     p.ring = reinterpret_cast<unsigned long long *>(workspace);
-    const size_t wring = (size_t)nstrips * 12 * NR * 32 * sizeof(unsigned long long);
-    if ((size_t)(reinterpret_cast<char *>(p.flag) - reinterpret_cast<char *>(workspace)) < wring) return PB200_OK;   // ring must end before the flag
-    void *args[] = {(void *)&p};
+    NarrowParams q1 = p, q2 = p;
+    if (peers != nullptr) {
+        // edge buffers of a column-tiled multi-GPU run: pass 1 travels left -> right, pass 2 (flipped frame) right -> left
+        q1.peer_in_l = peers->in[0]; q1.peer_out_l = peers->ack_out[0]; q1.peer_out_r = peers->out[0]; q1.peer_in_r = peers->ack_in[0];
+        q2.peer_in_l = peers->in[1]; q2.peer_out_l = peers->ack_out[1]; q2.peer_out_r = peers->out[1]; q2.peer_in_r = peers->ack_in[1];
+        q1.tag_base = q2.tag_base = peers->epoch << 16;
+        q1.c_off = peers->c_off[0]; q2.c_off = peers->c_off[1];
+        q1.Wg = q2.Wg = peers->Wg;
+        q1.sheared_store = q2.sheared_store = 1;
+    }
+    void *args1[] = {(void *)&q1}, *args2[] = {(void *)&q2};
     PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
     PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(threads), args, smem1, s));
+    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(threads), args1, smem1, s));
     PB200_LAUNCH_CHECK("sgm_wave1_kernel<down, census>");
     PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-    // pass 2 runs on the flipped frame: its logical left is the physical right
-    NarrowParams p2 = p;
-    p2.peer_in_l = p.peer_in_r; p2.peer_out_l = p.peer_out_r; p2.peer_in_r = p.peer_in_l; p2.peer_out_r = p.peer_out_l;
-    if (p2.peer_in_l) p2.peer_in_l += 12 * NR * 32;       // second block of every edge buffer = pass 2
-    if (p2.peer_out_l) p2.peer_out_l += 12 * NR * 32;
-    if (p2.peer_in_r) p2.peer_in_r += 12 * NR * 32;
-    if (p2.peer_out_r) p2.peer_out_r += 12 * NR * 32;
-    void *args2[] = {(void *)&p2};
     PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(threads), args2, smem2, s));
     PB200_LAUNCH_CHECK("sgm_wave1_kernel<up>");
     note_path(STAGE_SGM, PATH_SGM_WAVE1_CENSUS, NR * 10 + CB);
@@ -432,18 +453,36 @@ int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, cudaStream
 
 }  // namespace
 
-// One-column wavefront for the fused Census -> SGM stage.  `peer` (optional): the four edge buffers of a column-tiled
-// multi-GPU run in the order {in_left, out_left, in_right, out_right} (physical sides) and the epoch of this call.
-int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace, cudaStream_t s, bool *done) {
-    *done = false;
-    const int nsm = sm_count();
-    int K = ceil_div(p.W, nsm);
+size_t sgm_wave1_ring_bytes(int W, int D) {     // boundary blocks of one GPU's strips (at most one strip per 4 columns)
+    const int NR = (D + 63) / 64;
+    return ((size_t)(W + 3) / 4 + 1) * ((size_t)W1_NRG * 4 * NR * 32 + 16) * sizeof(unsigned long long);
+}
+size_t sgm_wave1_edge_bytes(int D) {            // one edge buffer of a column-tiled run: a boundary block (data | ack)
+    const int NR = (D + 63) / 64;
+    return ((size_t)W1_NRG * 4 * NR * 32 + 16) * sizeof(unsigned long long);
+}
+
+int sgm_wave1_strip_width(int W) {              // columns per strip, or 0 when one co-resident wave cannot hold the image
+    int K = ceil_div(W, sm_count());
     if (K < 4) K = 4;
-    if (K > W1_MAXK) return PB200_OK;
+    while (K <= W1_MAXK && W > 1 && W % K == 1) ++K;         // a strip's out-relay forwards its last TWO columns
+    return K <= W1_MAXK ? K : 0;
+}
+
+// Skewed one-column wavefront for the fused Census -> SGM stage.  p.W = columns of this GPU's tile (= the image width on
+// one GPU); `peers` (optional) = the edge buffers, ring geometry and epoch of a column-tiled multi-GPU run.
+int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace, size_t ring_room, const Wave1Peers *peers, cudaStream_t s,
+                            bool *done) {
+    *done = false;
+    const int K = sgm_wave1_strip_width(p.W);
+    if (K == 0 || p.descR4 == nullptr) return PB200_OK;
     const int nstrips = ceil_div(p.W, K);
-    if (NR == 4) return bytes ? launch_wave1<4, 1>(p, K, nstrips, workspace, s, done) : launch_wave1<4, 2>(p, K, nstrips, workspace, s, done);
-    if (NR == 2) return bytes ? launch_wave1<2, 1>(p, K, nstrips, workspace, s, done) : launch_wave1<2, 2>(p, K, nstrips, workspace, s, done);
-    return launch_wave1<1, 2>(p, K, nstrips, workspace, s, done);
+    if (peers == nullptr) { p.Wg = p.W; p.c_off = 0; p.sheared_store = 0; p.tag_base = 0; }
+    if (NR == 4) return bytes ? launch_wave1<4, 1>(p, K, nstrips, workspace, ring_room, peers, s, done)
+                              : launch_wave1<4, 2>(p, K, nstrips, workspace, ring_room, peers, s, done);
+    if (NR == 2) return bytes ? launch_wave1<2, 1>(p, K, nstrips, workspace, ring_room, peers, s, done)
+                              : launch_wave1<2, 2>(p, K, nstrips, workspace, ring_room, peers, s, done);
+    return launch_wave1<1, 2>(p, K, nstrips, workspace, ring_room, peers, s, done);
 }
 
 }  // namespace pb200

@@ -88,6 +88,20 @@ class Engine:
             _native.check(self.lib.pb200_census_descriptors_rows(_ptr(left), _ptr(right), H, W, window, _ptr(ws), ws.numel(), int(r0), int(r1),
                                                                  self._stream()))
 
+    def census_sgm_descriptors(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int, p1: float, p2: float) -> bool:
+        """The census descriptors of both images in the layout ``census_sgm(..., descriptors_ready=True)`` will read for the
+        same arguments (``pb200_census_sgm_descriptors``).  False when the configuration is not eligible for the fused stage."""
+        import ctypes  # noqa: PLC0415
+
+        H, W = self._hw(left)
+        D = dmax - dmin + 1
+        ws = self._workspace("census", self.lib.pb200_census_sgm_workspace_bytes(H, W, window, dmin, D))
+        ok = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_sgm_descriptors(_ptr(left), _ptr(right), H, W, window, dmin, D, float(p1), float(p2), _ptr(ws),
+                                                                ws.numel(), ctypes.addressof(ok), self._stream()))
+        return bool(ok.value)
+
     def census_sgm(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int, p1: float, p2: float,
                    overcounting: bool = False, out: Optional[torch.Tensor] = None, fuse_wta: bool = True, invalid_disparity: float = -9999.0,
                    disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, descriptors_ready: bool = False):
@@ -102,7 +116,7 @@ class Engine:
         if fuse_wta and disp is None:
             disp = self.empty((H, W))
             flags = self.empty((H, W), torch.uint8)
-        cws = self._workspace("census", self.lib.pb200_census_workspace_bytes(H, W, window))
+        cws = self._workspace("census", self.lib.pb200_census_sgm_workspace_bytes(H, W, window, dmin, D))
         sws = self._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, W, D))
         ran = ctypes.c_int(0)
         with torch.cuda.device(self.device):

@@ -21,6 +21,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import numpy as np
+
 DIR_NAMES = ("E", "W", "S", "SE", "SW", "N", "NE", "NW")
 HORIZONTAL, DOWN, UP = (0, 1), (2, 3, 4), (5, 6, 7)
 
@@ -221,3 +223,148 @@ class TiledStereoPipeline:
                                    self.flags, self.dmin, self.invalid_disparity)
         run_tiled_sgm(backend, self.rank, self.world, self.dist, self.pg_down, self.pg_up)
         return self.disp
+
+
+# ====================================================================================================================
+# Column tiles: the skewed wavefront as ONE wave across all GPUs (pb200_census_sgm_tile)
+# ====================================================================================================================
+def sheared_owner(Wg: int, Wt: int, tile: int, H: int):
+    """Index maps that un-shear image tile ``tile``: pixel (y, j) of the tile -- image column tile * Wt + j -- lives in the
+    sheared tile of rank ``owner[y, j]`` at column ``col[y, j]`` (sheared column = (image column + row) mod Wg)."""
+    y = np.arange(H, dtype=np.int64)[:, None]
+    t = (tile * Wt + np.arange(Wt, dtype=np.int64)[None, :] + y) % Wg
+    return t // Wt, t % Wt
+
+
+def unshear_gathered(gathered, Wg: int, tile: int):
+    """``gathered``: (ntiles, H, Wt[, ...]) sheared tiles of every rank (numpy or torch) -> image tile ``tile`` (H, Wt[, ...])."""
+    ntiles, H, Wt = gathered.shape[:3]
+    owner, col = sheared_owner(Wg, Wt, tile, H)
+    rows = np.broadcast_to(np.arange(H)[:, None], owner.shape)
+    if isinstance(gathered, np.ndarray):
+        return gathered[owner, rows, col]
+    import torch  # noqa: PLC0415
+
+    dev = gathered.device
+    return gathered[torch.from_numpy(owner).to(dev), torch.from_numpy(np.ascontiguousarray(rows)).to(dev), torch.from_numpy(col).to(dev)]
+
+
+class TileLinks:
+    """This rank's link buffer (peer-visible device memory, ``pb200_ipc_alloc``) and the two neighbours' buffers mapped into
+    this process.  The 64-byte CUDA IPC handles travel through ``dist.all_gather_object``; nothing else is exchanged."""
+
+    def __init__(self, lib, dist, rank: int, world: int, D: int):
+        import ctypes  # noqa: PLC0415
+
+        from . import _native  # noqa: PLC0415
+
+        self.lib, self.rank, self.world = lib, rank, world
+        self.nbytes = int(lib.pb200_tile_link_bytes(D))
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _native.check(lib.pb200_ipc_alloc(self.nbytes, ctypes.byref(ptr), handle))
+        self.local = ptr.value
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle))
+        self._opened = {}
+
+        def mapped(r):
+            if r == rank:
+                return self.local
+            if r not in self._opened:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                _native.check(lib.pb200_ipc_open(buf, ctypes.byref(p)))
+                self._opened[r] = p.value
+            return self._opened[r]
+
+        self.left, self.right = mapped((rank - 1) % world), mapped((rank + 1) % world)
+
+    def close(self):
+        for p in self._opened.values():
+            self.lib.pb200_ipc_close(p)
+        self._opened = {}
+        if self.local:
+            self.lib.pb200_ipc_free(self.local)
+            self.local = None
+
+
+class ColumnTiledStereoPipeline:
+    """Census -> SGM -> WTA on an image ``Wg`` columns wide, column-tiled over the ranks of one node: every rank runs the
+    two skewed-wavefront passes on its ``Wt = Wg / world`` sheared columns and the border path states cross the GPU
+    boundaries inside the kernels (NVLink peer stores).  Bit-identical to the one-GPU result.
+
+    ``run(left, right)`` takes the WHOLE images on the device (a tile's pixels drift ``Wt + H - 1`` image columns to the
+    left) and returns this rank's disparity tile in sheared layout; ``unshear`` turns it into the normal-layout image tile
+    (one neighbour exchange when ``H <= Wt``, an all-gather otherwise)."""
+
+    def __init__(self, H: int, Wg: int, dmin: int, dmax: int, rank: int, world: int, dist, window: int = 5, p1: float = 8.0,
+                 p2: float = 32.0, overcounting: bool = False, invalid_disparity: float = -9999.0, device=None):
+        import torch  # noqa: PLC0415
+
+        from ._common import get_engine  # noqa: PLC0415
+
+        if Wg % world:
+            raise ValueError(f"the image width ({Wg}) must be a multiple of the number of ranks ({world})")
+        self.torch, self.dist = torch, dist
+        self.eng = get_engine(device)
+        self.lib = self.eng.lib
+        self.H, self.Wg, self.Wt, self.dmin, self.dmax, self.D = H, Wg, Wg // world, dmin, dmax, dmax - dmin + 1
+        self.rank, self.world, self.window = rank, world, window
+        self.p1, self.p2, self.over, self.invalid = float(p1), float(p2), bool(overcounting), float(invalid_disparity)
+        with torch.cuda.device(self.eng.device):
+            self.links = TileLinks(self.lib, dist, rank, world, self.D)
+        e = self.eng
+        self.cv = e.empty((H, self.Wt, self.D))
+        self.disp = e.empty((H, self.Wt))
+        self.flags = e.empty((H, self.Wt), torch.uint8)
+        self.cws = e._workspace("census", self.lib.pb200_census_sgm_workspace_bytes(H, Wg, window, dmin, self.D))
+        self.sws = e._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, self.Wt, self.D))
+        self.epoch = 0
+        self._recv = None
+        self._idx = None
+        if world > 1:
+            dist.barrier()                                 # every link buffer exists and is mapped before the first wave
+
+    def run(self, left, right, want_volume: bool = True):
+        """``left`` / ``right``: float32 (H, Wg) device tensors holding at least the image columns this tile visits."""
+        from . import _native  # noqa: PLC0415
+
+        t = self.torch
+        assert tuple(left.shape) == (self.H, self.Wg) and left.is_contiguous() and right.is_contiguous()
+        self.epoch += 1
+        with t.cuda.device(self.eng.device):
+            _native.check(self.lib.pb200_census_sgm_tile(
+                left.data_ptr(), right.data_ptr(), self.H, self.Wg, self.window, self.dmin, self.D, self.p1, self.p2, int(self.over),
+                self.rank, self.world, self.cv.data_ptr(), self.cws.data_ptr(), self.cws.numel(), self.sws.data_ptr(), self.sws.numel(),
+                self.disp.data_ptr(), self.invalid, self.flags.data_ptr(), self.links.local, self.links.left, self.links.right,
+                self.epoch, t.cuda.current_stream(self.eng.device).cuda_stream))
+        return self.disp
+
+    def visited_columns(self):
+        """(lo, n): the cyclic range of image columns [lo, lo + n) mod Wg whose pixels this tile processes."""
+        n = min(self.Wg, self.Wt + self.H - 1)
+        return (self.rank * self.Wt - (self.H - 1)) % self.Wg, n
+
+    def unshear(self, tile=None):
+        """Sheared tile (default: the disparity map of the last run) -> normal-layout image tile of this rank."""
+        t, dist = self.torch, self.dist
+        src = self.disp if tile is None else tile
+        if self.world == 1:
+            return unshear_gathered(src[None], self.Wg, 0)
+        if self.H <= self.Wt and src.dim() == 2:
+            # row y of image tile g = sheared columns [y, y + Wt) of ranks g and g + 1: one exchange with the neighbours
+            if self._recv is None or self._recv.shape != src.shape:
+                self._recv = t.empty_like(src)
+                y = t.arange(self.H, device=src.device)[:, None]
+                self._idx = t.arange(self.Wt, device=src.device)[None, :] + y
+            ops = [dist.P2POp(dist.isend, src, (self.rank - 1) % self.world), dist.P2POp(dist.irecv, self._recv, (self.rank + 1) % self.world)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            return t.gather(t.cat([src, self._recv], dim=1), 1, self._idx)
+        gathered = [t.empty_like(src) for _ in range(self.world)]
+        dist.all_gather(gathered, src.contiguous())
+        return unshear_gathered(t.stack(gathered), self.Wg, self.rank)
+
+    def close(self):
+        self.links.close()

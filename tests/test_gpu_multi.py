@@ -85,3 +85,95 @@ if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as d:
         run_case(n, 96 * n // 2, 320, 64, d)
         print(f"tiled == single GPU on {n} ranks: OK", flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# column tiles: the skewed wavefront as one wave across the GPUs (pb200_census_sgm_tile)
+# ----------------------------------------------------------------------------------------------------------------------
+def _col_worker(rank, world, port, H, Wg, D, dmin, steps, tmpdir):
+    import torch
+    import torch.distributed as dist
+
+    from pandora_b200.synthetic import synthetic_pair
+    from pandora_b200.tiling import ColumnTiledStereoPipeline
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    left, right, _ = synthetic_pair(H, Wg, D)
+    pipe = ColumnTiledStereoPipeline(H, Wg, dmin, dmin + D - 1, rank, world, dist, 5, 8.0, 32.0, device=f"cuda:{rank}")
+    lt, rt = pipe.eng.to_device(np.ascontiguousarray(left)), pipe.eng.to_device(np.ascontiguousarray(right))
+    for it in range(steps):                  # back-to-back images: the links are never cleared, only the epoch changes
+        pipe.run(lt, rt)
+        tile = pipe.unshear()
+        torch.cuda.synchronize()
+        _log(rank, f"column-tiled step {it} done")
+    np.save(os.path.join(tmpdir, f"cdisp{rank}.npy"), tile.cpu().numpy())
+    np.save(os.path.join(tmpdir, f"cS{rank}.npy"), pipe.unshear(pipe.cv).cpu().numpy())
+    dist.barrier()
+    pipe.close()
+    dist.destroy_process_group()
+
+
+def run_column_case(world, H, Wg, D, dmin, tmpdir, steps=2):
+    import torch.multiprocessing as mp
+
+    import pandora_b200
+    from pandora_b200.synthetic import synthetic_pair
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_col_worker, args=(world, port, H, Wg, D, dmin, steps, str(tmpdir)), nprocs=world, join=True)
+    left, right, _ = synthetic_pair(H, Wg, D)
+    eng = pandora_b200.get_engine("cuda:0")
+    out = eng.census_sgm(eng.to_device(left), eng.to_device(right), 5, dmin, dmin + D - 1, 8.0, 32.0)
+    assert out is not None
+    S, whole = out[0].cpu().numpy(), out[1].cpu().numpy()
+    tiled = np.concatenate([np.load(os.path.join(tmpdir, f"cdisp{r}.npy")) for r in range(world)], axis=1)
+    St = np.concatenate([np.load(os.path.join(tmpdir, f"cS{r}.npy")) for r in range(world)], axis=1)
+    np.testing.assert_array_equal(tiled, whole)
+    np.testing.assert_array_equal(St, S)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,D,dmin", [(40, 300, 64, -63), (33, 4096, 256, -255), (70, 36, 64, -20), (25, 610, 128, -100)])
+def test_column_tile_self_linked_on_one_gpu_vs_oracle(H, W, D, dmin, oracle):
+    """ntiles = 1: the wave's cyclic boundary goes through a LINK buffer (the code path of a GPU boundary: tagged words with
+    an epoch, credits, sheared storage, the pass-2 tile origin) instead of the in-kernel L2 ring -- bit-exact against the
+    oracle chain, three images back to back."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pandora_b200.tiling import ColumnTiledStereoPipeline
+
+    g = np.random.default_rng(H * W)
+    base = g.integers(0, 9, (H, W + 8)).astype(np.float32)
+    left, right = np.ascontiguousarray(base[:, 4:4 + W]), np.ascontiguousarray(np.roll(base, 3, axis=1)[:, 4:4 + W])
+    right[g.random((H, W)) < 0.2] += 1.0
+    cv, attrs = oracle.census_cost_volume(left, right, 5, dmin, dmin + D - 1)
+    S = oracle.sgm_cost_volume(cv, 8, 32, cmax=attrs["cmax"])
+    disp, inv = oracle.wta(S, np.arange(dmin, dmin + D))
+    pipe = ColumnTiledStereoPipeline(H, W, dmin, dmin + D - 1, 0, 1, None, 5, 8.0, 32.0, device="cuda:0")
+    lt, rt = pipe.eng.to_device(left), pipe.eng.to_device(right)
+    for _ in range(3):
+        pipe.run(lt, rt)
+        np.testing.assert_array_equal(pipe.unshear().cpu().numpy(), disp)
+    np.testing.assert_array_equal(pipe.unshear(pipe.cv).cpu().numpy(), S)
+    np.testing.assert_array_equal(pipe.unshear(pipe.flags).cpu().numpy().astype(bool), inv)
+    pipe.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,H,W,D,dmin", [(2, 96, 320, 64, -63), (2, 48, 1400, 256, -255), (2, 300, 128, 128, -100), (4, 64, 512, 64, -63),
+                                              (8, 40, 2048, 256, -255)])
+def test_column_tiled_pipeline_equals_single_gpu(world, H, W, D, dmin, tmp_path):
+    """One wave across `world` GPUs (NVLink peer stores inside the kernels) == the one-GPU run, volume and disparity map, bit for
+    bit; H > Wt exercises tiles that drift across more than one neighbour, two images back to back the epoch tags."""
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices")
+    run_column_case(world, H, W, D, dmin, tmp_path)

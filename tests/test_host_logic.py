@@ -296,7 +296,7 @@ def test_library_options_and_path_record():
     assert b"no.such.option" in lib.pb200_last_error()
     assert _native.last_path("sgm") == ("none", 0)
     assert lib.pb200_last_path(b"nothing", None) == _native.ERR_BAD_ARG
-    src = open(os.path.join(ROOT, "pandora_b200", "csrc", "sgm_narrow.cu")).read()
+    src = open(os.path.join(ROOT, "pandora_b200", "csrc", "sgm_packed.cuh")).read()
     for name in os.listdir(os.path.join(ROOT, "pandora_b200", "csrc")):
         if name.endswith((".cu", ".cuh")):
             text = open(os.path.join(ROOT, "pandora_b200", "csrc", name)).read()

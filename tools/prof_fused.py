@@ -19,11 +19,11 @@ left, right, _ = synthetic_pair(H, W, D)
 dl, dr = eng.to_device(left), eng.to_device(right)
 disp = eng.empty((H, W))
 flags = eng.empty((H, W), torch.uint8)
-eng.census_descriptors(dl, dr, 5)
 outs = {}
 for k in kernels:
     out = eng.empty((H, W, D))
     with pandora_b200.option("sgm.wave_kernel", k):
+        eng.census_sgm_descriptors(dl, dr, 5, -(D - 1), 0, 8, 32)
         for _ in range(2 if reps > 1 else 0):
             eng.census_sgm(dl, dr, 5, -(D - 1), 0, 8, 32, out=out, disp=disp, flags=flags, descriptors_ready=True)
         torch.cuda.synchronize()
