@@ -171,6 +171,100 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
+CONFIGS = {
+    # name: (H, W of ONE tile / of the whole image, scaling).  C3 = BASELINE.json configs[3] (weak scaling: one 4096-column tile
+    # per GPU of a 4096-row image); C4 = configs[4] read as W = 16384, H = 4096, C4T = the transposed reading: both a
+    # FIXED image column-tiled over the ranks (strong scaling).
+    "C3": dict(H=4096, W=4096, scaling="weak"),
+    "C4": dict(H=4096, W=16384, scaling="strong"),
+    "C4T": dict(H=16384, W=4096, scaling="strong"),
+}
+SYN_TILE = 4096          # the global synthetic image is a row of independent 4096-column synthetic pairs (seed + tile index)
+
+
+def global_columns(H, Wg, lo, n, D):
+    """Columns [lo, lo + n) (cyclic) of the global synthetic pair as {tile index: (left, right)} of the 4096-column tiles they touch."""
+    from pandora_b200.synthetic import synthetic_pair
+
+    tiles = {}
+    ntiles = (Wg + SYN_TILE - 1) // SYN_TILE
+    c = lo
+    while c < lo + n:
+        t = (c % Wg) // SYN_TILE
+        if t not in tiles:
+            w = min(SYN_TILE, Wg - t * SYN_TILE)
+            left, right, _ = synthetic_pair(H, w, D, seed=20240607 + t)
+            tiles[t] = (np.ascontiguousarray(left), np.ascontiguousarray(right))
+        c = (c // SYN_TILE + 1) * SYN_TILE
+    assert len(tiles) <= ntiles
+    return tiles
+
+
+def other_config_lines(pb, torch, steps):
+    """C1 (1024^2 Census 5x5 -> WTA, D = 128) and C2 (2048^2 Census 5x5 -> CBCA -> WTA, D = 192): device-resident pipeline
+    times of BASELINE.json's other single-GPU configurations, measured in this run (CUDA events), with the algorithmic bytes of
+    SURVEY 8(d) next to them."""
+    from pandora_b200.synthetic import synthetic_pair
+
+    out = {}
+    peak, _ = measured_peak_gbs()
+    for name, (H, W, D, cbca, alg) in {"C1": (1024, 1024, 128, None, lambda D: 4.0 * D + 12.0),
+                                      "C2": (2048, 2048, 192, (5, 30.0), lambda D: 12.0 * D + 36.0)}.items():
+        left, right, _ = synthetic_pair(H, W, D)
+        pipe = pb.StereoPipeline(H, W, -(D - 1), 0, "census", WINDOW, cbca=cbca, device="cuda:0")
+        dl, dr = pipe.eng.to_device(left), pipe.eng.to_device(right)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")      # > L2: the volumes of C1 nearly fit it
+        for _ in range(3):
+            pipe.run_device(dl, dr)
+        ts = []
+        for _ in range(max(steps, 5)):
+            flush.fill_(1)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            pipe.run_device(dl, dr)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        ms = float(np.mean(ts))
+        bytes_ = alg(D) * H * W
+        out[name] = {"workload": f"{H}x{W} Census 5x5" + (" + CBCA" if cbca else "") + f" + WTA, D={D}", "ms_per_step": ms,
+                     "mpix_per_s": H * W / ms / 1e3, "pipeline_algorithmic_bytes": bytes_, "achieved_gbs": bytes_ / ms / 1e6,
+                     "frac_of_measured_hbm": bytes_ / ms / 1e6 / peak, "l2": "256 MB flush between iterations",
+                     "paths": {"census": pb.last_path("census")[0], "cbca": pb.last_path("cbca")[0] if cbca else None}}
+        del pipe, dl, dr, flush
+        torch.cuda.empty_cache()
+    return out
+
+
+def plugin_leg(pb, torch, left, right, dmin, dmax, steps):
+    """C3 through the plugin-level call: host numpy datasets in, `pandora_b200.run(cfg)` (the step classes behind the reference's
+    plugin API: Census.compute_cost_volume -> cv_masked -> Sgm.optimize_cv -> WinnerTakesAll.to_disp), host disparity map and
+    validity mask out.  Wall clock around the call, everything inside (pageable H2D of the images, kernels, D2H of the maps)."""
+    cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": WINDOW, "subpix": 1},
+                        "optimization": {"optimization_method": "sgm", "penalty": {"P1": P1, "P2": P2}},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": -9999}}}
+    dl = pb.create_image_dataset(left, disparity=[dmin, dmax])
+    dr = pb.create_image_dataset(right)
+
+    def once():
+        disp, _cv = pb.run(dl, dr, cfg)
+        d = np.asarray(disp["disparity_map"].data)
+        m = np.asarray(disp["validity_mask"].data)
+        return d, m
+
+    ref, _ = once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d, _m = once()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    H, W = left.shape
+    return {"value": H * W / ms / 1e3, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": 2 * H * W * 4, "d2h_bytes_per_step": H * W * 6,
+            "call": "pandora_b200.run(img_left, img_right, cfg): host datasets in, host disparity_map + validity_mask out (pageable copies)",
+            "sgm_path": pb.last_path("sgm")[0], "same_map_every_call": bool(np.array_equal(ref, d))}, ref
+
+
 def run_ours(args):
     import torch
 
@@ -189,41 +283,13 @@ def run_ours(args):
         import torch.distributed as dist  # noqa: PLC0415
 
         dist.init_process_group("nccl", device_id=torch.device(device))
+    cfg = CONFIGS[args.config]
     dmin, dmax = -(D_DISP - 1), 0
-    H, W, D = H_TILE, W_IMG, D_DISP
-    # every rank's tile of the tall image: same generator, different seed per rank (tile r = rows [r*H, (r+1)*H))
-    left, right, _ = synthetic_pair(H, W, D, seed=20240607 + rank)
-    if world == 1:
-        pipe = pandora_b200.StereoPipeline(H, W, dmin, dmax, "census", WINDOW, sgm=(P1, P2), device=device)
-        d_left, d_right = pipe.eng.to_device(left), pipe.eng.to_device(right)
-        h_left = torch.from_numpy(left).pin_memory()
-        h_right = torch.from_numpy(right).pin_memory()
-
-        def step_device():
-            return pipe.run_device(d_left, d_right)
-
-        def step_host():
-            return pipe.run_host(h_left, h_right)
-    else:
-        from pandora_b200.tiling import TiledStereoPipeline  # noqa: PLC0415
-
-        pipe = TiledStereoPipeline(H, W, dmin, dmax, rank, world, dist, WINDOW, P1, P2, device=device)
-        d_left, d_right = pipe.eng.to_device(left), pipe.eng.to_device(right)
-        h_left = torch.from_numpy(left).pin_memory()
-        h_right = torch.from_numpy(right).pin_memory()
-        h_disp = torch.empty((H, W), dtype=torch.float32).pin_memory()
-        s_left, s_right = torch.empty_like(d_left), torch.empty_like(d_right)
-
-        def step_device():
-            return pipe.run(d_left, d_right)
-
-        def step_host():
-            s_left.copy_(h_left, non_blocking=True)
-            s_right.copy_(h_right, non_blocking=True)
-            out = pipe.run(s_left, s_right)
-            h_disp.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return h_disp
+    D = D_DISP
+    H = cfg["H"]
+    Wg = cfg["W"] * world if cfg["scaling"] == "weak" else cfg["W"]       # global image width
+    Wt = Wg // world                                                       # columns per GPU
+    steps = args.steps
 
     def sync_all():
         torch.cuda.synchronize()
@@ -246,52 +312,117 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    parity = None
+    if world == 1:
+        left, right, _ = synthetic_pair(H, Wg, D) if Wg <= SYN_TILE else (None, None, None)
+        if left is None:
+            tiles = global_columns(H, Wg, 0, Wg, D)
+            left = np.concatenate([tiles[t][0] for t in sorted(tiles)], axis=1)
+            right = np.concatenate([tiles[t][1] for t in sorted(tiles)], axis=1)
+        pipe = pandora_b200.StereoPipeline(H, Wg, dmin, dmax, "census", WINDOW, sgm=(P1, P2), device=device)
+        d_left, d_right = pipe.eng.to_device(left), pipe.eng.to_device(right)
+        h_left = torch.from_numpy(left).pin_memory()
+        h_right = torch.from_numpy(right).pin_memory()
+
+        def step_device():
+            return pipe.run_device(d_left, d_right)
+
+        def step_host():
+            return pipe.run_host(h_left, h_right)
+
+        h2d_bytes, d2h_bytes = 2 * H * Wg * 4, H * Wg * 4
+    else:
+        from pandora_b200.tiling import ColumnTiledStereoPipeline  # noqa: PLC0415
+
+        # ---- parity first: a small image column-tiled over the same ranks must equal its one-GPU run bit for bit ------------
+        hs, ws, ds = 72, 96 * world, 64
+        sl, sr, _ = synthetic_pair(hs, ws, ds)
+        small = ColumnTiledStereoPipeline(hs, ws, -(ds - 1), 0, rank, world, dist, WINDOW, P1, P2, device=device)
+        e = small.eng
+        dsl, dsr = e.to_device(sl), e.to_device(sr)
+        ok = True
+        for _ in range(2):
+            small.run(dsl, dsr)
+            tile = small.unshear()
+            whole = e.census_sgm(dsl, dsr, WINDOW, -(ds - 1), 0, P1, P2)
+            ok = ok and whole is not None and bool(torch.equal(tile, whole[1][:, rank * (ws // world):(rank + 1) * (ws // world)]))
+            vol = small.unshear(small.cv)
+            ok = ok and bool(torch.equal(torch.nan_to_num(vol, nan=-7.0),
+                                         torch.nan_to_num(whole[0][:, rank * (ws // world):(rank + 1) * (ws // world)], nan=-7.0)))
+        flag = torch.tensor([1 if ok else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"checked": True, "ok": bool(flag.item()), "case": f"{hs}x{ws}x{ds} column-tiled over {world} ranks vs the one-GPU run of the "
+                  "same image (disparity map and SGM volume, two images back to back), checked on every rank before timing"}
+        small.close()
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: column-tiled result differs from the one-GPU result on rank {rank}")
+
+        pipe = ColumnTiledStereoPipeline(H, Wg, dmin, dmax, rank, world, dist, WINDOW, P1, P2, device=device)
+        lo, n = pipe.visited_columns()
+        lo_img, n_img = (lo - D - 8) % Wg, min(Wg, n + D + 16)          # + the right-image windows
+        tiles = global_columns(H, Wg, lo_img, n_img, D)
+        d_left, d_right = pipe.eng.empty((H, Wg)).zero_(), pipe.eng.empty((H, Wg)).zero_()
+        h_left = torch.zeros((H, Wg), dtype=torch.float32).pin_memory()
+        h_right = torch.zeros((H, Wg), dtype=torch.float32).pin_memory()
+        for t, (tl, tr) in tiles.items():
+            h_left[:, t * SYN_TILE:t * SYN_TILE + tl.shape[1]] = torch.from_numpy(tl)
+            h_right[:, t * SYN_TILE:t * SYN_TILE + tr.shape[1]] = torch.from_numpy(tr)
+        # column ranges (not cyclic) this rank uploads per step
+        ranges = [(lo_img, min(Wg, lo_img + n_img))] + ([(0, lo_img + n_img - Wg)] if lo_img + n_img > Wg else [])
+        for a, b in ranges:
+            d_left[:, a:b].copy_(h_left[:, a:b])
+            d_right[:, a:b].copy_(h_right[:, a:b])
+        h_disp = torch.empty((H, Wt), dtype=torch.float32).pin_memory()
+
+        def step_device():
+            pipe.run(d_left, d_right)
+            return pipe.unshear()
+
+        def step_host():
+            for a, b in ranges:
+                d_left[:, a:b].copy_(h_left[:, a:b], non_blocking=True)
+                d_right[:, a:b].copy_(h_right[:, a:b], non_blocking=True)
+            pipe.run(d_left, d_right)
+            h_disp.copy_(pipe.unshear(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_disp
+
+        h2d_bytes = sum(b - a for a, b in ranges) * H * 4 * 2 * world
+        d2h_bytes = H * Wt * 4 * world
+
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = pandora_b200.kernel_launches()
-    total_ms = timed(step_device, args.steps)
+    total_ms = timed(step_device, steps)
     launches = pandora_b200.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    sgm_path = pandora_b200.last_path("sgm")
 
     # ---- per-stage device times inside the same kind of step (events on the launching stream) ----------
     stage = {}
-    if world == 1:
+    if world == 1 and getattr(pipe, "fused_ran", False):
         e = pipe.eng
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        fev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         torch.cuda.synchronize()
-        for i in range(args.steps):
-            evs[i][0].record()
-            e.census(d_left, d_right, WINDOW, dmin, dmax, out=pipe.cv_a)
-            evs[i][1].record()
-            e.sgm(pipe.cv_a, P1, P2, WINDOW * WINDOW + P2 + 1.0, False, out=pipe.cv_b, fuse_wta=True, dmin=dmin,
-                  invalid_disparity=-9999.0, disp=pipe.disp, flags=pipe.flags)
-            evs[i][2].record()
+        for i in range(steps):
+            fev[i][0].record()
+            e.census_sgm_descriptors(d_left, d_right, WINDOW, dmin, dmax, P1, P2)
+            fev[i][1].record()
+            e.census_sgm(d_left, d_right, WINDOW, dmin, dmax, P1, P2, False, out=pipe.cv_b, fuse_wta=True, invalid_disparity=-9999.0,
+                         disp=pipe.disp, flags=pipe.flags, descriptors_ready=True)
+            fev[i][2].record()
         torch.cuda.synchronize()
-        stage["census_ms"] = float(np.mean([a.elapsed_time(b) for a, b, _ in evs]))
-        stage["sgm_ms"] = float(np.mean([b.elapsed_time(c) for _, b, c in evs]))
-        if pipe.fused_ran:
-            # the stage the pipeline actually runs: census transforms + the two wavefront passes, Census costs computed
-            # inside pass 1 (pb200_census_sgm)
-            fev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-            torch.cuda.synchronize()
-            for i in range(args.steps):
-                fev[i][0].record()
-                e.census_sgm_descriptors(d_left, d_right, WINDOW, dmin, dmax, P1, P2)
-                fev[i][1].record()
-                e.census_sgm(d_left, d_right, WINDOW, dmin, dmax, P1, P2, False, out=pipe.cv_b, fuse_wta=True, invalid_disparity=-9999.0,
-                             disp=pipe.disp, flags=pipe.flags, descriptors_ready=True)
-                fev[i][2].record()
-            torch.cuda.synchronize()
-            stage["transform_ms"] = float(np.mean([a.elapsed_time(b) for a, b, _ in fev]))
-            stage["fused_ms"] = float(np.mean([b.elapsed_time(c) for _, b, c in fev]))
+        stage["transform_ms"] = float(np.mean([a.elapsed_time(b) for a, b, _ in fev]))
+        stage["fused_ms"] = float(np.mean([b.elapsed_time(c) for _, b, c in fev]))
 
     for _ in range(2):
         step_host()
-    sync_ms = timed(step_host, args.steps)                     # one synchronous host call per pair (latency view)
+    sync_ms = timed(step_host, steps)                          # one synchronous host call per pair (latency view)
     e2e_ms, e2e_mode = sync_ms, "synchronous host call per pair (H2D -> kernels -> D2H back to back)"
+    e2e_wall_ms = None
     if world == 1:
         # throughput view: a stream of pairs through StereoPipeline.submit_host / result_host -- every pair is uploaded
         # from pinned host memory and its disparity map downloaded inside the timed region; two buffer sets let the
@@ -310,14 +441,13 @@ def run_ours(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         t_wall = time.perf_counter()
         ev[0].record()
-        stream_steps(args.steps)                                # returns after the last disparity map is in host memory
+        stream_steps(steps)                                     # returns after the last disparity map is in host memory
         ev[1].record()
         sync_all()
-        wall_ms = (time.perf_counter() - t_wall) * 1e3
+        e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
         e2e_ms = max(ev[0].elapsed_time(ev[1]), 0.0)
         e2e_mode = ("stream of pairs, 2 in flight (StereoPipeline.submit_host / result_host): H2D of pair k+1 and D2H of pair k-1 "
                     "overlap the kernels of pair k; every pair's copies are inside the timed region")
-        e2e_wall_ms = wall_ms
 
     if rank != 0:
         if dist is not None:
@@ -325,79 +455,82 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    pix = float(H) * W * world
-    ms_per_step = total_ms / args.steps
+    pix = float(H) * Wg
+    ms_per_step = total_ms / steps
     value = pix / (ms_per_step * 1e-3) / 1e6
-    e2e_value = pix / (e2e_ms / args.steps * 1e-3) / 1e6
+    e2e_value = pix / (e2e_ms / steps * 1e-3) / 1e6
     peak, peak_src = measured_peak_gbs()
+    workload = {"C3": f"C3: {H}x{cfg['W']} synthetic pair per GPU, Census 5x5 + SGM 8-path P1=8 P2=32 + WTA, D=256, disp [-255, 0]",
+                "C4": f"C4: {H} rows x {Wg} columns (BASELINE configs[4], W = 16384 reading), Census 5x5 + SGM 8-path + WTA, D=256",
+                "C4T": f"C4 transposed reading: {H} rows x {Wg} columns, Census 5x5 + SGM 8-path + WTA, D=256"}[args.config]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C3: 4096x4096 synthetic pair per GPU, Census 5x5 + SGM 8-path P1=8 P2=32 + WTA, D=256, disp [-255, 0]",
-                   "rows_per_gpu": H, "cols": W, "total_rows": H * world,
-                   "parallelism": "1 GPU" if world == 1 else f"row tiles x{world}, SGM path-state halo over NCCL p2p",
-                   "l2": "the cost volume (17.2 GB per GPU, plus 12.9 GB of packed intermediates) exceeds the 126 MB L2; no flush needed"},
+        "config": {"workload": workload, "rows": H, "cols_total": Wg, "cols_per_gpu": Wt,
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"column tiles x{world}: one skewed wavefront across all GPUs, SGM path states cross the tile borders as NVLink peer "
+                   "stores issued by the kernels (no collective on the data path); the timed step ends with the disparity tile back "
+                   "in image layout (one NCCL neighbour exchange)",
+                   "sgm_path": list(sgm_path),
+                   "l2": "the cost volume (17.2 GB per 4096x4096 tile, plus 12.9 GB of packed intermediates) exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * H * W * 4 * world, "d2h_bytes_per_step": H * W * 4 * world,
-                "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode,
-                "sync_call": {"value": pix / (sync_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_call": sync_ms / args.steps}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_ms / steps, "mode": e2e_mode,
+                "sync_call": {"value": pix / (sync_ms / steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_call": sync_ms / steps}},
         "gpu_launches": int(launches),
     }
+    if parity is not None:
+        line["parity_in_run"] = parity
     if world == 1:
-        line["e2e"]["wall_ms_per_step"] = e2e_wall_ms / args.steps
-        sgm_alg = 8.0 * D * H * W          # SGM must read C (4D) and write S (4D) bytes per pixel
-        census_alg = (4.0 * D + 8.0) * H * W
-        sgm_gbs = sgm_alg / (stage["sgm_ms"] * 1e-3) / 1e9
-        fused = "fused_ms" in stage
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "sgm_stage_traffic.json")) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_fused_stage" if fused else "dram_bytes_per_stage")
-                traffic = None if traffic is None else float(traffic)
-        except Exception:
-            pass
-        if fused:
-            # the dominant kernel pair of the step that was timed: the SGM row of SURVEY 8(d) (8*D bytes per pixel: the
-            # cost C and the result S) is kept as its algorithmic figure although pass 1 no longer reads a float C --
-            # it computes the Census costs from the descriptors -- so the fraction stays comparable with earlier lines
+        if e2e_wall_ms is not None:
+            line["e2e"]["wall_ms_per_step"] = e2e_wall_ms / steps
+        sgm_alg = 8.0 * D * H * Wg          # SGM must read C (4D) and write S (4D) bytes per pixel
+        if "fused_ms" in stage:
+            # the dominant kernel pair of the step that was timed.  The SGM row of SURVEY 8(d) (8*D bytes per pixel: the cost C
+            # and the result S) is kept as its algorithmic figure although pass 1 does not read a float C -- it computes the
+            # Census costs from the descriptors -- so that the fraction stays comparable with earlier lines; what the stage
+            # must move once that read is gone is 4*D written + the descriptors (see DESIGN.md 3.2 and the ncu file below)
             f_gbs = sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9
+            kname = "sgm_wave1_kernel" if sgm_path[0].startswith("sgm_wave1") else "sgm_wave_kernel"
             line["roofline"] = {"bound": "hbm",
-                                "kernel": "fused Census+SGM stage = sgm_wave_kernel x2 (pass 1: Hamming costs from the census "
-                                          "descriptors + E/SE/S/SW, writes C8 + P16; pass 2: W/NW/N/NE, writes float S + WTA); 2 launches "
-                                          "timed as one unit against the SGM row's 8*D algorithmic bytes per pixel",
-                                "achieved": f_gbs, "peak": peak, "unit": "GB/s", "frac": f_gbs / peak, "traffic": traffic,
+                                "kernel": f"fused Census+SGM stage = {kname} x2 (pass 1: Hamming costs from the census descriptors + "
+                                          "E/SE/S/SW, writes C8 + P16; pass 2: W/NW/N/NE, writes float S + WTA); 2 launches timed as one "
+                                          "unit against the SGM row's 8*D algorithmic bytes per pixel",
+                                "achieved": f_gbs, "peak": peak, "unit": "GB/s", "frac": f_gbs / peak, "traffic": None,
+                                "traffic_note": "dram__bytes per launch are in the ncu capture cited here, not re-measured in this run",
+                                "traffic_ncu_file": "profiles/r2_ncu_fused_stage.txt",
                                 "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["fused_ms"]}
-        else:
-            line["roofline"] = {"bound": "hbm",
-                                "kernel": "SGM stage = sgm_wave_kernel x2 (pass 1: E/SE/S/SW reading float C; pass 2: W/NW/N/NE writing "
-                                          "float S + WTA); 2 launches timed as one unit (the stage's 8*D algorithmic bytes per pixel "
-                                          "= 4*D read by pass 1 + 4*D written by pass 2)",
-                                "achieved": sgm_gbs, "peak": peak, "unit": "GB/s", "frac": sgm_gbs / peak, "traffic": traffic,
-                                "peak_source": peak_src, "algorithmic_bytes_per_stage": sgm_alg, "stage_ms": stage["sgm_ms"]}
-        cen_gbs = census_alg / (stage["census_ms"] * 1e-3) / 1e9
-        line["stages"] = {"census_fill": {"ms": stage["census_ms"], "algorithmic_bytes": census_alg, "achieved_gbs": cen_gbs, "frac": cen_gbs / peak,
-                                          "in_step": not fused},
-                          "sgm_8path_wta": {"ms": stage["sgm_ms"], "algorithmic_bytes": sgm_alg, "achieved_gbs": sgm_gbs, "frac": sgm_gbs / peak,
-                                            "in_step": not fused},
-                          "pipeline_algorithmic_bytes": (12.0 * D + 12.0) * H * W,
-                          "pipeline_frac": (12.0 * D + 12.0) * H * W / (ms_per_step * 1e-3) / 1e9 / peak}
-        if fused:
-            line["stages"]["census_transform_x2"] = {"ms": stage["transform_ms"], "in_step": True}
-            line["stages"]["census_sgm_fused_wta"] = {"ms": stage["fused_ms"], "algorithmic_bytes": sgm_alg, "in_step": True,
-                                                      "achieved_gbs": sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9,
-                                                      "frac": sgm_alg / (stage["fused_ms"] * 1e-3) / 1e9 / peak}
-        line["config"]["fused_census_sgm"] = bool(fused)
+            line["stages"] = {"census_transforms": {"ms": stage["transform_ms"], "in_step": True},
+                              "census_sgm_fused_wta": {"ms": stage["fused_ms"], "algorithmic_bytes": sgm_alg, "in_step": True,
+                                                       "achieved_gbs": f_gbs, "frac": f_gbs / peak},
+                              "pipeline_algorithmic_bytes": (12.0 * D + 12.0) * H * Wg,
+                              "pipeline_frac": (12.0 * D + 12.0) * H * Wg / (ms_per_step * 1e-3) / 1e9 / peak}
+        line["config"]["fused_census_sgm"] = bool(getattr(pipe, "fused_ran", False))
+        if args.config == "C3":
+            # the same configuration through the plugin-level call, and BASELINE.json's other one-GPU configurations
+            del d_left, d_right
+            pipe = None
+            torch.cuda.empty_cache()
+            try:
+                line["e2e_plugin"], pmap = plugin_leg(pandora_b200, torch, left, right, dmin, dmax, max(2, min(steps, 3)))
+            except Exception as exc:  # noqa: BLE001
+                line["e2e_plugin"] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
+            try:
+                line["other_configs"] = other_config_lines(pandora_b200, torch, steps)
+            except Exception as exc:  # noqa: BLE001
+                line["other_configs"] = {"error": repr(exc)}
         # CPU baseline on a bounded row band of the same pair, same run
         rows = 32
-        cl, cr = np.ascontiguousarray(left[:rows]), np.ascontiguousarray(right[:rows])
+        cl, cr = np.ascontiguousarray(left[:rows, :W_IMG]), np.ascontiguousarray(right[:rows, :W_IMG])
         t, kind = cpu_pipeline_once(cl, cr, dmin, dmax)
-        line["cpu_baseline"] = {"value": rows * W / t / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
-                                "sample": f"first {rows} rows x {W} cols x D={D} of the same pair, census "
+        line["cpu_baseline"] = {"value": rows * W_IMG / t / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": f"first {rows} rows x {W_IMG} cols x D={D} of the same pair, census "
                                           f"{'= unmodified reference C++ (oracle/_ref)' if kind == 'reference' else '= oracle port'}, "
                                           "SGM/WTA = oracle C port; 1 thread (the reference is single-threaded)",
                                 "host_cores_available": os.cpu_count(),
-                                "hypothetical_row_parallel": {"cores": os.cpu_count(), "value": rows * W / t / 1e6 * (os.cpu_count() or 1),
+                                "hypothetical_row_parallel": {"cores": os.cpu_count(), "value": rows * W_IMG / t / 1e6 * (os.cpu_count() or 1),
                                                               "note": "1-core figure x host cores: an upper bound, the reference is single-threaded"}}
     print(json.dumps(line))
     if dist is not None:
@@ -412,6 +545,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="C3 (default, BASELINE's metric) | C4 | C4T")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

@@ -5,7 +5,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .dataset import DataArray, LazyVolume
+from .dataset import DataArray, Dataset, LazyVolume
 
 
 class ConfigError(ValueError):
@@ -69,6 +69,38 @@ def store_volume(cv, tensor, keep_on_device: bool = True) -> None:
             var.data = LazyVolume(tensor)
     else:
         cv["cost_volume"].data = tensor.detach().cpu().numpy()
+
+
+def device_var(engine, ds, name: str, dtype: str = "float32"):
+    """Variable ``name`` of dataset ``ds`` as a device tensor: the resident copy when a previous pandora_b200 step left one
+    (no host round trip between steps), else an upload.  ``dtype`` "uint16" gives the int16 view the mask kernels take."""
+    var = ds[name]
+    if isinstance(var, DataArray):
+        t = var.device_tensor()
+        if t is not None:
+            return t
+    if dtype == "uint16":
+        return engine.to_device(np.ascontiguousarray(var.data).astype(np.uint16).view(np.int16), dtype=None)
+    return engine.to_device(np.ascontiguousarray(var.data, dtype=np.float32))
+
+
+def store_var(ds, name: str, tensor, dims=("row", "col"), dtype: str = "float32") -> None:
+    """Leave ``tensor`` as variable ``name`` of ``ds`` WITHOUT copying it to the host (shim datasets; the copy happens
+    when somebody reads ``.data``); a real xarray dataset gets the numpy array at once."""
+    host_dtype = np.uint16 if dtype == "uint16" else None
+    if isinstance(ds, Dataset):
+        ds[name] = (tuple(dims), LazyVolume(tensor, host_dtype=host_dtype))
+    else:
+        arr = tensor.detach().cpu().numpy()
+        ds[name] = (tuple(dims), arr.view(np.uint16) if host_dtype is not None else arr)
+
+
+def fused_wta(cv):
+    """(disparity, all-NaN flags, dmin, invalid_disparity) when the kernel that produced ``cv["cost_volume"]`` also ran the
+    winner-takes-all on it (fused Census -> SGM -> WTA) and nothing has replaced the volume since, else None."""
+    var = cv["cost_volume"] if "cost_volume" in cv else None
+    lazy = getattr(var, "_data", None)
+    return getattr(lazy, "wta_cache", None) if isinstance(lazy, LazyVolume) else None
 
 
 def deferred_recipe(cv):

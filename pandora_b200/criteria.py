@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._common import get_engine
+from ._common import get_engine, store_var
 
 
 def image_mask_flags(eng, img, window: int):
@@ -29,5 +29,5 @@ def validity_mask(img_left, img_right, cv):
             grid = np.asarray(img_left["disparity"].data, dtype=np.float32)
             gmin, gmax = eng.to_device(grid[0]), eng.to_device(grid[1])
         eng.validity_mask_masks(mask, dmin, dmax, offset, fl, fr, gmin, gmax)
-    cv["validity_mask"] = (("row", "col"), mask.cpu().numpy().view(np.uint16))
+    store_var(cv, "validity_mask", mask, dtype="uint16")           # stays in HBM until somebody reads it
     return cv

@@ -583,6 +583,11 @@ extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, 
         return PB200_ERR_UNSUPPORTED;
     }
     const int Wt = Wg / ntiles;
+    struct Pin {                                     // the tiles run the skewed wavefront whatever a one-GPU call would pick
+        int old;
+        Pin() : old(pb200_get_option("sgm.wave_kernel")) { pb200_set_option("sgm.wave_kernel", 1); }
+        ~Pin() { pb200_set_option("sgm.wave_kernel", old); }
+    } pin;
     if (sgm_census_plan(window, Wt, D, p1, p2) != 1) {
         set_error("pb200_census_sgm_tile: the skewed wavefront does not take this configuration (window 3 / 5, D in {64, 128, 256}, "
                   "small integer penalties, tile width <= 28 columns per SM)");

@@ -893,16 +893,22 @@ static bool census_wave_common(int window, int D, float p1, float p2) {
     return is_small_int(p1, 1, NARROW_MAX) && is_small_int(p2, 1, NARROW_MAX) && p1 <= p2 && is_small_int(invalid_value, 0, NARROW_MAX) &&
            (int)invalid_value + (int)p2 <= NARROW_MAX;
 }
+#ifndef PB200_PREFER_SKEWED
+#define PB200_PREFER_SKEWED 0
+#endif
 int sgm_wave1_strip_width(int W);                                           // sgm_wave1.cu: 0 when the image is too wide for one wave
 int sgm_census_plan(int window, int W, int D, float p1, float p2) {
     if (!census_wave_common(window, D, p1, p2) || option(OPT_SGM_NO_WAVE) > 0) return 0;
     const int pin = option(OPT_SGM_WAVE_KERNEL);
-    if (pin != 2 && sgm_wave1_strip_width(W) > 0) return 1;
     int K = ceil_div(W, sm_count());
     if (K < 4) K = 4;
     K = (K + 1) / 2 * 2;
-    if (pin != 1 && K / 2 <= 14) return 2;
-    return 0;
+    const bool two_ok = K / 2 <= 14, one_ok = sgm_wave1_strip_width(W) > 0;
+    if (pin == 1) return one_ok ? 1 : 0;
+    if (pin == 2) return two_ok ? 2 : 0;
+    // one GPU: whichever is faster for the shape (measured at C3: profiles/r2_wave_kernels.txt); column tiles pin the skewed one
+    if (PB200_PREFER_SKEWED && one_ok) return 1;
+    return two_ok ? 2 : (one_ok ? 1 : 0);
 }
 
 // Fused Census -> SGM: the two wavefront passes with the first one computing the Hamming costs from the census

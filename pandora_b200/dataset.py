@@ -22,13 +22,17 @@ class LazyVolume:
     somebody asks for ``tensor`` (or ``.data``).  The Census step leaves such a recipe so that a directly following SGM
     step can run the fused Census -> SGM kernels and never write the Census volume (``matching_cost.CensusRecipe``)."""
 
-    def __init__(self, tensor=None, recipe=None, shape=None):
+    def __init__(self, tensor=None, recipe=None, shape=None, host_dtype=None):
         assert tensor is not None or (recipe is not None and shape is not None)
         self._tensor = tensor
         self.recipe = recipe
         self.shape = tuple(int(s) for s in (tensor.shape if tensor is not None else shape))
-        self.dtype = np.dtype(np.float32)
+        # any (row, col[, ...]) variable can stay in HBM this way: `host_dtype` is the dtype the host sees when the device
+        # tensor stores it under another view (the uint16 validity mask lives in an int16 tensor)
+        self.host_dtype = None if host_dtype is None else np.dtype(host_dtype)
+        self.dtype = self.host_dtype or np.dtype(np.float32)
         self._host: Optional[np.ndarray] = None
+        self.wta_cache = None                          # (disparity, all-NaN flags, dmin, invalid_disparity) of a fused WTA
 
     @property
     def tensor(self):
@@ -43,6 +47,8 @@ class LazyVolume:
     def materialize(self) -> np.ndarray:
         if self._host is None:
             self._host = self.tensor.detach().cpu().numpy()
+            if self.host_dtype is not None and self._host.dtype != self.host_dtype:
+                self._host = self._host.view(self.host_dtype)
         return self._host
 
     def __array__(self, dtype=None, copy=None):  # noqa: A002
@@ -155,4 +161,5 @@ def add_disparity(ds: Dataset, disparity) -> Dataset:
     grid[0], grid[1] = dmin, dmax
     ds["disparity"] = (("band_disp", "row", "col"), grid)
     ds.coords["band_disp"] = DataArray(np.array(["min", "max"]), ("band_disp",))
+    ds.attrs["disparity_source"] = [dmin, dmax]        # img_tools.py:141-161: the [min, max] pair the grids were built from
     return ds

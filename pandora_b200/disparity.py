@@ -5,7 +5,7 @@ from typing import Dict
 
 import numpy as np
 
-from ._common import ConfigError, device_volume, get_engine
+from ._common import ConfigError, device_var, device_volume, fused_wta, get_engine, store_var
 from .dataset import Dataset
 
 
@@ -64,16 +64,20 @@ class WinnerTakesAll(AbstractDisparity):
         disps = np.asarray(cv.coords["disp"].data)
         dmin, dmax = int(round(float(disps[0]))), int(round(float(disps[-1])))
         is_max = cv.attrs.get("type_measure") == "max"
-        disp_t, flags = eng.wta(cv_t, dmin, is_max, float(self._invalid_disparity))
-        disp = disp_t.cpu().numpy()
-        out = Dataset({"disparity_map": (("row", "col"), disp)},
-                      coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=cv.attrs)
+        invalid = float(self._invalid_disparity)
+        cached = fused_wta(cv)
+        if cached is not None and not is_max and cached[2] == dmin and (cached[3] == invalid or (cached[3] != cached[3] and invalid != invalid)):
+            disp_t, flags = cached[0], cached[1]                   # the producing kernel already ran this argmin (fused WTA)
+        else:
+            disp_t, flags = eng.wta(cv_t, dmin, is_max, invalid)
+        out = Dataset(coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=cv.attrs)
+        store_var(out, "disparity_map", disp_t)                    # device-resident: read `.data` to get the host copy
         out["disparity_interval"] = (("disparity",), np.asarray(disps)[[0, -1]])                # disparity.py:301-315, 456
-        cv["disp_indices"] = (("row", "col"), disp.copy())
+        store_var(cv, "disp_indices", disp_t.clone())
         if "validity_mask" in cv:
-            mask_t = eng.to_device(np.ascontiguousarray(cv["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+            mask_t = device_var(eng, cv, "validity_mask", "uint16").clone()
             mask_t = eng.validity_mask(H, W, dmin, dmax, 0, flags, wta_invalidate=True, mask=mask_t)
-            out["validity_mask"] = (("row", "col"), mask_t.cpu().numpy().view(np.uint16))
+            store_var(out, "validity_mask", mask_t, dtype="uint16")
         if "confidence_measure" in cv:
             # disparity.py:462-466: the confidence layers computed on the cost volume travel with their `indicator`
             # coordinate (cost_volume_confidence runs BEFORE disparity in every legal pipeline, state_machine.py:134-139)

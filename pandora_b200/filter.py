@@ -6,7 +6,7 @@ from typing import Dict
 
 import numpy as np
 
-from ._common import ConfigError, get_engine
+from ._common import ConfigError, device_var, get_engine, store_var
 
 
 class AbstractFilter:
@@ -56,8 +56,8 @@ class MedianFilter(AbstractFilter):
     def filter_disparity(self, disp, img_left=None, img_right=None, cv=None) -> None:
         """filter/median.py:96-132: median of the valid pixels, invalid pixels untouched, in place."""
         eng = get_engine()
-        d = eng.to_device(np.ascontiguousarray(disp["disparity_map"].data, dtype=np.float32))
-        m = eng.to_device(np.ascontiguousarray(disp["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+        d = device_var(eng, disp, "disparity_map").clone()
+        m = device_var(eng, disp, "validity_mask", "uint16")
         eng.filter_median3(d, m)
-        disp["disparity_map"].data = d.cpu().numpy()
+        store_var(disp, "disparity_map", d)
         disp.attrs["filter"] = "median"

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import constants as cst
 from . import _native
-from ._common import ConfigError, deferred_recipe, device_volume, get_engine, image_array, store_deferred_volume, store_volume
+from ._common import ConfigError, deferred_recipe, device_var, device_volume, store_var, get_engine, image_array, store_deferred_volume, store_volume
 from .dataset import Dataset
 
 
@@ -96,6 +96,16 @@ class AbstractMatchingCost:
         return int(np.nanmin(disp_min)), int(np.nanmax(disp_max))
 
     @staticmethod
+    def constant_range(image):
+        """(dmin, dmax) when the image's disparity grids are constant BY CONSTRUCTION -- ``attrs["disparity_source"]`` is the
+        [min, max] pair ``add_disparity`` built them from (img_tools.py:141-161) -- else None.  Saves four NaN-reductions over
+        the (row, col) grids per step (70 ms of host time at 4096 x 4096)."""
+        src = getattr(image, "attrs", {}).get("disparity_source")
+        if isinstance(src, (list, tuple)) and len(src) == 2 and all(isinstance(v, (int, np.integer)) for v in src):
+            return int(src[0]), int(src[1])
+        return None
+
+    @staticmethod
     def get_disparity_range(disparity_min: int, disparity_max: int, subpix: int = 1) -> np.ndarray:
         if subpix != 1:
             raise ConfigError("subpix: only 1 is implemented")
@@ -107,7 +117,7 @@ class AbstractMatchingCost:
         the device by compute_cost_volume (17 GB at 4096x4096x256 would be written twice otherwise)."""
         c_row = np.asarray(image.coords["row"].data)
         c_col = np.asarray(image.coords["col"].data)
-        dmin, dmax = self.get_min_max_from_grid(*disparity_grids)
+        dmin, dmax = self.constant_range(image) or self.get_min_max_from_grid(*disparity_grids)
         disps = self.get_disparity_range(dmin, dmax, self._subpix)
         index_col = np.arange(c_col[0], c_col[-1] + 1, self._step_col)
         cv = Dataset(coords={"row": c_row, "col": index_col, "disp": disps}, attrs=dict(image.attrs))
@@ -143,8 +153,12 @@ class AbstractMatchingCost:
         off = int(cost_volume.attrs["offset_row_col"])
         fl, fr = image_mask_flags(eng, img_left, self._window_size), image_mask_flags(eng, img_right, self._window_size)
         gmin_h, gmax_h = np.asarray(disp_min, dtype=np.float32)[:H, :W], np.asarray(disp_max, dtype=np.float32)[:H, :W]
-        variable = bool(np.nanmax(gmin_h) != np.nanmin(gmin_h) or np.nanmax(gmax_h) != np.nanmin(gmax_h)
-                        or int(np.nanmin(gmin_h)) != dmin or int(np.nanmax(gmax_h)) != dmax)
+        own_grids = "disparity" in getattr(img_left, "data_vars", {}) and np.may_share_memory(gmin_h, img_left["disparity"].data)
+        if own_grids and self.constant_range(img_left) == (dmin, dmax):
+            variable = False                                   # the grids of this very image, constant by construction
+        else:
+            variable = bool(np.nanmax(gmin_h) != np.nanmin(gmin_h) or np.nanmax(gmax_h) != np.nanmin(gmax_h)
+                            or int(np.nanmin(gmin_h)) != dmin or int(np.nanmax(gmax_h)) != dmax)
         recipe = deferred_recipe(cost_volume)
         if recipe is not None and fl is None and fr is None and not variable:
             # nothing to mask: the step only needs the all-NaN pixels, which a deferred Census volume knows from its
@@ -157,11 +171,11 @@ class AbstractMatchingCost:
             flags = eng.cv_masked(cv_t, dmin, fl, fr, gmin, gmax)            # masks the volume, reports all-NaN pixels
             store_volume(cost_volume, cv_t)
         if "validity_mask" in cost_volume:
-            mask = eng.to_device(np.ascontiguousarray(cost_volume["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+            mask = device_var(eng, cost_volume, "validity_mask", "uint16")
         else:
             mask = eng.validity_mask_init(H, W, dmin, dmax, off)
         mask = eng.validity_mask(H, W, dmin, dmax, off, flags, mask=mask)
-        cost_volume["validity_mask"] = (("row", "col"), mask.cpu().numpy().view(np.uint16))
+        store_var(cost_volume, "validity_mask", mask, dtype="uint16")
 
 
 class CensusRecipe:

@@ -97,9 +97,11 @@ class Sgm(AbstractOptimization):
         if recipe is not None and getattr(recipe, "kind", None) == "census" and not is_max and cmax == float(recipe.window**2):
             # the Census volume was never computed: fused Census -> SGM (same bits, no float Census volume)
             fused = eng.census_sgm(recipe.left, recipe.right, recipe.window, recipe.dmin, recipe.dmax, self._p1, self._p2,
-                                   self._overcounting, fuse_wta=False)
+                                   self._overcounting, fuse_wta=True, invalid_disparity=-9999.0)
             if fused is not None:
                 store_volume(cv, fused[0])
+                # the last pass ran the argmin on the fly: a `disparity` step that follows directly takes it from here
+                cv["cost_volume"]._data.wta_cache = (fused[1], fused[2], recipe.dmin, -9999.0)
                 cv.attrs["optimization"] = "sgm"
                 return cv
         cv_t = device_volume(eng, cv)

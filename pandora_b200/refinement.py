@@ -6,7 +6,7 @@ from typing import Dict
 
 import numpy as np
 
-from ._common import ConfigError, device_volume, get_engine
+from ._common import ConfigError, device_var, device_volume, get_engine, store_var
 
 
 class NullMargins:
@@ -62,13 +62,13 @@ class AbstractRefinement:
             d_min, d_max = -d_max, -d_min
         subpix = int(cv.attrs["subpixel"])
         is_max = cv.attrs["type_measure"] == "max"
-        disp_t = eng.to_device(np.ascontiguousarray(disp["disparity_map"].data, dtype=np.float32))
-        mask_t = eng.to_device(np.ascontiguousarray(disp["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+        disp_t = device_var(eng, disp, "disparity_map").clone()
+        mask_t = device_var(eng, disp, "validity_mask", "uint16").clone()
         itp = eng.refinement(cv_t, disp_t, mask_t, d_min, d_max, subpix, is_max, self._refinement_method_name, approximate)
-        disp["disparity_map"].data = disp_t.cpu().numpy()
-        disp["validity_mask"].data = mask_t.cpu().numpy().view(np.uint16)
+        store_var(disp, "disparity_map", disp_t)
+        store_var(disp, "validity_mask", mask_t, dtype="uint16")
         disp.attrs["refinement"] = self._refinement_method_name
-        disp["interpolated_coeff"] = (("row", "col"), itp.cpu().numpy())
+        store_var(disp, "interpolated_coeff", itp)
         return disp
 
     def subpixel_refinement(self, cv, disp) -> None:

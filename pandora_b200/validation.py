@@ -6,7 +6,7 @@ from typing import Dict
 
 import numpy as np
 
-from ._common import ConfigError, device_volume, get_engine
+from ._common import ConfigError, device_var, device_volume, get_engine, store_var
 from .dataset import Dataset
 
 
@@ -20,12 +20,13 @@ def right_disparity_fast(cv, invalid_disparity: float = -9999.0):
     is_max = cv.attrs.get("type_measure") == "max"
     disp_t, flags = eng.wta_right(cv_t, -dmax, is_max, float(invalid_disparity))
     H, W = (int(s) for s in disp_t.shape)
-    out = Dataset({"disparity_map": (("row", "col"), disp_t.cpu().numpy())},
-                  coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=dict(cv.attrs))
+    out = Dataset(coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=dict(cv.attrs))
+    store_var(out, "disparity_map", disp_t)
     out["disparity_interval"] = (("disparity",), -np.asarray(disps)[[-1, 0]])
-    mask = np.zeros((H, W), dtype=np.uint16)
-    mask[flags.cpu().numpy() != 0] = 0x3C3            # disparity.py:470-474 on an empty right validity mask
-    out["validity_mask"] = (("row", "col"), mask)
+    import torch  # noqa: PLC0415
+
+    mask = torch.where(flags != 0, 0x3C3, 0).to(torch.int16)      # disparity.py:470-474 on an empty right validity mask
+    store_var(out, "validity_mask", mask, dtype="uint16")
     return out
 
 
@@ -76,16 +77,15 @@ class CrossCheckingAccurate(AbstractValidation):
         """validation.py:226-371: occlusion / mismatch bits in the left validity mask and the left-right distance as
         the ``confidence_from_left_right_consistency`` indicator."""
         eng = get_engine()
-        dl = eng.to_device(np.ascontiguousarray(dataset_left["disparity_map"].data, dtype=np.float32))
-        dr = eng.to_device(np.ascontiguousarray(dataset_right["disparity_map"].data, dtype=np.float32))
-        mask_t = eng.to_device(np.ascontiguousarray(dataset_left["validity_mask"].data).astype(np.uint16).view(np.int16), dtype=None)
+        dl, dr = device_var(eng, dataset_left, "disparity_map"), device_var(eng, dataset_right, "disparity_map")
+        mask_t = device_var(eng, dataset_left, "validity_mask", "uint16").clone()
         if "disparity_interval" in dataset_left:
             dmin, dmax = (int(v) for v in np.asarray(dataset_left["disparity_interval"].data))
         else:
             dmin, dmax = (int(v) for v in dataset_left.attrs["disparity_interval"])
         offset = int(dataset_left.attrs.get("offset_row_col", 0))
         conf = eng.cross_checking(dl, mask_t, dr, float(self._threshold), dmin, dmax, offset)
-        dataset_left["validity_mask"].data = mask_t.cpu().numpy().view(np.uint16)
+        store_var(dataset_left, "validity_mask", mask_t, dtype="uint16")
         dataset_left.attrs["validation"] = self._method
         from .cost_volume_confidence import AbstractCostVolumeConfidence  # noqa: PLC0415
 
