@@ -131,23 +131,27 @@ PB200_API int pb200_census_sgm(const float *d_left, const float *d_right, int H,
  * ntiles, and hands the path states of its last column to the next GPU through a LINK buffer in that GPU's memory (NVLink peer
  * stores issued by the kernel itself; credits flow back the same way).  There is no host-side step and no collective between
  * the tiles: all GPUs run one wave.  The result is bit-identical to pb200_census_sgm on one GPU.
- *   - d_left / d_right: the WHOLE images (H, Wg) on every GPU (a tile's pixels drift Wt + H - 1 image columns to the left; only
- *     the descriptors of those columns are computed).
- *   - d_cv_tile (H, Wt, D), d_disp_tile / d_all_nan_tile (H, Wt): the tile in SHEARED layout: element (y, c) belongs to image
- *     column (tile * Wt + c - y) mod Wg.
+ *   - d_left / d_right: nimg WHOLE images (nimg, H, Wg) on every GPU (a tile's pixels drift Wt + nimg * H - 1 image columns to
+ *     the left; only the descriptors of those columns are computed).  The images of a batch follow each other in ONE wave -- the
+ *     first row of image i + 1 enters the pipeline behind the last row of image i, every path starting afresh -- so the time a
+ *     wave needs to cross all GPUs is paid once per pass and batch instead of once per pass and image (stream throughput).
+ *   - d_cv_tile (nimg, H, Wt, D), d_disp_tile / d_all_nan_tile (nimg, H, Wt): the tiles in SHEARED layout: element (i, y, c)
+ *     belongs to image column (tile * Wt + c - (i * H + y)) mod Wg of image i.
  *   - link_local: this GPU's link buffer (pb200_tile_link_bytes, zero-initialised once, e.g. by pb200_ipc_alloc); link_left /
  *     link_right: the link buffers of tiles (tile - 1) and (tile + 1) mod ntiles mapped into this process (pb200_ipc_open);
  *     with ntiles == 1 all three are the same buffer.
- *   - epoch: a counter that is the same on all GPUs for one image and differs between consecutive images (the links are never
- *     cleared; every word carries the epoch).
+ *   - epoch (1 .. 65535): the same on all GPUs for one call, different for consecutive calls (the links are never cleared;
+ *     every word carries the epoch); prev_epoch / prev_rows: epoch and nimg * H of the call that used the links before (0: none).
+ *   - passes: 1 = descriptors + the top-down pass, 2 = the bottom-up pass (+ WTA), 3 = both (the usual call).
+ *   - census workspace: nimg * pb200_census_sgm_workspace_bytes(H, Wg, ...).
  * pb200_ipc_*: device memory that other processes of the node can map (cudaIpc; the 64-byte handle travels through any host
  * channel, e.g. torch.distributed). */
 PB200_API size_t pb200_tile_link_bytes(int D);
-PB200_API int pb200_census_sgm_tile(const float *d_left, const float *d_right, int H, int Wg, int window, int dmin, int D, float p1,
+PB200_API int pb200_census_sgm_tile(const float *d_left, const float *d_right, int nimg, int H, int Wg, int window, int dmin, int D, float p1,
                           float p2, int overcounting, int tile, int ntiles, float *d_cv_tile, void *d_census_workspace,
                           size_t census_workspace_bytes, void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp_tile,
                           float invalid_disparity, uint8_t *d_all_nan_tile, void *link_local, void *link_left, void *link_right,
-                          unsigned epoch, void *stream);
+                          unsigned epoch, unsigned prev_epoch, unsigned prev_rows, int passes, void *stream);
 PB200_API int pb200_ipc_alloc(size_t bytes, void **d_ptr, void *handle64);
 PB200_API int pb200_ipc_open(const void *handle64, void **d_ptr);
 PB200_API int pb200_ipc_close(void *d_ptr);

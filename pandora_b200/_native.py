@@ -56,8 +56,8 @@ PROTOTYPES = {
     "pb200_census_sgm_descriptors": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _vp, _sz, _vp, _vp]),
     "pb200_census_sgm": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _ci, _vp, _vp]),
     "pb200_tile_link_bytes": (_sz, [_ci]),
-    "pb200_census_sgm_tile": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _vp, _vp,
-                                    _vp, ctypes.c_uint, _vp]),
+    "pb200_census_sgm_tile": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _vp,
+                                    _vp, _vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, _ci, _vp]),
     "pb200_ipc_alloc": (_ci, [_sz, _vp, _vp]),
     "pb200_ipc_open": (_ci, [_vp, _vp]),
     "pb200_ipc_close": (_ci, [_vp]),

@@ -568,18 +568,37 @@ extern "C" size_t pb200_tile_link_bytes(int D) {
     return 2 * blk + 512;
 }
 
-extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, int H, int Wg, int window, int dmin, int D, float p1,
+// left descriptors + four shifted right copies of the image columns [col0, col1) (see census_sgm_descriptors), explicit placement
+static int census_tile_descriptors(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D, uint32_t *descL,
+                                   uint32_t *desc4, int col0, int col1, cudaStream_t s) {
+    const int pitch = census_pitch(W), pitch4 = census_pitch4(W, dmin, D), padl = census_padl(dmin);
+    int rc = window == 3 ? launch_transform<3>(d_left, H, W, pitch, descL, 0, H, s, col0, col1)
+                         : launch_transform<5>(d_left, H, W, pitch, descL, 0, H, s, col0, col1);
+    if (rc != PB200_OK) return rc;
+    int i0 = col0 + dmin + padl - 4, i1 = col1 + dmin + D + padl + 4;
+    if (i0 < 0) i0 = 0;
+    if (i1 > pitch4 + 3) i1 = pitch4 + 3;
+    if (i1 <= i0) return PB200_OK;
+    dim3 grid(ceil_div(i1 - i0, 256), H);
+    if (window == 3) census_transform_shifted_kernel<3><<<grid, 256, 0, s>>>(d_right, H, W, pitch4, padl, desc4, i0, i1);
+    else census_transform_shifted_kernel<5><<<grid, 256, 0, s>>>(d_right, H, W, pitch4, padl, desc4, i0, i1);
+    PB200_LAUNCH_CHECK("census_transform_shifted_kernel");
+    return PB200_OK;
+}
+
+extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, int nimg, int H, int Wg, int window, int dmin, int D, float p1,
                                      float p2, int overcounting, int tile, int ntiles, float *d_cv_tile, void *d_census_workspace,
                                      size_t census_workspace_bytes, void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp_tile,
                                      float invalid_disparity, uint8_t *d_all_nan_tile, void *link_local, void *link_left, void *link_right,
-                                     unsigned epoch, void *stream) {
+                                     unsigned epoch, unsigned prev_epoch, unsigned prev_rows, int passes, void *stream) {
     if (!d_left || !d_right || !d_cv_tile || !d_census_workspace || !d_sgm_workspace || !link_local || !link_left || !link_right || H <= 0 ||
-        Wg <= 0 || D <= 0 || ntiles < 1 || tile < 0 || tile >= ntiles || Wg % ntiles != 0) {
+        Wg <= 0 || D <= 0 || nimg < 1 || ntiles < 1 || tile < 0 || tile >= ntiles || Wg % ntiles != 0 || (passes & 3) == 0 ||
+        (epoch & 0xFFFFu) == 0) {
         set_error("pb200_census_sgm_tile: bad argument (the image width must be a multiple of the number of tiles)");
         return PB200_ERR_BAD_ARG;
     }
-    if (H >= 65535) {
-        set_error("pb200_census_sgm_tile: at most 65534 rows (row tags share a word with the epoch)");
+    if ((long)nimg * H >= 65535) {
+        set_error("pb200_census_sgm_tile: at most 65534 rows per call (row tags share a word with the epoch)");
         return PB200_ERR_UNSUPPORTED;
     }
     const int Wt = Wg / ntiles;
@@ -593,28 +612,35 @@ extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, 
                   "small integer penalties, tile width <= 28 columns per SM)");
         return PB200_ERR_UNSUPPORTED;
     }
-    if (census_workspace_bytes < pb200_census_sgm_workspace_bytes(H, Wg, window, dmin, D)) {
-        set_error("pb200_census_sgm_tile: census workspace too small (pb200_census_sgm_workspace_bytes of the WHOLE image)");
+    if (census_workspace_bytes < (size_t)nimg * pb200_census_sgm_workspace_bytes(H, Wg, window, dmin, D)) {
+        set_error("pb200_census_sgm_tile: census workspace too small (nimg x pb200_census_sgm_workspace_bytes of the WHOLE image)");
         return PB200_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    // descriptors, indexed by global image column; only the columns this tile's pixels visit are computed: the sheared tile
-    // [tile * Wt, (tile + 1) * Wt) drifts one image column to the left per row, Wt + H - 1 columns in all (cyclically)
-    const int span = Wt + H - 1 < Wg ? Wt + H - 1 : Wg;
-    const int lo = ((tile * Wt - (H - 1)) % Wg + Wg) % Wg;
-    int rc;
-    if (span == Wg) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s);
-    else if (lo + span <= Wg) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, lo, lo + span);
-    else {
-        rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, lo, Wg);
-        if (rc == PB200_OK) rc = census_sgm_descriptors(1, d_left, d_right, H, Wg, window, dmin, D, d_census_workspace, s, 0, lo + span - Wg);
+    const int pitch = census_pitch(Wg), pitch4 = census_pitch4(Wg, dmin, D);
+    // workspace: [nimg][H][pitch] left descriptors, then [nimg][4][H][pitch4] shifted right copies -- indexed by global image column
+    uint32_t *descL = (uint32_t *)d_census_workspace, *desc4 = descL + (size_t)nimg * H * pitch;
+    if (passes & 1) {
+        // only the columns this tile's pixels visit are computed: the sheared tile [tile * Wt, (tile + 1) * Wt) drifts one image
+        // column to the left per row (the drift continues through the images of a batch), cyclically
+        const long rows = (long)nimg * H;
+        const int span = Wt + rows - 1 < Wg ? (int)(Wt + rows - 1) : Wg;
+        const int lo = (int)((((long)tile * Wt - (rows - 1)) % Wg + Wg) % Wg);
+        for (int im = 0; im < nimg; ++im) {
+            const float *l = d_left + (size_t)im * H * Wg, *r = d_right + (size_t)im * H * Wg;
+            uint32_t *dl = descL + (size_t)im * H * pitch, *d4 = desc4 + (size_t)im * 4 * H * pitch4;
+            int rc;
+            if (lo + span <= Wg) rc = census_tile_descriptors(l, r, H, Wg, window, dmin, D, dl, d4, lo, lo + span, s);
+            else {
+                rc = census_tile_descriptors(l, r, H, Wg, window, dmin, D, dl, d4, lo, Wg, s);
+                if (rc == PB200_OK) rc = census_tile_descriptors(l, r, H, Wg, window, dmin, D, dl, d4, 0, lo + span - Wg, s);
+            }
+            if (rc != PB200_OK) return rc;
+        }
     }
-    if (rc != PB200_OK) return rc;
-    const int pitch = census_pitch(Wg);
     CensusDesc desc;
-    desc.L = (uint32_t *)d_census_workspace; desc.R = desc.L + (size_t)H * pitch; desc.pitch = pitch;
-    desc.R4 = desc.R + (size_t)H * pitch;
-    desc.pitch4 = census_pitch4(Wg, dmin, D); desc.padl = census_padl(dmin);
+    desc.L = descL; desc.R = nullptr; desc.pitch = pitch;
+    desc.R4 = desc4; desc.pitch4 = pitch4; desc.padl = census_padl(dmin);
     // link buffers: [in pass 1 | in pass 2 | credit pass 1 | credit pass 2].  Pass 1 travels left -> right (data comes from the
     // left tile, credits come from the right one), pass 2 right -> left.
     const size_t blk = (sgm_wave1_edge_bytes(D) + 255) & ~(size_t)255;
@@ -625,12 +651,18 @@ extern "C" int pb200_census_sgm_tile(const float *d_left, const float *d_right, 
     peers.out[0] = at(link_right, 0);           peers.ack_out[0] = at(link_left, 2 * blk);
     peers.out[1] = at(link_left, blk);          peers.ack_out[1] = at(link_right, 2 * blk + 256);
     peers.Wg = Wg;
+    // the two passes walk the batch as ONE image of nimg * H rows: the shear (and the pass-2 tile origin) use that height
+    const long rows = (long)nimg * H;
     peers.c_off[0] = tile * Wt;
-    peers.c_off[1] = (((H - 1 - (tile + 1) * Wt) % Wg) + Wg) % Wg;
+    peers.c_off[1] = (int)((((rows - 1 - (long)(tile + 1) * Wt) % Wg) + Wg) % Wg);
     peers.epoch = epoch & 0xFFFFu;
+    peers.prev_epoch = prev_epoch & 0xFFFFu;
+    peers.prev_rows = prev_rows;
+    peers.passes = passes & 3;
+    peers.nimg = nimg;
     bool done = false;
-    rc = sgm_census_wave_try(desc, window, d_cv_tile, H, Wt, D, p1, p2, overcounting, d_disp_tile, dmin, invalid_disparity, d_all_nan_tile,
-                             d_sgm_workspace, sgm_workspace_bytes, s, &done, &peers);
+    int rc = sgm_census_wave_try(desc, window, d_cv_tile, H, Wt, D, p1, p2, overcounting, d_disp_tile, dmin, invalid_disparity, d_all_nan_tile,
+                                 d_sgm_workspace, sgm_workspace_bytes, s, &done, &peers);
     if (rc != PB200_OK) return rc;
     if (!done) {
         set_error("pb200_census_sgm_tile: the wavefront kernels could not be made co-resident (workspace or shared memory)");

@@ -73,6 +73,11 @@ struct Wave1Peers {
     int c_off[2];
     int Wg;
     uint32_t epoch;
+    uint32_t prev_rows;       // rows (images x H) of the call that used these links last
+    uint32_t prev_epoch;      // epoch of the image that used these links last (0: none): a pass first waits until the neighbour
+                              // has consumed that image's last row, so that back-to-back passes of the SAME direction are safe
+    int passes;               // bit 0: pass 1, bit 1: pass 2
+    int nimg;                 // images of the batch (they follow each other in one wave)
 };
 
 // ---- device helpers -----------------------------------------------------------------------------

@@ -40,8 +40,10 @@ struct NarrowParams {
     int K;
     unsigned long long *peer_in_l, *peer_out_l, *peer_in_r, *peer_out_r;
     uint32_t tag_base;        // added to every ring tag: (epoch << 16) for peer rings that are never cleared
+    uint32_t prev_ack;        // peer links: the credit word value that says "the previous image has left this link" (0: none)
     int Wg, c_off;            // skewed wavefront: width of the (global) sheared ring, sheared column of this tile's column 0
     int sheared_store;        // 1: the volume / disparity tile is stored by sheared column (multi-GPU tiles), 0: by image column
+    int nimg;                 // images of a batch that follow each other in one wave (descriptors, volume, disparity: [nimg][...])
 };
 
 

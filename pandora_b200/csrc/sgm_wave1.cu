@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     const int K = p.K, NVM = K + 2;                      // mailbox columns: 0 / 1 = previous strip's last two columns, 2 .. K+1 = ours
     const int strip = blockIdx.x, nstrips = gridDim.x;
     const int H = p.H, D = p.D;
+    const int HT = p.nimg * H;                           // rows of the whole batch: the images follow each other in ONE wave
     const int Wt = p.W, Wg = p.Wg;                       // local (tile) width = storage pitch, global width of the sheared ring
     const int x0 = strip * K;
     const int nce = min(K, Wt - x0);                     // sheared columns of this strip
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
         const size_t bl = (size_t)(strip == 0 ? nstrips - 1 : strip - 1) * G::BLK;
         const unsigned long long *rin = peer ? p.peer_in_l : p.ring + bl;
         unsigned long long *ack = peer ? p.peer_out_l : p.ring + bl + (size_t)W1_NRG * 4 * VS;
-        for (int y = 0; y < H; ++y) {
+        for (int y = 0; y < HT; ++y) {
             uint32_t v[NR];
             if (y >= 1) flag_wait_sleep(prog_base + 3u * 4u, (uint32_t)(y - 1));     // columns 2 / 3 have loaded their inputs of row y - 2
             if (y > 0) {                                  // B(y-1): S, SE of the previous column and SE of the one before, row y - 1
@@ -187,13 +188,15 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
         unsigned long long *rout = peer ? p.peer_out_r : p.ring + br;
         const unsigned long long *ack = peer ? p.peer_in_r : p.ring + br + (size_t)W1_NRG * 4 * VS;
         uint32_t acked = tag0;                            // rows the receiver has consumed (tag space)
-        for (int y = 0; y < H; ++y) {
+        if (peer && p.prev_ack != 0u)                     // the neighbour still reads the previous image's last rows from this link
+            while ((uint32_t)ll_load(ack) != p.prev_ack) __nanosleep(500);
+        for (int y = 0; y < HT; ++y) {
             uint32_t v[NR];
             if (y >= W1_NRG) {                            // ring credit: row y - NRG has left the block
                 const uint32_t need = tag0 + (uint32_t)(y - W1_NRG + 1);
                 while ((int)(acked - need) < 0) {
                     const uint32_t a = (uint32_t)ll_load(ack);
-                    if ((int)(a - tag0) >= 0 && (int)(a - tag0) <= H) acked = a;     // words of an older epoch are not credits
+                    if ((int)(a - tag0) >= 0 && (int)(a - tag0) <= HT) acked = a;     // words of an older epoch are not credits
                     if ((int)(acked - need) < 0) __nanosleep(200);
                 }
             }
@@ -228,48 +231,53 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
     const bool is_last = warp + 1 == nce, is_prev = warp + 2 == nce;
     // storage: by image coordinates (one GPU: the (H, W, D) volume of the C-ABI) or by sheared column (a tile of a multi-GPU run)
-    auto pixel = [&](int y, int kk) -> size_t {
-        const int yi = FINAL ? H - 1 - y : y;
+    // (`im` = image of the batch, `yl` = row inside it, travel order)
+    auto pixel = [&](int im, int yl, int kk) -> size_t {
+        const int yi = FINAL ? H - 1 - yl : yl;
+        const int imi = FINAL ? p.nimg - 1 - im : im;    // the second pass walks the batch backwards, like the rows of an image
         const int col = p.sheared_store ? (FINAL ? Wt - 1 - (x0 + warp) : x0 + warp) : (FINAL ? Wg - 1 - kk : kk);
-        return (size_t)yi * Wt + col;
+        return ((size_t)imi * H + yi) * Wt + col;
     };
     // private staging ring [NSTG][K][SIN].  First pass: a pixel's block = its D right descriptors (lane-major) | the left one;
     // second pass: [32][RW] cost words | [32][NR] partial sums.
     const uint32_t stg_pix = (uint32_t)SIN * 4u, stg_stage = (uint32_t)K * stg_pix;
     const uint32_t stg_me = stg_base0 + (uint32_t)warp * stg_pix;
     const uint32_t off0 = (uint32_t)(lane * RW) * 4u, off1 = (uint32_t)(32 * RW + lane * NR) * 4u;
-    int kpf = k;                                          // image column of the row being prefetched
+    int kpf = k, ylpf = 0, impf = 0;                      // image column / row / image of the row being prefetched
     auto stage_row = [&](int r) {
-        if (r < H) {
+        if (r < HT) {
             const uint32_t sg = stg_me + (uint32_t)(r & (NSTG - 1)) * stg_stage;
             if (CENSUS) {
                 // the window [kpf + dmin, kpf + dmin + D) starts 16-byte aligned in the copy whose shift is (kpf + dmin) & 3
                 const int ws = kpf + p.dmin, sh = ws & 3;
-                const uint32_t *src = p.descR4 + ((size_t)sh * H + r) * p.pitch4 + (ws - sh + p.padl) + lane * NR;
+                const uint32_t *src = p.descR4 + (((size_t)impf * 4 + sh) * H + ylpf) * p.pitch4 + (ws - sh + p.padl) + lane * NR;
                 cp_async_words<NR>(sg + lane_b, src);
                 cp_async_words<NR>(sg + VB + lane_b, src + VS);
-                if (lane == 0) cp_async_words<1>(sg + 2u * VB, p.descL + (size_t)r * p.pitch + kpf);
+                if (lane == 0) cp_async_words<1>(sg + 2u * VB, p.descL + ((size_t)impf * H + ylpf) * p.pitch + kpf);
             } else {
-                const uint32_t *src = p.buf + pixel(r, kpf) * D;
+                const uint32_t *src = p.buf + pixel(impf, ylpf, kpf) * D;
                 cp_async_words<RW>(sg + off0, src + lane * RW);
                 cp_async_words<NR>(sg + off1, src + poff);
             }
         }
         kpf = kpf == 0 ? Wg - 1 : kpf - 1;
+        if (++ylpf == H) { ylpf = 0; ++impf; }
     };
     for (int r = 0; r < PFD; ++r) {
         stage_row(r);
         cp_async_commit();
     }
+    int yl = 0, im = 0;                                   // row inside the current image, image of the batch
     uint32_t SW[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) SW[j] = 0u;
     const uint32_t nan2 = (p.inv | Tier<CB>::FLAG1) * 0x10001u;
 
 #pragma unroll 1
-    for (int y = 0; y < H; ++y) {
+    for (int y = 0; y < HT; ++y) {
         const uint32_t par = (uint32_t)(y & 1) * SLOTB, prv = SLOTB - par;
-        uint32_t *grow = p.buf + pixel(y, k) * D;
+        const size_t pix = pixel(im, yl, k);
+        uint32_t *grow = p.buf + pix * D;
         // ---- the pixel's cost codes (16 bits each, NaN flag in bit 15 / 7) and the partial sums so far -------------------------
         uint32_t c16[NR], cc[NR], tot[NR];
         stage_row(y + PFD);
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 
         uint32_t Lp[NR], Lq[NR], L[NR];
         // ---- SW: this column's own state of the previous row (the pixel up-right); a path start at the right image border --------
-        if (k == Wg - 1) {
+        if (k == Wg - 1 || yl == 0) {                     // also the first row of every image of the batch: all paths start
 #pragma unroll
             for (int j = 0; j < NR; ++j) SW[j] = 0u;
         }
@@ -323,12 +331,20 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
             ev_wait(ev_base + (vme - 1u) * 16u, y);
             lds_words<NR>(e_base + par + (vme - 1u) * VB, Lp);
             lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
+            if (yl == 0) {                                // first row of an image: S (and SE below) are path starts
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Lq[j] = 0u;
+            }
             nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
             sts_words<NR>(e_base + par + vme * VB, L);
             ev_signal(ev_base + vme * 16u, y, lane);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += L[j];
             lds_words<NR>(se_base + prv + (vme - 2u) * VB, Lp);
+            if (yl == 0) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Lp[j] = 0u;
+            }
             nstep<NR>(cc, Lq, L, lane, p1p1, p2p2);                       // S
             sts_words<NR>(s_base + par + vme * VB, L);
 #pragma unroll
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
         } else {
             // ---- chain start (left image border): E and SE are path starts, S comes from the left neighbour's previous row, which
             // that neighbour finished as a chain start itself; everything is stored BEFORE the E-event (see the file header) ---------
-            if (y > 0) {
+            if (yl > 0) {
                 if (vme == 2u) flag_wait_sleep(rdc_flag, (uint32_t)y);    // across the strip boundary: the in-relay has delivered row y - 1
                 lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
             } else {
@@ -394,7 +410,6 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
                 uint32_t best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
                 best = __reduce_min_sync(0xffffffffu, best);
                 if (lane == 0) {
-                    const size_t pix = pixel(y, k);
                     const bool none = (best >> 16) >= ((CB == 1) ? 0xFF80u : 0xFFFFu);
                     p.disp[pix] = none ? p.invalid_disparity : (float)(p.dmin + (int)(best & 0xFFFFu));
                     if (p.all_nan) p.all_nan[pix] = none ? 1 : 0;
@@ -402,6 +417,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
             }
         }
         k = k == 0 ? Wg - 1 : k - 1;
+        if (++yl == H) { yl = 0; ++im; }
     }
 }
 
@@ -434,18 +450,25 @@ int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, size_t rin
         q1.peer_in_l = peers->in[0]; q1.peer_out_l = peers->ack_out[0]; q1.peer_out_r = peers->out[0]; q1.peer_in_r = peers->ack_in[0];
         q2.peer_in_l = peers->in[1]; q2.peer_out_l = peers->ack_out[1]; q2.peer_out_r = peers->out[1]; q2.peer_in_r = peers->ack_in[1];
         q1.tag_base = q2.tag_base = peers->epoch << 16;
+        q1.prev_ack = q2.prev_ack = peers->prev_epoch ? (peers->prev_epoch << 16) + (uint32_t)(peers->prev_rows) : 0u;
         q1.c_off = peers->c_off[0]; q2.c_off = peers->c_off[1];
         q1.Wg = q2.Wg = peers->Wg;
         q1.sheared_store = q2.sheared_store = 1;
+        q1.nimg = q2.nimg = peers->nimg;
     }
     void *args1[] = {(void *)&q1}, *args2[] = {(void *)&q2};
-    PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
-    PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(threads), args1, smem1, s));
-    PB200_LAUNCH_CHECK("sgm_wave1_kernel<down, census>");
-    PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
-    PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(threads), args2, smem2, s));
-    PB200_LAUNCH_CHECK("sgm_wave1_kernel<up>");
+    const int passes = peers != nullptr ? peers->passes : 3;
+    if (passes & 1) {
+        PB200_CUDA(cudaMemsetAsync(p.flag, 0, sizeof(int), s));
+        PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+        PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w1, dim3(nstrips), dim3(threads), args1, smem1, s));
+        PB200_LAUNCH_CHECK("sgm_wave1_kernel<down, census>");
+    }
+    if (passes & 2) {
+        PB200_CUDA(cudaMemsetAsync(p.ring, 0, wring, s));
+        PB200_CUDA(cudaLaunchCooperativeKernel((const void *)w2, dim3(nstrips), dim3(threads), args2, smem2, s));
+        PB200_LAUNCH_CHECK("sgm_wave1_kernel<up>");
+    }
     note_path(STAGE_SGM, PATH_SGM_WAVE1_CENSUS, NR * 10 + CB);
     *done = true;
     return PB200_OK;
@@ -478,6 +501,7 @@ int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace,
     if (K == 0 || p.descR4 == nullptr) return PB200_OK;
     const int nstrips = ceil_div(p.W, K);
     if (peers == nullptr) { p.Wg = p.W; p.c_off = 0; p.sheared_store = 0; p.tag_base = 0; }
+    if (p.nimg < 1) p.nimg = 1;
     if (NR == 4) return bytes ? launch_wave1<4, 1>(p, K, nstrips, workspace, ring_room, peers, s, done)
                               : launch_wave1<4, 2>(p, K, nstrips, workspace, ring_room, peers, s, done);
     if (NR == 2) return bytes ? launch_wave1<2, 1>(p, K, nstrips, workspace, ring_room, peers, s, done)

@@ -290,13 +290,13 @@ class TileLinks:
 
 
 class ColumnTiledStereoPipeline:
-    """Census -> SGM -> WTA on an image ``Wg`` columns wide, column-tiled over the ranks of one node: every rank runs the
+    """Census -> SGM -> WTA on images ``Wg`` columns wide, column-tiled over the ranks of one node: every rank runs the
     two skewed-wavefront passes on its ``Wt = Wg / world`` sheared columns and the border path states cross the GPU
     boundaries inside the kernels (NVLink peer stores).  Bit-identical to the one-GPU result.
 
-    ``run(left, right)`` takes the WHOLE images on the device (a tile's pixels drift ``Wt + H - 1`` image columns to the
-    left) and returns this rank's disparity tile in sheared layout; ``unshear`` turns it into the normal-layout image tile
-    (one neighbour exchange when ``H <= Wt``, an all-gather otherwise)."""
+    ``run(left, right)`` takes WHOLE images on the device -- one (H, Wg) pair, or a batch (n, H, Wg) whose images follow
+    each other in one wave (stream throughput: the time a wave needs to cross all GPUs is paid once per pass and batch) -- and
+    returns this rank's disparity tile(s) in sheared layout; ``unshear`` turns them into normal-layout image tiles."""
 
     def __init__(self, H: int, Wg: int, dmin: int, dmax: int, rank: int, world: int, dist, window: int = 5, p1: float = 8.0,
                  p2: float = 32.0, overcounting: bool = False, invalid_disparity: float = -9999.0, device=None):
@@ -314,57 +314,111 @@ class ColumnTiledStereoPipeline:
         self.p1, self.p2, self.over, self.invalid = float(p1), float(p2), bool(overcounting), float(invalid_disparity)
         with torch.cuda.device(self.eng.device):
             self.links = TileLinks(self.lib, dist, rank, world, self.D)
-        e = self.eng
-        self.cv = e.empty((H, self.Wt, self.D))
-        self.disp = e.empty((H, self.Wt))
-        self.flags = e.empty((H, self.Wt), torch.uint8)
-        self.cws = e._workspace("census", self.lib.pb200_census_sgm_workspace_bytes(H, Wg, window, dmin, self.D))
-        self.sws = e._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, self.Wt, self.D))
-        self.epoch = 0
-        self._recv = None
-        self._idx = None
+        self._bufs = {}
+        self.sws = self.eng._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(H, self.Wt, self.D))
+        self.epoch, self._prev = 0, (0, 0)                 # (epoch, rows) of the call that used the links last
+        self.nimg = 1
+        self.cv = self.disp = self.flags = None
+        self._cache = {}
         if world > 1:
             dist.barrier()                                 # every link buffer exists and is mapped before the first wave
 
-    def run(self, left, right, want_volume: bool = True):
-        """``left`` / ``right``: float32 (H, Wg) device tensors holding at least the image columns this tile visits."""
+    def _buffers(self, n: int):
+        """Volume / disparity / flag tiles and the descriptor workspace of a batch of ``n`` images."""
+        if n not in self._bufs:
+            e, t = self.eng, self.torch
+            self._bufs[n] = (e.empty((n, self.H, self.Wt, self.D)), e.empty((n, self.H, self.Wt)), e.empty((n, self.H, self.Wt), t.uint8))
+        self.cws = self.eng._workspace("census", n * self.lib.pb200_census_sgm_workspace_bytes(self.H, self.Wg, self.window, self.dmin, self.D))
+        return self._bufs[n]
+
+    def run(self, left, right):
+        """``left`` / ``right``: float32 (H, Wg) or (n, H, Wg) device tensors holding at least the image columns this tile visits.
+        Returns this rank's disparity tile(s) (H, Wt) / (n, H, Wt) in sheared layout (``unshear`` gives the image tiles)."""
         from . import _native  # noqa: PLC0415
 
         t = self.torch
-        assert tuple(left.shape) == (self.H, self.Wg) and left.is_contiguous() and right.is_contiguous()
-        self.epoch += 1
+        single = left.dim() == 2
+        n = 1 if single else int(left.shape[0])
+        assert tuple(left.shape[-2:]) == (self.H, self.Wg) and left.is_contiguous() and right.is_contiguous() and right.shape == left.shape
+        cv, disp, flags = self._buffers(n)
+        self.epoch = self.epoch % 65535 + 1                # 1 .. 65535: every ring word carries it, 0 means "never written"
         with t.cuda.device(self.eng.device):
             _native.check(self.lib.pb200_census_sgm_tile(
-                left.data_ptr(), right.data_ptr(), self.H, self.Wg, self.window, self.dmin, self.D, self.p1, self.p2, int(self.over),
-                self.rank, self.world, self.cv.data_ptr(), self.cws.data_ptr(), self.cws.numel(), self.sws.data_ptr(), self.sws.numel(),
-                self.disp.data_ptr(), self.invalid, self.flags.data_ptr(), self.links.local, self.links.left, self.links.right,
-                self.epoch, t.cuda.current_stream(self.eng.device).cuda_stream))
+                left.data_ptr(), right.data_ptr(), n, self.H, self.Wg, self.window, self.dmin, self.D, self.p1, self.p2, int(self.over),
+                self.rank, self.world, cv.data_ptr(), self.cws.data_ptr(), self.cws.numel(), self.sws.data_ptr(), self.sws.numel(),
+                disp.data_ptr(), self.invalid, flags.data_ptr(), self.links.local, self.links.left, self.links.right,
+                self.epoch, self._prev[0], self._prev[1], 3, t.cuda.current_stream(self.eng.device).cuda_stream))
+        self._prev = (self.epoch, n * self.H)
+        self.nimg = n
+        self.cv, self.disp, self.flags = (cv[0], disp[0], flags[0]) if single else (cv, disp, flags)
         return self.disp
 
-    def visited_columns(self):
-        """(lo, n): the cyclic range of image columns [lo, lo + n) mod Wg whose pixels this tile processes."""
-        n = min(self.Wg, self.Wt + self.H - 1)
-        return (self.rank * self.Wt - (self.H - 1)) % self.Wg, n
+    def visited_columns(self, nimg: int = 1):
+        """(lo, n): the cyclic range of image columns [lo, lo + n) mod Wg whose pixels this tile processes in a batch of ``nimg``."""
+        rows = nimg * self.H
+        n = min(self.Wg, self.Wt + rows - 1)
+        return (self.rank * self.Wt - (rows - 1)) % self.Wg, n
 
     def unshear(self, tile=None):
-        """Sheared tile (default: the disparity map of the last run) -> normal-layout image tile of this rank."""
+        """Sheared tile(s) (default: the disparity tiles of the last run) -> normal-layout image tile(s) of this rank.  A batch is
+        one tall sheared image: row y of image i sits at sheared row i * H + y."""
         t, dist = self.torch, self.dist
         src = self.disp if tile is None else tile
-        if self.world == 1:
-            return unshear_gathered(src[None], self.Wg, 0)
-        if self.H <= self.Wt and src.dim() == 2:
-            # row y of image tile g = sheared columns [y, y + Wt) of ranks g and g + 1: one exchange with the neighbours
-            if self._recv is None or self._recv.shape != src.shape:
-                self._recv = t.empty_like(src)
-                y = t.arange(self.H, device=src.device)[:, None]
-                self._idx = t.arange(self.Wt, device=src.device)[None, :] + y
-            ops = [dist.P2POp(dist.isend, src, (self.rank - 1) % self.world), dist.P2POp(dist.irecv, self._recv, (self.rank + 1) % self.world)]
+        batched = tuple(src.shape[:2]) != (self.H, self.Wt)       # (n, H, Wt[, ...]) rather than (H, Wt[, ...])
+        assert tuple(src.shape[1:3] if batched else src.shape[:2]) == (self.H, self.Wt), "not a sheared tile of this pipeline"
+        n = int(src.shape[0]) if batched else 1
+        rows = n * self.H
+        flat = src.reshape((rows, self.Wt) + tuple(src.shape[3 if batched else 2:]))
+        if self.world > 1 and flat.dim() == 2 and self.Wt % self.H == 0:
+            out = self._unshear_neighbours(flat.view(n, self.H, self.Wt))
+            return out if batched else out[0]
+        # general case (tiles that drift across several neighbours inside one image, or a volume): all-gather + one indexed read
+        key = (tuple(flat.shape), flat.dtype)
+        if key not in self._cache:
+            owner, col = sheared_owner(self.Wg, self.Wt, self.rank, rows)
+            idx = (owner * rows + np.arange(rows, dtype=np.int64)[:, None]) * self.Wt + col             # into (world, rows, Wt)
+            self._cache[key] = (t.empty((self.world,) + tuple(flat.shape), dtype=flat.dtype, device=flat.device),
+                                t.from_numpy(idx.reshape(-1)).to(flat.device))
+        buf, idx = self._cache[key]
+        if self.world > 1:
+            dist.all_gather_into_tensor(buf, flat.contiguous())
+        else:
+            buf[0].copy_(flat)
+        inner = int(np.prod(flat.shape[2:])) if flat.dim() > 2 else 1
+        out = buf.view(self.world * rows * self.Wt, inner).index_select(0, idx).view(flat.shape)
+        return out.view(src.shape)
+
+    def _unshear_neighbours(self, tiles):
+        """(n, H, Wt) sheared disparity tiles with Wt a multiple of H: the sheared rows of image i all lie in one block of Wt rows,
+        so image tile g of image i = columns [o + y, o + y + Wt) of ranks g + q and g + q + 1, q = (i * H) // Wt, o = (i * H) % Wt:
+        every rank sends the tile of image i to the two ranks that need it (NCCL point-to-point over NVLink) and reads its own
+        image tile out of the two it receives."""
+        t, dist = self.torch, self.dist
+        n, N, r = int(tiles.shape[0]), self.world, self.rank
+        key = ("nb", n)
+        if key not in self._cache:
+            y = t.arange(self.H, device=tiles.device)[:, None]
+            j = t.arange(self.Wt, device=tiles.device)[None, :]
+            self._cache[key] = (t.empty((n, 2, self.H, self.Wt), dtype=tiles.dtype, device=tiles.device),
+                                [((i * self.H) % self.Wt + y + j) for i in range(n)])
+        recv, idx = self._cache[key]
+        ops, local = [], []
+        for i in range(n):
+            q = (i * self.H) // self.Wt
+            for which, dst in enumerate(((r - q) % N, (r - q - 1) % N)):       # the image tiles my sheared tile contributes to
+                src_rank = (r + q + which) % N                                # ... and who contributes part `which` of mine
+                if dst == r:
+                    local.append((i, which))
+                else:
+                    ops.append(dist.P2POp(dist.isend, tiles[i], dst))
+                if src_rank != r:
+                    ops.append(dist.P2POp(dist.irecv, recv[i, which], src_rank))
+        for i, which in local:
+            recv[i, which].copy_(tiles[i])
+        if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-            return t.gather(t.cat([src, self._recv], dim=1), 1, self._idx)
-        gathered = [t.empty_like(src) for _ in range(self.world)]
-        dist.all_gather(gathered, src.contiguous())
-        return unshear_gathered(t.stack(gathered), self.Wg, self.rank)
+        return t.stack([t.gather(t.cat([recv[i, 0], recv[i, 1]], dim=1), 1, idx[i]) for i in range(n)])
 
     def close(self):
         self.links.close()

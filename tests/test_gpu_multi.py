@@ -109,6 +109,15 @@ def _col_worker(rank, world, port, H, Wg, D, dmin, steps, tmpdir):
         tile = pipe.unshear()
         torch.cuda.synchronize()
         _log(rank, f"column-tiled step {it} done")
+    # a batch of three images in one wave (image 1 differs: its paths must not leak into its neighbours)
+    l3, r3 = torch.stack([lt, rt, lt]), torch.stack([rt, lt, rt])
+    pipe.run(l3, r3)
+    out3 = pipe.unshear()
+    assert torch.equal(out3[0], tile) and torch.equal(out3[2], tile), "batched image differs"
+    vol3 = pipe.unshear(pipe.cv)
+    pipe.run(rt, lt)                         # the swapped pair alone, after a batch (link epochs / credits of both passes)
+    assert torch.equal(pipe.unshear(), out3[1]) and torch.equal(torch.nan_to_num(pipe.unshear(pipe.cv)), torch.nan_to_num(vol3[1]))
+    pipe.run(lt, rt)
     np.save(os.path.join(tmpdir, f"cdisp{rank}.npy"), tile.cpu().numpy())
     np.save(os.path.join(tmpdir, f"cS{rank}.npy"), pipe.unshear(pipe.cv).cpu().numpy())
     dist.barrier()
@@ -161,6 +170,12 @@ def test_column_tile_self_linked_on_one_gpu_vs_oracle(H, W, D, dmin, oracle):
     for _ in range(3):
         pipe.run(lt, rt)
         np.testing.assert_array_equal(pipe.unshear().cpu().numpy(), disp)
+    pipe.run(torch.stack([lt, rt, lt]), torch.stack([rt, lt, rt]))            # a batch in one wave; image 1 is another pair
+    out3 = pipe.unshear().cpu().numpy()
+    np.testing.assert_array_equal(out3[0], disp)
+    np.testing.assert_array_equal(out3[2], disp)
+    np.testing.assert_array_equal(pipe.unshear(pipe.cv)[2].cpu().numpy(), S)
+    pipe.run(lt, rt)
     np.testing.assert_array_equal(pipe.unshear(pipe.cv).cpu().numpy(), S)
     np.testing.assert_array_equal(pipe.unshear(pipe.flags).cpu().numpy().astype(bool), inv)
     pipe.close()
