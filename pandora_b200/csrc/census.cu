@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) census_transform_shifted_kernel(const flo
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s)
-        if (i - s >= 0 && i - s < pitch4) desc4[((size_t)s * H + y) * pitch4 + (i - s)] = word;
+        if (i - s >= 0 && i - s < pitch4) desc4[((size_t)y * 4 + s) * pitch4 + (i - s)] = word;      // [row][copy][column]
 }
 static inline int census_padl(int dmin) { return (((dmin < 0 ? -dmin : 0) + 3) & ~3) + 4; }
 static inline int census_pitch4(int W, int dmin, int D) {

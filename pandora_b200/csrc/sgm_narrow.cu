@@ -368,22 +368,25 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
     // p.debug (PB200_SGM_DEBUG, timing experiments only, wrong results): bit 0 = no strip exchange, bit 2 = no mailbox waits
     const bool has_left = strip > 0 && !(p.debug & 1), has_right = strip + 1 < nstrips && !(p.debug & 1);
     // shared: e[4][NV][VS] | se[4][NV][VS] | sw[4][NV][VS] | fe[32] fs[32] | staging
-    const int state_words = 12 * NV * VS + 64;
+    const int state_words = 12 * NV * VS + 64 + 256;    // + the hand-over events: FE[16][4] | FS[16][4] mbarriers
     // mailboxes, counters AND the staging ring start as zeros (columns right of the image are never staged and must
     // read as zero costs, which also pass the data check; a strip without a neighbour reads flat zero states)
     const int stage_words = CENSUS ? NSTG * nc * CW : NSTG * nc * 2 * 32 * SIN;
     for (int i = threadIdx.x; i < state_words + stage_words; i += blockDim.x) wave_smem[i] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (!has_left) wave_smem[12 * NV * VS + 0] = 0xFFFFFFFFu;                // fe[0]: the image border never makes anyone wait
-        if (!has_right) wave_smem[12 * NV * VS + 32 + NV - 1] = 0xFFFFFFFFu;      // fs[nc + 1]
-    }
+    // Hand-over events are mbarrier phases, not spin flags: a warp that is early sleeps in hardware (mbarrier.try_wait)
+    // instead of looping LDS / ISETP / BRA through the issue slots of the working warps -- those loops were 44 % of all
+    // issued instructions of this kernel (profiles/r1_ncu_fused_pass1.txt).  Event r of a stream completes phase r >> 2 of
+    // its barrier r & 3; the four-slot discipline below keeps a producer at most three events ahead of a waiter, i.e.
+    // never a whole phase ahead on one barrier.  An image border is a neighbour that is never waited for.
+    if (threadIdx.x < 128)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(wave_smem + 12 * NV * VS + 64) + threadIdx.x * 8u) : "memory");
     __syncthreads();
     const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
     const uint32_t e_base = smem_u32(wave_smem) + lane_b;
     const uint32_t se_base = e_base + (uint32_t)(4 * NV * VS) * 4u;
     const uint32_t sw_base = se_base + (uint32_t)(4 * NV * VS) * 4u;
-    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(12 * NV * VS) * 4u, fs_base = fe_base + 128u;
+    const uint32_t fe_base = smem_u32(wave_smem) + (uint32_t)(12 * NV * VS) * 4u + 256u, fs_base = fe_base + 512u;   // event streams: + 32 v
     const uint32_t SLOT = (uint32_t)(NV * VS) * 4u, VB = (uint32_t)VS * 4u;      // bytes per mailbox slot / per vector
     // ring, per strip boundary b (between strips b and b + 1): 12 vectors of VS 64-bit words: e[4] | se[4] | sw[4]
     unsigned long long *ring_l = p.ring + (size_t)(strip - 1) * 12 * VS;         // boundary on our left (used when has_left)
@@ -396,14 +399,13 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             const uint32_t tag = (uint32_t)(i + 1);
             uint32_t v[NR];
             // outbound: SW_A(i) of the first compute warp (published one row early, see phase 1)
-            if (!nowait) flag_wait(fs_base + 1u * 4u, tag);
+            if (!nowait) ev4_wait(fs_base + 1u * 32u, i);
             lds_words<NR>(sw_base + (uint32_t)(i & 3) * SLOT + 1u * VB, v);
             ll_send_u32<NR>(ring_l + (size_t)(8 + (i & 3)) * VS, lane, tag, v);
             // inbound: E(i), then SE(i), of the left strip's last column
             ll_recv_u32<NR>(ring_l + (size_t)(0 + (i & 3)) * VS, lane, tag, v);
             sts_words<NR>(e_base + (uint32_t)(i & 3) * SLOT, v);
-            __syncwarp();
-            if (lane == 0) flag_publish(fe_base, tag, relaxed);
+            ev4_signal(fe_base, i, lane);
             ll_recv_u32<NR>(ring_l + (size_t)(4 + (i & 3)) * VS, lane, tag, v);
             sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT, v);                 // visible with the next E flag
         }
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             const uint32_t tag = (uint32_t)(i + 1);
             uint32_t v[NR];
             // outbound: E_B(i), SE_B(i) of the last compute warp
-            if (!nowait) flag_wait(fe_base + (uint32_t)nc * 4u, tag);
+            if (!nowait) ev4_wait(fe_base + (uint32_t)nc * 32u, i);
             lds_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + (uint32_t)nc * VB, v);
             ll_send_u32<NR>(ring_r + (size_t)(0 + (i & 3)) * VS, lane, tag, v);
             lds_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + (uint32_t)nc * VB, v);
@@ -423,14 +425,14 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
             // inbound: SW_A(i) of the right strip's first column
             ll_recv_u32<NR>(ring_r + (size_t)(8 + (i & 3)) * VS, lane, tag, v);
             sts_words<NR>(sw_base + (uint32_t)(i & 3) * SLOT + (uint32_t)(nc + 1) * VB, v);
-            __syncwarp();
-            if (lane == 0) flag_publish(fs_base + (uint32_t)(nc + 1) * 4u, tag, relaxed);
+            ev4_signal(fs_base + (uint32_t)(nc + 1) * 32u, i, lane);
         }
         return;
     }
 
     // ---- compute warps -------------------------------------------------------------------------------------------
     const uint32_t vme = (uint32_t)(warp + 1);            // this warp's mailbox column
+    const bool wait_l = has_left || warp > 0, wait_r = has_right || warp + 1 < nc;
     uint32_t *stg = wave_smem + state_words;              // [NSTG][nc][2 pixels][32 * SIN]
     // a pixel's staging block holds two lane-major parts so that every lane's vectors stay naturally aligned:
     // pass 1: [32][NR] low-half floats | [32][NR] high-half floats;  pass 2: [32][RW] cost words | [32][NR] partial sums
@@ -606,8 +608,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         for (int j = 0; j < NR; ++j) ccA[j] = c16A[j] & Tier<CB>::VALUES;
         nstep<NR>(ccA, zero, SWA_cur, lane, p1p1, p2p2);     // SW_A(0): a path start
         sts_words<NR>(sw_base + vme * VB, SWA_cur);
-        __syncwarp();
-        if (lane == 0) flag_publish(fs_base + vme * 4u, 1u, relaxed);
+        ev4_signal(fs_base + vme * 32u, 0, lane);
     }
 
 #pragma unroll 2
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
         for (int j = 0; j < NR; ++j) SW_in[j] = 0u;
         if (i > 0) {
-            if (!nowait) flag_wait(fs_base + (vme + 1u) * 4u, tag - 1);
+            if (!nowait && wait_r) ev4_wait(fs_base + (vme + 1u) * 32u, i - 1);
             lds_words<NR>(sw_base + (uint32_t)((i - 1) & 3) * SLOT + (vme + 1u) * VB, SW_in);
         }
         // Independent recurrence steps sit in one basic block (no flag, no warp barrier between them) so that the
@@ -653,13 +654,12 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         for (int j = 0; j < NR; ++j) Sv[0][j] = L0[j];
         sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, SWA_next);
         sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
-        __syncwarp();
-        if (lane == 0) flag_publish(fs_base + vme * 4u, tag + 1, relaxed);
+        ev4_signal(fs_base + vme * 32u, i + 1, lane);
 
         // ---- phase 2: the E chain -- wait, two steps, publish; SE_A (the left neighbour's SE state of the previous row is
         // visible since its E flag of this row) fills the bubbles of the E_A -> E_B chain ----------------------------------
         uint32_t E_in[NR], SE_in[NR], L_E_A[NR], L_E_B[NR], L_SE_A[NR];
-        if (!nowait) flag_wait(fe_base + (vme - 1u) * 4u, tag);
+        if (!nowait && wait_l) ev4_wait(fe_base + (vme - 1u) * 32u, i);
         lds_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + (vme - 1u) * VB, E_in);
 #pragma unroll
         for (int j = 0; j < NR; ++j) SE_in[j] = 0u;
@@ -668,8 +668,7 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         nstep<NR>(cc[0], SE_in, L_SE_A, lane, p1p1, p2p2);
         nstep<NR>(cc[1], L_E_A, L_E_B, lane, p1p1, p2p2);
         sts_words<NR>(e_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_E_B);
-        __syncwarp();
-        if (lane == 0) flag_publish(fe_base + vme * 4u, tag, relaxed);
+        ev4_signal(fe_base + vme * 32u, i, lane);
 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -739,7 +738,7 @@ int launch_wave(NarrowParams p, int nstrips, int nwarp, void *workspace, cudaStr
     void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false, CENSUS>;
     void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
     const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
-    const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64) * sizeof(uint32_t);
+    const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64 + 256) * sizeof(uint32_t);
     const size_t smem1 = state + (CENSUS ? (size_t)8 * nwarp * (2 * NR * 32 + 8) : (size_t)4 * nwarp * 2 * 32 * (2 * NR)) * sizeof(uint32_t);
     const size_t smem2 = state + (size_t)4 * nwarp * 2 * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
     int occ1 = 0, occ2 = 0;

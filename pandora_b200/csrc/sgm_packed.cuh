@@ -28,7 +28,7 @@ struct NarrowParams {
     // fused Census source of the first wavefront pass (CENSUS = true): planar one-word descriptors (census.cu)
     const uint32_t *descL, *descR;
     int pitch, half;
-    // skewed wavefront: the right descriptors as FOUR word-shifted, padded copies [s][H][pitch4]: copy s, index i holds the
+    // skewed wavefront: the right descriptors as FOUR word-shifted, padded copies [row][s][pitch4]: copy s, index i holds the
     // descriptor of image column i + s - padl (flagged outside the image), so that the D-wide window of ANY pixel starts
     // on a 16-byte boundary in the copy s = (column + dmin) & 3 and needs no bounds check
     const uint32_t *descR4;
@@ -173,6 +173,11 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
     }
 }
 
+// (Measured and dropped: the same step with its additions written as a * 1 + c with the 1 in a register the compiler cannot
+// see through, i.e. IMAD on the idle FMA pipe instead of IADD3 on the ALU pipe that the packed min-ops saturate.  Two IMAD
+// replace one IADD3 and the dependent chain gets longer: 15.40 -> 16.26 ms for the two-column kernels at C3, 17.42 -> 18.42 ms
+// for the skewed ones, profiles/r2_wave_kernels.txt.)
+
 // float32 cost -> 16-bit code (value, or invalid_value | 0x8000 for NaN); `bad` is raised for anything else
 template <int CB>
 __device__ __forceinline__ uint32_t encode_cost(float v, uint32_t inv, float ok_max, bool &bad) {
@@ -251,6 +256,32 @@ __device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t target) {
     do {
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     } while (v < target);
+}
+
+// Hand-over events as mbarrier phases, four barriers per stream: event r completes phase r >> 2 of barrier r & 3 (32 bytes per
+// stream).  The waiter sleeps in hardware; one predicated arrival (lane 0) with release semantics, the warp barrier in front
+// orders the other lanes' data stores before it.
+__device__ __forceinline__ void ev4_wait(uint32_t stream, int r) {
+    const uint32_t addr = stream + (uint32_t)(r & 3) * 8u, parity = (uint32_t)(r >> 2) & 1u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EV4_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EV4_DONE;\n"
+        "bra EV4_WAIT;\n"
+        "EV4_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ev4_signal(uint32_t stream, int r, int lane) {
+    const uint32_t addr = stream + (uint32_t)(r & 3) * 8u;
+    __syncwarp();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(addr), "r"(lane) : "memory");
 }
 
 }  // namespace

@@ -37,6 +37,8 @@
 //   5  total = [P16 +] SW + S + E + SE -> global
 // k = 0 (chain start, once per W rows): no wait, E_in = SE_in = flat, and steps 3 / 4 swap so that S and SE are stored
 // before the E-event: the right neighbour starts the NEXT row's chain and has no later event of ours to acquire.
+#include <type_traits>
+
 #include "sgm_packed.cuh"
 
 namespace pb200 {
@@ -92,16 +94,40 @@ __device__ __forceinline__ void ev_wait(uint32_t bar, int i) {
         "{\n"
         ".reg .pred p;\n"
         "W1_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // suspend-time hint: sleep, do not poll
+        // (no suspend-time hint: with one, ptxas wraps the wait in NANOSLEEP.SYNCS, which every arrive on ANY barrier of the
+        // SM wakes up -- 50 re-checks per row and waiting warp, profiles/r2_ncu_wave1_hint.txt; the plain form sleeps in hardware)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra W1_DONE;\n"
         "bra W1_WAIT;\n"
         "W1_DONE:\n"
-        "}\n" ::"r"(addr), "r"(parity), "r"(1000000u) : "memory");
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 // one arrival (lane 0, predicated: no divergent branch) with release semantics; the warp barrier in front orders the
 // other lanes' data stores before it
 __device__ __forceinline__ void ev_signal(uint32_t bar, int i, int lane) {
     const uint32_t addr = bar + (uint32_t)(i & 1) * 8u;
+    __syncwarp();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(addr), "r"(lane) : "memory");
+}
+
+// the same with the barrier address and the phase parity resolved by the caller (compile-time constants in the unrolled row loop)
+__device__ __forceinline__ void ev_wait_c(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W1C_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra W1C_DONE;\n"
+        "bra W1C_WAIT;\n"
+        "W1C_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ev_signal_c(uint32_t addr, int lane) {
     __syncwarp();
     asm volatile(
         "{\n"
@@ -122,7 +148,10 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     constexpr int NSTG = 4, PFD = 3;                     // input staging (per warp, cp.async): rows in the ring / in flight
     constexpr int SIN = CENSUS ? G::CIN : 32 * (RW + NR);   // staged words per pixel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int K = p.K, NVM = K + 2;                      // mailbox columns: 0 / 1 = previous strip's last two columns, 2 .. K+1 = ours
+    const int K = p.K;
+    constexpr int NVM = W1_MAXK + 2;                     // mailbox columns: 0 / 1 = previous strip's last two columns, 2 .. K+1 = ours
+    // (the geometry of the shared arrays is that of the widest strip whatever K is: every mailbox / staging address of a warp
+    // is then ONE base register plus an immediate)
     const int strip = blockIdx.x, nstrips = gridDim.x;
     const int H = p.H, D = p.D;
     const int HT = p.nimg * H;                           // rows of the whole batch: the images follow each other in ONE wave
@@ -130,15 +159,15 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     const int x0 = strip * K;
     const int nce = min(K, Wt - x0);                     // sheared columns of this strip
     // shared: e[2][NVM][VS] | s[2][NVM][VS] | se[2][NVM][VS] | events, counters | staging
-    const int mbox_words = 6 * NVM * VS;
-    const int stage_words = NSTG * K * SIN;
+    constexpr int mbox_words = 6 * NVM * VS;
+    constexpr int stage_words = NSTG * W1_MAXK * SIN;
     for (int i = threadIdx.x; i < mbox_words + W1_FLAG_WORDS + stage_words; i += blockDim.x) w1_smem[i] = 0u;
     __syncthreads();
     if (threadIdx.x < 68)                                                        // E[32][2] | RD[2][2], one arrival per phase
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(w1_smem + mbox_words) + threadIdx.x * 8u) : "memory");
     __syncthreads();
     const uint32_t lane_b = (uint32_t)(lane * NR) * 4u;
-    const uint32_t VB = (uint32_t)VS * 4u, SLOTB = (uint32_t)(NVM * VS) * 4u;     // bytes per vector / per mailbox slot
+    constexpr uint32_t VB = (uint32_t)VS * 4u, SLOTB = (uint32_t)(NVM * VS) * 4u; // bytes per vector / per mailbox slot
     const uint32_t e_base = smem_u32(w1_smem) + lane_b;
     const uint32_t s_base = e_base + 2u * SLOTB;
     const uint32_t se_base = s_base + 2u * SLOTB;
@@ -226,64 +255,78 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
     // ---- compute warps: one sheared column each -----------------------------------------------------------------------------
     if (warp >= nce) return;
     const uint32_t vme = (uint32_t)(warp + 2);            // this column's mailbox column
+    const uint32_t mb = e_base + vme * VB;                // its e[0] vector (this lane's words); every other mailbox vector = mb + immediate
+    const uint32_t evme = ev_base + vme * 16u, progme = prog_base + vme * 4u;
     int k = (p.c_off + x0 + warp) % Wg;                   // image column (travel frame) of this sheared column in row 0
     const int poff = p16_off<CB>(D) + lane * NR;
     const uint32_t p1p1 = p.p1p1, p2p2 = p.p2p2;
     const bool is_last = warp + 1 == nce, is_prev = warp + 2 == nce;
-    // storage: by image coordinates (one GPU: the (H, W, D) volume of the C-ABI) or by sheared column (a tile of a multi-GPU run)
-    // (`im` = image of the batch, `yl` = row inside it, travel order)
-    auto pixel = [&](int im, int yl, int kk) -> size_t {
-        const int yi = FINAL ? H - 1 - yl : yl;
-        const int imi = FINAL ? p.nimg - 1 - im : im;    // the second pass walks the batch backwards, like the rows of an image
-        const int col = p.sheared_store ? (FINAL ? Wt - 1 - (x0 + warp) : x0 + warp) : (FINAL ? Wg - 1 - kk : kk);
-        return ((size_t)imi * H + yi) * Wt + col;
-    };
+    // Storage: by image coordinates (one GPU: the (H, W, D) volume of the C-ABI) or by sheared column (a tile of a multi-GPU
+    // run).  The pixel index moves by a constant from row to row -- also from the last row of an image of the batch to the
+    // first row of the next one (the second pass walks rows AND images backwards) -- plus a fix-up where the image column wraps.
+    const int col0 = p.sheared_store ? (FINAL ? Wt - 1 - (x0 + warp) : x0 + warp) : (FINAL ? Wg - 1 - k : k);
+    uint32_t pix = (uint32_t)((FINAL ? HT - 1 : 0) * Wt + col0);
+    const int pstep = (FINAL ? -Wt : Wt) + (p.sheared_store ? 0 : (FINAL ? 1 : -1));
+    const int pfix = p.sheared_store ? 0 : (FINAL ? -Wg : Wg);
     // private staging ring [NSTG][K][SIN].  First pass: a pixel's block = its D right descriptors (lane-major) | the left one;
     // second pass: [32][RW] cost words | [32][NR] partial sums.
-    const uint32_t stg_pix = (uint32_t)SIN * 4u, stg_stage = (uint32_t)K * stg_pix;
+    constexpr uint32_t stg_pix = (uint32_t)SIN * 4u, stg_stage = (uint32_t)W1_MAXK * stg_pix;
     const uint32_t stg_me = stg_base0 + (uint32_t)warp * stg_pix;
     const uint32_t off0 = (uint32_t)(lane * RW) * 4u, off1 = (uint32_t)(32 * RW + lane * NR) * 4u;
-    int kpf = k, ylpf = 0, impf = 0;                      // image column / row / image of the row being prefetched
-    auto stage_row = [&](int r) {
+    // prefetch cursors (PFD rows ahead of the row being computed); the descriptor rows of a batch are contiguous:
+    // row r of the batch = [r][copy][pitch4] / [r][pitch]
+    int kpf = k;
+    uint32_t pfpix = pix;
+    const int lane_w = lane * NR + p.padl;
+    auto stage_row = [&](uint32_t sg, int r) {
         if (r < HT) {
-            const uint32_t sg = stg_me + (uint32_t)(r & (NSTG - 1)) * stg_stage;
             if (CENSUS) {
                 // the window [kpf + dmin, kpf + dmin + D) starts 16-byte aligned in the copy whose shift is (kpf + dmin) & 3
                 const int ws = kpf + p.dmin, sh = ws & 3;
-                const uint32_t *src = p.descR4 + (((size_t)impf * 4 + sh) * H + ylpf) * p.pitch4 + (ws - sh + p.padl) + lane * NR;
+                const uint32_t *src = p.descR4 + (size_t)(uint32_t)(4 * r + sh) * (uint32_t)p.pitch4 + (ws - sh + lane_w);
                 cp_async_words<NR>(sg + lane_b, src);
                 cp_async_words<NR>(sg + VB + lane_b, src + VS);
-                if (lane == 0) cp_async_words<1>(sg + 2u * VB, p.descL + ((size_t)impf * H + ylpf) * p.pitch + kpf);
+                if (lane == 0) cp_async_words<1>(sg + 2u * VB, p.descL + (size_t)(uint32_t)r * (uint32_t)p.pitch + kpf);
             } else {
-                const uint32_t *src = p.buf + pixel(impf, ylpf, kpf) * D;
+                const uint32_t *src = p.buf + (size_t)pfpix * D;
                 cp_async_words<RW>(sg + off0, src + lane * RW);
                 cp_async_words<NR>(sg + off1, src + poff);
             }
         }
-        kpf = kpf == 0 ? Wg - 1 : kpf - 1;
-        if (++ylpf == H) { ylpf = 0; ++impf; }
+        if (!CENSUS) pfpix += (uint32_t)pstep;
+        if (--kpf < 0) { kpf = Wg - 1; if (!CENSUS) pfpix += (uint32_t)pfix; }
     };
-    for (int r = 0; r < PFD; ++r) {
-        stage_row(r);
-        cp_async_commit();
-    }
-    int yl = 0, im = 0;                                   // row inside the current image, image of the batch
+    stage_row(stg_me, 0);
+    cp_async_commit();
+    stage_row(stg_me + stg_stage, 1);
+    cp_async_commit();
+    stage_row(stg_me + 2u * stg_stage, 2);
+    cp_async_commit();
+    static_assert(PFD == 3 && NSTG == 4, "the row loop below hard-wires the rotation of the four staging slots");
+    // the row loop is unrolled by two: the mailbox slot and the event barrier of a row (y & 1) are immediates; what changes
+    // every second row -- the phase parity of the events and the half of the staging ring in use -- lives in three registers
+    uint32_t ph = 0u, sg_cur = stg_me, sg_oth = stg_me + 2u * stg_stage;
     uint32_t SW[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) SW[j] = 0u;
     const uint32_t nan2 = (p.inv | Tier<CB>::FLAG1) * 0x10001u;
+    int yl = 0;                                           // row inside the current image of the batch
+    int y = 0;                                            // row of the batch
 
-#pragma unroll 1
-    for (int y = 0; y < HT; ++y) {
-        const uint32_t par = (uint32_t)(y & 1) * SLOTB, prv = SLOTB - par;
-        const size_t pix = pixel(im, yl, k);
-        uint32_t *grow = p.buf + pix * D;
+    auto row = [&](auto uc) {
+        constexpr int U = decltype(uc)::value;            // y & 1
+        constexpr uint32_t par = (uint32_t)U * SLOTB, prv = SLOTB - par;
+        constexpr uint32_t EV = (uint32_t)U * 8u;
+        const uint32_t PH = ph;
+        constexpr uint32_t S_OFF = 2u * SLOTB, SE_OFF = 4u * SLOTB;       // the s / se streams behind the e stream
+        uint32_t *grow = p.buf + (size_t)pix * D;
         // ---- the pixel's cost codes (16 bits each, NaN flag in bit 15 / 7) and the partial sums so far -------------------------
         uint32_t c16[NR], cc[NR], tot[NR];
-        stage_row(y + PFD);
+        // row y sits in slot y & 3 = 2 * half + U; row y + 3 goes to slot (y + 3) & 3: the other half's slot 1 (U = 0) or this half's slot 0
+        stage_row(U == 0 ? sg_oth + stg_stage : sg_cur, y + PFD);
         cp_async_commit();
         cp_async_wait<PFD>();                              // this lane's copies of row y have landed
-        const uint32_t sg = stg_me + (uint32_t)(y & (NSTG - 1)) * stg_stage;
+        const uint32_t sg = sg_cur + (uint32_t)U * stg_stage;
         if (CENSUS) {
             __syncwarp();                                  // the left descriptor was copied by lane 0
             uint32_t lw[1], ra[NR], rb[NR];
@@ -297,9 +340,9 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
                     const uint32_t xlo = lw[0] ^ ra[j], xhi = lw[0] ^ rb[j];          // bit 31 = the right window leaves the image
-                    const uint32_t pk = __byte_perm(__popc(xlo), __popc(xhi), 0x5410);
-                    uint32_t fl;                                                     // sign-replicated top bytes: 0xFFFF per flagged half
-                    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(fl) : "r"(xlo), "r"(xhi));
+                    uint32_t pk, fl;
+                    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk) : "r"(__popc(xhi)), "r"(__popc(xlo)));   // both counts in one word
+                    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(fl) : "r"(xlo), "r"(xhi));   // sign-replicated top bytes: 0xFFFF per flagged half
                     c16[j] = (pk & ~fl) | (nan2 & fl);
                 }
             }
@@ -316,8 +359,9 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
         for (int j = 0; j < NR; ++j) cc[j] = c16[j] & Tier<CB>::VALUES;
 
         uint32_t Lp[NR], Lq[NR], L[NR];
+        const bool first = yl == 0;                       // first row of an image of the batch: every path starts
         // ---- SW: this column's own state of the previous row (the pixel up-right); a path start at the right image border --------
-        if (k == Wg - 1 || yl == 0) {                     // also the first row of every image of the batch: all paths start
+        if (k == Wg - 1 || first) {
 #pragma unroll
             for (int j = 0; j < NR; ++j) SW[j] = 0u;
         }
@@ -325,40 +369,40 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 #pragma unroll
         for (int j = 0; j < NR; ++j) { SW[j] = L[j]; tot[j] += L[j]; }
         // slot credit: e / s / se[y & 1] of this column still hold row y - 2 until column v + 2 has loaded its inputs of row y - 1
-        flag_wait_sleep(prog_base + (vme + 2u) * 4u, (uint32_t)y);
+        flag_wait_sleep(progme + 8u, (uint32_t)y);
         if (k != 0) {
             // ---- the E chain: wait for the left neighbour, one step, publish; S and SE behind it -----------------------------------
-            ev_wait(ev_base + (vme - 1u) * 16u, y);
-            lds_words<NR>(e_base + par + (vme - 1u) * VB, Lp);
-            lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
-            if (yl == 0) {                                // first row of an image: S (and SE below) are path starts
+            ev_wait_c(evme - 16u + EV, PH);
+            lds_words<NR>(mb - VB + par, Lp);
+            lds_words<NR>(mb - VB + S_OFF + prv, Lq);
+            if (first) {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) Lq[j] = 0u;
             }
             nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);
-            sts_words<NR>(e_base + par + vme * VB, L);
-            ev_signal(ev_base + vme * 16u, y, lane);
+            sts_words<NR>(mb + par, L);
+            ev_signal_c(evme + EV, lane);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += L[j];
-            lds_words<NR>(se_base + prv + (vme - 2u) * VB, Lp);
-            if (yl == 0) {
+            lds_words<NR>(mb - 2u * VB + SE_OFF + prv, Lp);
+            if (first) {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) Lp[j] = 0u;
             }
             nstep<NR>(cc, Lq, L, lane, p1p1, p2p2);                       // S
-            sts_words<NR>(s_base + par + vme * VB, L);
+            sts_words<NR>(mb + S_OFF + par, L);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += L[j];
             nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);                       // SE
-            sts_words<NR>(se_base + par + vme * VB, L);
+            sts_words<NR>(mb + SE_OFF + par, L);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += L[j];
         } else {
             // ---- chain start (left image border): E and SE are path starts, S comes from the left neighbour's previous row, which
             // that neighbour finished as a chain start itself; everything is stored BEFORE the E-event (see the file header) ---------
-            if (yl > 0) {
+            if (!first) {
                 if (vme == 2u) flag_wait_sleep(rdc_flag, (uint32_t)y);    // across the strip boundary: the in-relay has delivered row y - 1
-                lds_words<NR>(s_base + prv + (vme - 1u) * VB, Lq);
+                lds_words<NR>(mb - VB + S_OFF + prv, Lq);
             } else {
 #pragma unroll
                 for (int j = 0; j < NR; ++j) Lq[j] = 0u;
@@ -366,48 +410,86 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
 #pragma unroll
             for (int j = 0; j < NR; ++j) Lp[j] = 0u;
             nstep<NR>(cc, Lq, L, lane, p1p1, p2p2);                       // S
-            sts_words<NR>(s_base + par + vme * VB, L);
+            sts_words<NR>(mb + S_OFF + par, L);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += L[j];
             nstep<NR>(cc, Lp, L, lane, p1p1, p2p2);                       // E = SE = a path start: c itself
-            sts_words<NR>(se_base + par + vme * VB, L);
-            sts_words<NR>(e_base + par + vme * VB, L);
-            ev_signal(ev_base + vme * 16u, y, lane);
+            sts_words<NR>(mb + SE_OFF + par, L);
+            sts_words<NR>(mb + par, L);
+            ev_signal_c(evme + EV, lane);
 #pragma unroll
             for (int j = 0; j < NR; ++j) tot[j] += 2u * L[j];
         }
-        sts_u32(prog_base + vme * 4u, (uint32_t)(y + 1));                 // inputs of row y are in registers: credit for column v - 2
-        if (is_last) ev_signal(rd_base, y, lane);                          // the out-relay forwards S / SE of row y
-        if (is_prev) ev_signal(rd_base + 16u, y, lane);
+        sts_u32(progme, (uint32_t)(y + 1));                 // inputs of row y are in registers: credit for column v - 2
+        if (is_last) ev_signal_c(rd_base + EV, lane);                      // the out-relay forwards S / SE of row y
+        if (is_prev) ev_signal_c(rd_base + 16u + EV, lane);
         // ---- out ------------------------------------------------------------------------------------------------------------------
         if (!FINAL) {
             st_words<NR>(grow + poff, tot);
         } else {
-            float fa[NR], fb[NR];
-            uint32_t bl = 0xFFFFFFFFu, bh = 0xFFFFFFFFu;
+            uint32_t anyflag = 0u;
 #pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                uint32_t t = tot[j];
-                if (p.overcounting) t = t - 7u * cc[j];   // S >= 8 C in every half: no borrow
-                // 16-bit integer -> float32: PRMT builds 0x4B00'nnnn, one FADD removes the 2^23.  A NaN cell gets the upper
-                // half 0x7F80 / 0x7FFF instead of 0x4B00: exponent all ones over a non-zero mantissa, i.e. a NaN that the
-                // same FADD passes through -- no select.
-                const uint32_t fl = c16[j] & Tier<CB>::FLAGS;
-                const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;     // 0xFF80 / 0xFFFF per NaN half
-                const uint32_t hx = 0x4B004B00u | (sat & 0x34FF34FFu);
-                fa[j] = __uint_as_float(__byte_perm(t, hx, 0x5410)) - 8388608.0f;
-                fb[j] = __uint_as_float(__byte_perm(t, hx, 0x7632)) - 8388608.0f;
-                if (WTA) {
-                    const uint32_t tk = t | sat;
-                    bl = min(bl, __byte_perm(tk, (uint32_t)j, 0x1054));      // (low sum << 16) | j
-                    bh = min(bh, __byte_perm(tk, (uint32_t)j, 0x3254));      // (high sum << 16) | j
-                }
+            for (int j = 0; j < NR; ++j) anyflag |= c16[j];
+            const bool nans = __any_sync(0xffffffffu, (anyflag & Tier<CB>::FLAGS) != 0u);   // rare: pixels near the image border
+            if (p.overcounting) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) tot[j] -= 7u * cc[j];        // S >= 8 C in every half: no borrow
             }
             float *o = reinterpret_cast<float *>(grow) + lane * NR;
-            st_floats<NR>(o, fa);
-            st_floats<NR>(o + D / 2, fb);
+            uint32_t best;
+            if (!nans) {
+                // 16-bit integer -> float32: PRMT builds 0x4B00'nnnn, one FADD removes the 2^23
+                {
+                    float f[NR];
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) f[j] = __uint_as_float(__byte_perm(tot[j], 0x4B004B00u, 0x5410)) - 8388608.0f;
+                    st_floats<NR>(o, f);
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) f[j] = __uint_as_float(__byte_perm(tot[j], 0x4B004B00u, 0x7632)) - 8388608.0f;
+                    st_floats<NR>(o + D / 2, f);
+                }
+                if (WTA) {
+                    if (CB == 1 && NR == 4) {
+                        // byte tier: sums < 2^10, so (sum << 2 | register index) fits a half: two packed min-ops find, per half,
+                        // the smallest sum and the FIRST register that holds it (the keys are built on the FMA pipe)
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(tot[j]) : "r"(tot[j]), "r"((uint32_t)j * 0x10001u));
+                        const uint32_t m = __vminu2(__vimin3_u16x2(tot[0], tot[1], tot[2]), tot[3]);
+                        const uint32_t lo = m & 0xFFFFu, hi = m >> 16;
+                        best = min(((lo >> 2) << 16) + (lo & 3u) + (uint32_t)(lane * NR),
+                                   ((hi >> 2) << 16) + (hi & 3u) + (uint32_t)(D / 2 + lane * NR));
+                    } else {
+                        uint32_t bl = 0xFFFFFFFFu, bh = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) {
+                            bl = min(bl, __byte_perm(tot[j], (uint32_t)j, 0x1054));      // (low sum << 16) | j
+                            bh = min(bh, __byte_perm(tot[j], (uint32_t)j, 0x3254));      // (high sum << 16) | j
+                        }
+                        best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
+                    }
+                }
+            } else {
+                // A NaN cell gets the upper half 0x7F80 / 0x7FFF instead of 0x4B00: exponent all ones over a non-zero mantissa,
+                // i.e. a NaN that the same FADD passes through -- no select.  In the WTA it saturates its half (no valid sum
+                // reaches the sentinel).
+                uint32_t bl = 0xFFFFFFFFu, bh = 0xFFFFFFFFu;
+                float fa[NR], fb[NR];
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const uint32_t fl = c16[j] & Tier<CB>::FLAGS;
+                    const uint32_t sat = (CB == 1) ? fl * 0x1FFu : (fl >> 15) * 0xFFFFu;     // 0xFF80 / 0xFFFF per NaN half
+                    const uint32_t hx = 0x4B004B00u | (sat & 0x34FF34FFu);
+                    fa[j] = __uint_as_float(__byte_perm(tot[j], hx, 0x5410)) - 8388608.0f;
+                    fb[j] = __uint_as_float(__byte_perm(tot[j], hx, 0x7632)) - 8388608.0f;
+                    const uint32_t tk = tot[j] | sat;
+                    bl = min(bl, __byte_perm(tk, (uint32_t)j, 0x1054));
+                    bh = min(bh, __byte_perm(tk, (uint32_t)j, 0x3254));
+                }
+                st_floats<NR>(o, fa);
+                st_floats<NR>(o + D / 2, fb);
+                best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
+            }
             if (WTA) {
-                uint32_t best = min(bl + (uint32_t)(lane * NR), bh + (uint32_t)(D / 2 + lane * NR));
                 best = __reduce_min_sync(0xffffffffu, best);
                 if (lane == 0) {
                     const bool none = (best >> 16) >= ((CB == 1) ? 0xFF80u : 0xFFFFu);
@@ -416,9 +498,21 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
                 }
             }
         }
-        k = k == 0 ? Wg - 1 : k - 1;
-        if (++yl == H) { yl = 0; ++im; }
+        pix += (uint32_t)pstep;
+        if (--k < 0) { k = Wg - 1; pix += (uint32_t)pfix; }
+        if (++yl == H) yl = 0;
+        ++y;
+    };
+#pragma unroll 1
+    while (y + 2 <= HT) {
+        row(std::integral_constant<int, 0>{});
+        row(std::integral_constant<int, 1>{});
+        ph ^= 1u;
+        const uint32_t t = sg_cur;
+        sg_cur = sg_oth;
+        sg_oth = t;
     }
+    if (y < HT) row(std::integral_constant<int, 0>{});
 }
 
 template <int NR, int CB>
@@ -429,9 +523,9 @@ int launch_wave1(NarrowParams p, int K, int nstrips, void *workspace, size_t rin
     void (*w1)(const NarrowParams) = sgm_wave1_kernel<NR, CB, false, false, true>;
     void (*w2)(const NarrowParams) = wta ? sgm_wave1_kernel<NR, CB, true, true, false> : sgm_wave1_kernel<NR, CB, true, false, false>;
     const int threads = (K + 2) * 32;
-    const size_t fixed = ((size_t)6 * (K + 2) * NR * 32 + W1_FLAG_WORDS) * sizeof(uint32_t);
-    const size_t smem1 = fixed + (size_t)4 * K * G::CIN * sizeof(uint32_t);
-    const size_t smem2 = fixed + (size_t)4 * K * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
+    const size_t fixed = ((size_t)6 * (W1_MAXK + 2) * NR * 32 + W1_FLAG_WORDS) * sizeof(uint32_t);
+    const size_t smem1 = fixed + (size_t)4 * W1_MAXK * G::CIN * sizeof(uint32_t);
+    const size_t smem2 = fixed + (size_t)4 * W1_MAXK * 32 * (NR * CB / 2 + NR) * sizeof(uint32_t);
     if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return PB200_OK;
     const size_t wring = (size_t)nstrips * G::BLK * sizeof(unsigned long long);
     if (wring > ring_room) return PB200_OK;                                      // the boundary blocks must end before the flag
