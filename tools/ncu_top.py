@@ -27,8 +27,14 @@ rows = list(csv.reader(io.StringIO(src)))
 # one block per profiled kernel: a "Kernel Name" row, a header row, then the SASS lines; argv[3] picks the block
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
 kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-b0 = starts[kidx]
-b1 = starts[kidx + 1] if kidx + 1 < len(starts) else len(rows)
+# the source page repeats a block per view; take the kidx-th DISTINCT kernel, in launch order
+names, firsts = [], []
+for i in starts:
+    if rows[i][1] not in names:
+        names.append(rows[i][1])
+        firsts.append(i)
+b0 = firsts[min(kidx, len(firsts) - 1)]
+b1 = min([i for i in starts if i > b0] + [len(rows)])
 print("source block:", rows[b0][1][:100])
 hdr = rows[b0 + 1]
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
