@@ -282,6 +282,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist  # noqa: PLC0415
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"                  # the version banner goes to stdout: keep the JSON line alone there
         dist.init_process_group("nccl", device_id=torch.device(device))
     cfg = CONFIGS[args.config]
     dmin, dmax = -(D_DISP - 1), 0
@@ -396,10 +398,18 @@ def run_ours(args):
                 pipe.unshear()
                 done += m
 
+        # the host side of a step: the column ranges this rank needs as CONTIGUOUS pinned arrays (a strided pinned -> device copy
+        # takes a slow path), copied to a device staging buffer and from there into place
+        h_parts = [(torch.from_numpy(np.ascontiguousarray(h_left[:, a:b].numpy())).pin_memory(),
+                    torch.from_numpy(np.ascontiguousarray(h_right[:, a:b].numpy())).pin_memory()) for a, b in ranges]
+        d_parts = [(torch.empty_like(hl, device=device), torch.empty_like(hr, device=device)) for hl, hr in h_parts]
+
         def step_host():
-            for a, b in ranges:
-                d_left[:, a:b].copy_(h_left[:, a:b], non_blocking=True)
-                d_right[:, a:b].copy_(h_right[:, a:b], non_blocking=True)
+            for (a, b), (hl, hr), (dl, dr) in zip(ranges, h_parts, d_parts):
+                dl.copy_(hl, non_blocking=True)
+                dr.copy_(hr, non_blocking=True)
+                d_left[:, a:b].copy_(dl)
+                d_right[:, a:b].copy_(dr)
             pipe.run(d_left, d_right)
             h_disp.copy_(pipe.unshear(), non_blocking=True)
             torch.cuda.current_stream().synchronize()

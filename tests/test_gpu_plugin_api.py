@@ -213,3 +213,50 @@ def test_reference_sample_config_a_semi_global_matching(pb, oracle):
     ok = (disp["validity_mask"].data & oracle.MSK_INVALID) == 0
     sel = ok & (gt > 0)
     assert float(np.mean(np.abs(disp["disparity_map"].data[sel] + gt[sel]) > 1.0)) <= 0.20
+
+
+@pytest.mark.gpu
+def test_pandora_plugin_classes_run_the_pipeline(pb, oracle):
+    """The classes `pandora_plugin_b200` registers with Pandora's factories (here: stand-in factories with the same decorator
+    API), driven like the state machine drives them -- compute_cost_volume, cv_masked, optimize_cv, to_disp -- give the oracle's
+    disparity map, with and without host copies between the steps."""
+    import pandora_plugin_b200 as plug
+
+    def factory(key):
+        class Base:
+            avail = {}
+
+            def __new__(cls, *args, **cfg):
+                return super().__new__(cls.avail[cfg[key]] if cls is Base else cls)
+
+            @classmethod
+            def register_subclass(cls, name, *aliases):
+                def deco(sub):
+                    cls.avail[name] = sub
+                    return sub
+                return deco
+        return Base
+
+    mc_f, agg_f, opt_f, disp_f = (factory(k) for k in ("matching_cost_method", "aggregation_method", "optimization_method", "disparity_method"))
+    plug.build_classes(mc_f, agg_f, opt_f, disp_f)
+    H, W, D = 40, 200, 64
+    left, right, _ = oracle.synthetic_pair(H, W, D)
+    dmin, dmax = -(D - 1), 0
+    cv_ref, attrs = oracle.census_cost_volume(left, right, 5, dmin, dmax)
+    exp, _ = oracle.wta(oracle.sgm_cost_volume(cv_ref, 8, 32, cmax=attrs["cmax"]), np.arange(dmin, dmax + 1))
+    for keep in (True, False):
+        plug.keep_host_copy = keep
+        try:
+            il, ir = pb.create_image_dataset(left, disparity=[dmin, dmax]), pb.create_image_dataset(right)
+            mc = mc_f(matching_cost_method="census_b200", window_size=5, subpix=1)
+            grids = (il["disparity"].data[0], il["disparity"].data[1])
+            cv = pb.AbstractMatchingCost.allocate_cost_volume(mc._impl, il, grids)
+            cv = pb.validity_mask(il, ir, cv)
+            cv = mc.compute_cost_volume(il, ir, cv)
+            mc.cv_masked(il, ir, cv, *grids)
+            cv = opt_f(il, optimization_method="sgm_b200", penalty={"P1": 8, "P2": 32}).optimize_cv(cv, il, ir)
+            assert cv.attrs["pb200_resident"]["cost_volume"].is_cuda
+            disp = disp_f(disparity_method="wta_b200").to_disp(cv, il, ir)
+            np.testing.assert_array_equal(np.asarray(disp["disparity_map"].data), exp)
+        finally:
+            plug.keep_host_copy = True

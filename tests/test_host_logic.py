@@ -328,3 +328,44 @@ def test_sgm_rejects_too_many_disparities_before_any_work():
     cv = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3), "disp": np.arange(600)}, attrs={"cmax": 25, "type_measure": "min"})
     with pytest.raises(pb.ConfigError, match="exceed"):
         pb.AbstractOptimization(None, optimization_method="sgm").optimize_cv(cv, None, None)
+
+
+def test_pandora_plugin_module_imports_and_registers_on_stand_in_factories():
+    """pandora_plugin_b200 (the module the `pandora.plugin` entry point of pyproject.toml names): importing it without
+    Pandora has no effect; on abstract bases with Pandora's `register_subclass` API it registers the seven B200 steps under
+    their names, and the factories dispatch to them (src/pandora/__init__.py:141-148, matching_cost.py:88-131)."""
+    import pandora_plugin_b200 as plug
+
+    assert plug.register() is False and plug.REGISTERED == {}        # Pandora is not installed here
+    text = open(os.path.join(ROOT, "pyproject.toml")).read()
+    assert '[project.entry-points."pandora.plugin"]' in text and 'pandora_b200 = "pandora_plugin_b200"' in text
+
+    def factory(key):
+        class Base:
+            avail = {}
+
+            def __new__(cls, *args, **cfg):
+                if cls is Base:
+                    return super().__new__(cls.avail[cfg[key]])
+                return super().__new__(cls)
+
+            @classmethod
+            def register_subclass(cls, name, *aliases):
+                def deco(sub):
+                    for n in (name,) + aliases:
+                        cls.avail[n] = sub
+                    return sub
+                return deco
+        return Base
+
+    mc, agg, opt, disp = factory("matching_cost_method"), factory("aggregation_method"), factory("optimization_method"), factory("disparity_method")
+    classes = plug.build_classes(mc, agg, opt, disp)
+    assert sorted(classes) == ["cbca_b200", "census_b200", "sad_b200", "sgm_b200", "ssd_b200", "wta_b200", "zncc_b200"]
+    step = mc(matching_cost_method="census_b200", window_size=5, subpix=1)
+    assert isinstance(step, classes["census_b200"]) and step.cfg["matching_cost_method"] == "census_b200" and step.cfg["window_size"] == 5
+    with pytest.raises(pb.ConfigError):
+        mc(matching_cost_method="census_b200", window_size=4)                      # same config errors as the mirror classes
+    o = opt(None, optimization_method="sgm_b200", penalty={"P1": 4, "P2": 20})
+    assert o.cfg["optimization_method"] == "sgm_b200" and o.cfg["penalty"]["P2"] == 20
+    assert agg(aggregation_method="cbca_b200", cbca_distance=3).cfg["cbca_distance"] == 3
+    assert np.isnan(disp(disparity_method="wta_b200", invalid_disparity="NaN").cfg["invalid_disparity"])
