@@ -76,6 +76,8 @@ def build_classes(mc_base, agg_base, opt_base, disp_base):
             def compute_cost_volume(self, img_left, img_right, cost_volume):       # matching_cost.py:233-267
                 self._impl.compute_cost_volume(img_left, img_right, cost_volume)
                 lazy = getattr(cost_volume["cost_volume"], "_data", None)
+                if getattr(lazy, "deferred", False):
+                    return cost_volume                    # Census left a recipe: a following sgm_b200 fuses it away
                 tensor = lazy.tensor if hasattr(lazy, "tensor") else get_engine().to_device(cost_volume["cost_volume"].data)
                 _leave(cost_volume, "cost_volume", tensor)
                 return cost_volume
