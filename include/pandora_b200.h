@@ -98,6 +98,15 @@ PB200_API int pb200_census_cost_volume_rows(const float *d_left, const float *d_
                                   float *d_cv, void *d_workspace, size_t workspace_bytes, float *d_disp,
                                   float invalid_disparity, uint8_t *d_all_nan, int row_begin, int row_end, void *stream);
 
+/* Sub-pixel Census (subpix 2 / 4): compute_matching_costs with the LIST of shifted right images (census.cpp:128-155; the images
+ * come from img_tools.shift_right_img, img_tools.py:713-752).  d_rights: HOST array of n_right device pointers; image 0 is the
+ * right image (H, W), image i > 0 its copy resampled at column offset i / n_right, (H, W - 1), contiguous.  Cell k of the
+ * (H, W, n_disp) volume = Hamming cost between the left descriptor at x and the descriptor of image k % n_right at column
+ * x + k / n_right + dmin, NaN where either window leaves its image.  n_right == 1 is the integer case. */
+PB200_API size_t pb200_census_subpix_workspace_bytes(int H, int W, int window, int n_right);
+PB200_API int pb200_census_cost_volume_subpix(const float *d_left, const float *const *d_rights, int n_right, int H, int W, int window,
+                                    int dmin, int n_disp, float *d_cv, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Census transform only: the planar descriptors of rows [row_begin, row_end) of both images into d_workspace
  * (census_transform, matching_cost/cpp/src/census.cpp:45-95).  Feeds pb200_census_sgm(descriptors_ready = 1). */
 PB200_API int pb200_census_descriptors_rows(const float *d_left, const float *d_right, int H, int W, int window, void *d_workspace,
@@ -312,6 +321,10 @@ PB200_API int pb200_confidence(const float *d_cv, int H, int W, int D, int is_ma
 /* compute_matching_costs(img_left, [img_right], cv, disps, w, w): dmin = lround(disps[0]) (census.cpp:109). */
 PB200_API int pb200_census_cost_volume_host(const float *left, const float *right, int H, int W, int window,
                                   const float *disps, int D, float *cv);
+/* compute_matching_costs(img_left, imgs_right_shift, cv, disps, w, h) with the whole list of shifted right images
+ * (census.hpp:44-51): rights[0] is (H, W), rights[i > 0] are (H, W - 1). */
+PB200_API int pb200_census_cost_volume_multi_host(const float *left, const float *const *rights, int n_right, int H, int W, int window,
+                                        const float *disps, int n_disp, float *cv);
 PB200_API int pb200_reverse_cost_volume_host(const float *left_cv, int H, int W, int D, int min_disp, float *right_cv);
 PB200_API int pb200_cross_support_host(const float *image, int H, int W, int len_arms, float intensity, int16_t *cross);
 /* one aggregation_cpp.cbca call: (H, W) float32 slice, supports (H, W, 4), n valid columns

@@ -55,6 +55,12 @@ def device_volume(engine, cv):
         t = var.device_tensor()
         if t is not None:
             return t
+    # a real xarray dataset driven through pandora_plugin_b200 with keep_host_copy = False: the host array is a placeholder,
+    # the volume is the tensor the previous B200 step recorded
+    if cv.attrs.get("pb200_resident_trusted"):
+        t = (cv.attrs.get("pb200_resident") or {}).get("cost_volume")
+        if t is not None:
+            return t
     return engine.to_device(np.ascontiguousarray(var.data, dtype=np.float32))
 
 

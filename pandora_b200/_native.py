@@ -51,6 +51,9 @@ PROTOTYPES = {
     "pb200_census_workspace_bytes": (_sz, [_ci, _ci, _ci]),
     "pb200_census_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _vp]),
     "pb200_census_cost_volume_rows": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _cf, _vp, _ci, _ci, _vp]),
+    "pb200_census_subpix_workspace_bytes": (_sz, [_ci, _ci, _ci, _ci]),
+    "pb200_census_cost_volume_subpix": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp]),
+    "pb200_census_cost_volume_multi_host": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _ci, _vp]),
     "pb200_census_descriptors_rows": (_ci, [_vp, _vp, _ci, _ci, _ci, _vp, _sz, _ci, _ci, _vp]),
     "pb200_census_sgm_workspace_bytes": (_sz, [_ci, _ci, _ci, _ci, _ci]),
     "pb200_census_sgm_descriptors": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _vp, _sz, _vp, _vp]),

@@ -159,6 +159,41 @@ extern "C" int pb200_census_cost_volume_host(const float *left, const float *rig
     return PB200_OK;
 }
 
+// compute_matching_costs(img_left, imgs_right_shift, cv, disps, w, h) with the whole list of shifted right images
+// (census.hpp:44-51, census.cpp:97-180): rights[0] is (H, W), rights[i > 0] are (H, W - 1), all contiguous float32.
+extern "C" int pb200_census_cost_volume_multi_host(const float *left, const float *const *rights, int n_right, int H, int W, int window,
+                                                   const float *disps, int n_disp, float *cv) {
+    if (!left || !rights || n_right < 1 || !disps || !cv || H <= 0 || W <= 0 || n_disp <= 0) {
+        set_error("pb200_census_cost_volume_multi_host: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (n_right == 1) return pb200_census_cost_volume_host(left, rights[0], H, W, window, disps, n_disp, cv);
+    if (W < 2) {
+        set_error("pb200_census_cost_volume_multi_host: shifted images need at least two columns");
+        return PB200_ERR_BAD_ARG;
+    }
+    const int dmin = (int)lroundf(disps[0]);                     // census.cpp:109
+    const size_t vol = (size_t)H * W * n_disp * sizeof(float);
+    std::vector<DevBuf> imgs(n_right + 1);
+    std::vector<const float *> ptrs(n_right);
+    PB200_RC(imgs[0].alloc((size_t)H * W * 4));
+    PB200_CUDA(cudaMemcpy(imgs[0].p, left, (size_t)H * W * 4, cudaMemcpyHostToDevice));
+    for (int i = 0; i < n_right; ++i) {
+        if (!rights[i]) { set_error("pb200_census_cost_volume_multi_host: NULL right image"); return PB200_ERR_BAD_ARG; }
+        const size_t bytes = (size_t)H * (i == 0 ? W : W - 1) * 4;
+        PB200_RC(imgs[i + 1].alloc(bytes));
+        PB200_CUDA(cudaMemcpy(imgs[i + 1].p, rights[i], bytes, cudaMemcpyHostToDevice));
+        ptrs[i] = imgs[i + 1].as<float>();
+    }
+    DevBuf dcv, ws;
+    const size_t wsb = pb200_census_subpix_workspace_bytes(H, W, window, n_right);
+    PB200_RC(dcv.alloc(vol)); PB200_RC(ws.alloc(wsb));
+    PB200_RC(pb200_census_cost_volume_subpix(imgs[0].as<float>(), ptrs.data(), n_right, H, W, window, dmin, n_disp, dcv.as<float>(), ws.p,
+                                             wsb, nullptr));
+    PB200_CUDA(cudaMemcpy(cv, dcv.p, vol, cudaMemcpyDeviceToHost));
+    return PB200_OK;
+}
+
 extern "C" int pb200_reverse_cost_volume_host(const float *left_cv, int H, int W, int D, int min_disp, float *right_cv) {
     if (!left_cv || !right_cv || H <= 0 || W <= 0 || D <= 0) {
         set_error("pb200_reverse_cost_volume_host: bad argument");

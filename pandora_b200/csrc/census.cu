@@ -560,6 +560,97 @@ extern "C" int pb200_census_sgm(const float *d_left, const float *d_right, int H
     return PB200_OK;
 }
 
+// ---- sub-pixel Census (census.cpp:128-155: a list of shifted right images) -------------------------------------------------
+// Cell k of the volume uses the (k % subpix)-th right image at column x + k / subpix + dmin.  Image 0 is the right image
+// itself; image i > 0 is resampled at column offset i / subpix and is one column shorter (img_tools.py:713-752), so its own
+// transform flags the centres whose window would leave IT -- exactly the reference's extra bound (census.cpp:144-150).
+// One warp per pixel, lanes over consecutive cells: 128-byte coalesced stores, descriptor reads served by L1 / L2.
+template <int NW>
+__global__ void __launch_bounds__(256) census_fill_subpix_kernel(const uint32_t *__restrict__ descL, const uint32_t *__restrict__ descR,
+                                                                 float *__restrict__ cv, int H, int W, int n_disp, int dmin, int subpix,
+                                                                 int pitch) {
+    const int lane = threadIdx.x & 31;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const size_t plane = (size_t)H * pitch;                 // words per descriptor word-plane
+    for (long pix = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < (long)H * W; pix += nwarps) {
+        const int row = (int)(pix / W), col = (int)(pix % W);
+        uint32_t lw[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) lw[i] = descL[i * plane + (size_t)row * pitch + col];
+        const bool left_ok = (lw[NW - 1] >> 31) == 0;
+        float *out = cv + (size_t)pix * n_disp;
+        for (int k = lane; k < n_disp; k += 32) {
+            const int kd = k / subpix, id = k - kd * subpix, rx = col + kd + dmin;
+            float v = nan_f();
+            if (left_ok && rx >= 0 && rx < W) {
+                const uint32_t *r = descR + (size_t)id * NW * plane + (size_t)row * pitch + rx;
+                uint32_t rw[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) rw[i] = r[i * plane];
+                if ((rw[NW - 1] >> 31) == 0) {
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) c += __popc(lw[i] ^ rw[i]);
+                    v = (float)c;
+                }
+            }
+            out[k] = v;
+        }
+    }
+}
+
+extern "C" size_t pb200_census_subpix_workspace_bytes(int H, int W, int window, int n_right) {
+    if (H <= 0 || W <= 0 || window < 3 || n_right < 1) return 0;
+    return (size_t)(1 + n_right) * census_nwords(window) * H * census_pitch(W) * sizeof(uint32_t);
+}
+
+extern "C" int pb200_census_cost_volume_subpix(const float *d_left, const float *const *d_rights, int n_right, int H, int W, int window,
+                                               int dmin, int n_disp, float *d_cv, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!d_left || !d_rights || n_right < 1 || !d_cv || !d_workspace || H <= 0 || W <= 0 || n_disp <= 0) {
+        set_error("pb200_census_cost_volume_subpix: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (window != 3 && window != 5 && window != 7 && window != 9 && window != 11 && window != 13) {
+        set_error("pb200_census_cost_volume_subpix: window_size %d not in {3,5,7,9,11,13}", window);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < pb200_census_subpix_workspace_bytes(H, W, window, n_right)) {
+        set_error("pb200_census_cost_volume_subpix: workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nw = census_nwords(window), pitch = census_pitch(W);
+    uint32_t *descL = (uint32_t *)d_workspace, *descR = descL + (size_t)nw * H * pitch;
+    int rc = PB200_OK;
+#define PB200_T(WIN)                                                                                             \
+    case WIN:                                                                                                    \
+        rc = launch_transform<WIN>(d_left, H, W, pitch, descL, 0, H, s);                                         \
+        for (int i = 0; i < n_right && rc == PB200_OK; ++i) {                                                    \
+            if (!d_rights[i]) { set_error("pb200_census_cost_volume_subpix: NULL right image"); return PB200_ERR_BAD_ARG; } \
+            /* image i > 0 has W - 1 columns (contiguous); same pitch, so the missing column reads as flagged */   \
+            rc = launch_transform<WIN>(d_rights[i], H, i == 0 ? W : W - 1, pitch, descR + (size_t)i * nw * H * pitch, 0, H, s); \
+        }                                                                                                        \
+        break;
+    switch (window) {
+        PB200_T(3) PB200_T(5) PB200_T(7) PB200_T(9) PB200_T(11) PB200_T(13)
+        default: rc = PB200_ERR_UNSUPPORTED;
+    }
+#undef PB200_T
+    if (rc != PB200_OK) return rc;
+    long blocks = ((long)H * W + 7) / 8;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    switch (nw) {
+#define PB200_F(N) case N: census_fill_subpix_kernel<N><<<(int)blocks, 256, 0, s>>>(descL, descR, d_cv, H, W, n_disp, dmin, n_right, pitch); break;
+        PB200_F(1) PB200_F(2) PB200_F(3) PB200_F(4) PB200_F(6)
+#undef PB200_F
+        default: set_error("census: unexpected descriptor size"); return PB200_ERR_UNSUPPORTED;
+    }
+    PB200_LAUNCH_CHECK("census_fill_subpix_kernel");
+    note_path(STAGE_CENSUS, PATH_CENSUS_SUBPIX, nw);
+    return PB200_OK;
+}
+
 // ---- column-tiled multi-GPU runs of the fused stage -----------------------------------------------------------------------
 extern "C" size_t pb200_tile_link_bytes(int D) {
     if (D <= 0) return 0;

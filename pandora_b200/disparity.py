@@ -65,6 +65,9 @@ class WinnerTakesAll(AbstractDisparity):
         dmin, dmax = int(round(float(disps[0]))), int(round(float(disps[-1])))
         is_max = cv.attrs.get("type_measure") == "max"
         invalid = float(self._invalid_disparity)
+        subpix = int(cv.attrs.get("subpixel", 1) or 1)
+        if subpix > 1:
+            return self._to_disp_subpix(eng, cv, cv_t, disps, dmin, dmax, is_max, invalid, subpix)
         cached = fused_wta(cv)
         if cached is not None and not is_max and cached[2] == dmin and (cached[3] == invalid or (cached[3] != cached[3] and invalid != invalid)):
             disp_t, flags = cached[0], cached[1]                   # the producing kernel already ran this argmin (fused WTA)
@@ -78,10 +81,32 @@ class WinnerTakesAll(AbstractDisparity):
             mask_t = device_var(eng, cv, "validity_mask", "uint16").clone()
             mask_t = eng.validity_mask(H, W, dmin, dmax, 0, flags, wta_invalidate=True, mask=mask_t)
             store_var(out, "validity_mask", mask_t, dtype="uint16")
+        self._carry_confidence(cv, out)
+        return out
+
+    def _to_disp_subpix(self, eng, cv, cv_t, disps, dmin, dmax, is_max, invalid, subpix):
+        """Sub-pixel volumes (disparity.py:434-455: ``disp["disp"].data[indices]``): the argmin index k maps to dmin + k / subpix."""
+        import torch  # noqa: PLC0415
+
+        H, W, D = (int(s) for s in cv_t.shape)
+        idx_t, flags = eng.wta(cv_t, 0, is_max, -1.0)                     # index map, -1 where every cell is NaN
+        disp_t = torch.where(flags != 0, torch.full_like(idx_t, invalid), float(disps[0]) + idx_t / float(subpix))
+        out = Dataset(coords={"row": cv.coords["row"].data, "col": cv.coords["col"].data}, attrs=cv.attrs)
+        store_var(out, "disparity_map", disp_t)
+        out["disparity_interval"] = (("disparity",), np.asarray(disps)[[0, -1]])
+        store_var(cv, "disp_indices", disp_t.clone())
+        if "validity_mask" in cv:
+            mask_t = device_var(eng, cv, "validity_mask", "uint16").clone()
+            mask_t = eng.validity_mask(H, W, dmin, dmax, 0, flags, wta_invalidate=True, mask=mask_t)
+            store_var(out, "validity_mask", mask_t, dtype="uint16")
+        self._carry_confidence(cv, out)
+        return out
+
+    @staticmethod
+    def _carry_confidence(cv, out) -> None:
         if "confidence_measure" in cv:
             # disparity.py:462-466: the confidence layers computed on the cost volume travel with their `indicator`
             # coordinate (cost_volume_confidence runs BEFORE disparity in every legal pipeline, state_machine.py:134-139)
             out["confidence_measure"] = cv["confidence_measure"]
             if "indicator" in cv.coords:
                 out.coords["indicator"] = cv.coords["indicator"]
-        return out

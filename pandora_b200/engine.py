@@ -79,6 +79,21 @@ class Engine:
                 self._stream()))
         return (cv, disp, flags) if fuse_wta else cv
 
+    def census_subpix(self, left: torch.Tensor, rights, window: int, dmin: int, n_disp: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sub-pixel Census volume (``pb200_census_cost_volume_subpix``): ``rights`` = [right (H, W), shifted copies (H, W - 1) ...]."""
+        import ctypes  # noqa: PLC0415
+
+        H, W = self._hw(left)
+        for i, r in enumerate(rights):
+            assert r.dtype == torch.float32 and r.is_contiguous() and tuple(r.shape) == (H, W if i == 0 else W - 1)
+        cv = self.empty((H, W, n_disp)) if out is None else out
+        ws = self._workspace("census", self.lib.pb200_census_subpix_workspace_bytes(H, W, window, len(rights)))
+        ptrs = (ctypes.c_void_p * len(rights))(*[r.data_ptr() for r in rights])
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_cost_volume_subpix(_ptr(left), ptrs, len(rights), H, W, window, int(dmin), int(n_disp), _ptr(cv),
+                                                                   _ptr(ws), ws.numel(), self._stream()))
+        return cv
+
     def census_descriptors(self, left: torch.Tensor, right: torch.Tensor, window: int, rows: Optional[Tuple[int, int]] = None) -> None:
         """Census transform of both images (or of a band of rows) into the engine's descriptor workspace."""
         H, W = self._hw(left)

@@ -23,6 +23,7 @@ class AbstractMatchingCost:
 
     matching_cost_methods_avail: Dict[str, type] = {}
     _WINDOW_SIZE, _SUBPIX, _BAND, _STEP_COL, _SPLINE_ORDER = 5, 1, None, 1, 1
+    _SUBPIX_KERNELS = False          # measures whose kernels take the list of shifted right images (subpix 2 / 4)
     _VALID_WINDOWS: Optional[Tuple[int, ...]] = None
 
     def __new__(cls, **cfg):
@@ -79,8 +80,8 @@ class AbstractMatchingCost:
             raise ConfigError(f"window_size {w} must be odd and > 0")
         if cfg["subpix"] not in (1, 2, 4):
             raise ConfigError(f"subpix {cfg['subpix']} not in [1, 2, 4]")
-        if cfg["subpix"] != 1:
-            raise ConfigError("subpix: only 1 is implemented by the B200 kernels (SURVEY.md 8d: subpix=1 on the hot path)")
+        if cfg["subpix"] != 1 and not self._SUBPIX_KERNELS:
+            raise ConfigError("subpix: only 1 is implemented by the B200 kernels of this measure (Census takes 2 and 4)")
         if not (cfg["band"] is None or isinstance(cfg["band"], str)):
             raise ConfigError("band must be a str or None")
         if not (isinstance(cfg["spline_order"], int) and 1 <= cfg["spline_order"] <= 5):
@@ -107,9 +108,10 @@ class AbstractMatchingCost:
 
     @staticmethod
     def get_disparity_range(disparity_min: int, disparity_max: int, subpix: int = 1) -> np.ndarray:
-        if subpix != 1:
-            raise ConfigError("subpix: only 1 is implemented")
-        return np.arange(disparity_min, disparity_max + 1)
+        """matching_cost.py:410-427."""
+        if subpix == 1:
+            return np.arange(disparity_min, disparity_max + 1)
+        return np.append(np.arange(disparity_min, disparity_max, 1 / float(subpix), dtype=np.float64), [disparity_max])
 
     def allocate_cost_volume(self, image, disparity_grids, cfg=None) -> Dataset:
         """Empty cost-volume dataset with the reference's coordinates and attributes (matching_cost.py:
@@ -165,6 +167,8 @@ class AbstractMatchingCost:
             # geometry -- the volume stays deferred (a following SGM step then runs the fused Census -> SGM kernels)
             flags = recipe.all_nan_flags()
         else:
+            if self._subpix > 1 and (fl is not None or fr is not None or variable):
+                raise ConfigError("subpix > 1 together with image masks or variable disparity grids is not implemented by the B200 kernels")
             cv_t = device_volume(eng, cost_volume)
             gmin = eng.to_device(gmin_h) if variable else None
             gmax = eng.to_device(gmax_h) if variable else None
@@ -176,6 +180,18 @@ class AbstractMatchingCost:
             mask = eng.validity_mask_init(H, W, dmin, dmax, off)
         mask = eng.validity_mask(H, W, dmin, dmax, off, flags, mask=mask)
         store_var(cost_volume, "validity_mask", mask, dtype="uint16")
+
+
+def shift_right_img(right: np.ndarray, subpix: int, order: int = 1):
+    """img_tools.shift_right_img (img_tools.py:713-752) on a plain array: [right, right resampled at +1/subpix, ...]; the
+    resampled copies are one column shorter."""
+    from scipy.ndimage import zoom  # noqa: PLC0415
+
+    nx = right.shape[1]
+    out = [right]
+    for ind in range(1, subpix):
+        out.append(zoom(right, (1, (nx * subpix - (subpix - 1)) / float(nx)), order=order)[:, ind::subpix])
+    return out
 
 
 class CensusRecipe:
@@ -212,12 +228,22 @@ class Census(AbstractMatchingCost):
     """Census matching cost (reference: matching_cost/census.py:39-153, cpp/src/census.cpp)."""
 
     _VALID_WINDOWS = (3, 5, 7, 9, 11, 13)
+    _SUBPIX_KERNELS = True
 
     def compute_cost_volume(self, img_left, img_right, cost_volume):
         eng = get_engine()
         dmin, dmax = self._disp_bounds(cost_volume)
         cost_volume.attrs.update({"type_measure": "min", "cmax": int(self._window_size**2)})     # census.py:116-122
         left = eng.to_device(image_array(img_left, self._band))
+        if self._subpix > 1:
+            # census.py:113 + img_tools.shift_right_img (img_tools.py:713-752): the right image and its subpix - 1 copies
+            # resampled at column offsets i / subpix -- the same scipy.ndimage.zoom call as the reference, on the host (an
+            # O(H W) pre-processing of the input image); the list goes to the device like compute_matching_costs takes it
+            rights = [eng.to_device(np.ascontiguousarray(r, dtype=np.float32)) for r in shift_right_img(image_array(img_right, self._band),
+                                                                                                     self._subpix, self._spline_order)]
+            n_disp = len(np.asarray(cost_volume.coords["disp"].data))
+            store_volume(cost_volume, eng.census_subpix(left, rights, self._window_size, dmin, n_disp))
+            return cost_volume
         right = eng.to_device(image_array(img_right, self._band))
         if _native.get_option("fuse_census_sgm") != 0:
             # deferred: computed when something reads it; a directly following SGM step fuses it away (CensusRecipe)

@@ -39,6 +39,7 @@ def _resident(ds, name="cost_volume"):
 def _leave(ds, name, tensor, dims=("row", "col", "disp")):
     """Record ``tensor`` as the resident copy of ``ds[name]`` and give the host side what it needs."""
     ds.attrs.setdefault("pb200_resident", {})[name] = tensor
+    ds.attrs["pb200_resident_trusted"] = not keep_host_copy     # with host copies around, the host array stays authoritative
     if keep_host_copy:
         host = tensor.detach().cpu().numpy()
     else:

@@ -583,3 +583,67 @@ def test_disparity_host_pipelines(eng, oracle):
         np.testing.assert_array_equal(out, cv)
         np.testing.assert_array_equal(disp, exp)
         np.testing.assert_array_equal(vm, oracle.wta_validity_mask(mask, inv))
+
+
+# ------------------------------------------------------------------------------------------------
+# sub-pixel Census (subpix 2 / 4): census.cpp:128-155 with the list of shifted right images
+# ------------------------------------------------------------------------------------------------
+def test_census_subpix_reference_golden(eng, oracle, goldens):
+    """tests/test_matching_cost/test_matching_cost_census.py:637-683 (window 3, subpix 2): the reference's own golden volume."""
+    k = f"{CENSUS}::test_census[7]::"
+    assert int(goldens[k + "subpix"]) == 2 and int(goldens[k + "window_size"]) == 3
+    left, right = goldens[k + "left_data"].astype(np.float32), goldens[k + "right_data"].astype(np.float32)
+    dmin, dmax = (int(v) for v in goldens[k + "disp_interval"])
+    rights = [np.ascontiguousarray(r, dtype=np.float32) for r in oracle.shift_right_img(right, 2, 1)]
+    got = host(eng.census_subpix(dev(eng, left), [dev(eng, r) for r in rights], 3, dmin, (dmax - dmin) * 2 + 1))
+    np.testing.assert_array_equal(got, goldens[k + "ref_out"])
+
+
+@pytest.mark.parametrize("w", [3, 5, 7, 11])
+@pytest.mark.parametrize("subpix", [2, 4])
+@pytest.mark.parametrize("shape,rng", [((19, 37), (-7, 5)), ((12, 40), (-25, -2)), ((9, 21), (3, 14))])
+def test_census_subpix_vs_oracle(eng, oracle, w, subpix, shape, rng):
+    """Every branch of census.cpp:128-155: ranges leaving the image on either side, the shorter shifted images (their last
+    usable centre is one column earlier), one- to four-word descriptors -- and the `compute_matching_costs`-style host entry."""
+    import ctypes
+
+    from pandora_b200 import _native
+
+    g = np.random.default_rng(w * 100 + subpix + shape[1])
+    left, right = (g.integers(0, 50, shape).astype(np.float32) for _ in range(2))
+    dmin, dmax = rng
+    ref, _ = oracle.census_cost_volume_subpix(left, right, w, dmin, dmax, subpix)
+    rights = [np.ascontiguousarray(r, dtype=np.float32) for r in oracle.shift_right_img(right, subpix, 1)]
+    n_disp = (dmax - dmin) * subpix + 1
+    got = host(eng.census_subpix(dev(eng, left), [dev(eng, r) for r in rights], w, dmin, n_disp))
+    np.testing.assert_array_equal(got, ref)
+    import pandora_b200 as pb
+
+    assert pb.last_path("census")[0] == "census_subpix"
+    out = np.empty(shape + (n_disp,), dtype=np.float32)
+    ptrs = (ctypes.c_void_p * subpix)(*[r.ctypes.data for r in rights])
+    disps = np.append(np.arange(dmin, dmax, 1 / subpix), [dmax]).astype(np.float32)
+    _native.check(_native.load().pb200_census_cost_volume_multi_host(left.ctypes.data, ptrs, subpix, shape[0], shape[1], w, disps.ctypes.data,
+                                                                     n_disp, out.ctypes.data))
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_census_subpix_through_the_step_classes(oracle):
+    """matching_cost (census, subpix 4 -- the reference's a_local_block_matching.json uses it) -> disparity through run(cfg):
+    fractional disparities disps[argmin] like disparity.py:434-455."""
+    import pandora_b200 as pb
+
+    H, W = 30, 64
+    g = np.random.default_rng(5)
+    left, right = (g.integers(0, 255, (H, W)).astype(np.float32) for _ in range(2))
+    cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": 5, "subpix": 4},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": -9999}}}
+    disp, cv = pb.run(pb.create_image_dataset(left, disparity=[-6, 3]), pb.create_image_dataset(right), cfg)
+    ref, _ = oracle.census_cost_volume_subpix(left, right, 5, -6, 3, 4)
+    np.testing.assert_array_equal(np.asarray(cv["cost_volume"].data), ref)
+    disps = np.asarray(cv.coords["disp"].data)
+    assert len(disps) == 37 and disps[1] == -5.75
+    filled = np.where(np.isnan(ref), np.inf, ref)
+    exp = disps[np.argmin(filled, axis=2)].astype(np.float32)
+    exp[np.all(np.isnan(ref), axis=2)] = -9999
+    np.testing.assert_array_equal(np.asarray(disp["disparity_map"].data), exp)

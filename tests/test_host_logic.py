@@ -312,8 +312,8 @@ def test_wta_keeps_the_indicator_coordinate_of_the_confidence_layers():
 
     from pandora_b200 import disparity
 
-    body = inspect.getsource(disparity.WinnerTakesAll.to_disp)
-    assert 'out.coords["indicator"] = cv.coords["indicator"]' in body
+    body = inspect.getsource(disparity.WinnerTakesAll)
+    assert 'out.coords["indicator"] = cv.coords["indicator"]' in body and body.count("self._carry_confidence(cv, out)") == 2
     # the append that used to fail with KeyError('indicator') on a dataset built like to_disp builds it
     cv = pb.Dataset(coords={"row": np.arange(2), "col": np.arange(3)})
     _, cv = pb.AbstractCostVolumeConfidence.allocate_confidence_map("ambiguity", np.ones((2, 3), np.float32), None, cv)
