@@ -61,6 +61,9 @@ static inline int debug_switches() {
 #endif
 }
 
+#ifndef PB200_RELAY_BACKOFF_NS
+#define PB200_RELAY_BACKOFF_NS 40
+#endif
 constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger than any state, INF + P cannot wrap
 constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
 
@@ -212,13 +215,17 @@ template <int NR>
 __device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int lane, uint32_t tag, uint32_t (&v)[NR]) {
     unsigned long long w[NR];
     bool ok;
-    do {
+    // a failed poll backs off for a few dozen nanoseconds: polled flat out, the two relay warps of a CTA issue a third of
+    // all instructions of the kernel (profiles/r2_ncu_wave2_pass1.txt: 134 M iterations), on the ALU pipe the compute warps need
+    for (;;) {
         ok = true;
 #pragma unroll
         for (int j = 0; j < NR; ++j) w[j] = ll_load(slot + j * 32 + lane);
 #pragma unroll
         for (int j = 0; j < NR; ++j) ok = ok && ((uint32_t)(w[j] >> 32) == tag);
-    } while (!__all_sync(0xffffffffu, ok));
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(PB200_RELAY_BACKOFF_NS);
+    }
 #pragma unroll
     for (int j = 0; j < NR; ++j) v[j] = (uint32_t)w[j];
 }

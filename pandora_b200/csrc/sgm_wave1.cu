@@ -192,18 +192,18 @@ __global__ void __launch_bounds__(W1_THREADS, 1) sgm_wave1_kernel(const NarrowPa
             if (y > 0) {                                  // B(y-1): S, SE of the previous column and SE of the one before, row y - 1
                 const unsigned long long *src = rin + (size_t)((y - 1) & (W1_NRG - 1)) * 4 * VS;
                 const uint32_t pb = (uint32_t)((y - 1) & 1) * SLOTB;
-                while (!ll_try_recv_u32<NR>(src + 1 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                while (!ll_try_recv_u32<NR>(src + 1 * VS, lane, tag0 + (uint32_t)y, v)) __nanosleep(PB200_RELAY_BACKOFF_NS);
                 sts_words<NR>(s_base + pb + VB, v);
-                while (!ll_try_recv_u32<NR>(src + 2 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                while (!ll_try_recv_u32<NR>(src + 2 * VS, lane, tag0 + (uint32_t)y, v)) __nanosleep(PB200_RELAY_BACKOFF_NS);
                 sts_words<NR>(se_base + pb + VB, v);
                 flag_set(rdc_flag, (uint32_t)y);          // the chain start of row y (column 2 when its k = 0) waits for this
                 // SE of the column before the previous one: when that column closed the chain of row y - 1 it arrives a whole
                 // traversal later -- nobody needs it before E(y), which it always precedes
-                while (!ll_try_recv_u32<NR>(src + 3 * VS, lane, tag0 + (uint32_t)y, v)) {}
+                while (!ll_try_recv_u32<NR>(src + 3 * VS, lane, tag0 + (uint32_t)y, v)) __nanosleep(PB200_RELAY_BACKOFF_NS);
                 sts_words<NR>(se_base + pb, v);
             }
             const unsigned long long *src = rin + (size_t)(y & (W1_NRG - 1)) * 4 * VS;
-            while (!ll_try_recv_u32<NR>(src, lane, tag0 + (uint32_t)(y + 1), v)) {}      // A(y): E of the previous column
+            while (!ll_try_recv_u32<NR>(src, lane, tag0 + (uint32_t)(y + 1), v)) __nanosleep(PB200_RELAY_BACKOFF_NS);      // A(y): E of the previous column
             sts_words<NR>(e_base + (uint32_t)(y & 1) * SLOTB + VB, v);
             ev_signal(ev_base + 16u, y, lane);
             if (lane == 0) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(ack), "l"((unsigned long long)(tag0 + (uint32_t)(y + 1))) : "memory");
