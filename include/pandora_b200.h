@@ -8,6 +8,7 @@
  *
  *   compute_matching_costs   matching_cost/cpp/includes/census.hpp:44-51       -> pb200_census_cost_volume[_host]
  *   reverse_cost_volume      matching_cost/cpp/includes/matching_cost.hpp:39-46 -> pb200_reverse_cost_volume[_host]
+ *   reverse_disp_range       matching_cost/cpp/includes/matching_cost.hpp:48-54 -> pb200_reverse_disp_range[_host]
  *   cross_support            aggregation/cpp/includes/aggregation.hpp:47-53     -> pb200_cross_support[_host]
  *   cbca                     aggregation/cpp/includes/aggregation.hpp:55-65     -> pb200_cbca_aggregate / pb200_cbca_host
  *
@@ -178,6 +179,12 @@ PB200_API int pb200_zncc_cost_volume(const float *d_left, const float *d_right, 
 /* right(i,j,k) = left(i, j+k+min_disp, D-1-k) or NaN (matching_cost.cpp:26-57). */
 PB200_API int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, int D, int min_disp, float *d_right_cv, void *stream);
 
+/* Right disparity grids from the left ones (matching_cost.cpp:59-131, called by state_machine.py:673-675): for every left
+ * pixel (row, col) with non-NaN bounds and every d in [int(min), int(max)], right pixel col + d sees -d; right_min / right_max
+ * are the extrema of what a right pixel sees, NaN where it sees nothing.  All four grids are float32 (H, W). */
+PB200_API int pb200_reverse_disp_range(const float *d_left_min, const float *d_left_max, int H, int W, float *d_right_min,
+                             float *d_right_max, void *stream);
+
 /* ---- aggregation (CBCA) ----------------------------------------------------------------------- */
 /* 3x3 NaN-aware median; border ring and NaN pixels unchanged (filter/median.py:134-179). */
 PB200_API int pb200_median3(const float *d_in, int H, int W, float *d_out, void *stream);
@@ -326,6 +333,8 @@ PB200_API int pb200_census_cost_volume_host(const float *left, const float *righ
 PB200_API int pb200_census_cost_volume_multi_host(const float *left, const float *const *rights, int n_right, int H, int W, int window,
                                         const float *disps, int n_disp, float *cv);
 PB200_API int pb200_reverse_cost_volume_host(const float *left_cv, int H, int W, int D, int min_disp, float *right_cv);
+/* reverse_disp_range(left_min, left_max) -> (right_min, right_max) (matching_cost.hpp:48-54). */
+PB200_API int pb200_reverse_disp_range_host(const float *left_min, const float *left_max, int H, int W, float *right_min, float *right_max);
 PB200_API int pb200_cross_support_host(const float *image, int H, int W, int len_arms, float intensity, int16_t *cross);
 /* one aggregation_cpp.cbca call: (H, W) float32 slice, supports (H, W, 4), n valid columns
  * range_col[i] -> range_col_right[i]; outputs step4 and sum4 (H, W) like aggregation.cpp:323-355. */

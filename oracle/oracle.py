@@ -74,6 +74,8 @@ def lib() -> ctypes.CDLL:
         _LIB.pbo_cbca_volume.restype = ci
         _LIB.pbo_reverse_cost_volume.argtypes = [f32p, ci, ci, ci, ci, f32p]
         _LIB.pbo_reverse_cost_volume.restype = None
+        _LIB.pbo_reverse_disp_range.argtypes = [f32p, f32p, ci, ci, f32p, f32p]
+        _LIB.pbo_reverse_disp_range.restype = None
         _LIB.pbo_sgm.argtypes = [f32p, ci, ci, ci, cf, cf, cf, ci, ci, f32p]
         _LIB.pbo_sgm.restype = ci
         _LIB.pbo_sgm_direction.argtypes = [f32p, f32p, ci, ci, ci, cf, cf, ci, ci, f32p, f32p]
@@ -484,6 +486,15 @@ def reverse_cost_volume(left_cv: np.ndarray, min_disp: int) -> np.ndarray:
     out = np.empty_like(left_cv)
     lib().pbo_reverse_cost_volume(_p(left_cv, ctypes.c_float), H, W, D, int(min_disp), _p(out, ctypes.c_float))
     return out
+
+
+def reverse_disp_range(left_min: np.ndarray, left_max: np.ndarray):
+    """matching_cost/cpp/src/matching_cost.cpp:59-131 (called by state_machine.py:673-675)."""
+    left_min, left_max = _f32(left_min), _f32(left_max)
+    H, W = left_min.shape
+    rmin, rmax = np.empty_like(left_min), np.empty_like(left_max)
+    lib().pbo_reverse_disp_range(_p(left_min, ctypes.c_float), _p(left_max, ctypes.c_float), H, W, _p(rmin, ctypes.c_float), _p(rmax, ctypes.c_float))
+    return rmin, rmax
 
 
 # --------------------------------------------------------------------------------------------

@@ -212,6 +212,32 @@ PBO_API void pbo_reverse_cost_volume(const float *left_cv, int H, int W, int D, 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Right disparity grids from the left ones: matching_cost/cpp/src/matching_cost.cpp:59-131       */
+/* (scatter of -d over [int(min), int(max)], NaN bounds skipped, unseen right pixels -> NaN)      */
+/* ------------------------------------------------------------------------------------------ */
+PBO_API void pbo_reverse_disp_range(const float *left_min, const float *left_max, int H, int W, float *right_min, float *right_max) {
+    for (size_t i = 0; i < (size_t)H * W; ++i) {
+        right_min[i] = INFINITY;
+        right_max[i] = -INFINITY;
+    }
+    for (int row = 0; row < H; ++row)
+        for (int col = 0; col < W; ++col) {
+            const float a = left_min[(size_t)row * W + col], b = left_max[(size_t)row * W + col];
+            if (isnan(a) || isnan(b)) continue;
+            for (int d = (int)a; d <= (int)b; ++d) {
+                const int rc = col + d;
+                if (rc < 0) continue;
+                if (rc >= W) break;
+                float *mn = right_min + (size_t)row * W + rc, *mx = right_max + (size_t)row * W + rc;
+                if ((float)(-d) < *mn) *mn = (float)(-d);
+                if ((float)(-d) > *mx) *mx = (float)(-d);
+            }
+        }
+    for (size_t i = 0; i < (size_t)H * W; ++i)
+        if (isinf(right_min[i])) right_min[i] = right_max[i] = NAN;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* SGM 8-path regularisation.  PARITY UNPINNED against pandora_plugin_libsgm==1.5.7 / libSGM     */
 /* (not vendored, pyproject.toml:59-61; behaviour documented in                                  */
 /* docs/source/userguide/plugins/plugin_libsgm.rst:9-146, boundary optimization/optimization.py  */

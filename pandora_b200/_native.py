@@ -69,6 +69,8 @@ PROTOTYPES = {
     "pb200_zncc_workspace_bytes": (_sz, [_ci, _ci]),
     "pb200_zncc_cost_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _sz, _vp]),
     "pb200_reverse_cost_volume": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _vp]),
+    "pb200_reverse_disp_range": (_ci, [_vp, _vp, _ci, _ci, _vp, _vp, _vp]),
+    "pb200_reverse_disp_range_host": (_ci, [_vp, _vp, _ci, _ci, _vp, _vp]),
     "pb200_median3": (_ci, [_vp, _ci, _ci, _vp, _vp]),
     "pb200_cross_support": (_ci, [_vp, _ci, _ci, _ci, _ci, _cf, _ci, _vp, _vp]),
     "pb200_cbca_aggregate": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _ci, _vp]),

@@ -32,7 +32,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 static std::atomic<int> g_options[OPT_COUNT];
 static const char *const g_option_names[OPT_COUNT] = {"sgm.no_wave", "sgm.no_byte_tier", "sgm.wave_kernel", "census.direct", "census.tile",
-                                                      "cbca.pipe", "cbca.bands", "reverse.gather", "fuse_census_sgm"};
+                                                      "cbca.pipe", "cbca.bands", "reverse.gather", "fuse_census_sgm", "sad.taps"};
 static bool g_options_init = [] {
     for (auto &o : g_options) o.store(-1);
     return true;
@@ -205,6 +205,22 @@ extern "C" int pb200_reverse_cost_volume_host(const float *left_cv, int H, int W
     PB200_CUDA(cudaMemcpy(a.p, left_cv, vol, cudaMemcpyHostToDevice));
     PB200_RC(pb200_reverse_cost_volume(a.as<float>(), H, W, D, min_disp, b.as<float>(), nullptr));
     PB200_CUDA(cudaMemcpy(right_cv, b.p, vol, cudaMemcpyDeviceToHost));
+    return PB200_OK;
+}
+
+extern "C" int pb200_reverse_disp_range_host(const float *left_min, const float *left_max, int H, int W, float *right_min, float *right_max) {
+    if (!left_min || !left_max || !right_min || !right_max || H <= 0 || W <= 0) {
+        set_error("pb200_reverse_disp_range_host: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    const size_t n = (size_t)H * W * sizeof(float);
+    DevBuf a, b, c, d;
+    PB200_RC(a.alloc(n)); PB200_RC(b.alloc(n)); PB200_RC(c.alloc(n)); PB200_RC(d.alloc(n));
+    PB200_CUDA(cudaMemcpy(a.p, left_min, n, cudaMemcpyHostToDevice));
+    PB200_CUDA(cudaMemcpy(b.p, left_max, n, cudaMemcpyHostToDevice));
+    PB200_RC(pb200_reverse_disp_range(a.as<float>(), b.as<float>(), H, W, c.as<float>(), d.as<float>(), nullptr));
+    PB200_CUDA(cudaMemcpy(right_min, c.p, n, cudaMemcpyDeviceToHost));
+    PB200_CUDA(cudaMemcpy(right_max, d.p, n, cudaMemcpyDeviceToHost));
     return PB200_OK;
 }
 

@@ -42,6 +42,7 @@ enum Option {
     OPT_CBCA_BANDS,           // row bands of the register kernel
     OPT_REVERSE_GATHER,       // 1: plain gather kernel for reverse_cost_volume
     OPT_FUSE_CENSUS_SGM,      // 0: pb200_disparity_host keeps Census and SGM apart
+    OPT_SAD_TAPS,             // 1: tap-ordered SAD / SSD / ZNCC kernel instead of the running sums
     OPT_COUNT
 };
 int option(Option o);

@@ -9,6 +9,8 @@
 // (value, index) pair is reduced with warp shuffles, lowest index winning ties like np.argmin.
 #include <cstdlib>
 
+#include <climits>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -171,6 +173,49 @@ __global__ void __launch_bounds__(256) filter_select_kernel(float *__restrict__ 
     if (m == m && fabsf(m) != CUDART_INF_F) disp[i] = med[i];      // np.isfinite(masked_data)
 }
 
+// reverse_disp_range (matching_cost/cpp/src/matching_cost.cpp:59-131): the reference scatters, for every left pixel
+// (row, col) and every d in [int(min), int(max)], the value -d into running min / max of the right pixel col + d.  As a
+// gather: left pixel c covers the right interval [c + dmin(c), c + dmax(c)], so right_min(rc) = (smallest covering c) - rc
+// and right_max(rc) = (largest covering c) - rc.  One CTA per row: the row's own bounds of d limit the columns a right
+// pixel has to look at, and both scans stop at their first hit (constant ranges: the first candidate).
+__global__ void __launch_bounds__(256) reverse_disp_range_kernel(const float *__restrict__ lmin, const float *__restrict__ lmax, int H, int W,
+                                                                 float *__restrict__ rmin, float *__restrict__ rmax) {
+    __shared__ int s_lo[8], s_hi[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float *a = lmin + (size_t)row * W, *b = lmax + (size_t)row * W;
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int c = tid; c < W; c += blockDim.x) {
+        const float u = __ldg(a + c), v = __ldg(b + c);
+        if (u == u && v == v) {
+            lo = min(lo, (int)u);
+            hi = max(hi, (int)v);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
+    __syncthreads();
+    lo = s_lo[0]; hi = s_hi[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+    for (int rc = tid; rc < W; rc += blockDim.x) {
+        float mn = nan_f(), mx = nan_f();
+        if (lo <= hi) {
+            const int c0 = max(0L, (long)rc - hi), c1 = (int)min((long)W - 1, (long)rc - lo);
+            for (int c = c0; c <= c1; ++c) {
+                const float u = __ldg(a + c), v = __ldg(b + c);
+                if (u == u && v == v && (int)u <= rc - c && rc - c <= (int)v) { mn = (float)(c - rc); break; }
+            }
+            if (mn == mn)
+                for (int c = c1; c >= c0; --c) {
+                    const float u = __ldg(a + c), v = __ldg(b + c);
+                    if (u == u && v == v && (int)u <= rc - c && rc - c <= (int)v) { mx = (float)(c - rc); break; }
+                }
+        }
+        rmin[(size_t)row * W + rc] = mn;
+        rmax[(size_t)row * W + rc] = mx;
+    }
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -257,5 +302,16 @@ extern "C" int pb200_reverse_cost_volume(const float *d_left_cv, int H, int W, i
     reverse_cv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_left_cv, H, W, D, min_disp, d_right_cv);
     PB200_LAUNCH_CHECK("reverse_cv_kernel");
     note_path(STAGE_REVERSE, PATH_REVERSE_GATHER);
+    return PB200_OK;
+}
+
+extern "C" int pb200_reverse_disp_range(const float *d_left_min, const float *d_left_max, int H, int W, float *d_right_min,
+                                        float *d_right_max, void *stream) {
+    if (!d_left_min || !d_left_max || !d_right_min || !d_right_max || H <= 0 || W <= 0) {
+        set_error("pb200_reverse_disp_range: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    reverse_disp_range_kernel<<<H, 256, 0, (cudaStream_t)stream>>>(d_left_min, d_left_max, H, W, d_right_min, d_right_max);
+    PB200_LAUNCH_CHECK("reverse_disp_range_kernel");
     return PB200_OK;
 }

@@ -178,6 +178,14 @@ class Engine:
             _native.check(self.lib.pb200_reverse_cost_volume(_ptr(left_cv), H, W, D, int(min_disp), _ptr(out), self._stream()))
         return out
 
+    def reverse_disp_range(self, left_min: torch.Tensor, left_max: torch.Tensor):
+        """matching_cost.cpp:59-131 on the device: (right_min, right_max) float32 (H, W) grids."""
+        H, W = self._hw(left_min)
+        rmin, rmax = torch.empty_like(left_min), torch.empty_like(left_max)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_reverse_disp_range(_ptr(left_min), _ptr(left_max), H, W, _ptr(rmin), _ptr(rmax), self._stream()))
+        return rmin, rmax
+
     # ---- aggregation --------------------------------------------------------------------------------
     def median3(self, img: torch.Tensor) -> torch.Tensor:
         H, W = self._hw(img)

@@ -107,6 +107,15 @@ class AbstractMatchingCost:
         return None
 
     @staticmethod
+    def reverse_disp_range(left_min: np.ndarray, left_max: np.ndarray):
+        """Right disparity grids from the left ones (matching_cost.py:937-950 -> matching_cost_cpp.reverse_disp_range,
+        cpp/src/matching_cost.cpp:59-131), computed on the device: float32 (row, col) arrays in, (right_min, right_max) out."""
+        eng = get_engine()
+        rmin, rmax = eng.reverse_disp_range(eng.to_device(np.asarray(left_min, dtype=np.float32)),
+                                            eng.to_device(np.asarray(left_max, dtype=np.float32)))
+        return rmin.cpu().numpy(), rmax.cpu().numpy()
+
+    @staticmethod
     def get_disparity_range(disparity_min: int, disparity_max: int, subpix: int = 1) -> np.ndarray:
         """matching_cost.py:410-427."""
         if subpix == 1:

@@ -41,7 +41,7 @@ def run(img_left, img_right, cfg: dict, return_right: bool = False):
     """
     from .cost_volume_confidence import AbstractCostVolumeConfidence  # noqa: PLC0415
     from .criteria import validity_mask  # noqa: PLC0415
-    from .dataset import add_disparity  # noqa: PLC0415
+    from .dataset import DataArray, add_disparity  # noqa: PLC0415
     from .filter import AbstractFilter  # noqa: PLC0415
     from .refinement import AbstractRefinement  # noqa: PLC0415
     from .validation import AbstractValidation, right_disparity_fast  # noqa: PLC0415
@@ -56,9 +56,17 @@ def run(img_left, img_right, cfg: dict, return_right: bool = False):
     accurate = right_mode == "cross_checking_accurate"
     right_grids = None
     if accurate:
-        if "disparity" not in getattr(img_right, "data_vars", {}):                # state_machine.py:651-657
+        if "disparity" not in getattr(img_right, "data_vars", {}):                # state_machine.py:668-683
             img_right = img_right.copy(deep=False)
-            add_disparity(img_right, (-int(np.nanmax(disp_grids[1])), -int(np.nanmin(disp_grids[0]))))
+            const = AbstractMatchingCost.constant_range(img_left)
+            if const is not None:
+                # constant left range: reverse_disp_range only trims the right grids where the left column leaves the image, i.e.
+                # where every cost is NaN already, and their extrema are (-max, -min) -- the constant right range is equivalent
+                add_disparity(img_right, (-const[1], -const[0]))
+            else:
+                rmin, rmax = AbstractMatchingCost.reverse_disp_range(disp_grids[0], disp_grids[1])
+                img_right["disparity"] = (("band_disp", "row", "col"), np.stack([rmin, rmax], axis=0))
+                img_right.coords["band_disp"] = DataArray(np.array(["min", "max"]), ("band_disp",))
         right_grids = (img_right["disparity"].data[0], img_right["disparity"].data[1])
     cv = right_cv = None
     disp = right_disp = None

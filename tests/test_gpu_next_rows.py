@@ -344,3 +344,43 @@ def test_confidence_generic_inputs_sequential_sums(eng, oracle):
     out2 = eng.confidence(dev(eng, cv), etas, grids, dr, ambiguity=False, risk=True)
     for key, exp in zip(["risk_max", "risk_min", "disp_sup", "disp_inf"], exp_risk2):
         np.testing.assert_array_equal(host(out2[key]), exp)
+
+
+# ---- reverse_disp_range (matching_cost.cpp:59-131) -------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,H,W,lo,hi", [(0, 9, 31, -7, 2), (1, 5, 64, -3, 3), (2, 7, 40, 2, 9), (3, 6, 50, -30, -20), (4, 12, 300, -120, 40),
+                                            (5, 3, 1000, -260, 0)])
+def test_reverse_disp_range_vs_oracle(eng, oracle, seed, H, W, lo, hi):
+    gen = np.random.default_rng(seed)
+    a = gen.integers(lo, hi + 1, (H, W)).astype(np.float32)
+    b = a + gen.integers(0, 9, (H, W)).astype(np.float32)
+    if seed % 2:
+        a += 0.5
+    a[gen.random((H, W)) < 0.1] = np.nan
+    b[gen.random((H, W)) < 0.1] = np.nan
+    if seed == 4:
+        a[3], b[3] = np.nan, np.nan                                # a row nothing is seen from
+    rmin, rmax = eng.reverse_disp_range(eng.to_device(a), eng.to_device(b))
+    emin, emax = oracle.reverse_disp_range(a, b)
+    np.testing.assert_array_equal(rmin.cpu().numpy(), emin)
+    np.testing.assert_array_equal(rmax.cpu().numpy(), emax)
+
+
+def test_reverse_disp_range_host_entry_and_mirror(eng, oracle):
+    import ctypes
+
+    import pandora_b200
+    from pandora_b200.matching_cost import AbstractMatchingCost
+
+    gen = np.random.default_rng(11)
+    a = gen.integers(-9, 3, (10, 37)).astype(np.float32)
+    b = a + gen.integers(0, 5, a.shape).astype(np.float32)
+    emin, emax = oracle.reverse_disp_range(a, b)
+    lib = pandora_b200.load()
+    rmin, rmax = np.empty_like(a), np.empty_like(a)
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    assert lib.pb200_reverse_disp_range_host(p(a), p(b), 10, 37, p(rmin), p(rmax)) == 0
+    np.testing.assert_array_equal(rmin, emin)
+    np.testing.assert_array_equal(rmax, emax)
+    mmin, mmax = AbstractMatchingCost.reverse_disp_range(a, b)
+    np.testing.assert_array_equal(mmin, emin)
+    np.testing.assert_array_equal(mmax, emax)

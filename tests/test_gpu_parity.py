@@ -128,6 +128,64 @@ def test_sad_reference_goldens(eng, goldens):
     np.testing.assert_array_equal(got, goldens[k + "ground_truth"])
 
 
+@pytest.mark.parametrize("method", ["sad", "ssd"])
+@pytest.mark.parametrize("H,W,dmin,dmax,w", [(90, 75, -40, 3, 5), (70, 50, -150, 20, 3), (41, 37, -5, 70, 7), (37, 33, -3, 3, 13),
+                                             (20, 18, 2, 9, 1), (9, 70, -20, 0, 11)])
+def test_sad_ssd_running_sums(eng, oracle, method, H, W, dmin, dmax, w):
+    """Integer images take the separable running-sum kernel (several row blocks, bands, disparity chunks, ranges leaving
+    the image on both sides): bit-exact vs the oracle and vs the tap-ordered kernel."""
+    import pandora_b200
+
+    left, right = rand_pair(H + w, H, W)
+    ref, _ = oracle.sad_ssd_cost_volume(left, right, w, dmin, dmax, method)
+    got = host(eng.sad_ssd(dev(eng, left), dev(eng, right), w, dmin, dmax, squared=(method == "ssd")))
+    assert pandora_b200.last_path("sad")[0] == "sad_running"
+    np.testing.assert_array_equal(got, ref)
+    with pandora_b200.option("sad.taps", 1):
+        taps = host(eng.sad_ssd(dev(eng, left), dev(eng, right), w, dmin, dmax, squared=(method == "ssd")))
+        assert pandora_b200.last_path("sad")[0] == "sad_taps"
+    np.testing.assert_array_equal(taps, ref)
+
+
+@pytest.mark.parametrize("case", ["fraction", "nan", "large", "negative", "float16bit"])
+def test_sad_running_sums_data_condition(eng, oracle, case):
+    """A CTA that stages anything but a small integer falls back to the reference's tap order before using the value:
+    one fractional / NaN / huge pixel in the middle of a band, negative integers (still exact), 16-bit data."""
+    left, right = rand_pair(77, 120, 64)
+    if case == "fraction":
+        left[70, 30] = 17.25
+        right[33, 11] = 0.5
+    elif case == "nan":
+        right[64, 20] = np.nan
+    elif case == "large":
+        left[50, 40] = 3.0e7
+    elif case == "negative":
+        left -= 100.0
+        right -= 60.0
+    else:
+        left, right = rand_pair(78, 120, 64, levels=65536)
+    import pandora_b200
+
+    for method in ("sad", "ssd"):
+        if case == "nan":                         # the oracle's cmax attribute cannot take a NaN image: tap-ordered kernel as the checker
+            with pandora_b200.option("sad.taps", 1):
+                ref = host(eng.sad_ssd(dev(eng, left), dev(eng, right), 5, -30, 4, squared=(method == "ssd")))
+            assert np.isnan(ref[64, 50, 0]) and np.isfinite(ref[64, 56, 0])
+        else:
+            ref, _ = oracle.sad_ssd_cost_volume(left, right, 5, -30, 4, method)
+        got = host(eng.sad_ssd(dev(eng, left), dev(eng, right), 5, -30, 4, squared=(method == "ssd")))
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_zncc_running_sums(eng, oracle):
+    left, right = rand_pair(5, 100, 90)
+    for w, dmin, dmax in ((5, -70, 3), (3, -10, 140), (9, -4, 4)):
+        ref, _ = oracle.zncc_cost_volume(left, right, w, dmin, dmax)
+        got = host(eng.zncc(dev(eng, left), dev(eng, right), w, dmin, dmax))
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("w", [1, 3, 5, 9])
 @pytest.mark.parametrize("as_float", [False, True])
 def test_zncc_vs_oracle(eng, oracle, w, as_float):

@@ -122,3 +122,34 @@ def test_reverse_cost_volume_vs_reference(oracle, ref_modules):
     cv[gen.random(cv.shape) < 0.2] = np.nan
     for min_disp in (-5, -2, 0, 3):
         np.testing.assert_array_equal(oracle.reverse_cost_volume(cv, min_disp), mc.reverse_cost_volume(cv, min_disp))
+
+
+def _disp_grids(seed, H, W, lo, hi, nan_frac=0.1):
+    gen = np.random.default_rng(seed)
+    a = gen.integers(lo, hi + 1, (H, W)).astype(np.float32)
+    b = a + gen.integers(0, 6, (H, W)).astype(np.float32)
+    if seed % 2:
+        a += 0.5                                                  # static_cast<int> truncates toward zero
+    a[gen.random((H, W)) < nan_frac] = np.nan
+    b[gen.random((H, W)) < nan_frac] = np.nan
+    return a, b
+
+
+@pytest.mark.parametrize("seed,lo,hi", [(0, -7, 2), (1, -3, 3), (2, 2, 9), (3, -30, -20), (4, -40, 40)])
+def test_reverse_disp_range_vs_reference(oracle, ref_modules, seed, lo, hi):
+    """matching_cost.cpp:59-131: the oracle against the compiled reference, NaN bounds, ranges leaving the row, right
+    pixels that nothing reaches."""
+    mc, _ = ref_modules
+    a, b = _disp_grids(seed, 9, 31, lo, hi)
+    rmin, rmax = oracle.reverse_disp_range(a, b)
+    ref_min, ref_max = mc.reverse_disp_range(a, b)
+    np.testing.assert_array_equal(rmin, ref_min)
+    np.testing.assert_array_equal(rmax, ref_max)
+
+
+def test_reverse_disp_range_constant_grid(oracle):
+    """A constant left range [-3, 1]: right pixel rc sees col - rc for every col in [rc - 1, rc + 3] inside the row."""
+    a, b = np.full((2, 8), -3, np.float32), np.full((2, 8), 1, np.float32)
+    rmin, rmax = oracle.reverse_disp_range(a, b)
+    np.testing.assert_array_equal(rmin[0], [-0.0, -1, -1, -1, -1, -1, -1, -1])
+    np.testing.assert_array_equal(rmax[0], [3, 3, 3, 3, 3, 2, 1, 0])
