@@ -225,6 +225,49 @@ class TiledStereoPipeline:
         return self.disp
 
 
+def local_halo_rows(window: int, cbca_distance: Optional[int] = None) -> int:
+    """Rows of INPUT image a row tile needs from each neighbour so that a pipeline WITHOUT SGM is bit-identical to the
+    untiled run.  Matching cost / WTA: the half window.  CBCA on top: a pixel's vertical arms reach
+    ``distance - 1`` rows (aggregation.cpp:259-313), the horizontal sums of those rows need their costs (half window
+    more) and their horizontal arms, taken on the 3x3-median image (one more row): (distance - 1) + half + 1 -- 7 rows
+    for the C2 configuration.  The vertical arms of the halo rows themselves are wrong (truncated) and never used."""
+    half = window // 2
+    return half if not cbca_distance else (cbca_distance - 1) + half + 1
+
+
+class TiledLocalPipeline:
+    """Row tiles of a pipeline without SGM (Census / SAD / SSD / ZNCC [-> CBCA] -> WTA; C1 / C2): every rank extends its
+    tile by ``local_halo_rows`` input rows from each neighbour (one point-to-point exchange of the two images per pair,
+    no collective on the data path), runs the single-GPU pipeline on the extended tile and keeps its own rows.
+
+    ``compute(left_ext, right_ext) -> disparity_ext`` replaces the device pipeline in the CPU (gloo) tests."""
+
+    def __init__(self, tile_rows: int, W: int, dmin: int, dmax: int, rank: int, world: int, dist=None, method: str = "census",
+                 window: int = 5, cbca=None, invalid_disparity: float = -9999.0, device: Optional[str] = None, compute=None):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.rows, self.W = tile_rows, W
+        self.halo = local_halo_rows(window, cbca[0] if cbca else None)
+        if world > 1 and tile_rows < self.halo:
+            raise ValueError(f"row tiles of {tile_rows} rows are shorter than the {self.halo}-row halo")
+        self.top = self.halo if rank > 0 else 0
+        self.bot = self.halo if rank < world - 1 else 0
+        self.compute = compute
+        self.pipe = None
+        if compute is None:
+            from .pipeline import StereoPipeline  # noqa: PLC0415
+
+            self.pipe = StereoPipeline(tile_rows + self.top + self.bot, W, dmin, dmax, method, window, cbca=cbca,
+                                       invalid_disparity=invalid_disparity, device=device)
+
+    def run(self, left_tile, right_tile):
+        """``left_tile`` / ``right_tile``: this rank's (rows, W) float32 tensors.  Returns the (rows, W) disparity tile."""
+        l_ext, top = exchange_image_halo(left_tile, self.halo, self.rank, self.world, self.dist)
+        r_ext, _ = exchange_image_halo(right_tile, self.halo, self.rank, self.world, self.dist)
+        assert top == self.top and l_ext.shape[0] == self.rows + self.top + self.bot
+        disp = self.compute(l_ext, r_ext) if self.compute is not None else self.pipe.run_device(l_ext.contiguous(), r_ext.contiguous())
+        return disp[self.top: self.top + self.rows]
+
+
 # ====================================================================================================================
 # Column tiles: the skewed wavefront as ONE wave across all GPUs (pb200_census_sgm_tile)
 # ====================================================================================================================

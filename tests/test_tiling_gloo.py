@@ -114,3 +114,55 @@ def test_tiled_sgm_over_gloo_matches_untiled(world, tmp_path, oracle):
     whole = oracle.sgm_cost_volume(C, 8, 32, cmax=25)
     tiled = np.concatenate([np.load(tmp_path / f"S{r}.npy") for r in range(world)])
     np.testing.assert_array_equal(tiled, whole)
+
+
+def _oracle_local(orc, left, right, dmin, dmax, cbca):
+    cv, _ = orc.census_cost_volume(left, right, 5, dmin, dmax)
+    if cbca:
+        cv = orc.cbca_cost_volume(left, right, cv, 2, dmin, cbca[0], cbca[1])
+        cv = cv[0] if isinstance(cv, tuple) else cv
+    return orc.wta(cv, np.arange(dmin, dmax + 1))[0]
+
+
+def _local_worker(rank, world, port, H, W, dmin, dmax, cbca, tmpdir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as orc
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.random.default_rng(9)
+    left = g.integers(0, 60, (H, W)).astype(np.float32)
+    right = g.integers(0, 60, (H, W)).astype(np.float32)
+    rows = tiling.split_rows(H, world)[rank]
+
+    def compute(l_ext, r_ext):
+        return torch.from_numpy(_oracle_local(orc, l_ext.numpy(), r_ext.numpy(), dmin, dmax, cbca))
+
+    pipe = tiling.TiledLocalPipeline(len(rows), W, dmin, dmax, rank, world, dist, "census", 5, cbca=cbca, compute=compute)
+    assert pipe.halo == (7 if cbca else 2)
+    disp = pipe.run(torch.from_numpy(left[rows.start: rows.stop].copy()), torch.from_numpy(right[rows.start: rows.stop].copy()))
+    np.save(os.path.join(tmpdir, f"D{rank}.npy"), disp.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cbca", [(2, None), (2, (5, 30.0)), (3, (5, 30.0))])
+def test_tiled_local_pipeline_over_gloo_matches_untiled(world, cbca, tmp_path, oracle):
+    """Row tiles of Census [-> CBCA] -> WTA with the static input halo of SURVEY 8(e) (2 rows; 7 with CBCA): bit-identical
+    to the untiled oracle chain -- the halo really covers the median, the arms and the window."""
+    H, W, dmin, dmax = 33, 24, -6, 2
+    port = _free_port()
+    mp.spawn(_local_worker, args=(world, port, H, W, dmin, dmax, cbca, str(tmp_path)), nprocs=world, join=True)
+    g = np.random.default_rng(9)
+    left = g.integers(0, 60, (H, W)).astype(np.float32)
+    right = g.integers(0, 60, (H, W)).astype(np.float32)
+    whole = _oracle_local(oracle, left, right, dmin, dmax, cbca)
+    tiled = np.concatenate([np.load(tmp_path / f"D{r}.npy") for r in range(world)])
+    np.testing.assert_array_equal(tiled, whole)
+
+
+def test_local_halo_rows():
+    assert tiling.local_halo_rows(5) == 2 and tiling.local_halo_rows(5, 5) == 7 and tiling.local_halo_rows(3, 9) == 10
