@@ -141,8 +141,7 @@ __device__ __forceinline__ void st_cost(uint32_t *pix, int lane, const uint32_t 
 template <int CB> __device__ __forceinline__ int p16_off(int D) { return CB == 2 ? D / 2 : D / 4; }
 __device__ __forceinline__ int p8_off(int D) { return 3 * (D / 4); }
 
-// One recurrence step on packed states: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m)
-// = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1], m + P2 - P1) + P1) - m).
+// One recurrence step on packed states: L = cc + (min(Lp[d], min(Lp[d-1], Lp[d+1]) + P1, m + P2) - m).
 // Register j of a lane holds disparity NR*lane + j (low half) and D/2 + NR*lane + j (high half).
 template <int NR>
 __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (&Lp)[NR], uint32_t (&L)[NR], int lane, uint32_t p1p1,
@@ -160,7 +159,7 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
     // replicated in both halves, i.e. the word the step needs -- no mask, no multiply
     mn = __vminu2(mn, __byte_perm(mn, 0u, 0x1032));
     const uint32_t mm = __reduce_min_sync(0xffffffffu, mn);
-    const uint32_t mq = mm + (p2p2 - p1p1);             // min + P2 - P1 (P1 <= P2 is a condition of the packed path)
+    const uint32_t mp2 = mm + p2p2;
     const uint32_t up = __shfl_sync(0xffffffffu, Lp[NR - 1], (lane + 31) & 31);
     const uint32_t dn = __shfl_sync(0xffffffffu, Lp[0], (lane + 1) & 31);
     // lane 0: d-1 of its low half does not exist, d-1 of its high half (D/2 - 1) is lane 31's last LOW half:
@@ -172,13 +171,14 @@ __device__ __forceinline__ void nstep(const uint32_t (&cc)[NR], const uint32_t (
     for (int j = 0; j < NR; ++j) {
         const uint32_t lo = (j == 0) ? lo0 : Lp[j - 1];
         const uint32_t hi = (j == NR - 1) ? hiN : Lp[j + 1];
-        // min(Lp[d], min(Lp[d-1], Lp[d+1], m + P2 - P1) + P1): one 3-input minimum and one fused add-then-minimum
-        // (VIMNMX3.U16x2 + VIADDMNMX.U16x2) instead of minimum, add, 3-input minimum
-        const uint32_t t = __viaddmin_u16x2(__vimin3_u16x2(lo, hi, mq), p1p1, Lp[j]);
+        const uint32_t t = __vimin3_u16x2(Lp[j], __vminu2(lo, hi) + p1p1, mp2);    // INF16 + P1 stays inside its half
         L[j] = cc[j] + (t - mm);          // t >= m in both halves: no borrow, and cc + P2 < 2^16: no carry
     }
 }
 
+// (Measured and dropped, round 2: t = __viaddmin_u16x2(__vimin3_u16x2(lo, hi, m + P2 - P1), P1, Lp[j]) -- VIMNMX3 + VIADDMNMX.U16x2,
+// one instruction less per register and direction, 16 per pixel and pass -- ran the two-column stage at 14.61 ms instead of 14.07 ms
+// at C3 (one-column 17.42 -> 17.26 ms): the fused add-minimum issues slower than the add and the minimum it replaces.)
 // (Measured and dropped: the same step with its additions written as a * 1 + c with the 1 in a register the compiler cannot
 // see through, i.e. IMAD on the idle FMA pipe instead of IADD3 on the ALU pipe that the packed min-ops saturate.  Two IMAD
 // replace one IADD3 and the dependent chain gets longer: 15.40 -> 16.26 ms for the two-column kernels at C3, 17.42 -> 18.42 ms
