@@ -261,7 +261,8 @@ def plugin_leg(pb, torch, left, right, dmin, dmax, steps):
     ms = (time.perf_counter() - t0) * 1e3 / steps
     H, W = left.shape
     return {"value": H * W / ms / 1e3, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": 2 * H * W * 4, "d2h_bytes_per_step": H * W * 6,
-            "call": "pandora_b200.run(img_left, img_right, cfg): host datasets in, host disparity_map + validity_mask out (pageable copies)",
+            "call": "pandora_b200.run(img_left, img_right, cfg): host numpy datasets in (pageable H2D), host disparity_map + validity_mask out "
+                    "(page-locked result arrays from the caching host allocator)",
             "sgm_path": pb.last_path("sgm")[0], "same_map_every_call": bool(np.array_equal(ref, d))}, ref
 
 
