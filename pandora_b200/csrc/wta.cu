@@ -4,9 +4,9 @@
 // 400-553), mask_invalid_variable_disparity_range + mask_border (criteria.py:291-353) and
 // reverse_cost_volume (matching_cost/cpp/src/matching_cost.cpp:26-57).
 //
-// WTA is HBM-read bound (4*D bytes per pixel in, 4 out): one warp per pixel, lanes read 16-byte
-// vectors so a warp instruction covers 512 contiguous bytes of the pixel's disparity vector; the
-// (value, index) pair is reduced with warp shuffles, lowest index winning ties like np.argmin.
+// WTA is HBM-read bound (4*D bytes per pixel in, 4 out): a warp takes four pixels per trip, lanes read 16-byte
+// vectors so a warp instruction covers 512 contiguous bytes of a pixel's disparity vector; the (value, index)
+// pair is reduced with REDUX on ordered integer keys, lowest index winning ties like np.argmin.
 #include <cstdlib>
 
 #include <climits>
@@ -23,6 +23,17 @@ __device__ __forceinline__ void wta_take(float v, int k, float &bv, int &bk, boo
     else if (v == bv && k < bk) bk = k;
 }
 
+// float -> unsigned key with the same order (-0 was folded into +0 by the caller)
+__device__ __forceinline__ uint32_t wta_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// WTA_PPW pixels per warp and trip: the loads of all of them are in flight before the first comparison, and the
+// (value, index) pair is reduced with two REDUX instructions on ordered integer keys (minimum / maximum key, then the
+// lowest index among the lanes that hold it) instead of five rounds of three shuffles.
+constexpr int WTA_PPW = 4;
+
 template <bool IS_MAX, bool VEC4>
 __global__ void __launch_bounds__(256) wta_kernel(const float *__restrict__ cv, long n_pix, int D, int dmin,
                                                   float invalid_disparity, float *__restrict__ disp,
@@ -30,37 +41,49 @@ __global__ void __launch_bounds__(256) wta_kernel(const float *__restrict__ cv, 
     const int lane = threadIdx.x & 31;
     const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long pix = warp0; pix < n_pix; pix += nwarps) {
-        const float *src = cv + pix * D;
-        float bv = IS_MAX ? -CUDART_INF_F : CUDART_INF_F;
-        int bk = 0x7fffffff;
-        bool any = false;
+    const float init = IS_MAX ? -CUDART_INF_F : CUDART_INF_F;
+    for (long pix0 = warp0 * WTA_PPW; pix0 < n_pix; pix0 += nwarps * WTA_PPW) {
+        float bv[WTA_PPW];
+        int bk[WTA_PPW];
+        bool any[WTA_PPW];
+#pragma unroll
+        for (int q = 0; q < WTA_PPW; ++q) { bv[q] = init; bk[q] = 0x7fffffff; any[q] = false; }
         if (VEC4) {
             for (int k = lane * 4; k < D; k += 128) {
-                const float4 v = ld_cs_f4(src + k);
-                wta_take<IS_MAX>(v.x, k, bv, bk, any);
-                wta_take<IS_MAX>(v.y, k + 1, bv, bk, any);
-                wta_take<IS_MAX>(v.z, k + 2, bv, bk, any);
-                wta_take<IS_MAX>(v.w, k + 3, bv, bk, any);
+                float4 v[WTA_PPW];
+#pragma unroll
+                for (int q = 0; q < WTA_PPW; ++q)
+                    v[q] = (pix0 + q < n_pix) ? ld_cs_f4(cv + (pix0 + q) * D + k) : make_float4(nan_f(), nan_f(), nan_f(), nan_f());
+#pragma unroll
+                for (int q = 0; q < WTA_PPW; ++q) {
+                    wta_take<IS_MAX>(v[q].x, k, bv[q], bk[q], any[q]);
+                    wta_take<IS_MAX>(v[q].y, k + 1, bv[q], bk[q], any[q]);
+                    wta_take<IS_MAX>(v[q].z, k + 2, bv[q], bk[q], any[q]);
+                    wta_take<IS_MAX>(v[q].w, k + 3, bv[q], bk[q], any[q]);
+                }
             }
         } else {
-            for (int k = lane; k < D; k += 32) wta_take<IS_MAX>(__ldcs(src + k), k, bv, bk, any);
+            for (int k = lane; k < D; k += 32) {
+                float v[WTA_PPW];
+#pragma unroll
+                for (int q = 0; q < WTA_PPW; ++q) v[q] = (pix0 + q < n_pix) ? __ldcs(cv + (pix0 + q) * D + k) : nan_f();
+#pragma unroll
+                for (int q = 0; q < WTA_PPW; ++q) wta_take<IS_MAX>(v[q], k, bv[q], bk[q], any[q]);
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            const bool oany = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
-            if (IS_MAX ? (ov > bv) : (ov < bv)) { bv = ov; bk = ok; }
-            else if (ov == bv && ok < bk) bk = ok;
-            any = any || oany;
-        }
-        if (lane == 0) {
+        for (int q = 0; q < WTA_PPW; ++q) {
+            const uint32_t key = wta_key(bv[q] + 0.0f);                       // -0 == +0 for np.argmin / np.argmax
+            const uint32_t best = IS_MAX ? __reduce_max_sync(0xffffffffu, key) : __reduce_min_sync(0xffffffffu, key);
+            int k = __reduce_min_sync(0xffffffffu, key == best ? bk[q] : 0x7fffffff);
+            const bool anyw = __any_sync(0xffffffffu, any[q]);
             // best value still the initial +-inf: every entry is +-inf or NaN, and since NaNs were replaced by
             // the same inf np.argmin / np.argmax return index 0
-            if (bv == (IS_MAX ? -CUDART_INF_F : CUDART_INF_F)) bk = 0;
-            disp[pix] = any ? (float)(dmin + bk) : invalid_disparity;
-            if (all_nan) all_nan[pix] = any ? 0 : 1;
+            if (best == wta_key(init)) k = 0;
+            if (lane == q && pix0 + q < n_pix) {
+                disp[pix0 + q] = anyw ? (float)(dmin + k) : invalid_disparity;
+                if (all_nan) all_nan[pix0 + q] = anyw ? 0 : 1;
+            }
         }
     }
 }
@@ -245,7 +268,7 @@ extern "C" int pb200_wta(const float *d_cv, int H, int W, int D, int dmin, int i
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long n_pix = (long)H * W;
-    long blocks = (n_pix + 7) / 8;                    // 8 warps per block, one pixel per warp per trip
+    long blocks = (n_pix + 8 * WTA_PPW - 1) / (8 * WTA_PPW);     // 8 warps per block, WTA_PPW pixels per warp per trip
     const long cap = (long)sm_count() * 8 * 8;
     if (blocks > cap) blocks = cap;
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_cv) & 15) == 0);
