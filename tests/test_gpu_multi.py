@@ -192,3 +192,76 @@ def test_column_tiled_pipeline_equals_single_gpu(world, H, W, D, dmin, tmp_path)
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} CUDA devices")
     run_column_case(world, H, W, D, dmin, tmp_path)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# row tiles of the pipelines without SGM (C1 / C2): static input halo, no collective on the data path
+# ----------------------------------------------------------------------------------------------------------------------
+def _local_worker(rank, world, port, H, W, D, method, cbca, tmpdir):
+    import torch
+    import torch.distributed as dist
+
+    from pandora_b200.synthetic import synthetic_pair
+    from pandora_b200.tiling import TiledLocalPipeline, split_rows
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    left, right, _ = synthetic_pair(H, W, D)
+    rows = split_rows(H, world)[rank]
+    pipe = TiledLocalPipeline(len(rows), W, -(D - 1), 0, rank, world, dist, method, 5, cbca=cbca, device=f"cuda:{rank}")
+    lt = pipe.pipe.eng.to_device(np.ascontiguousarray(left[rows.start: rows.stop]))
+    rt = pipe.pipe.eng.to_device(np.ascontiguousarray(right[rows.start: rows.stop]))
+    for _ in range(2):
+        disp = pipe.run(lt, rt)
+        torch.cuda.synchronize()
+    np.save(os.path.join(tmpdir, f"ldisp{rank}.npy"), disp.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,cbca,shape", [("census", (5, 30.0), (120, 260, 192)), ("census", None, (90, 200, 128)), ("sad", None, (90, 200, 64))])
+def test_two_rank_local_pipeline_equals_single_gpu(method, cbca, shape, tmp_path):
+    """C2 / C1 / C0-style pipelines row-tiled over 2 GPUs (7-row halo with CBCA) == the one-GPU run of the whole image."""
+    import torch
+    import torch.multiprocessing as mp
+
+    import pandora_b200
+    from pandora_b200.synthetic import synthetic_pair
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    H, W, D = shape
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_local_worker, args=(2, port, H, W, D, method, cbca, str(tmp_path)), nprocs=2, join=True)
+    left, right, _ = synthetic_pair(H, W, D)
+    pipe = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, method, 5, cbca=cbca, device="cuda:0")
+    whole = pipe.run_host(left, right).copy()
+    tiled = np.concatenate([np.load(os.path.join(tmp_path, f"ldisp{r}.npy")) for r in range(2)])
+    np.testing.assert_array_equal(tiled, whole)
+
+
+def test_local_pipeline_single_rank_on_one_gpu():
+    """world = 1: the tiled wrapper is the plain pipeline (runs on the driver's one-GPU box)."""
+    import torch
+
+    import pandora_b200
+    from pandora_b200.synthetic import synthetic_pair
+    from pandora_b200.tiling import TiledLocalPipeline
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    H, W, D = 64, 128, 64
+    left, right, _ = synthetic_pair(H, W, D)
+    tl = TiledLocalPipeline(H, W, -(D - 1), 0, 0, 1, None, "census", 5, cbca=(5, 30.0), device="cuda:0")
+    eng = tl.pipe.eng
+    got = tl.run(eng.to_device(left), eng.to_device(right)).cpu().numpy()
+    ref = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, cbca=(5, 30.0), device="cuda:0").run_host(left, right)
+    np.testing.assert_array_equal(got, ref)
+
+
+test_local_pipeline_single_rank_on_one_gpu = pytest.mark.gpu(test_local_pipeline_single_rank_on_one_gpu)
