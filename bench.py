@@ -284,7 +284,8 @@ def run_ours(args):
         import torch.distributed as dist  # noqa: PLC0415
 
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"                  # the version banner goes to stdout: keep the JSON line alone there
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version banner goes to stdout otherwise: keep the JSON line alone there
         dist.init_process_group("nccl", device_id=torch.device(device))
     cfg = CONFIGS[args.config]
     dmin, dmax = -(D_DISP - 1), 0
@@ -399,24 +400,33 @@ def run_ours(args):
                 pipe.unshear()
                 done += m
 
-        # the host side of a step: the column ranges this rank needs as CONTIGUOUS pinned arrays (a strided pinned -> device copy
-        # takes a slow path), copied to a device staging buffer and from there into place
+        # the host side of a step (ONE image per call): the image columns this rank's sheared tile visits for one image -- its
+        # own Wt columns plus the H - 1 columns the shear drifts over, plus the right-image windows -- as CONTIGUOUS pinned
+        # arrays (a strided pinned -> device copy takes a slow path), copied to a device staging buffer and from there into place
+        lo1, n1 = pipe.visited_columns(1)
+        lo1_img, n1_img = (lo1 - D - 8) % Wg, min(Wg, n1 + D + 16)
+        ranges1 = [(lo1_img, min(Wg, lo1_img + n1_img))] + ([(0, lo1_img + n1_img - Wg)] if lo1_img + n1_img > Wg else [])
         h_parts = [(torch.from_numpy(np.ascontiguousarray(h_left[:, a:b].numpy())).pin_memory(),
-                    torch.from_numpy(np.ascontiguousarray(h_right[:, a:b].numpy())).pin_memory()) for a, b in ranges]
+                    torch.from_numpy(np.ascontiguousarray(h_right[:, a:b].numpy())).pin_memory()) for a, b in ranges1]
         d_parts = [(torch.empty_like(hl, device=device), torch.empty_like(hr, device=device)) for hl, hr in h_parts]
+        host_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
         def step_host():
-            for (a, b), (hl, hr), (dl, dr) in zip(ranges, h_parts, d_parts):
+            host_ev[0].record()
+            for (a, b), (hl, hr), (dl, dr) in zip(ranges1, h_parts, d_parts):
                 dl.copy_(hl, non_blocking=True)
                 dr.copy_(hr, non_blocking=True)
                 d_left[:, a:b].copy_(dl)
                 d_right[:, a:b].copy_(dr)
+            host_ev[1].record()
             pipe.run(d_left, d_right)
+            host_ev[2].record()
             h_disp.copy_(pipe.unshear(), non_blocking=True)
+            host_ev[3].record()
             torch.cuda.current_stream().synchronize()
             return h_disp
 
-        h2d_bytes = sum(b - a for a, b in ranges) * H * 4 * 2 * world
+        h2d_bytes = sum(b - a for a, b in ranges1) * H * 4 * 2 * world
         d2h_bytes = H * Wt * 4 * world
 
     for _ in range(max(args.warmup, 3)):
@@ -453,6 +463,10 @@ def run_ours(args):
     for _ in range(2):
         step_host()
     sync_ms = timed(step_host, steps)                          # one synchronous host call per pair (latency view)
+    host_parts = None
+    if world > 1:
+        host_parts = {"upload_ms": host_ev[0].elapsed_time(host_ev[1]), "kernels_ms": host_ev[1].elapsed_time(host_ev[2]),
+                      "unshear_d2h_ms": host_ev[2].elapsed_time(host_ev[3]), "note": "rank 0, last timed call"}
     e2e_ms, e2e_mode = sync_ms, "synchronous host call per pair (H2D -> kernels -> D2H back to back)"
     e2e_wall_ms = None
     if world == 1:
@@ -518,6 +532,7 @@ def run_ours(args):
                                   "(pb200_census_sgm_tile, nimg > 1), so that the time a wave needs to cross all GPUs is paid once per pass "
                                   "and batch; `one_image_at_a_time` is the same step with one image per call")
         line["one_image_at_a_time"] = {"ms_per_step": single_ms / steps, "value": pix / (single_ms / steps * 1e-3) / 1e6, "unit": UNIT}
+        line["e2e"]["parts"] = host_parts
     if world == 1:
         if e2e_wall_ms is not None:
             line["e2e"]["wall_ms_per_step"] = e2e_wall_ms / steps

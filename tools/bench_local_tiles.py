@@ -20,6 +20,7 @@ torch.cuda.set_device(lr)
 dev = f"cuda:{lr}"
 if world > 1:
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device(dev))
 for name, rows, W, D, cbca in (("C1", 1024, 1024, 128, None), ("C2", 2048, 2048, 192, (5, 30.0))):
     left, right, _ = synthetic_pair(rows, W, D, seed=20240607 + rank)
