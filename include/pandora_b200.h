@@ -134,6 +134,14 @@ PB200_API int pb200_census_sgm(const float *d_left, const float *d_right, int H,
                      int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
                      void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
                      uint8_t *d_all_nan, int descriptors_ready, int *ran, void *stream);
+/* A batch of `nimg` pairs through one wave per pass (two-column wavefront kernels): d_left / d_right (nimg, H, W), d_cv_out
+ * (nimg, H, W, D), d_disp / d_all_nan (nimg, H, W); the results are those of nimg pb200_census_sgm calls, bit for bit, and the
+ * fill and drain of the wave across the SMs are paid once per batch.  Census workspace: nimg * pb200_census_sgm_workspace_bytes.
+ * *ran = 0: nothing was computed (shape / parameters not eligible): call pb200_census_sgm per pair. */
+PB200_API int pb200_census_sgm_batch(const float *d_left, const float *d_right, int nimg, int H, int W, int window, int dmin, int D, float p1,
+                           float p2, int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
+                           void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
+                           uint8_t *d_all_nan, int *ran, void *stream);
 
 /* ---- the fused stage column-tiled over several GPUs (one process per GPU) ---------------------------------------------------
  * The skewed wavefront (pandora_b200/csrc/sgm_wave1.cu) walks SHEARED columns c = (image column + row) mod Wg, in which every

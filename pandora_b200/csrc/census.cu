@@ -393,7 +393,7 @@ static int launch_fill(const FillParams &p, size_t smem, int grid, cudaStream_t 
 int sgm_census_plan(int window, int W, int D, float p1, float p2);   // sgm_narrow.cu: 0 = not eligible, 1 = skewed wavefront, 2 = two-column wavefront
 int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, int W, int D, float p1,
                         float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
-                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers = nullptr);   // sgm_narrow.cu
+                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers = nullptr, int period = 0);   // sgm_narrow.cu
 size_t sgm_wave1_edge_bytes(int D);                                            // sgm_wave1.cu
 
 // Right descriptors in the layout of the skewed wavefront (sgm_wave1.cu): copy s, index i = descriptor of image column
@@ -555,6 +555,49 @@ extern "C" int pb200_census_sgm(const float *d_left, const float *d_right, int H
     bool done = false;
     const int rc = sgm_census_wave_try(desc, window, d_cv_out, H, W, D, p1, p2, overcounting, d_disp, dmin, invalid_disparity,
                                        d_all_nan, d_sgm_workspace, sgm_workspace_bytes, s, &done);
+    if (rc != PB200_OK) return rc;
+    *ran = done ? 1 : 0;
+    return PB200_OK;
+}
+
+// A batch of `nimg` pairs (d_left / d_right: (nimg, H, W); d_cv_out: (nimg, H, W, D); d_disp / d_all_nan: (nimg, H, W)) through ONE
+// wave per pass of the two-column wavefront kernels: the images are stacked into one tall image whose vertical and diagonal
+// paths restart at every image's first row, so the time the wave needs to cross the strips (fill and drain, 1.6 ms of a 14 ms
+// stage at 4096 x 4096 x 256) is paid once per batch.  Results are those of `nimg` pb200_census_sgm calls, bit for bit.
+// Census workspace: nimg * pb200_census_sgm_workspace_bytes(H, W, ...).  *ran = 0: nothing was computed (not eligible).
+extern "C" int pb200_census_sgm_batch(const float *d_left, const float *d_right, int nimg, int H, int W, int window, int dmin, int D, float p1,
+                                      float p2, int overcounting, float *d_cv_out, void *d_census_workspace, size_t census_workspace_bytes,
+                                      void *d_sgm_workspace, size_t sgm_workspace_bytes, float *d_disp, float invalid_disparity,
+                                      uint8_t *d_all_nan, int *ran, void *stream) {
+    if (!ran) {
+        set_error("pb200_census_sgm_batch: ran must not be NULL");
+        return PB200_ERR_BAD_ARG;
+    }
+    *ran = 0;
+    if (!d_left || !d_right || !d_cv_out || !d_census_workspace || !d_sgm_workspace || nimg <= 0 || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_census_sgm_batch: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (sgm_census_plan(window, W, D, p1, p2) != 2 || H < 4 || (long)nimg * H > 0x3FFFFFFF) return PB200_OK;
+    if (census_workspace_bytes < (size_t)nimg * pb200_census_sgm_workspace_bytes(H, W, window, dmin, D)) {
+        set_error("pb200_census_sgm_batch: census workspace too small (nimg * pb200_census_sgm_workspace_bytes)");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int pitch = census_pitch(W);
+    uint32_t *descL = (uint32_t *)d_census_workspace;
+    uint32_t *descR = descL + (size_t)nimg * H * pitch;
+    for (int i = 0; i < nimg; ++i) {                 // every image keeps its own borders: a window never crosses into its neighbour
+        const int rc = census_transform_pair(d_left + (size_t)i * H * W, d_right + (size_t)i * H * W, H, W, window,
+                                             descL + (size_t)i * H * pitch, descR + (size_t)i * H * pitch, 0, H, s);
+        if (rc != PB200_OK) return rc;
+    }
+    CensusDesc desc;
+    desc.L = descL; desc.R = descR; desc.pitch = pitch;
+    desc.R4 = nullptr; desc.pitch4 = 0; desc.padl = 0;
+    bool done = false;
+    const int rc = sgm_census_wave_try(desc, window, d_cv_out, nimg * H, W, D, p1, p2, overcounting, d_disp, dmin, invalid_disparity,
+                                       d_all_nan, d_sgm_workspace, sgm_workspace_bytes, s, &done, nullptr, nimg > 1 ? H : 0);
     if (rc != PB200_OK) return rc;
     *ran = done ? 1 : 0;
     return PB200_OK;

@@ -24,6 +24,8 @@
 // The data condition (integer costs in [0, 8191 - P2]) is verified by pass E on every cell; a violation raises a
 // device flag, the remaining narrow kernels return at once and the float kernels, enqueued behind them and gated
 // on the same flag, redo the whole stage.  No host synchronisation is involved.
+#include <type_traits>
+
 #include "sgm_packed.cuh"
 
 namespace pb200 {
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(512, 1) sgm_narrow_vsweep_kernel(const NarrowP
 // i+3 / i+4 -- proof that its reader finished row i+1, the last row that looks at the slot.  Column 0 / nc+1 of every
 // mailbox belong to the relay warps (the neighbouring strips); at an image border their counters start at "infinity"
 // and the slots stay zero: a flat state, i.e. a path start.
-template <int NR, int CB, bool FINAL, bool WTA, bool CENSUS = false>
+template <int NR, int CB, bool FINAL, bool WTA, bool CENSUS = false, bool BATCH = false>
 __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) {
     static_assert(!(CENSUS && FINAL), "the Census source only exists for the first pass");
     if (FINAL && *p.flag != 0) return;
@@ -611,8 +613,17 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         ev4_signal(fs_base + vme * 32u, 0, lane);
     }
 
-#pragma unroll 2
-    for (int i = 0; i < H; ++i) {
+    // BATCH: a batch of images stacked into one tall image (p.period rows each; the volume, the descriptors and the disparity
+    // map of image k + 1 follow those of image k, so no address changes): the wave runs through all of them and its fill and
+    // drain across the strips are paid once per pass and batch.  Every vertical / diagonal path restarts at an image's first
+    // row (in travel order): the PRODUCERS of the hand-over states publish zeros -- a flat state, i.e. a path start -- for an
+    // image's last row (SW_A, SE_B in the mailboxes, and through the relays in the rings), the in-register states (S,
+    // the pair's own SE_A -> SE_B and SW_B -> SW_A) are reset.  Waits and events are untouched.  The row program is a
+    // lambda instantiated twice in that case: the hot loop carries none of the boundary conditions (this kernel sits at the
+    // register limit: two more live values in the loop cost 10 %), the last two rows of every image run the TAIL copy.
+    int iend = H;
+    auto row = [&](const int i, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         const uint32_t tag = (uint32_t)(i + 1);
         stage_pix(0, i + PFD + 1);
         stage_pix(1, i + PFD);
@@ -648,12 +659,17 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
         nstep<NR>(cc[1], Sv[1], L0, lane, p1p1, p2p2);                       // S_B(i)
 #pragma unroll
         for (int j = 0; j < NR; ++j) Sv[1][j] = L0[j];
-        nstep<NR>(ccAn, L_SW_B, SWA_next, lane, p1p1, p2p2);                 // SW_A(i + 1), one row ahead
+        if (TAIL && i == iend - 1) nstep<NR>(ccAn, zero, SWA_next, lane, p1p1, p2p2);     // row i + 1 starts an image: a path start
+        else nstep<NR>(ccAn, L_SW_B, SWA_next, lane, p1p1, p2p2);                       // SW_A(i + 1), one row ahead
         nstep<NR>(cc[0], Sv[0], L0, lane, p1p1, p2p2);                       // S_A(i)
 #pragma unroll
         for (int j = 0; j < NR; ++j) Sv[0][j] = L0[j];
-        sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, SWA_next);
-        sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
+        // SW_A(i + 1) is the left neighbour's predecessor in row i + 2, SE_B(i) the right neighbour's in row i + 1: zeros when
+        // that row starts an image
+        if (TAIL && i == iend - 2) sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, zero);
+        else sts_words<NR>(sw_base + (uint32_t)((i + 1) & 3) * SLOT + vme * VB, SWA_next);
+        if (TAIL && i == iend - 1) sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, zero);
+        else sts_words<NR>(se_base + (uint32_t)(i & 3) * SLOT + vme * VB, L_SE_B);
         ev4_signal(fs_base + vme * 32u, i + 1, lane);
 
         // ---- phase 2: the E chain -- wait, two steps, publish; SE_A (the left neighbour's SE state of the previous row is
@@ -725,6 +741,24 @@ __global__ void __launch_bounds__(512, 1) sgm_wave_kernel(const NarrowParams p) 
 #pragma unroll
             for (int j = 0; j < 2 * NR; ++j) rawA[j] = rawAn[j];
         }
+    };
+    if (!BATCH) {
+#pragma unroll 2
+        for (int i = 0; i < H; ++i) row(i, std::false_type{});
+    } else {
+        const int Hp = (p.period > 0 && p.period < H) ? p.period : H;
+        for (int ibeg = 0; ibeg < H; ibeg += Hp) {
+            iend = min(H, ibeg + Hp);
+            if (ibeg > 0) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) Sv[0][j] = Sv[1][j] = SEA_prev[j] = 0u;
+            }
+            int i = ibeg;
+#pragma unroll 2
+            for (; i < iend - 2; ++i) row(i, std::false_type{});
+#pragma unroll 1
+            for (; i < iend; ++i) row(i, std::true_type{});
+        }
     }
     if (!FINAL && !CENSUS && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
 }
@@ -737,6 +771,11 @@ int launch_wave(NarrowParams p, int nstrips, int nwarp, void *workspace, cudaStr
     const bool wta = p.disp != nullptr;
     void (*w1)(const NarrowParams) = sgm_wave_kernel<NR, CB, false, false, CENSUS>;
     void (*w2)(const NarrowParams) = wta ? sgm_wave_kernel<NR, CB, true, true> : sgm_wave_kernel<NR, CB, true, false>;
+    if (p.period > 0) {                               // a batch of images in one wave: pb200_census_sgm_batch (fused WTA only)
+        if (!CENSUS || !wta) return PB200_OK;
+        w1 = sgm_wave_kernel<NR, CB, false, false, CENSUS, true>;
+        w2 = sgm_wave_kernel<NR, CB, true, true, false, true>;
+    }
     const int wthreads = (nwarp + 2) * 32;                       // + the two relay warps
     const size_t state = ((size_t)12 * (nwarp + 2) * NR * 32 + 64 + 256) * sizeof(uint32_t);
     const size_t smem1 = state + (CENSUS ? (size_t)8 * nwarp * (2 * NR * 32 + 8) : (size_t)4 * nwarp * 2 * 32 * (2 * NR)) * sizeof(uint32_t);
@@ -916,11 +955,13 @@ int sgm_census_plan(int window, int W, int D, float p1, float p2) {
 // shape / parameters are not eligible (the caller then runs the Census fill and pb200_sgm separately).
 int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, int W, int D, float p1,
                         float p2, int overcounting, float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace,
-                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers) {
+                        size_t workspace_bytes, cudaStream_t s, bool *done, const Wave1Peers *peers, int period) {
     // `peers` != NULL: W is the width of this GPU's column tile of a peers->Wg wide image (skewed wavefront only)
+    // `period` > 0: H rows are a batch of H / period images stacked into one tall image (two-column wavefront only)
     *done = false;
     const int plan = sgm_census_plan(window, W, D, p1, p2);
     if (plan == 0 || (plan == 1 && desc.R4 == nullptr) || (peers != nullptr && plan != 1)) return PB200_OK;
+    if (period > 0 && (plan != 2 || period < 4 || H % period != 0 || disp == nullptr)) return PB200_OK;
     if (reinterpret_cast<uintptr_t>(out) & 15) return PB200_OK;
     const float invalid_value = (float)(window * window) + p2 + 1.f;
     const int NR = D / 64;
@@ -940,6 +981,7 @@ int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, i
     p.debug = debug_switches();
     p.descL = desc.L; p.descR = desc.R; p.pitch = desc.pitch; p.half = window / 2;
     p.descR4 = desc.R4; p.pitch4 = desc.pitch4; p.padl = desc.padl;
+    p.period = period;
     if (plan == 1) return sgm_census_wave1_launch(p, NR, bytes, workspace, flag_off - 256, peers, s, done);
     int K = ceil_div(W, sm_count());
     if (K < 4) K = 4;

@@ -44,6 +44,7 @@ struct NarrowParams {
     int Wg, c_off;            // skewed wavefront: width of the (global) sheared ring, sheared column of this tile's column 0
     int sheared_store;        // 1: the volume / disparity tile is stored by sheared column (multi-GPU tiles), 0: by image column
     int nimg;                 // images of a batch that follow each other in one wave (descriptors, volume, disparity: [nimg][...])
+    int period;               // two-column wavefront: rows per image of a batch stacked into one tall image of H rows (0: one image)
 };
 
 

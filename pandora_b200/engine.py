@@ -143,6 +143,30 @@ class Engine:
             return None
         return (res, disp, flags) if fuse_wta else (res, None, None)
 
+    def census_sgm_batch(self, left: torch.Tensor, right: torch.Tensor, window: int, dmin: int, dmax: int, p1: float, p2: float,
+                         overcounting: bool = False, out: Optional[torch.Tensor] = None, invalid_disparity: float = -9999.0,
+                         disp: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
+        """``pb200_census_sgm_batch``: a batch (n, H, W) of pairs through ONE wave per pass of the fused Census -> SGM -> WTA
+        stage (the fill and drain of the wave across the SMs are paid once per batch); the results equal ``n`` calls of
+        ``census_sgm`` bit for bit.  Returns ``None`` when not eligible, else (volumes (n, H, W, D), disparities, all-NaN flags)."""
+        import ctypes  # noqa: PLC0415
+
+        assert left.dim() == 3 and left.shape == right.shape and left.is_contiguous() and right.is_contiguous() and left.dtype == torch.float32
+        n, H, W = (int(v) for v in left.shape)
+        D = dmax - dmin + 1
+        res = self.empty((n, H, W, D)) if out is None else out
+        if disp is None:
+            disp = self.empty((n, H, W))
+            flags = self.empty((n, H, W), torch.uint8)
+        cws = self._workspace("census", n * self.lib.pb200_census_sgm_workspace_bytes(H, W, window, dmin, D))
+        sws = self._workspace("sgm", self.lib.pb200_sgm_workspace_bytes(n * H, W, D))
+        ran = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_census_sgm_batch(
+                _ptr(left), _ptr(right), n, H, W, window, dmin, D, float(p1), float(p2), int(bool(overcounting)), _ptr(res), _ptr(cws),
+                cws.numel(), _ptr(sws), sws.numel(), _ptr(disp), float(invalid_disparity), _ptr(flags), ctypes.addressof(ran), self._stream()))
+        return (res, disp, flags) if ran.value else None
+
     def sad_ssd(self, left, right, window: int, dmin: int, dmax: int, squared: bool = False, out=None) -> torch.Tensor:
         H, W = self._hw(left)
         D = dmax - dmin + 1

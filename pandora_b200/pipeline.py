@@ -204,6 +204,38 @@ class StereoPipeline:
             self.final_cv = self.cv_b
         return out is not None
 
+    def run_device_batch(self, left, right):
+        """A batch of pairs, ``left`` / ``right``: float32 (n, H, W) device tensors, as ONE wave per pass of the fused
+        Census -> SGM -> WTA stage (stream throughput: the time the wave needs to cross the SMs is paid once per batch).
+        Returns the (n, H, W) disparity tensor; ``final_cv`` is the (n, H, W, D) SGM volume.  Same results as ``run_device``
+        per pair, bit for bit; falls back to exactly that when the configuration is not eligible for the batched stage."""
+        n = int(left.shape[0])
+        key = ("batch", n)
+        bufs = getattr(self, "_batch_bufs", None)
+        if bufs is None or bufs[0] != key:
+            e = self.eng
+            bufs = (key, e.empty((n, self.H, self.W, self.D)) if self.sgm else None, e.empty((n, self.H, self.W)),
+                    e.empty((n, self.H, self.W), self.torch.uint8))
+            self._batch_bufs = bufs
+        _, cv, disp, flags = bufs
+        if self.fuse_census_sgm and n > 1:
+            p1, p2 = float(self.sgm[0]), float(self.sgm[1])
+            over = bool(self.sgm[2]) if len(self.sgm) > 2 else False
+            out = self.eng.census_sgm_batch(left, right, self.window, self.dmin, self.dmax, p1, p2, over, out=cv,
+                                            invalid_disparity=self.invalid_disparity, disp=disp, flags=flags)
+            if out is not None:
+                self.fused_ran, self.batched_ran = True, True
+                self.final_cv, self.disp_batch, self.flags_batch = cv, disp, flags
+                return disp
+        self.batched_ran = False
+        for i in range(n):                                     # not eligible: one pair at a time
+            disp[i].copy_(self.run_device(left[i], right[i]))
+            flags[i].copy_(self.flags)
+            if cv is not None:
+                cv[i].copy_(self.final_cv)
+        self.final_cv, self.disp_batch, self.flags_batch = cv, disp, flags
+        return disp
+
     def run_device(self, left, right):
         """``left`` / ``right``: float32 (H, W) device tensors.  Returns the disparity tensor (device)."""
         if self.fuse_census_sgm and self._fused(left, right):

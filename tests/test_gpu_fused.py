@@ -235,3 +235,46 @@ def test_plugin_steps_fuse_census_into_sgm(eng, oracle):
     ref, cmax = oracle.cbca_cost_volume(left, right, ref, 2, -63, 5, 30.0, attrs["cmax"])
     ref = oracle.sgm_cost_volume(ref, 8, 32, cmax=cmax)
     np.testing.assert_array_equal(disp3["disparity_map"].data, oracle.wta(ref, np.arange(-63, 1))[0])
+
+
+# ---- batches of pairs through one wave (pb200_census_sgm_batch) ---------------------------------------------------------------
+@pytest.mark.parametrize("n,H,W,D,dmin,w,p2", [(3, 40, 200, 64, -63, 5, 32), (2, 33, 4100, 256, -255, 5, 32), (4, 24, 700, 128, -100, 3, 32),
+                                               (2, 50, 333, 256, -200, 5, 120), (5, 4, 96, 64, -20, 5, 32)])
+def test_census_sgm_batch_equals_single_calls(eng, oracle, n, H, W, D, dmin, w, p2):
+    """A batch stacked into one wave: every image's volume, disparity map and all-NaN flags equal its own pb200_census_sgm
+    call bit for bit (different images in the batch; paths restart at every image's first row in both passes); the first
+    image is also checked against the oracle chain."""
+    import torch
+
+    pairs = [oracle.synthetic_pair(H, W, D, seed=100 + 7 * i)[:2] for i in range(n)]
+    left = torch.stack([eng.to_device(p[0]) for p in pairs]).contiguous()
+    right = torch.stack([eng.to_device(p[1]) for p in pairs]).contiguous()
+    got = eng.census_sgm_batch(left, right, w, dmin, dmin + D - 1, 8, p2)
+    assert got is not None
+    for i in range(n):
+        one = eng.census_sgm(left[i].contiguous(), right[i].contiguous(), w, dmin, dmin + D - 1, 8, p2)
+        assert one is not None
+        assert torch.equal(torch.nan_to_num(got[0][i], nan=-7.0), torch.nan_to_num(one[0], nan=-7.0)), f"volume of image {i}"
+        assert torch.equal(got[1][i], one[1]) and torch.equal(got[2][i], one[2]), f"maps of image {i}"
+    cv, attrs = oracle.census_cost_volume(pairs[0][0], pairs[0][1], w, dmin, dmin + D - 1)
+    ref = oracle.sgm_cost_volume(cv, 8, p2, cmax=attrs["cmax"])
+    np.testing.assert_array_equal(got[0][0].cpu().numpy(), ref)
+
+
+def test_stereo_pipeline_batch(eng, oracle):
+    import torch
+
+    import pandora_b200
+
+    n, H, W, D = 3, 48, 256, 128
+    pairs = [oracle.synthetic_pair(H, W, D, seed=5 + i)[:2] for i in range(n)]
+    pipe = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, sgm=(8, 32), device="cuda:0")
+    left = torch.stack([eng.to_device(p[0]) for p in pairs]).contiguous()
+    right = torch.stack([eng.to_device(p[1]) for p in pairs]).contiguous()
+    disp = pipe.run_device_batch(left, right).clone()
+    assert pipe.batched_ran
+    for i in range(n):
+        assert torch.equal(disp[i], pipe.run_device(left[i].contiguous(), right[i].contiguous()))
+    with pandora_b200.option("sgm.wave_kernel", 1):            # the one-column kernels have no batched entry here: per-pair fall-back
+        disp2 = pipe.run_device_batch(left, right)
+        assert not pipe.batched_ran and torch.equal(disp2, disp)

@@ -41,3 +41,26 @@ if len(outs) == 2:
     (a, da), (b, db) = outs.values()
     same = torch.equal(da, db) and torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
     print("outputs identical:", same, flush=True)
+
+# batches of pairs through one wave (two-column kernels): time per image
+if os.environ.get("PROF_BATCH"):
+    for n in [int(v) for v in os.environ["PROF_BATCH"].split(",")]:
+        bl = dl.unsqueeze(0).expand(n, -1, -1).contiguous()
+        br = dr.unsqueeze(0).expand(n, -1, -1).contiguous()
+        out = eng.empty((n, H, W, D))
+        bd, bf = eng.empty((n, H, W)), eng.empty((n, H, W), torch.uint8)
+        for _ in range(2):
+            assert eng.census_sgm_batch(bl, br, 5, -(D - 1), 0, 8, 32, out=out, disp=bd, flags=bf) is not None
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.census_sgm_batch(bl, br, 5, -(D - 1), 0, 8, 32, out=out, disp=bd, flags=bf)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print(f"batch of {n}: {min(ts):.3f} ms = {min(ts) / n:.3f} ms per image (incl. the transforms), {n * H * W / min(ts) / 1e3:.1f} Mpix/s; "
+              f"image 0 == single call: {torch.equal(bd[0], outs[2][1]) if 2 in outs else None}", flush=True)
+        del out, bl, br, bd, bf
+        torch.cuda.empty_cache()
