@@ -84,6 +84,85 @@ __global__ void __launch_bounds__(256) validity_masks_kernel(uint16_t *__restric
     mask[i] = m;
 }
 
+// Row version of the kernel above (one CTA per image row): the per-pixel loops over the disparity range -- D byte gathers
+// per pixel, 4.3 G of them at 4096 x 4096 x 256 -- become differences of three per-row prefix counts (INVALID,
+// NODATA_DILATED, NOT_VALID of the right image's flags) built once in shared memory: O(H * W) instead of O(H * W * D).
+__global__ void __launch_bounds__(256) validity_masks_rows_kernel(uint16_t *__restrict__ mask, int H, int W, int dmin, int dmax, int off,
+                                                                  const uint8_t *__restrict__ fl, const uint8_t *__restrict__ fr,
+                                                                  const float *__restrict__ gmin, const float *__restrict__ gmax) {
+    extern __shared__ uint32_t vm_pre[];                 // [3][W + 1] exclusive prefix counts: INVALID | NODATA_DILATED | NOT_VALID
+    __shared__ uint32_t warp_tot[3][8];
+    const long row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t *pI = vm_pre, *pN = vm_pre + (W + 1), *pV = vm_pre + 2 * (W + 1);
+    if (fr != nullptr) {
+        const uint8_t *r = fr + row * W;
+        const int chunk = (W + 255) / 256, c0 = min(W, tid * chunk), c1 = min(W, c0 + chunk);
+        uint32_t a = 0, b = 0, v = 0;
+        for (int c = c0; c < c1; ++c) {
+            const uint8_t f = r[c];
+            a += (f & FLAG_INVALID) ? 1u : 0u;
+            b += (f & FLAG_NODATA_DILATED) ? 1u : 0u;
+            v += (f & FLAG_NOT_VALID) ? 1u : 0u;
+        }
+        uint32_t sa = a, sb = b, sv = v;                 // inclusive scan over the 256 chunk sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o), tv = __shfl_up_sync(0xffffffffu, sv, o);
+            if (lane >= o) { sa += ta; sb += tb; sv += tv; }
+        }
+        if (lane == 31) { warp_tot[0][wid] = sa; warp_tot[1][wid] = sb; warp_tot[2][wid] = sv; }
+        __syncthreads();
+        uint32_t ba = 0, bb = 0, bv = 0;
+        for (int w = 0; w < wid; ++w) { ba += warp_tot[0][w]; bb += warp_tot[1][w]; bv += warp_tot[2][w]; }
+        uint32_t ea = ba + sa - a, eb = bb + sb - b, ev = bv + sv - v;      // exclusive prefix at this thread's first column
+        for (int c = c0; c < c1; ++c) {
+            pI[c] = ea; pN[c] = eb; pV[c] = ev;
+            const uint8_t f = r[c];
+            ea += (f & FLAG_INVALID) ? 1u : 0u;
+            eb += (f & FLAG_NODATA_DILATED) ? 1u : 0u;
+            ev += (f & FLAG_NOT_VALID) ? 1u : 0u;
+        }
+        if (c1 == W && c0 < W) { pI[W] = ea; pN[W] = eb; pV[W] = ev; }
+        __syncthreads();
+    }
+    const int nd = dmax - dmin + 1;
+    for (int c = tid; c < W; c += blockDim.x) {
+        const long i = row * W + c;
+        uint16_t m = mask[i];
+        if (fl != nullptr) {                              // allocate_left_mask
+            const uint8_t f = fl[i];
+            if (f & FLAG_NODATA_DILATED) m = (uint16_t)(m + 1);
+            if (f & FLAG_INVALID) m = (uint16_t)(m + 64);
+        }
+        if (fr != nullptr) {                              // allocate_right_mask
+            const bool bit_1 = (dmax < 0) ? (c + dmax < off) : ((dmin > 0) ? (c + dmin > W - 1 - off) : false);
+            if (!bit_1) {
+                // columns c + d inside [off, W - 1 - off] count their flags, the others count as flagged (criteria.py:216-288)
+                const int lo = max(c + dmin, off), hi = min(c + dmax, W - 1 - off);
+                const int inside_n = max(0, hi - lo + 1);
+                int b_2_7 = nd - inside_n, no_data_right = nd - inside_n;
+                if (inside_n > 0) {
+                    b_2_7 += (int)(pI[hi + 1] - pI[lo]);
+                    no_data_right += (int)(pN[hi + 1] - pN[lo]);
+                }
+                if (b_2_7 == nd) m = (uint16_t)(m + 128);
+                if (no_data_right == nd) m = (uint16_t)(m + 2);
+            }
+            if (gmin != nullptr && gmax != nullptr) {     // partially_missing_variable_ranges
+                const float gl = gmin[i], gh = gmax[i];
+                const bool finite = (gl == gl) && (gh == gh) && fabsf(gl) < 1e9f && fabsf(gh) < 1e9f;
+                const int lo = finite ? (int)gl + c : -1, hi = finite ? (int)gh + c : -1;
+                bool inside = finite && lo >= 0 && hi < W && lo <= hi;
+                // the per-pixel loop stops at the first pixel that is not valid: "all valid" == no NOT_VALID flag in [lo, hi]
+                if (inside) inside = (pV[hi + 1] - pV[lo]) == 0u;
+                if (!inside) m |= 4096;
+            }
+        }
+        mask[i] = m;
+    }
+}
+
 // one warp per pixel; every lane owns float4 groups of the disparity vector
 template <bool VEC4>
 __global__ void __launch_bounds__(256) cv_masked_kernel(float *__restrict__ cv, long n_pix, int W, int D, int dmin,
@@ -153,6 +232,14 @@ extern "C" int pb200_validity_mask_masks(uint16_t *d_mask, int H, int W, int dmi
     if (!d_mask || H <= 0 || W <= 0 || dmax < dmin || offset < 0) {
         set_error("pb200_validity_mask_masks: bad argument");
         return PB200_ERR_BAD_ARG;
+    }
+    const size_t smem = 3 * (size_t)(W + 1) * sizeof(uint32_t);
+    if (smem <= 200 * 1024) {                            // row kernel: prefix counts of the right flags in shared memory
+        PB200_CUDA(cudaFuncSetAttribute(validity_masks_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        validity_masks_rows_kernel<<<H, 256, smem, (cudaStream_t)stream>>>(d_mask, H, W, dmin, dmax, offset, d_flags_left, d_flags_right,
+                                                                           d_grid_min, d_grid_max);
+        PB200_LAUNCH_CHECK("validity_masks_rows_kernel");
+        return PB200_OK;
     }
     validity_masks_kernel<<<ceil_div((long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(d_mask, H, W, dmin, dmax, offset, d_flags_left,
                                                                                        d_flags_right, d_grid_min, d_grid_max);

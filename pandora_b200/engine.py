@@ -308,9 +308,13 @@ class Engine:
     # ---- input masks / disparity grids -------------------------------------------
     def mask_flags(self, msk, valid_pixels: int, no_data: int, window: int) -> torch.Tensor:
         """Per-pixel flag byte of an image mask (dilated no_data | invalid | not valid), criteria.py:36-63."""
-        host = np.ascontiguousarray(np.asarray(msk), dtype=np.int16)
-        H, W = host.shape
-        d_msk = torch.from_numpy(host).to(self.device)
+        if isinstance(msk, torch.Tensor):                        # already on the device (int16)
+            d_msk = msk.to(device=self.device, dtype=torch.int16).contiguous()
+            H, W = (int(v) for v in d_msk.shape)
+        else:
+            host = np.ascontiguousarray(np.asarray(msk), dtype=np.int16)
+            H, W = host.shape
+            d_msk = torch.from_numpy(host).to(self.device)
         flags = self.empty((H, W), torch.uint8)
         with torch.cuda.device(self.device):
             _native.check(self.lib.pb200_mask_flags(_ptr(d_msk), H, W, int(valid_pixels), int(no_data), int(window), _ptr(flags), self._stream()))

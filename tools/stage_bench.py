@@ -100,7 +100,9 @@ timeit("C3 reverse_cost_volume + wta (what wta_right replaces)", lambda: eng.wta
 timeit("C3 cv_masked pass (all-NaN detection, no masks)", lambda: eng.cv_masked(p3.cv_b, dmin3), (4 * D + 1) * H * W)
 msk = (torch.rand((H, W), device="cuda") < 0.02).to(torch.int16).cpu().numpy()
 fl3 = eng.mask_flags(msk, 0, 1, 5)
-timeit("C3 mask_flags (5x5 no_data dilation)", lambda: eng.mask_flags(msk, 0, 1, 5), 3 * H * W, reps=2)
+d_msk = torch.from_numpy(msk).to("cuda")
+timeit("C3 mask_flags (5x5 no_data dilation, mask resident)", lambda: eng.mask_flags(d_msk, 0, 1, 5), 3 * H * W, reps=3)
+timeit("C3 mask_flags incl. the pageable H2D of the 33 MB mask", lambda: eng.mask_flags(msk, 0, 1, 5), 3 * H * W, reps=2)
 vm3 = eng.validity_mask_init(H, W, dmin3, 0, 2)
 timeit("C3 validity_mask_masks (left + right msk)", lambda: eng.validity_mask_masks(vm3, dmin3, 0, 2, fl3, fl3), 6 * H * W)
 disp3, flags3 = eng.wta(p3.cv_b, dmin3)
