@@ -870,7 +870,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
                    float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
                    cudaStream_t s, const int **gate, int phase, int dy, int final, const float *halo_in, float *halo_out) {
     *gate = nullptr;
-    if (D != 64 && D != 128 && D != 256) return PB200_OK;
+    if (D != 64 && D != 128 && D != 192 && D != 256) return PB200_OK;
     if (!is_small_int(p1, 1, NARROW_MAX) || !is_small_int(p2, 1, NARROW_MAX) || p1 > p2 || !is_small_int(invalid_value, 0, NARROW_MAX) ||
         (int)invalid_value + (int)p2 > NARROW_MAX)
         return PB200_OK;
@@ -889,7 +889,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
     // byte tier (C8, and P8 between E and W) when cost + P2 fits 7 bits; else 16-bit storage
-    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
+    const bool bytes = (NR == 2 || NR == 4) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
     p.cost_ok_max = (float)((bytes ? 127 : NARROW_MAX) - (int)p2);
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
     p.dy = dy; p.overcounting = overcounting;
@@ -913,6 +913,7 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
                             : launch_narrow<4, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
     else if (NR == 2) rc = bytes ? launch_narrow<2, 1>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done)
                                  : launch_narrow<2, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
+    else if (NR == 3) rc = launch_narrow<3, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);   // D = 192: 16-bit tier only
     else rc = launch_narrow<1, 2>(p, phase, final, nstrips, nwarp, workspace, ring_bytes, s, &done);
     if (rc != PB200_OK) return rc;
     if (done) *gate = p.flag;
@@ -925,7 +926,7 @@ int sgm_census_wave1_launch(NarrowParams p, int NR, bool bytes, void *workspace,
 // Which fused Census -> SGM kernels take a configuration: 0 = none (the caller runs the Census fill and pb200_sgm), 1 = the
 // skewed one-column wavefront (sgm_wave1.cu; reads the shifted descriptor layout), 2 = the two-column wavefront.
 static bool census_wave_common(int window, int D, float p1, float p2) {
-    if (D != 64 && D != 128 && D != 256) return false;
+    if (D != 64 && D != 128 && D != 192 && D != 256) return false;
     if (window != 3 && window != 5) return false;                          // one-word descriptors
     const float invalid_value = (float)(window * window) + p2 + 1.f;       // cmax + P2 + 1 (census.py:116 gives cmax = w^2)
     return is_small_int(p1, 1, NARROW_MAX) && is_small_int(p2, 1, NARROW_MAX) && p1 <= p2 && is_small_int(invalid_value, 0, NARROW_MAX) &&
@@ -941,7 +942,7 @@ int sgm_census_plan(int window, int W, int D, float p1, float p2) {
     int K = ceil_div(W, sm_count());
     if (K < 4) K = 4;
     K = (K + 1) / 2 * 2;
-    const bool two_ok = K / 2 <= 14, one_ok = sgm_wave1_strip_width(W) > 0;
+    const bool two_ok = K / 2 <= 14, one_ok = sgm_wave1_strip_width(W) > 0 && D != 192;    // D = 192 (three registers per lane): two-column kernels only
     if (pin == 1) return one_ok ? 1 : 0;
     if (pin == 2) return two_ok ? 2 : 0;
     // one GPU: whichever is faster for the shape (measured at C3: profiles/r2_wave_kernels.txt); column tiles pin the skewed one
@@ -972,7 +973,7 @@ int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, i
     p.cv = nullptr; p.buf = reinterpret_cast<uint32_t *>(out); p.H = H; p.W = W; p.D = D;
     p.p1p1 = (uint32_t)p1 * 0x10001u; p.p2p2 = (uint32_t)p2 * 0x10001u;
     p.inv = (uint32_t)invalid_value;
-    const bool bytes = (NR >= 2) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
+    const bool bytes = (NR == 2 || NR == 4) && ((int)invalid_value + (int)p2 <= 127) && option(OPT_SGM_NO_BYTE_TIER) <= 0;
     p.cost_ok_max = 0.f;
     p.flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + flag_off);
     p.dy = 1; p.overcounting = overcounting;
@@ -990,6 +991,7 @@ int sgm_census_wave_try(const CensusDesc &desc, int window, float *out, int H, i
     const int nstrips = ceil_div(W, K);
     if (NR == 4) return bytes ? launch_wave<4, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<4, 2, true>(p, nstrips, nwarp, workspace, s, done);
     if (NR == 2) return bytes ? launch_wave<2, 1, true>(p, nstrips, nwarp, workspace, s, done) : launch_wave<2, 2, true>(p, nstrips, nwarp, workspace, s, done);
+    if (NR == 3) return launch_wave<3, 2, true>(p, nstrips, nwarp, workspace, s, done);
     return launch_wave<1, 2, true>(p, nstrips, nwarp, workspace, s, done);
 }
 

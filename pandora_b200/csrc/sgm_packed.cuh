@@ -69,35 +69,43 @@ constexpr uint32_t INF16 = 0x7FFFu;          // "+inf" for a 16-bit lane: larger
 constexpr int NARROW_MAX = 8191;             // 8 directions x (cost + P2) must stay below 2^16
 
 
-template <int NR> struct Words;
-template <> struct Words<4> { using T = uint4; };
-template <> struct Words<2> { using T = uint2; };
-template <> struct Words<1> { using T = uint32_t; };
-
+// NR = registers per lane of one packed state vector = D / 64: 1, 2, 4 (one aligned vector access per lane) and 3 (D = 192:
+// no 12-byte vector access exists and a lane's block is only 4-byte aligned, so three scalar accesses).
 template <int NR>
 __device__ __forceinline__ void ld_words(const uint32_t *p, uint32_t (&v)[NR]) {
-    const typename Words<NR>::T t = *reinterpret_cast<const typename Words<NR>::T *>(p);
-    if constexpr (NR == 4) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else if constexpr (NR == 2) { v[0] = t.x; v[1] = t.y; }
-    else v[0] = t;
+    if constexpr (NR == 4) { const uint4 t = *reinterpret_cast<const uint4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (NR == 2) { const uint2 t = *reinterpret_cast<const uint2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) v[j] = p[j];
+    }
 }
 template <int NR>
 __device__ __forceinline__ void st_words(uint32_t *p, const uint32_t (&v)[NR]) {
     if constexpr (NR == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]);
     else if constexpr (NR == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
-    else *p = v[0];
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) p[j] = v[j];
+    }
 }
 template <int NR>
 __device__ __forceinline__ void ld_floats(const float *p, float (&v)[NR]) {
     if constexpr (NR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     else if constexpr (NR == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
-    else v[0] = *p;
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) v[j] = p[j];
+    }
 }
 template <int NR>
 __device__ __forceinline__ void st_floats(float *p, const float (&v)[NR]) {
     if constexpr (NR == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
     else if constexpr (NR == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
-    else *p = v[0];
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) p[j] = v[j];
+    }
 }
 
 // ---- storage tiers ------------------------------------------------------------------------------------------
@@ -236,7 +244,13 @@ __device__ __forceinline__ void ll_recv_u32(const unsigned long long *slot, int 
 
 template <int NWORDS>
 __device__ __forceinline__ void cp_async_words(uint32_t smem_addr, const uint32_t *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(gsrc), "n"(NWORDS * 4) : "memory");
+    if constexpr (NWORDS == 1 || NWORDS == 2 || NWORDS == 4) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(gsrc), "n"(NWORDS * 4) : "memory");
+    } else {                                            // 3 words: cp.async copies 4, 8 or 16 bytes
+#pragma unroll
+        for (int j = 0; j < NWORDS; ++j)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr + 4u * j), "l"(gsrc + j) : "memory");
+    }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -247,13 +261,19 @@ template <int NR>
 __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&v)[NR]) {
     if constexpr (NR == 4) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
     else if constexpr (NR == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr));
-    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr));
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[j]) : "r"(addr + 4u * j));
+    }
 }
 template <int NR>
 __device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&v)[NR]) {
     if constexpr (NR == 4) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
     else if constexpr (NR == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
-    else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
+    else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 4u * j), "r"(v[j]) : "memory");
+    }
 }
 
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }

@@ -52,6 +52,7 @@ def oracle_chain(oracle, left, right, w, dmin, dmax, p1, p2, over):
     (21, 40, 64, -63), (21, 40, 64, -20), (16, 90, 64, 5), (9, 3, 64, -63), (1, 70, 64, -10), (30, 1, 64, -63),
     (33, 333, 128, -127), (18, 300, 128, -64), (12, 150, 128, 0),
     (24, 600, 256, -255), (10, 700, 256, -100), (7, 260, 256, 3),
+    (26, 500, 192, -191), (12, 4100, 192, -100), (9, 130, 192, 4),       # D = 192 (C2's disparity count): three registers per lane
 ])
 @pytest.mark.parametrize("w", [5, 3])
 def test_census_sgm_fused_vs_oracle(eng, oracle, H, W, D, dmin, w):
@@ -69,7 +70,7 @@ def test_census_sgm_fused_vs_oracle(eng, oracle, H, W, D, dmin, w):
 
 
 @pytest.mark.parametrize("over,p1,p2", [(True, 8, 32), (False, 10, 120), (True, 3, 200), (False, 1, 1)])
-@pytest.mark.parametrize("H,W,D", [(14, 200, 64), (11, 310, 128), (9, 420, 256)])
+@pytest.mark.parametrize("H,W,D", [(14, 200, 64), (11, 310, 128), (9, 420, 256), (10, 350, 192)])
 def test_census_sgm_fused_penalties_and_overcounting(eng, oracle, H, W, D, over, p1, p2):
     """Byte storage tier (cost + P2 <= 127) and 16-bit tier, overcounting, no fused WTA."""
     left, right = pair(p2 * 7 + D, H, W)
@@ -113,7 +114,7 @@ def test_census_sgm_fused_tall_image_repeatable(eng):
 
 @pytest.mark.parametrize("w,D", [(7, 64), (5, 100), (5, 300), (13, 256)])
 def test_census_sgm_not_eligible_returns_none(eng, w, D):
-    """Two-word descriptors and disparity counts outside {64, 128, 256}: nothing is computed, the caller falls back."""
+    """Two-word descriptors and disparity counts outside {64, 128, 192, 256}: nothing is computed, the caller falls back."""
     left, right = pair(1, 30, 80)
     assert eng.census_sgm(dev(eng, left), dev(eng, right), w, -(D - 1), 0, 8, 32) is None
 
@@ -239,7 +240,7 @@ def test_plugin_steps_fuse_census_into_sgm(eng, oracle):
 
 # ---- batches of pairs through one wave (pb200_census_sgm_batch) ---------------------------------------------------------------
 @pytest.mark.parametrize("n,H,W,D,dmin,w,p2", [(3, 40, 200, 64, -63, 5, 32), (2, 33, 4100, 256, -255, 5, 32), (4, 24, 700, 128, -100, 3, 32),
-                                               (2, 50, 333, 256, -200, 5, 120), (5, 4, 96, 64, -20, 5, 32)])
+                                               (2, 50, 333, 256, -200, 5, 120), (5, 4, 96, 64, -20, 5, 32), (3, 20, 300, 192, -150, 5, 32)])
 def test_census_sgm_batch_equals_single_calls(eng, oracle, n, H, W, D, dmin, w, p2):
     """A batch stacked into one wave: every image's volume, disparity map and all-NaN flags equal its own pb200_census_sgm
     call bit for bit (different images in the batch; paths restart at every image's first row in both passes); the first

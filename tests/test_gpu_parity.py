@@ -408,10 +408,10 @@ def test_sgm_strip_sweep_float_costs_repeatable(eng, oracle):
         np.testing.assert_array_equal(got, ref)
 
 
-@pytest.mark.parametrize("shape", [(9, 21, 64), (31, 333, 128), (16, 600, 256), (3, 4, 64), (1, 50, 128), (40, 1, 64)])
+@pytest.mark.parametrize("shape", [(9, 21, 64), (31, 333, 128), (16, 600, 256), (3, 4, 64), (1, 50, 128), (40, 1, 64), (23, 410, 192), (5, 33, 192)])
 @pytest.mark.parametrize("over,p1,p2", [(False, 8, 32), (True, 8, 32), (False, 10, 120), (True, 3, 200)])
 def test_sgm_packed_integer_path(eng, oracle, shape, over, p1, p2):
-    """D in {64, 128, 256} with integer costs takes the packed 16-bit path (sgm_narrow.cu): bit-identical to the
+    """D in {64, 128, 192, 256} with integer costs takes the packed 16-bit path (sgm_narrow.cu): bit-identical to the
     oracle, including NaN cells, all-NaN pixels, overcounting and the fused WTA."""
     g = np.random.default_rng(shape[0] * 1000 + shape[2] + p2)
     cv = g.integers(0, 26, shape).astype(np.float32)
@@ -426,7 +426,7 @@ def test_sgm_packed_integer_path(eng, oracle, shape, over, p1, p2):
     np.testing.assert_array_equal(host(flags).astype(bool), exp_inv)
 
 
-@pytest.mark.parametrize("shape", [(5, 4096, 256), (7, 3000, 128), (4, 4095, 64), (33, 1500, 256), (2, 4736, 64)])
+@pytest.mark.parametrize("shape", [(5, 4096, 256), (7, 3000, 128), (4, 4095, 64), (33, 1500, 256), (2, 4736, 64), (6, 4100, 192)])
 def test_sgm_wavefront_wide_images(eng, oracle, shape):
     """Wide images: strips of many warps (K = 2 * warps columns), partial last strips, odd widths -- the 4-direction
     wavefront passes (sgm_wave_kernel) against the oracle, bit-exact, with the fused WTA."""
