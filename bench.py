@@ -503,6 +503,8 @@ def run_ours(args):
         # from pinned host memory and its disparity map downloaded inside the timed region; two buffer sets let the
         # copies of the neighbouring pairs overlap the kernels of the current one
         def stream_steps(k):
+            # pair by pair (submit_host_batch exists, but a stream of whole batches pays the upload of its first batch and the
+            # download of its last one in the open: 1007 vs 1107 Mpix/s over 5 pairs, the same over 12 -- gpurun_out/r3t_*)
             prev = None
             for _ in range(k):
                 tk = pipe.submit_host(h_left, h_right)
@@ -522,7 +524,7 @@ def run_ours(args):
         e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
         e2e_ms = max(ev[0].elapsed_time(ev[1]), 0.0)
         e2e_mode = ("stream of pairs, 2 in flight (StereoPipeline.submit_host / result_host): H2D of pair k+1 and D2H of pair k-1 "
-                    "overlap the kernels of pair k; every pair's copies are inside the timed region")
+                    "overlap the kernels of pair k; every pair's copies are inside the timed region; one pair per wave")
 
     if rank != 0:
         if dist is not None:

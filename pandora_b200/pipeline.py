@@ -381,6 +381,68 @@ class StereoPipeline:
             s["ev_d2h"].record(ds)
         return ticket
 
+    def submit_host_batch(self, lefts, rights) -> int:
+        """``submit_host`` for a batch of pairs that goes through ONE wave per pass (``run_device_batch``): ``lefts`` / ``rights``
+        are sequences of n host images (pinned tensors are used in place).  Uploads and downloads of neighbouring batches
+        overlap the kernels of the current one; at most two batches in flight.  Returns a ticket for ``result_host_batch``."""
+        t = self.torch
+        dev = self.eng.device
+        n = len(lefts)
+        if getattr(self, "_bslots", None) is None:
+            self._bslots, self._bsubmitted, self._btickets = {}, 0, {}
+        if n not in self._bslots:                                 # one pair of buffer sets per batch size, allocated once
+            with t.cuda.device(dev):
+                mk = lambda pin: (t.empty((n, self.H, self.W), dtype=t.float32, pin_memory=True) if pin  # noqa: E731
+                                  else self.eng.empty((n, self.H, self.W)))
+                self._bslots[n] = [dict(d_left=mk(False), d_right=mk(False), d_disp=mk(False), h_left=mk(True), h_right=mk(True),
+                                        h_disp=mk(True), ev_h2d=None, ev_compute=None, ev_d2h=None, uses=0) for _ in range(2)]
+                self._copy_stream = self._copy_stream or t.cuda.Stream(device=dev)
+                self._d2h_stream = self._d2h_stream or t.cuda.Stream(device=dev)
+        ticket = self._bsubmitted
+        self._bsubmitted += 1
+        slots = self._bslots[n]
+        s = slots[0] if slots[0]["uses"] <= slots[1]["uses"] else slots[1]      # the set of this size used longest ago
+        s["uses"] = max(slots[0]["uses"], slots[1]["uses"]) + 1
+        self._btickets[ticket] = s
+        self._btickets.pop(ticket - 2, None)
+        cur = t.cuda.current_stream(dev)
+        if s["ev_h2d"] is not None:
+            s["ev_h2d"].synchronize()
+        srcs = [(self._pinned(lefts[i], s["h_left"][i]), self._pinned(rights[i], s["h_right"][i])) for i in range(n)]
+        cs = self._copy_stream
+        with t.cuda.stream(cs):
+            if s["ev_compute"] is not None:
+                cs.wait_event(s["ev_compute"])
+            else:
+                cs.wait_stream(cur)
+            for i, (hl, hr) in enumerate(srcs):
+                s["d_left"][i].copy_(hl, non_blocking=True)
+                s["d_right"][i].copy_(hr, non_blocking=True)
+            s["ev_h2d"] = t.cuda.Event()
+            s["ev_h2d"].record(cs)
+        cur.wait_event(s["ev_h2d"])
+        if s["ev_d2h"] is not None:
+            cur.wait_event(s["ev_d2h"])
+        disp = self.run_device_batch(s["d_left"], s["d_right"])
+        s["d_disp"].copy_(disp, non_blocking=True)
+        s["ev_compute"] = t.cuda.Event()
+        s["ev_compute"].record(cur)
+        ds = self._d2h_stream
+        with t.cuda.stream(ds):
+            ds.wait_event(s["ev_compute"])
+            s["h_disp"].copy_(s["d_disp"], non_blocking=True)
+            s["ev_d2h"] = t.cuda.Event()
+            s["ev_d2h"].record(ds)
+        return ticket
+
+    def result_host_batch(self, ticket: int) -> np.ndarray:
+        """(n, H, W) disparity maps of a submitted batch (host array, valid until two more batches have been submitted)."""
+        if ticket not in getattr(self, "_btickets", {}):
+            raise ValueError(f"batch ticket {ticket} is not in flight")
+        s = self._btickets[ticket]
+        s["ev_d2h"].synchronize()
+        return s["h_disp"].numpy()
+
     def result_host(self, ticket: int) -> np.ndarray:
         """Disparity map of a submitted pair (host array, valid until two more pairs have been submitted)."""
         if not (self._submitted - 2 <= ticket < self._submitted):

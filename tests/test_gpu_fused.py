@@ -279,3 +279,32 @@ def test_stereo_pipeline_batch(eng, oracle):
     with pandora_b200.option("sgm.wave_kernel", 1):            # the one-column kernels have no batched entry here: per-pair fall-back
         disp2 = pipe.run_device_batch(left, right)
         assert not pipe.batched_ran and torch.equal(disp2, disp)
+
+
+def test_stream_of_batches_equals_single_calls(eng, oracle):
+    """submit_host_batch / result_host_batch (batches of different sizes interleaved with single submissions, two in flight):
+    every pair's map equals its own blocking call."""
+    import pandora_b200
+
+    H, W, D = 40, 200, 64
+    pipe = pandora_b200.StereoPipeline(H, W, -(D - 1), 0, "census", 5, sgm=(8, 32), device="cuda:0")
+    pairs = [oracle.synthetic_pair(H, W, D, seed=300 + i)[:2] for i in range(9)]
+    want = [pipe.run_host(l, r).copy() for l, r in pairs]
+    plan = [(0, 4), (4, 1), (5, 3), (8, 1)]                     # (first pair, size)
+    got, prev = {}, None
+
+    def collect(p):
+        a, n, tk, batch = p
+        res = pipe.result_host_batch(tk) if batch else pipe.result_host(tk)[None]
+        for i in range(n):
+            got[a + i] = res[i].copy()
+
+    for a, n in plan:
+        ls, rs = [p[0] for p in pairs[a:a + n]], [p[1] for p in pairs[a:a + n]]
+        tk = (a, n, pipe.submit_host_batch(ls, rs), True) if n > 1 else (a, n, pipe.submit_host(ls[0], rs[0]), False)
+        if prev is not None:
+            collect(prev)
+        prev = tk
+    collect(prev)
+    for i in range(9):
+        np.testing.assert_array_equal(got[i], want[i])
