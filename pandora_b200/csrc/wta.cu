@@ -15,12 +15,16 @@
 
 namespace pb200 {
 
+// One element of a lane's scan.  Within a lane the index only grows, so a tie never moves it: one strict comparison (false
+// for NaN: NaN never wins, disparity.py:434-444) and two selects; `seen` = NaN-ignoring minimum of everything met, which stays
+// NaN exactly when every value was NaN (4 instructions per element; the first version took ~10, and the kernel was bound
+// by its instruction issue: profiles/r2_ncu_wta.txt).
 template <bool IS_MAX>
-__device__ __forceinline__ void wta_take(float v, int k, float &bv, int &bk, bool &any) {
-    if (v != v) return;                       // NaN never wins (disparity.py:434-444)
-    any = true;
-    if (IS_MAX ? (v > bv) : (v < bv)) { bv = v; bk = k; }
-    else if (v == bv && k < bk) bk = k;
+__device__ __forceinline__ void wta_take(float v, int k, float &bv, int &bk, float &seen) {
+    const bool better = IS_MAX ? (v > bv) : (v < bv);
+    bv = better ? v : bv;
+    bk = better ? k : bk;
+    seen = fminf(seen, v);
 }
 
 // float -> unsigned key with the same order (-0 was folded into +0 by the caller)
@@ -43,11 +47,10 @@ __global__ void __launch_bounds__(256) wta_kernel(const float *__restrict__ cv, 
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const float init = IS_MAX ? -CUDART_INF_F : CUDART_INF_F;
     for (long pix0 = warp0 * WTA_PPW; pix0 < n_pix; pix0 += nwarps * WTA_PPW) {
-        float bv[WTA_PPW];
+        float bv[WTA_PPW], any[WTA_PPW];
         int bk[WTA_PPW];
-        bool any[WTA_PPW];
 #pragma unroll
-        for (int q = 0; q < WTA_PPW; ++q) { bv[q] = init; bk[q] = 0x7fffffff; any[q] = false; }
+        for (int q = 0; q < WTA_PPW; ++q) { bv[q] = init; bk[q] = 0x7fffffff; any[q] = nan_f(); }
         if (VEC4) {
             for (int k = lane * 4; k < D; k += 128) {
                 float4 v[WTA_PPW];
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) wta_kernel(const float *__restrict__ cv, 
             const uint32_t key = wta_key(bv[q] + 0.0f);                       // -0 == +0 for np.argmin / np.argmax
             const uint32_t best = IS_MAX ? __reduce_max_sync(0xffffffffu, key) : __reduce_min_sync(0xffffffffu, key);
             int k = __reduce_min_sync(0xffffffffu, key == best ? bk[q] : 0x7fffffff);
-            const bool anyw = __any_sync(0xffffffffu, any[q]);
+            const bool anyw = __any_sync(0xffffffffu, any[q] == any[q]);
             // best value still the initial +-inf: every entry is +-inf or NaN, and since NaNs were replaced by
             // the same inf np.argmin / np.argmax return index 0
             if (best == wta_key(init)) k = 0;

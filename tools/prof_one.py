@@ -19,6 +19,9 @@ for _ in range(3):
         eng.sad_ssd(l, r, 5, -(D - 1), 0, squared=(what == "ssd"), out=cv)
     elif what == "zncc":
         eng.zncc(l, r, 5, -(D - 1), 0, out=cv)
+    elif what == "wta":
+        eng.census(l, r, 5, -(D - 1), 0, out=cv)
+        eng.wta(cv, -(D - 1))
     elif what == "cbca":
         eng.census(l, r, 5, -(D - 1), 0, out=cv)
         eng.cbca(l, r, cv, 2, -(D - 1))
