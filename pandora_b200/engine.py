@@ -39,7 +39,43 @@ class Engine:
         if isinstance(arr, torch.Tensor):
             return arr.to(device=self.device, dtype=dtype).contiguous()
         host = np.ascontiguousarray(arr, dtype=np.float32 if dtype == torch.float32 else None)
+        if host.ndim >= 2 and host.nbytes >= self.STAGED_H2D_MIN_BYTES and host.shape[0] >= 2 * self.STAGED_H2D_CHUNKS:
+            return self._staged_upload(host)
         return torch.from_numpy(host).to(self.device, non_blocking=False)
+
+    # A pageable numpy image (what Pandora hands over) reaches the device at ~11 GB/s through the driver's own staging
+    # (12 ms for C3's two 67 MB images: the largest part of a plugin-level call).  Large arrays are cut into row chunks that
+    # worker threads copy into a page-locked staging buffer (numpy releases the GIL for the copy) while the chunks already
+    # staged travel over PCIe: the upload then runs at the speed of the slower of the two, not at their sum.
+    STAGED_H2D_MIN_BYTES = 16 << 20
+    STAGED_H2D_CHUNKS = 8
+
+    def _staged_upload(self, host: np.ndarray) -> torch.Tensor:
+        from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
+        t_host = torch.from_numpy(host)
+        stage = getattr(self, "_h2d_stage", None)
+        if stage is None or stage[0].numel() < t_host.numel() or stage[0].dtype != t_host.dtype:
+            stage = (torch.empty(t_host.numel(), dtype=t_host.dtype, pin_memory=True), None)
+        if stage[1] is not None:
+            stage[1].synchronize()                            # the previous upload has left the staging buffer
+        pinned = stage[0][: t_host.numel()].view(t_host.shape)
+        pinned_np = pinned.numpy()
+        out = torch.empty(t_host.shape, dtype=t_host.dtype, device=self.device)
+        n = self.STAGED_H2D_CHUNKS
+        rows = host.shape[0]
+        edges = [rows * i // n for i in range(n + 1)]
+        if getattr(self, "_h2d_pool", None) is None:
+            self._h2d_pool = ThreadPoolExecutor(max_workers=4)
+        futs = [self._h2d_pool.submit(np.copyto, pinned_np[edges[i]: edges[i + 1]], host[edges[i]: edges[i + 1]]) for i in range(n)]
+        with torch.cuda.device(self.device):
+            for i, f in enumerate(futs):
+                f.result()
+                out[edges[i]: edges[i + 1]].copy_(pinned[edges[i]: edges[i + 1]], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        self._h2d_stage = (stage[0], ev)
+        return out
 
     def empty(self, shape, dtype=torch.float32) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)

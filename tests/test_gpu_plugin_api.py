@@ -260,3 +260,28 @@ def test_pandora_plugin_classes_run_the_pipeline(pb, oracle):
             np.testing.assert_array_equal(np.asarray(disp["disparity_map"].data), exp)
         finally:
             plug.keep_host_copy = True
+
+
+def test_staged_upload_of_large_host_arrays():
+    """Engine.to_device cuts large pageable arrays into row chunks staged through page-locked memory by worker threads:
+    same bytes on the device, also back to back (one shared staging buffer) and for non-float dtypes."""
+    import torch
+
+    import pandora_b200
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    eng = pandora_b200.get_engine("cuda:0")
+    g = np.random.default_rng(3)
+    a = g.random((2100, 4099), dtype=np.float32)                  # 34 MB, odd shape
+    b = g.random((2100, 4099), dtype=np.float32)
+    da, db = eng.to_device(a), eng.to_device(b)
+    a_copy = a.copy()
+    a[:] = -1.0                                                   # the caller may reuse its array as soon as to_device returns
+    assert torch.equal(da.cpu(), torch.from_numpy(a_copy)) and torch.equal(db.cpu(), torch.from_numpy(b))
+    m = g.integers(0, 3, (4096, 4096)).astype(np.int16)           # 33 MB mask
+    dm = eng.to_device(m, dtype=torch.int16)
+    assert dm.dtype == torch.int16 and torch.equal(dm.cpu(), torch.from_numpy(m))
+
+
+test_staged_upload_of_large_host_arrays = pytest.mark.gpu(test_staged_upload_of_large_host_arrays)
