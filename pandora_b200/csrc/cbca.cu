@@ -377,14 +377,14 @@ __global__ void __launch_bounds__(32 * CBCA_TX) cbca_aggregate_pipe_kernel(const
 // TX = 4 adjacent columns and marches down the rows.  Per row it loads the 4 + 2*MA costs its horizontal arm sums can
 // meet straight into registers (one row ahead: the loads of row i + 1 are in flight while row i is computed), adds the
 // arm taps with predicates (l, r <= 4: at most eight predicated adds around the centre), keeps the running column
-// prefixes of Eh (float32, the reference's step-3 order of additions) and Nh in registers and their last RING = 16
+// prefixes of Eh (float32, the reference's step-3 order of additions) and Nh in registers and their last RING = 12
 // rows in a THREAD-PRIVATE shared-memory ring ([slot][column][lane]: conflict-free, no synchronisation), from which
 // the vertical arm sums of row i - MA are two differences.  The vertical arms and the "centre cost is NaN" bits of the
 // last MA rows travel in two small register histories, so every support entry and every cost is loaded exactly once
 // per thread (halo columns: twice more from L2 by the neighbouring strips).
 // Integer costs: every sum is exact, one correctly rounded division -> bit-identical to the reference; float costs:
 // direct <= 9-term sums instead of row-prefix differences (more accurate; tests/test_gpu_parity.py states the tolerance).
-constexpr int CBR_TX = 4, CBR_MA = 4, CBR_RING = 16;      // ring slots: a power of two (slot arithmetic is one AND), >= 2 * MA + 3
+constexpr int CBR_TX = 4, CBR_MA = 4, CBR_RING = 12;
 
 __device__ __forceinline__ int2 ldg_support(const short4 *p) { return __ldg(reinterpret_cast<const int2 *>(p)); }
 
@@ -437,9 +437,6 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
     unsigned pn[TX], tbh[TX];
 #pragma unroll
     for (int c = 0; c < TX; ++c) { pe[c] = 0.f; pn[c] = 0u; tbh[c] = 0u; }
-    for (int sl = 0; sl < RING; ++sl)
-#pragma unroll
-        for (int c = 0; c < TX; ++c) { pe_st(sl, c, 0.f); pn_st(sl, c, 0u); }
     unsigned nanh = 0u;                           // centre-is-NaN bits, 4 per row, newest row in the low nibble
     int rm = 0;                                   // i mod RING: the ring slot row i is written to
     // Iteration i: (a) issue the loads of row i, (b) vertical stage of row yo = i - MA - 1 from the ring and the
@@ -472,14 +469,15 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
                 // so the same differences give e = 0, n = 1
                 const unsigned tb = tbh[c] >> 24;                           // pushed MA + 1 rows ago, shifted MA times since
                 const int t = (int)(tb >> 3) & 7, b = (int)(tb & 7u);
-                const int s1 = (rm - (MA + 1 - b)) & (RING - 1);            // slot of row yo + b
-                const int s0 = (rm - (MA + 2 + t)) & (RING - 1);            // slot of row yo - t - 1
-                // a row above the march never entered a prefix: its slot still holds the zeros the ring starts with (it is
-                // only written RING - (MA + 2 + t) >= 6 rows after this read)
-                const float e1 = pe_ld(s1, c), e0 = pe_ld(s0, c);
-                const unsigned n1 = pn_ld(s1, c), n0 = pn_ld(s0, c);
-                const float e = e1 - e0;
-                const unsigned n = ((n1 - n0) & 0xFFFFu) + (unsigned)(t + b + 1);
+                int s1 = rm - (MA + 1 - b);                                 // slot of row yo + b
+                s1 += (s1 < 0) ? RING : 0;
+                int s0 = rm - (MA + 2 + t);                                 // slot of row yo - t - 1
+                s0 += (s0 < 0) ? RING : 0;
+                const bool has0 = (yo - t - 1 >= i_start);                  // rows above the march never entered a prefix
+                const float e1 = pe_ld(s1, c), e0r = pe_ld(s0, c);
+                const unsigned n1 = pn_ld(s1, c), n0r = pn_ld(s0, c);
+                const float e = e1 - (has0 ? e0r : 0.f);
+                const unsigned n = ((n1 - (has0 ? n0r : 0u)) & 0xFFFFu) + (unsigned)(t + b + 1);
                 const bool cnan = ((nanh >> (4 * MA + c)) & 1u) != 0u;
                 if (act(c)) o[(size_t)c * D] = cnan ? nan_f() : e / (float)n;   // (0*c + E) / N
             }
@@ -522,7 +520,7 @@ __global__ void __launch_bounds__(256, 3) cbca_aggregate_reg_kernel(const float 
             for (int c = 0; c < TX; ++c) tbh[c] <<= 6;
         }
         nanh = (nanh << 4) | nan_i;
-        rm = (rm + 1) & (RING - 1);
+        rm = (rm + 1 == RING) ? 0 : rm + 1;
     }
     };
     if (fast) march(std::true_type{});

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """CBCA stage on C2-like input: python tools/prof_cbca.py H W D [reps] -- times the register kernel (default for
-cbca_distance <= 5) and the staged kernel (PB200_CBCA_PIPE=1) with CUDA events and checks that they agree."""
+cbca_distance <= 5) and the staged kernel (option cbca.pipe = 1) with CUDA events and checks that they agree."""
 import os
 import sys
 
@@ -19,10 +19,7 @@ cv = eng.census(l, r, 5, -(D - 1), 0)
 cl, cr = eng.cbca_supports(l, r, 2, 5, 30.0)
 outs = {}
 for name, env in (("register kernel", None), ("staged kernel", "1")):
-    if env is None:
-        os.environ.pop("PB200_CBCA_PIPE", None)
-    else:
-        os.environ["PB200_CBCA_PIPE"] = env
+    pandora_b200.set_option("cbca.pipe", 1 if env else -1)       # kernel selection is a library option, not an environment variable
     out = torch.empty_like(cv)
 
     def agg():
