@@ -14,5 +14,5 @@ if [ "${2:-}" = "full" ]; then
 timeout 300 python tools/stage_bench.py --json gpurun_out/${T}_stage_bench.json > gpurun_out/${T}_stage_bench.log 2>&1; echo "stage bench rc=$?"
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "ref rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv \
-   --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+   --log-file gpurun_out/${T}_launches.csv python bench.py --steps 4 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 fi
