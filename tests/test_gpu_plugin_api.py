@@ -285,3 +285,48 @@ def test_staged_upload_of_large_host_arrays():
 
 
 test_staged_upload_of_large_host_arrays = pytest.mark.gpu(test_staged_upload_of_large_host_arrays)
+
+
+@pytest.mark.gpu
+def test_variable_left_grids_with_accurate_cross_checking(pb, oracle):
+    """Per-pixel left disparity grids + cross_checking_accurate through run(): the right image's grids come from
+    reverse_disp_range (state_machine.py:668-683, matching_cost.cpp:59-131), both volumes are masked to their grids, and the
+    result equals the chain of oracle functions bit for bit (left and right maps, masks, left-right distances)."""
+    from pandora_b200.dataset import DataArray
+
+    H, W = 60, 140
+    left, right, _ = oracle.synthetic_pair(H, W, 24, seed=77)
+    lmin = np.full((H, W), -20, np.float32)
+    lmax = np.full((H, W), -3, np.float32)
+    lmin[:, 70:] = -12
+    lmax[:, 70:] = 0
+    lmin[20:40, 30:60] = -6                                       # a narrow window somewhere
+    lmax[20:40, 30:60] = -5
+    cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": 5, "subpix": 1},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"},
+                        "validation": {"validation_method": "cross_checking_accurate", "cross_checking_threshold": 1}}}
+    dl = pb.create_image_dataset(left)
+    dl["disparity"] = (("band_disp", "row", "col"), np.stack([lmin, lmax]))
+    dl.coords["band_disp"] = DataArray(np.array(["min", "max"]), ("band_disp",))
+    dr = pb.create_image_dataset(right)
+    disp, cv, rdisp = pb.run(dl, dr, cfg, return_right=True)
+
+    def side(a, b, gmin, gmax):
+        dmin, dmax = int(np.nanmin(gmin)), int(np.nanmax(gmax))
+        ccv, _ = oracle.census_cost_volume(a, b, 5, dmin, dmax)
+        vm = oracle.validity_mask(H, W, dmin, dmax, 2)
+        oracle.cv_masked_full(ccv, vm, 2, 5, dmin, grid_min=gmin, grid_max=gmax)
+        d, inv = oracle.wta(ccv, np.arange(dmin, dmax + 1), invalid_disparity=np.nan)
+        return ccv, d, oracle.wta_validity_mask(vm, inv), dmin, dmax
+
+    cv_l, d_l, m_l, dmin, dmax = side(left, right, lmin, lmax)
+    rmin, rmax = oracle.reverse_disp_range(lmin, lmax)
+    _, d_r, m_r, rdmin, rdmax = side(right, left, rmin, rmax)
+    m_l2, conf_l = oracle.cross_checking(d_l, m_l, d_r, 1, dmin, dmax, 2)
+    m_r2, _ = oracle.cross_checking(d_r, m_r, d_l, 1, rdmin, rdmax, 2)
+    np.testing.assert_array_equal(cv["cost_volume"].data, cv_l)
+    np.testing.assert_array_equal(disp["disparity_map"].data, d_l)
+    np.testing.assert_array_equal(rdisp["disparity_map"].data, d_r)
+    np.testing.assert_array_equal(disp["validity_mask"].data, m_l2)
+    np.testing.assert_array_equal(rdisp["validity_mask"].data, m_r2)
+    np.testing.assert_array_equal(np.asarray(disp["confidence_measure"].data)[:, :, 0], conf_l)
