@@ -19,6 +19,8 @@ for _ in range(3):
         eng.sad_ssd(l, r, 5, -(D - 1), 0, squared=(what == "ssd"), out=cv)
     elif what == "zncc":
         eng.zncc(l, r, 5, -(D - 1), 0, out=cv)
+    elif what == "census":
+        eng.census(l, r, 5, -(D - 1), 0, out=cv, fuse_wta=True)
     elif what == "wta":
         eng.census(l, r, 5, -(D - 1), 0, out=cv)
         eng.wta(cv, -(D - 1))
