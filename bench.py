@@ -201,17 +201,18 @@ def global_columns(H, Wg, lo, n, D):
 
 
 def other_config_lines(pb, torch, steps):
-    """C1 (1024^2 Census 5x5 -> WTA, D = 128) and C2 (2048^2 Census 5x5 -> CBCA -> WTA, D = 192): device-resident pipeline
+    """C0 (cones size, SAD 5x5 -> WTA, D = 64), C1 (1024^2 Census 5x5 -> WTA, D = 128) and C2 (2048^2 Census 5x5 -> CBCA -> WTA, D = 192): device-resident pipeline
     times of BASELINE.json's other single-GPU configurations, measured in this run (CUDA events), with the algorithmic bytes of
     SURVEY 8(d) next to them."""
     from pandora_b200.synthetic import synthetic_pair
 
     out = {}
     peak, _ = measured_peak_gbs()
-    for name, (H, W, D, cbca, alg) in {"C1": (1024, 1024, 128, None, lambda D: 4.0 * D + 12.0),
-                                      "C2": (2048, 2048, 192, (5, 30.0), lambda D: 12.0 * D + 36.0)}.items():
+    for name, (H, W, D, method, cbca, alg) in {"C0": (375, 450, 64, "sad", None, lambda D: 8.0 * D + 14.0),      # SAD fill + stand-alone WTA
+                                              "C1": (1024, 1024, 128, "census", None, lambda D: 4.0 * D + 12.0),
+                                              "C2": (2048, 2048, 192, "census", (5, 30.0), lambda D: 12.0 * D + 36.0)}.items():
         left, right, _ = synthetic_pair(H, W, D)
-        pipe = pb.StereoPipeline(H, W, -(D - 1), 0, "census", WINDOW, cbca=cbca, device="cuda:0")
+        pipe = pb.StereoPipeline(H, W, -(D - 1), 0, method, WINDOW, cbca=cbca, device="cuda:0")
         dl, dr = pipe.eng.to_device(left), pipe.eng.to_device(right)
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")      # > L2: the volumes of C1 nearly fit it
         for _ in range(3):
@@ -227,10 +228,13 @@ def other_config_lines(pb, torch, steps):
             ts.append(ev[0].elapsed_time(ev[1]))
         ms = float(np.mean(ts))
         bytes_ = alg(D) * H * W
-        out[name] = {"workload": f"{H}x{W} Census 5x5" + (" + CBCA" if cbca else "") + f" + WTA, D={D}", "ms_per_step": ms,
+        out[name] = {"workload": f"{H}x{W} {'SAD' if method == 'sad' else 'Census'} 5x5" + (" + CBCA" if cbca else "") + f" + WTA, D={D}"
+                                 + (" (cones-sized synthetic pair; the step includes the data-dependent cmax reduction of the SAD step)" if method == "sad" else ""),
+                     "ms_per_step": ms,
                      "mpix_per_s": H * W / ms / 1e3, "pipeline_algorithmic_bytes": bytes_, "achieved_gbs": bytes_ / ms / 1e6,
                      "frac_of_measured_hbm": bytes_ / ms / 1e6 / peak, "l2": "256 MB flush between iterations",
-                     "paths": {"census": pb.last_path("census")[0], "cbca": pb.last_path("cbca")[0] if cbca else None}}
+                     "paths": {"census": pb.last_path("census")[0] if method == "census" else None, "sad": pb.last_path("sad")[0] if method == "sad" else None,
+                               "cbca": pb.last_path("cbca")[0] if cbca else None}}
         del pipe, dl, dr, flush
         torch.cuda.empty_cache()
     return out
