@@ -240,6 +240,18 @@ PB200_API int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, int
               float *d_halo_out_bottom, float *d_halo_out_top, float *d_disp, int dmin, float invalid_disparity,
               uint8_t *d_all_nan, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* use_confidence of the SGM step (docs/source/userguide/plugins/plugin_libsgm.rst:38-47): out(p, d) = cv(p, d) * confidence(p),
+ * NaN costs stay NaN; d_out may be d_cv.  The scaled volume then goes through pb200_sgm (float costs: the float kernels). */
+PB200_API int pb200_scale_volume(const float *d_cv, const float *d_confidence, int H, int W, int D, float *d_out, void *stream);
+
+/* min_cost_paths of the SGM step (plugin_libsgm.rst:411-413): the 8-path optimisation like pb200_sgm (all directions, float
+ * kernels, one launch per direction) plus the map "optimization_plugin_libsgm_nb_of_directions" (float32 (H, W)): how many
+ * of the 8 directions have the minimum of their own path cost at the disparity where the summed cost is minimal (first
+ * minima; 0 for a pixel without any valid cost). */
+PB200_API size_t pb200_sgm_paths_workspace_bytes(int H, int W);
+PB200_API int pb200_sgm_min_cost_paths(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
+                             int overcounting, float *d_nb_of_directions, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- disparity (WTA) -------------------------------------------------------------------------- */
 /* d_disp[y,x] = dmin + argmin_k cv (is_max: argmax), NaN never wins, first index on ties, all-NaN ->
  * invalid_disparity (disparity.py:434-455, 483-553).  d_all_nan (optional) gets 1 for all-NaN pixels. */

@@ -429,6 +429,20 @@ def sgm_cost_volume(cv: np.ndarray, p1: float = 8, p2: float = 32, cmax: float =
     return -out if type_measure == "max" else out
 
 
+def sgm_min_cost_paths(cv: np.ndarray, p1: float = 8, p2: float = 32, cmax: float = 25, overcounting: bool = False):
+    """SGM with the plugin's ``min_cost_paths`` option (plugin_libsgm.rst:411-413): (optimised volume, nb_of_directions (H, W))."""
+    cv = _f32(cv)
+    H, W, D = cv.shape
+    out, nb = np.empty_like(cv), np.empty((H, W), dtype=np.float32)
+    fn = lib().pbo_sgm_min_cost_paths
+    fn.restype = ctypes.c_int
+    rc = fn(_p(cv, ctypes.c_float), ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(D), ctypes.c_float(p1), ctypes.c_float(p2),
+            ctypes.c_float(sgm_invalid_value(cmax, p2)), ctypes.c_int(int(bool(overcounting))), _p(out, ctypes.c_float), _p(nb, ctypes.c_float))
+    if rc:
+        raise ValueError(f"pbo_sgm_min_cost_paths failed: {rc}")
+    return out, nb
+
+
 def sgm_direction(C: np.ndarray, S: np.ndarray, p1: float, p2: float, direction: int, init: bool, halo_in=None, halo_out=None):
     """One direction (index into E, W, S, SE, SW, N, NE, NW) on a row tile, in place on S; C holds no NaN."""
     H, W, D = C.shape

@@ -274,9 +274,14 @@ static void sgm_step(const float *C, const float *Lp, float *L, int D, float P1,
 
 static const int SGM_DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {1, 1}, {1, -1}, {-1, 0}, {-1, 1}, {-1, -1}};
 
-PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
-                    int overcounting, int n_dirs, float *cv_out) {
+/* nb_dirs (optional, (H, W)): min_cost_paths of the plugin (plugin_libsgm.rst:411-413), "the number of sgm paths that give the
+ * same position for minimal optimized cost at each point": how many directions have the (first) minimum of their own L_r at the
+ * disparity where the sum is minimal over the valid cells (first minimum); 0 for a pixel without any valid cost. */
+static int sgm_impl(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
+                    int overcounting, int n_dirs, float *cv_out, float *nb_dirs) {
     if (n_dirs < 1 || n_dirs > 8) return -1;
+    int *dirmin = nb_dirs ? (int *)malloc((size_t)n_dirs * H * W * sizeof(int)) : NULL;
+    if (nb_dirs && !dirmin) return -2;
     const size_t n = (size_t)H * W * D;
     float *C = (float *)malloc(n * sizeof(float));
     float *bufa = (float *)malloc((size_t)D * sizeof(float));
@@ -297,6 +302,12 @@ PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2,
                     if (first) { memcpy(L, c, (size_t)D * sizeof(float)); first = 0; }
                     else sgm_step(c, Lp, L, D, P1, P2);
                     for (int d = 0; d < D; ++d) s[d] = s[d] + L[d];
+                    if (dirmin) {
+                        int best = 0;
+                        for (int d = 1; d < D; ++d)
+                            if (L[d] < L[best]) best = d;
+                        dirmin[((size_t)r * H + y) * W + x] = best;
+                    }
                     float *tmp = Lp; Lp = L; L = tmp;
                     y += dy; x += dx;
                 }
@@ -306,8 +317,28 @@ PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2,
         if (overcounting) cv_out[i] = cv_out[i] - (float)(n_dirs - 1) * C[i];
         if (isnan(cv_in[i])) cv_out[i] = NAN;
     }
-    free(C); free(bufa); free(bufb);
+    if (nb_dirs)
+        for (size_t p = 0; p < (size_t)H * W; ++p) {
+            const float *s = cv_out + p * D;
+            int best = -1;
+            for (int d = 0; d < D; ++d)
+                if (!isnan(s[d]) && (best < 0 || s[d] < s[best])) best = d;
+            int c = 0;
+            for (int r = 0; r < n_dirs && best >= 0; ++r) c += dirmin[(size_t)r * H * W + p] == best;
+            nb_dirs[p] = (float)c;
+        }
+    free(C); free(bufa); free(bufb); free(dirmin);
     return 0;
+}
+
+PBO_API int pbo_sgm(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
+                    int overcounting, int n_dirs, float *cv_out) {
+    return sgm_impl(cv_in, H, W, D, P1, P2, invalid_value, overcounting, n_dirs, cv_out, NULL);
+}
+
+PBO_API int pbo_sgm_min_cost_paths(const float *cv_in, int H, int W, int D, float P1, float P2, float invalid_value,
+                                   int overcounting, float *cv_out, float *nb_dirs) {
+    return sgm_impl(cv_in, H, W, D, P1, P2, invalid_value, overcounting, 8, cv_out, nb_dirs);
 }
 
 /* One direction of pbo_sgm on a row tile, with the path-state hand-over used by row-tiled (multi-GPU)

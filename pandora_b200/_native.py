@@ -58,6 +58,9 @@ PROTOTYPES = {
     "pb200_census_sgm_workspace_bytes": (_sz, [_ci, _ci, _ci, _ci, _ci]),
     "pb200_census_sgm_descriptors": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _vp, _sz, _vp, _vp]),
     "pb200_census_sgm": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _ci, _vp, _vp]),
+    "pb200_sgm_paths_workspace_bytes": (_sz, [_ci, _ci]),
+    "pb200_sgm_min_cost_paths": (_ci, [_vp, _vp, _ci, _ci, _ci, _cf, _cf, _cf, _ci, _vp, _vp, _sz, _vp]),
+    "pb200_scale_volume": (_ci, [_vp, _vp, _ci, _ci, _ci, _vp, _vp]),
     "pb200_census_sgm_batch": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _vp, _vp]),
     "pb200_tile_link_bytes": (_sz, [_ci]),
     "pb200_census_sgm_tile": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _cf, _cf, _ci, _ci, _ci, _vp, _vp, _sz, _vp, _sz, _vp, _cf, _vp, _vp,

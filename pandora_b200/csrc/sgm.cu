@@ -41,6 +41,7 @@ struct SgmParams {
     float invalid_disparity;
     const int *gate;        // when not NULL the kernel runs only if (*gate != 0) == (gate_run_if != 0) (narrow/wide path switch)
     int gate_run_if;
+    uint16_t *dir_argmin;   // min_cost_paths: (H, W) index of this direction's minimal L_r per pixel (first minimum), or NULL
 };
 
 template <int NPL, bool VEC, bool FULL = false>
@@ -168,6 +169,14 @@ __global__ void __launch_bounds__(128) sgm_path_kernel(const SgmParams p) {
         m = warp_min(lm);
 #pragma unroll
         for (int j = 0; j < NPL; ++j) Lp[j] = L[j];
+        if (p.dir_argmin != nullptr) {                          // min_cost_paths: where this path's own cost is minimal (first minimum)
+            int bk = 0x7fffffff;
+#pragma unroll
+            for (int j = NPL - 1; j >= 0; --j)
+                if (lane * NPL + j < D && L[j] == m) bk = lane * NPL + j;
+            bk = __reduce_min_sync(0xffffffffu, bk);
+            if (lane == 0) p.dir_argmin[(size_t)y * W + x] = (uint16_t)bk;
+        }
 
         // ---- accumulate / finalise ----------------------------------------------------------------
         if (p.mode == 0) {
@@ -509,6 +518,34 @@ int sgm_narrow_try(const float *cv, float *out, int H, int W, int D, float p1, f
                    float *disp, int dmin, float invalid_disparity, uint8_t *all_nan, void *workspace, size_t workspace_bytes,
                    cudaStream_t s, const int **gate, int phase, int dy, int final, const float *halo_in, float *halo_out);   // sgm_narrow.cu
 
+// use_confidence (plugin_libsgm.rst:38-47): E(D) = sum_p C(p, D_p) * Confidence(p) + the penalty terms -- every cost of a pixel is
+// scaled by that pixel's confidence before the recurrence; NaN costs stay NaN.  One warp-wide pass over the volume.
+__global__ void __launch_bounds__(256) scale_volume_kernel(const float *__restrict__ cv, const float *__restrict__ conf, long n_pix, int D,
+                                                          float *__restrict__ out) {
+    const long total = n_pix * (long)D;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        out[i] = cv[i] * __ldg(conf + i / D);
+}
+
+// min_cost_paths (plugin_libsgm.rst:411-413): "the number of sgm paths that give the same position for minimal optimized cost
+// at each point" = how many of the 8 directions have the minimum of their own L_r at the disparity where the sum S is minimal
+// (first minima; 0 for a pixel without any valid cost).
+__global__ void __launch_bounds__(256) sgm_nb_directions_kernel(const uint16_t *__restrict__ dir_argmin, const float *__restrict__ disp,
+                                                                const uint8_t *__restrict__ all_nan, long n_pix, int dmin,
+                                                                float *__restrict__ nb) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    float n = 0.f;
+    if (!all_nan[i]) {
+        const int k = (int)disp[i] - dmin;
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c += ((int)dir_argmin[(size_t)r * n_pix + i] == k) ? 1 : 0;
+        n = (float)c;
+    }
+    nb[i] = n;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -631,6 +668,7 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
         p.all_nan = is_final ? d_all_nan : nullptr;
         p.dmin = dmin; p.invalid_disparity = invalid_disparity;
         p.gate = gate; p.gate_run_if = 1;
+        p.dir_argmin = nullptr;
         int rc;
         if (D <= 32) rc = launch_dir<1>(p, s);
         else if (D <= 64) rc = launch_dir<2>(p, s);
@@ -639,5 +677,72 @@ extern "C" int pb200_sgm(const float *d_cv_in, float *d_cv_out, int H, int W, in
         else rc = launch_dir<16>(p, s);
         if (rc != PB200_OK) return rc;
     }
+    return PB200_OK;
+}
+
+extern "C" int pb200_scale_volume(const float *d_cv, const float *d_confidence, int H, int W, int D, float *d_out, void *stream) {
+    if (!d_cv || !d_confidence || !d_out || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_scale_volume: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    const long n_pix = (long)H * W;
+    long blocks = (n_pix * D + 255) / 256;
+    const long cap = (long)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    scale_volume_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_cv, d_confidence, n_pix, D, d_out);
+    PB200_LAUNCH_CHECK("scale_volume_kernel");
+    return PB200_OK;
+}
+
+extern "C" size_t pb200_sgm_paths_workspace_bytes(int H, int W) {
+    if (H <= 0 || W <= 0) return 0;
+    return (size_t)H * W * (8 * sizeof(uint16_t) + sizeof(float) + 1) + 64;
+}
+
+extern "C" int pb200_sgm_min_cost_paths(const float *d_cv_in, float *d_cv_out, int H, int W, int D, float p1, float p2, float invalid_value,
+                                        int overcounting, float *d_nb_of_directions, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!d_cv_in || !d_cv_out || !d_nb_of_directions || !d_workspace || d_cv_in == d_cv_out || H <= 0 || W <= 0 || D <= 0) {
+        set_error("pb200_sgm_min_cost_paths: bad argument");
+        return PB200_ERR_BAD_ARG;
+    }
+    if (D > PB200_SGM_MAX_DISP) {
+        set_error("pb200_sgm_min_cost_paths: D=%d above the supported maximum (%d)", D, PB200_SGM_MAX_DISP);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < pb200_sgm_paths_workspace_bytes(H, W)) {
+        set_error("pb200_sgm_min_cost_paths: workspace too small (pb200_sgm_paths_workspace_bytes)");
+        return PB200_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n_pix = (size_t)H * W;
+    uint16_t *argmin = reinterpret_cast<uint16_t *>(d_workspace);
+    float *disp = reinterpret_cast<float *>(reinterpret_cast<char *>(d_workspace) + ((8 * n_pix * sizeof(uint16_t) + 15) & ~(size_t)15));
+    uint8_t *all_nan = reinterpret_cast<uint8_t *>(disp + n_pix);
+    static const int dirs[8][2] = {{0, 1}, {0, -1}, {1, 0}, {1, 1}, {1, -1}, {-1, 0}, {-1, 1}, {-1, -1}};
+    note_path(STAGE_SGM, PATH_SGM_FLOAT, 8);
+    for (int r = 0; r < 8; ++r) {                               // one path kernel per direction: each records its own argmin
+        SgmParams p;
+        p.cv = d_cv_in; p.S = d_cv_out; p.H = H; p.W = W; p.D = D;
+        p.p1 = p1; p.p2 = p2; p.invalid_value = invalid_value;
+        p.dy = dirs[r][0]; p.dx = dirs[r][1];
+        p.mode = r == 0 ? 0 : (r == 7 ? 2 : 1);
+        p.overcounting = overcounting;
+        p.over_scale = 7.0f;
+        p.halo_in = nullptr; p.halo_out = nullptr;
+        p.disp = r == 7 ? disp : nullptr;
+        p.all_nan = r == 7 ? all_nan : nullptr;
+        p.dmin = 0; p.invalid_disparity = -1.f;
+        p.gate = nullptr; p.gate_run_if = 1;
+        p.dir_argmin = argmin + (size_t)r * n_pix;
+        int rc;
+        if (D <= 32) rc = launch_dir<1>(p, s);
+        else if (D <= 64) rc = launch_dir<2>(p, s);
+        else if (D <= 128) rc = launch_dir<4>(p, s);
+        else if (D <= 256) rc = launch_dir<8>(p, s);
+        else rc = launch_dir<16>(p, s);
+        if (rc != PB200_OK) return rc;
+    }
+    sgm_nb_directions_kernel<<<ceil_div((long)n_pix, 256), 256, 0, s>>>(argmin, disp, all_nan, (long)n_pix, 0, d_nb_of_directions);
+    PB200_LAUNCH_CHECK("sgm_nb_directions_kernel");
     return PB200_OK;
 }

@@ -314,6 +314,25 @@ class Engine:
         off = int(self.lib.pb200_sgm_flag_offset(W, D))
         return ws[off: off + 4].view(torch.int32)
 
+    def sgm_min_cost_paths(self, cv: torch.Tensor, p1: float, p2: float, invalid_value: float, overcounting: bool = False):
+        """SGM with ``min_cost_paths`` (plugin_libsgm.rst:411-413): (optimised volume, nb_of_directions (H, W) float32)."""
+        H, W, D = (int(v) for v in cv.shape)
+        out = torch.empty_like(cv)
+        nb = self.empty((H, W))
+        ws = self._workspace("sgm_paths", self.lib.pb200_sgm_paths_workspace_bytes(H, W))
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_sgm_min_cost_paths(_ptr(cv), _ptr(out), H, W, D, float(p1), float(p2), float(invalid_value),
+                                                            int(bool(overcounting)), _ptr(nb), _ptr(ws), ws.numel(), self._stream()))
+        return out, nb
+
+    def scale_volume(self, cv: torch.Tensor, confidence: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cv(p, d) * confidence(p) (``use_confidence`` of the SGM step, plugin_libsgm.rst:38-47)."""
+        H, W, D = (int(v) for v in cv.shape)
+        res = torch.empty_like(cv) if out is None else out
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pb200_scale_volume(_ptr(cv), _ptr(confidence), H, W, D, _ptr(res), self._stream()))
+        return res
+
     # ---- disparity ----------------------------------------------------------------------------------
     def wta(self, cv: torch.Tensor, dmin: int, is_max: bool = False, invalid_disparity: float = -9999.0):
         H, W, D = (int(s) for s in cv.shape)

@@ -330,3 +330,94 @@ def test_variable_left_grids_with_accurate_cross_checking(pb, oracle):
     np.testing.assert_array_equal(disp["validity_mask"].data, m_l2)
     np.testing.assert_array_equal(rdisp["validity_mask"].data, m_r2)
     np.testing.assert_array_equal(np.asarray(disp["confidence_measure"].data)[:, :, 0], conf_l)
+
+
+def _norm_percentile(amb):
+    """Ambiguity.normalize_with_percentile, ambiguity.py:172-186 (percentile 1)."""
+    a = np.copy(amb)
+    lo, hi = np.percentile(a, 1.0), np.percentile(a, 99.0)
+    np.clip(a, lo, hi, out=a)
+    return (a - np.min(a)) / (np.max(a) - np.min(a))
+
+
+@pytest.mark.gpu
+def test_sgm_use_confidence_sample_pipeline(pb, oracle):
+    """use_confidence (plugin_libsgm.rst:38-47: every cost of a pixel is multiplied by the pixel's ambiguity confidence before
+    the recurrence) on the pipeline of data_samples/json_conf_files/a_semi_global_matching_with_confidence.json up to the
+    disparity step: census -> ambiguity ".before" -> SGM on the weighted costs -> ambiguity ".after" -> WTA, against the same
+    chain of oracle functions; and a missing confidence band means confidence 1 (same result as without the option)."""
+    H, W, D = 40, 120, 32
+    left, right, _ = oracle.synthetic_pair(H, W, D, seed=9)
+    dmin, dmax = -(D - 1), 0
+    base = {"matching_cost": {"matching_cost_method": "census", "window_size": 5, "subpix": 1}}
+    sgm = {"optimization_method": "sgm", "overcounting": False, "penalty": {"penalty_method": "sgm_penalty", "P1": 8, "P2": 32, "p2_method": "constant"}}
+    cfg = {"pipeline": {**base,
+                        "cost_volume_confidence.before": {"confidence_method": "ambiguity", "eta_max": 0.7, "eta_step": 0.01},
+                        "optimization": {**sgm, "use_confidence": "cost_volume_confidence.before"},
+                        "cost_volume_confidence.after": {"confidence_method": "ambiguity", "eta_max": 0.7, "eta_step": 0.01},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"}}}
+    dl, dr = pb.create_image_dataset(left, disparity=[dmin, dmax]), pb.create_image_dataset(right)
+    disp, cv = pb.run(dl, dr, cfg)
+    assert list(disp.coords["indicator"].data) == ["confidence_from_ambiguity.before", "confidence_from_ambiguity.after"]
+
+    ccv, attrs = oracle.census_cost_volume(left, right, 5, dmin, dmax)
+    vm = oracle.validity_mask(H, W, dmin, dmax, 2)
+    oracle.cv_masked(ccv, vm, 2)
+    etas = np.arange(0.0, 0.7, 0.01)
+    grids = np.stack([np.full((H, W), dmin), np.full((H, W), dmax)]).astype(np.int64)
+    disps = np.arange(dmin, dmax + 1).astype(np.float32)
+    conf = (1 - _norm_percentile(oracle.ambiguity(ccv, etas, grids, disps))).astype(np.float32)
+    np.testing.assert_array_equal(np.asarray(disp["confidence_measure"].data)[:, :, 0], conf)
+    weighted = (ccv * conf[:, :, None]).astype(np.float32)
+    scv = oracle.sgm_cost_volume(weighted, 8, 32, cmax=attrs["cmax"])
+    np.testing.assert_array_equal(cv["cost_volume"].data, scv)
+    d, _ = oracle.wta(scv, np.arange(dmin, dmax + 1), invalid_disparity=np.nan)
+    np.testing.assert_array_equal(disp["disparity_map"].data, d)
+
+    # a band that does not exist: confidence 1 everywhere == the plain SGM step (the fused stage may run again)
+    cfg1 = {"pipeline": {**base, "optimization": {**sgm, "use_confidence": "cost_volume_confidence.before"},
+                         "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"}}}
+    cfg0 = {"pipeline": {**base, "optimization": sgm, "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"}}}
+    d1, _ = pb.run(pb.create_image_dataset(left, disparity=[dmin, dmax]), pb.create_image_dataset(right), cfg1)
+    d0, _ = pb.run(pb.create_image_dataset(left, disparity=[dmin, dmax]), pb.create_image_dataset(right), cfg0)
+    np.testing.assert_array_equal(d1["disparity_map"].data, d0["disparity_map"].data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,over", [((9, 21, 64), False), ((17, 40, 40), True), ((6, 33, 200), False), ((5, 12, 300), False), ((1, 1, 8), False)])
+def test_sgm_min_cost_paths_kernels_vs_oracle(pb, oracle, shape, over):
+    """pb200_sgm_min_cost_paths: optimised volume and nb_of_directions map against the oracle (NaN cells, whole pixels without
+    a valid cost, every per-lane register count of the path kernel)."""
+    eng = pb.get_engine("cuda:0")
+    g = np.random.default_rng(shape[1] + shape[2])
+    cv = g.integers(0, 26, shape).astype(np.float32)
+    cv[g.random(shape) < 0.12] = np.nan
+    if shape[0] > 2:
+        cv[2, 1, :] = np.nan
+    ref, nb_ref = oracle.sgm_min_cost_paths(cv, 8, 32, cmax=25, overcounting=over)
+    out, nb = eng.sgm_min_cost_paths(eng.to_device(cv), 8, 32, oracle.sgm_invalid_value(25, 32), overcounting=over)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    np.testing.assert_array_equal(nb.cpu().numpy(), nb_ref)
+
+
+@pytest.mark.gpu
+def test_sgm_min_cost_paths_through_run(pb, oracle):
+    """The option through run(cfg): the band optimization_plugin_libsgm_nb_of_directions (docs/source/userguide/output.rst:22)
+    joins the confidence measures of the cost volume and of the disparity dataset."""
+    H, W, D = 30, 90, 32
+    left, right, _ = oracle.synthetic_pair(H, W, D, seed=21)
+    dmin, dmax = -(D - 1), 0
+    cfg = {"pipeline": {"matching_cost": {"matching_cost_method": "census", "window_size": 5, "subpix": 1},
+                        "optimization": {"optimization_method": "sgm", "min_cost_paths": True, "penalty": {"P1": 8, "P2": 32}},
+                        "disparity": {"disparity_method": "wta", "invalid_disparity": "NaN"}}}
+    disp, cv = pb.run(pb.create_image_dataset(left, disparity=[dmin, dmax]), pb.create_image_dataset(right), cfg)
+    ccv, attrs = oracle.census_cost_volume(left, right, 5, dmin, dmax)
+    vm = oracle.validity_mask(H, W, dmin, dmax, 2)
+    oracle.cv_masked(ccv, vm, 2)
+    scv, nb = oracle.sgm_min_cost_paths(ccv, 8, 32, cmax=attrs["cmax"])
+    assert list(cv.coords["indicator"].data) == ["optimization_plugin_libsgm_nb_of_directions"]
+    np.testing.assert_array_equal(cv["cost_volume"].data, scv)
+    np.testing.assert_array_equal(np.asarray(cv["confidence_measure"].data)[:, :, 0], nb)
+    np.testing.assert_array_equal(np.asarray(disp["confidence_measure"].data)[:, :, 0], nb)
+    d, _ = oracle.wta(scv, np.arange(dmin, dmax + 1), invalid_disparity=np.nan)
+    np.testing.assert_array_equal(disp["disparity_map"].data, d)

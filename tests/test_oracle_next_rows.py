@@ -302,3 +302,25 @@ def test_validity_mask_with_masks_goldens(oracle, goldens, case):
     cv, _ = oracle.sad_ssd_cost_volume(left, right, w, dmin, dmax, "sad")
     oracle.cv_masked_full(cv, vm, off, w, dmin, lm, rm, valid, nodata, gmin, gmax)
     np.testing.assert_array_equal(vm, goldens[t + "gt_mask"])
+
+
+def test_sgm_min_cost_paths_known_answers(oracle):
+    """min_cost_paths (plugin_libsgm.rst:411-413).  A single pixel: every path starts there, L_r = C for all eight, so all eight
+    agree with the sum; a pixel without any valid cost counts 0; the optimised volume is the one of the plain call."""
+    cv = np.array([[[5, 2, 7, 2]]], dtype=np.float32)
+    out, nb = oracle.sgm_min_cost_paths(cv, 8, 32, cmax=25)
+    np.testing.assert_array_equal(out, 8 * cv)
+    assert nb[0, 0] == 8.0
+    g = np.random.default_rng(4)
+    cv = g.integers(0, 26, (6, 8, 5)).astype(np.float32)
+    cv[1, 2, :] = np.nan
+    cv[3, 3, 1] = np.nan
+    out, nb = oracle.sgm_min_cost_paths(cv, 8, 32, cmax=25)
+    np.testing.assert_array_equal(out, oracle.sgm_cost_volume(cv, 8, 32, cmax=25))
+    assert nb[1, 2] == 0.0 and nb.max() <= 8.0 and nb.min() >= 0.0 and nb.dtype == np.float32
+    # one row: E and W are the only paths longer than a pixel; at the first column W has seen the whole row, the other seven
+    # directions start there (L_r = C)
+    row = g.integers(0, 26, (1, 9, 4)).astype(np.float32)
+    out, nb = oracle.sgm_min_cost_paths(row, 8, 32, cmax=25)
+    k_c, k_s = int(np.argmin(row[0, 0])), int(np.argmin(out[0, 0]))
+    assert nb[0, 0] >= (7.0 if k_c == k_s else 0.0)
