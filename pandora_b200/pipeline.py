@@ -255,6 +255,8 @@ class StereoPipeline:
             return fuse, cmax
         e.matching_cost(self.method, left, right, self.window, self.dmin, self.dmax, out=cur)
         if cmax is None:
+            if not self.sgm:
+                return False, 0.0                              # SAD / SSD: the data-dependent cmax (a host round trip) only feeds SGM's invalid value
             mx = self.torch.maximum((left.max() - right.min()).abs(), (right.max() - left.min()).abs()).item()
             cmax = float(int((mx if self.method == "sad" else mx * mx) * self.window**2))
         return False, cmax
