@@ -210,14 +210,15 @@ class StereoPipeline:
         Returns the (n, H, W) disparity tensor; ``final_cv`` is the (n, H, W, D) SGM volume.  Same results as ``run_device``
         per pair, bit for bit; falls back to exactly that when the configuration is not eligible for the batched stage."""
         n = int(left.shape[0])
-        key = ("batch", n)
         bufs = getattr(self, "_batch_bufs", None)
-        if bufs is None or bufs[0] != key:
+        if bufs is None or bufs[0] < n:                        # one set of buffers for the largest batch seen; smaller batches use a prefix
             e = self.eng
-            bufs = (key, e.empty((n, self.H, self.W, self.D)) if self.sgm else None, e.empty((n, self.H, self.W)),
+            self._batch_bufs = bufs = None                     # release the smaller set before allocating the larger one
+            bufs = (n, e.empty((n, self.H, self.W, self.D)) if self.sgm else None, e.empty((n, self.H, self.W)),
                     e.empty((n, self.H, self.W), self.torch.uint8))
             self._batch_bufs = bufs
-        _, cv, disp, flags = bufs
+        cv = bufs[1][:n] if bufs[1] is not None else None
+        disp, flags = bufs[2][:n], bufs[3][:n]
         if self.fuse_census_sgm and n > 1:
             p1, p2 = float(self.sgm[0]), float(self.sgm[1])
             over = bool(self.sgm[2]) if len(self.sgm) > 2 else False
