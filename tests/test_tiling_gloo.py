@@ -166,3 +166,68 @@ def test_tiled_local_pipeline_over_gloo_matches_untiled(world, cbca, tmp_path, o
 
 def test_local_halo_rows():
     assert tiling.local_halo_rows(5) == 2 and tiling.local_halo_rows(5, 5) == 7 and tiling.local_halo_rows(3, 9) == 10
+
+
+# ---- column tiles: shear / un-shear host logic (the kernels need a GPU; the index maps and the neighbour exchange do not) ----
+def _sheared_tiles(img, ntiles):
+    """What the skewed wavefront leaves on every rank: sheared column c of row y of tile r = image column (r * Wt + c - y) mod Wg."""
+    H, Wg = img.shape
+    Wt = Wg // ntiles
+    y = np.arange(H)[:, None]
+    return np.stack([img[y, (r * Wt + np.arange(Wt)[None, :] - y) % Wg] for r in range(ntiles)])
+
+
+@pytest.mark.parametrize("H,Wg,ntiles", [(5, 12, 3), (16, 16, 2), (40, 24, 4), (7, 8, 1)])
+def test_unshear_gathered_inverts_the_shear(H, Wg, ntiles):
+    img = np.arange(H * Wg, dtype=np.float32).reshape(H, Wg)
+    tiles = _sheared_tiles(img, ntiles)
+    Wt = Wg // ntiles
+    for g in range(ntiles):
+        np.testing.assert_array_equal(tiling.unshear_gathered(tiles, Wg, g), img[:, g * Wt:(g + 1) * Wt])
+        np.testing.assert_array_equal(tiling.unshear_gathered(torch.from_numpy(tiles), Wg, g).numpy(), img[:, g * Wt:(g + 1) * Wt])
+
+
+def _nb_worker(rank, world, port, n, H, Wt, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Wg = Wt * world
+    # a batch is one tall sheared image: row y of image i sits at sheared row i * H + y
+    imgs = [np.arange(H * Wg, dtype=np.float32).reshape(H, Wg) + 1000.0 * i for i in range(n)]
+    tall = np.concatenate(imgs, axis=0)
+    mine = _sheared_tiles(tall, world)[rank].reshape(n, H, Wt)
+    pipe = object.__new__(tiling.ColumnTiledStereoPipeline)           # the exchange only needs these attributes
+    pipe.torch, pipe.dist, pipe.rank, pipe.world, pipe.H, pipe.Wt, pipe.Wg, pipe._cache = torch, dist, rank, world, H, Wt, Wg, {}
+    for _ in range(2):                                                 # twice: cached receive buffers
+        out = pipe._unshear_neighbours(torch.from_numpy(np.ascontiguousarray(mine)))
+    np.save(os.path.join(tmpdir, f"U{rank}.npy"), out.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,H,Wt", [(2, 1, 4, 8), (2, 3, 4, 8), (4, 2, 3, 6), (4, 5, 2, 4)])
+def test_unshear_neighbours_over_gloo(world, n, H, Wt, tmp_path):
+    """The neighbour exchange that brings sheared disparity tiles back to image layout (Wt a multiple of H; batches drift over
+    several ranks): every rank ends with its own image tile of every image of the batch."""
+    port = _free_port()
+    mp.spawn(_nb_worker, args=(world, port, n, H, Wt, str(tmp_path)), nprocs=world, join=True)
+    Wg = Wt * world
+    for r in range(world):
+        got = np.load(tmp_path / f"U{r}.npy")
+        for i in range(n):
+            img = np.arange(H * Wg, dtype=np.float32).reshape(H, Wg) + 1000.0 * i
+            np.testing.assert_array_equal(got[i], img[:, r * Wt:(r + 1) * Wt])
+
+
+@pytest.mark.parametrize("world,nimg,H,Wt", [(2, 1, 4, 8), (4, 2, 3, 6), (8, 1, 5, 4), (4, 6, 4, 8)])
+def test_visited_columns_cover_the_sheared_tile(world, nimg, H, Wt):
+    """visited_columns = the cyclic range of image columns a rank's sheared tile touches over a batch (what the host uploads)."""
+    Wg = Wt * world
+    for rank in range(world):
+        pipe = object.__new__(tiling.ColumnTiledStereoPipeline)
+        pipe.rank, pipe.H, pipe.Wt, pipe.Wg = rank, H, Wt, Wg
+        lo, n = pipe.visited_columns(nimg)
+        claimed = {(lo + k) % Wg for k in range(n)}
+        y = np.arange(nimg * H)[:, None]
+        touched = set(((rank * Wt + np.arange(Wt)[None, :] - y) % Wg).ravel().tolist())
+        assert touched <= claimed and (len(claimed) == len(touched) or n == Wg)
