@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) sad_ssd_kernel(const float *__restrict__ 
 // per-pixel window mean and std in float64 (valid centres only; others 0)
 __global__ void __launch_bounds__(256) zncc_stats_kernel(const float *__restrict__ img, int H, int W, int win,
                                                          double *__restrict__ mean, double *__restrict__ stdv,
-                                                         double *__restrict__ coefA, double *__restrict__ coefB, double scaleA) {
+                                                         double *__restrict__ coefA, double *__restrict__ coefB, double scaleA,
+                                                         int2 *__restrict__ pack) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)H * W) return;
     const int half = win / 2;
@@ -74,6 +75,9 @@ __global__ void __launch_bounds__(256) zncc_stats_kernel(const float *__restrict
     const double r = sd > 0.0 ? 1.0 / sd : 0.0;
     coefA[i] = r * scaleA;
     coefB[i] = m * r;
+    // integer-valued images (the running-sum kernel's fast mode): the window sum S as an exact integer and 1 / (w^2 * std) as
+    // float32 -- zncc = (w^2 * S_LR - S_L * S_R) * C_L * C_R has an exact integer numerator, so float32 factors are enough
+    pack[i] = make_int2(__double2int_rn(m * (double)(win * win)), __float_as_int((float)(r / (double)(win * win))));
 }
 
 __global__ void __launch_bounds__(256) zncc_kernel(const float *__restrict__ L, const float *__restrict__ R,
@@ -247,7 +251,8 @@ template <int WIN, int MODE>   // MODE 0: SAD, 1: SSD, 2: ZNCC
 __global__ void __launch_bounds__(128) window_cost_running_kernel(const float *__restrict__ L, const float *__restrict__ R, int H, int W,
                                                                   int dmin, int D, int band, float vmax, float *__restrict__ cv,
                                                                   const double *__restrict__ coefAL, const double *__restrict__ coefBL,
-                                                                  const double *__restrict__ coefAR, const double *__restrict__ coefBR) {
+                                                                  const double *__restrict__ coefAR, const double *__restrict__ coefBR,
+                                                                  const int2 *__restrict__ packL, const int2 *__restrict__ packR) {
     constexpr int HALF = WIN / 2, LW = RUN_TX + 2 * HALF, LWP = (LW + 3) & ~3, RS = RUN_RS;
     extern __shared__ __align__(16) float run_smem[];
     const int DC = blockDim.x, RW = LWP + DC;
@@ -356,7 +361,11 @@ __global__ void __launch_bounds__(128) window_cost_running_kernel(const float *_
                     for (int p = 0; p < RUN_TX; ++p) {
                         float res = c;
                         if (MODE == 2) {
-                            res = (float)fma((double)c, __ldg(coefAL + pix0 + p) * __ldg(coefAR + pix0 + p + d), -(__ldg(coefBL + pix0 + p) * __ldg(coefBR + pix0 + p + d)));
+                            {   // exact integer numerator w^2 * S_LR - S_L * S_R (|.| < 2^31 by the value bound), float32 factors 1 / (w^2 * std)
+                                const int2 pl = __ldg(packL + pix0 + p), pr = __ldg(packR + pix0 + p + d);
+                                const int num = (WIN * WIN) * __float2int_rn(c) - pl.x * pr.x;
+                                res = ((float)num * __int_as_float(pl.y)) * __int_as_float(pr.y);
+                            }
                         }
                         __stcs(dst + (size_t)p * D, res);
                         if (p + 1 < RUN_TX) c = (c + V[p + 2 * HALF + 1]) - V[p];
@@ -367,7 +376,11 @@ __global__ void __launch_bounds__(128) window_cost_running_kernel(const float *_
                         float res = nan_f();
                         if (p >= p_lo && p < p_hi) {
                             if (MODE == 2) {
-                                res = (float)fma((double)c, __ldg(coefAL + pix0 + p) * __ldg(coefAR + pix0 + p + d), -(__ldg(coefBL + pix0 + p) * __ldg(coefBR + pix0 + p + d)));
+                                {   // exact integer numerator w^2 * S_LR - S_L * S_R (|.| < 2^31 by the value bound), float32 factors 1 / (w^2 * std)
+                                const int2 pl = __ldg(packL + pix0 + p), pr = __ldg(packR + pix0 + p + d);
+                                const int num = (WIN * WIN) * __float2int_rn(c) - pl.x * pr.x;
+                                res = ((float)num * __int_as_float(pl.y)) * __int_as_float(pr.y);
+                            }
                             } else {
                                 res = c;
                             }
@@ -406,7 +419,8 @@ __global__ void __launch_bounds__(128) window_cost_running_kernel(const float *_
 
 template <int MODE>
 static int launch_window_running(const float *L, const float *R, int H, int W, int win, int dmin, int D, float *cv, const double *mL,
-                                 const double *sL, const double *mR, const double *sR, cudaStream_t s, bool *done) {
+                                 const double *sL, const double *mR, const double *sR, cudaStream_t s, bool *done,
+                                 const int2 *pkL = nullptr, const int2 *pkR = nullptr) {
     *done = false;
     if (win > 13 || option(OPT_SAD_TAPS) > 0) return PB200_OK;
     const int nw = ceil_div(D, 32), nchunk = ceil_div(nw, 4), DC = 32 * ceil_div(nw, nchunk);   // D = 192: two chunks of three warps
@@ -414,14 +428,16 @@ static int launch_window_running(const float *L, const float *R, int H, int W, i
     const size_t smem = (size_t)RS * (2 * LWP + DC) * sizeof(float);
     // largest |pixel| for which (w^2 + w) terms stay below 2^24: SAD term <= 2v, SSD <= 4v^2, ZNCC <= v^2
     const double room = 16777216.0 / (double)(win * win + win);
-    const float vmax = MODE == 0 ? (float)floor(room / 2.0 - 1.0) : MODE == 1 ? (float)floor(sqrt(room / 4.0) - 1.0) : (float)floor(sqrt(room) - 1.0);
+    // ZNCC also needs w^4 * v^2 < 2^31: its numerator w^2 * S_LR - S_L * S_R is formed in 32-bit integers
+    const float vmax = MODE == 0 ? (float)floor(room / 2.0 - 1.0) : MODE == 1 ? (float)floor(sqrt(room / 4.0) - 1.0)
+                                 : (float)floor(fmin(sqrt(room), 46340.0 / (double)(win * win)) - 1.0);
     const int gx = ceil_div(W, RUN_TX), gz = ceil_div(D, DC);
     int band = 64;                                       // shorter bands until the grid fills the SMs a few times over
     while (band > 16 && (long)gx * gz * ceil_div(H, band) < 4L * sm_count()) band >>= 1;
     dim3 grid(gx, ceil_div(H, band), gz);
 #define PB200_W(WIN)                                                                                                         \
     case WIN:                                                                                                                \
-        window_cost_running_kernel<WIN, MODE><<<grid, DC, smem, s>>>(L, R, H, W, dmin, D, band, vmax, cv, mL, sL, mR, sR);   \
+        window_cost_running_kernel<WIN, MODE><<<grid, DC, smem, s>>>(L, R, H, W, dmin, D, band, vmax, cv, mL, sL, mR, sR, pkL, pkR);   \
         break;
     switch (win) {
         PB200_W(1) PB200_W(3) PB200_W(5) PB200_W(7) PB200_W(9) PB200_W(11) PB200_W(13)
@@ -490,7 +506,7 @@ extern "C" int pb200_sad_ssd_cost_volume(const float *d_left, const float *d_rig
 
 extern "C" size_t pb200_zncc_workspace_bytes(int H, int W) {
     if (H <= 0 || W <= 0) return 0;
-    return 8 * (size_t)H * W * sizeof(double);
+    return 10 * (size_t)H * W * sizeof(double);
 }
 
 extern "C" int pb200_zncc_cost_volume(const float *d_left, const float *d_right, int H, int W, int window, int dmin, int D,
@@ -510,13 +526,14 @@ extern "C" int pb200_zncc_cost_volume(const float *d_left, const float *d_right,
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)H * W;
     double *mL = (double *)d_workspace, *sL = mL + n, *mR = sL + n, *sR = mR + n, *aL = sR + n, *bL = aL + n, *aR = bL + n, *bR = aR + n;
+    int2 *pkL = reinterpret_cast<int2 *>(bR + n), *pkR = pkL + n;
     const int g1 = ceil_div((long)n, 256);
-    zncc_stats_kernel<<<g1, 256, 0, s>>>(d_left, H, W, window, mL, sL, aL, bL, 1.0 / (double)(window * window));
+    zncc_stats_kernel<<<g1, 256, 0, s>>>(d_left, H, W, window, mL, sL, aL, bL, 1.0 / (double)(window * window), pkL);
     PB200_LAUNCH_CHECK("zncc_stats_kernel");
-    zncc_stats_kernel<<<g1, 256, 0, s>>>(d_right, H, W, window, mR, sR, aR, bR, 1.0);
+    zncc_stats_kernel<<<g1, 256, 0, s>>>(d_right, H, W, window, mR, sR, aR, bR, 1.0, pkR);
     PB200_LAUNCH_CHECK("zncc_stats_kernel");
     bool done = false;
-    int rc = launch_window_running<2>(d_left, d_right, H, W, window, dmin, D, d_cv, aL, bL, aR, bR, s, &done);
+    int rc = launch_window_running<2>(d_left, d_right, H, W, window, dmin, D, d_cv, aL, bL, aR, bR, s, &done, pkL, pkR);
     if (rc != PB200_OK || done) return rc;
     note_path(STAGE_SAD, PATH_SAD_TAPS);
     rc = launch_window_cost<2>(d_left, d_right, H, W, window, dmin, D, d_cv, mL, sL, mR, sR, s, &done);
