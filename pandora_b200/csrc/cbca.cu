@@ -612,7 +612,7 @@ static int launch_cbca(const float *in, float *out, float *out_n, int H, int W, 
 int cbca_dispatch(const float *in, float *out, float *out_n, int H, int W, int D, int dmin, int off, const int16_t *cl,
                   const int16_t *cr, int len_arms, cudaStream_t s) {
     const int ma = len_arms - 1;
-    // the register kernel takes the common case (cbca_distance <= 5, normalised output); PB200_CBCA_PIPE=1 keeps the staged one
+    // the register kernel takes the common case (cbca_distance <= 5, normalised output); the option "cbca.pipe" = 1 keeps the staged one
     if (ma <= CBR_MA && out_n == nullptr && option(OPT_CBCA_PIPE) <= 0) return launch_cbca_reg(in, out, H, W, D, dmin, off, cl, cr, s);
 #define PB200_C(MA)                                                                                     \
     return out_n ? launch_cbca<MA, true>(in, out, out_n, H, W, D, dmin, off, cl, cr, s)                 \

@@ -40,6 +40,6 @@ for name, env in (("register kernel", None), ("staged kernel", "1")):
     alg = (8 * D + 24) * H * W
     print(f"cbca aggregate {H}x{W}x{D} {name}: {min(ts):.3f} ms (min of {reps}); {alg / min(ts) / 1e6:.0f} GB/s algorithmic", flush=True)
     outs[name] = out
-os.environ.pop("PB200_CBCA_PIPE", None)
+pandora_b200.set_option("cbca.pipe", -1)
 a, b = (torch.nan_to_num(o, nan=-7.0) for o in outs.values())
 print("identical:", bool(torch.equal(a, b)), "mismatching cells:", int((a != b).sum()))
