@@ -21,4 +21,4 @@ from .cost_volume_confidence import AbstractCostVolumeConfidence, Ambiguity, Ris
 from .criteria import validity_mask  # noqa: F401
 from .filter import AbstractFilter, MedianFilter  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
