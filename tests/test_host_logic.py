@@ -369,3 +369,35 @@ def test_pandora_plugin_module_imports_and_registers_on_stand_in_factories():
     assert o.cfg["optimization_method"] == "sgm_b200" and o.cfg["penalty"]["P2"] == 20
     assert agg(aggregation_method="cbca_b200", cbca_distance=3).cfg["cbca_distance"] == 3
     assert np.isnan(disp(disparity_method="wta_b200", invalid_disparity="NaN").cfg["invalid_disparity"])
+
+
+def test_sgm_options_configuration_and_confidence_band_lookup():
+    """use_confidence names a cost_volume_confidence step; its ambiguity band is confidence_from_ambiguity[.suffix]
+    (state_machine.py:566-576), a missing band means confidence 1 (plugin_libsgm.rst:47); min_cost_paths is a bool."""
+    import numpy as np
+
+    from pandora_b200 import ConfigError, Dataset
+    from pandora_b200.dataset import DataArray
+    from pandora_b200.optimization import Sgm
+
+    with pytest.raises(ConfigError):
+        Sgm(None, optimization_method="sgm", use_confidence=3)
+    with pytest.raises(ConfigError):
+        Sgm(None, optimization_method="sgm", min_cost_paths="yes")
+    with pytest.raises(ConfigError):
+        Sgm(None, optimization_method="sgm", penalty={"P1": 8, "P2": 8})
+    sgm = Sgm(None, optimization_method="sgm", use_confidence="cost_volume_confidence.before", min_cost_paths=True)
+    assert sgm.cfg["min_cost_paths"] is True and sgm.cfg["penalty"]["P1"] == 8 and sgm.cfg["penalty"]["P2"] == 32
+    cv = Dataset(coords={"row": np.arange(2), "col": np.arange(3), "disp": np.arange(-1, 1)})
+    assert sgm._confidence_map(cv) is None                                  # no confidence measure at all
+    layers = np.stack([np.full((2, 3), 0.25, np.float32), np.full((2, 3), 0.75, np.float32)], axis=2)
+    cv["confidence_measure"] = (("row", "col", "indicator"), layers)
+    cv.coords["indicator"] = DataArray(np.array(["confidence_from_ambiguity", "confidence_from_ambiguity.before"]), ("indicator",))
+    np.testing.assert_array_equal(sgm._confidence_map(cv), np.full((2, 3), 0.75, np.float32))
+    plain = Sgm(None, optimization_method="sgm", use_confidence="cost_volume_confidence")
+    np.testing.assert_array_equal(plain._confidence_map(cv), np.full((2, 3), 0.25, np.float32))
+    other = Sgm(None, optimization_method="sgm", use_confidence="cost_volume_confidence.after")
+    assert other._confidence_map(cv) is None                                # band does not exist: confidence 1
+    Sgm._append_band(cv, np.full((2, 3), 8.0, np.float32))
+    assert list(cv.coords["indicator"].data)[-1] == "optimization_plugin_libsgm_nb_of_directions"
+    assert cv["confidence_measure"].data.shape == (2, 3, 3)
